@@ -1,0 +1,8 @@
+"""consul_b200 — B200-native SWIM/Serf gossip simulator behind Consul's serf surface.
+
+Only the gossip hot path of hashicorp/consul is implemented: memberlist's
+failure detector + dissemination and serf's Lamport-clocked piggyback, as sm_100a CUDA
+kernels behind the C ABI in include/gsim.h.
+"""
+from .pool import (Pool, GsimError, lan_config, wan_config, consul_test_config,  # noqa: F401
+                   PRED_RUMOR_CONVERGED, PRED_ALL_RUMORS_CONVERGED, PRED_CRASHED_ALL_DEAD, NEVER)

@@ -1,0 +1,1292 @@
+// gs_api.cpp — host side of libgsim: the C ABI declared in include/gsim.h.
+//
+// Everything here is control plane: configuration, the N-dependent scalar tables
+// (evaluated in double exactly like [U] memberlist/util.go and
+// suspicion.go and then quantised to ticks so no floating point runs on the GPU), the
+// serf-level operations that happen between ticks (Create/Join/Leave/UserEvent), and the
+// rumor-slot bookkeeping.  The data plane is gs_cuda.cu.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gsim.h"
+#include "gs_backend.h"
+
+#ifndef GS_MAKE_BACKEND
+#define GS_MAKE_BACKEND gs_make_cuda_backend
+#endif
+GsBackend* GS_MAKE_BACKEND(int device, char* err, size_t err_cap);
+
+// ---------------------------------------------------------------------------
+// pure formulas
+// ---------------------------------------------------------------------------
+extern "C" uint32_t gsim_retransmit_limit(uint32_t retransmit_mult, uint32_t n) {
+  // [U] memberlist/util.go retransmitLimit: mult * ceil(log10(n+1));
+  // doc form pinned by /root/reference/agent/config/runtime.go:1328-1330
+  double node_scale = ceil(log10((double)n + 1.0));
+  return retransmit_mult * (uint32_t)(int64_t)node_scale;
+}
+
+extern "C" uint64_t gsim_suspicion_timeout_ns(uint32_t suspicion_mult, uint32_t n,
+                                              uint64_t interval_ns) {
+  // [U] memberlist/util.go suspicionTimeout: mult * max(1, log10(max(1,n))) * interval,
+  // computed as mult * Duration(nodeScale*1000) * interval / 1000 in int64;
+  // doc form pinned by agent/config/runtime.go:1310-1312
+  double node_scale = fmax(1.0, log10(fmax(1.0, (double)n)));
+  int64_t scaled = (int64_t)(node_scale * 1000.0);
+  return (uint64_t)((int64_t)suspicion_mult * scaled * (int64_t)interval_ns / 1000);
+}
+
+static uint64_t suspicion_total_ns(uint32_t n_confirm, uint32_t k, uint64_t min_ns,
+                                   uint64_t max_ns) {
+  // [U] memberlist/suspicion.go remainingSuspicionTime without the elapsed term
+  if (k < 1) return min_ns;
+  double frac = log((double)n_confirm + 1.0) / log((double)k + 1.0);
+  double max_s = (double)max_ns / 1e9, min_s = (double)min_ns / 1e9;
+  double raw = max_s - frac * (max_s - min_s);
+  int64_t timeout = (int64_t)floor(1000.0 * raw) * 1000000ll;
+  if (timeout < (int64_t)min_ns) timeout = (int64_t)min_ns;
+  return (uint64_t)timeout;
+}
+
+extern "C" int64_t gsim_remaining_suspicion_ns(uint32_t n_confirm, uint32_t k, uint64_t elapsed_ns,
+                                               uint64_t min_ns, uint64_t max_ns) {
+  return (int64_t)suspicion_total_ns(n_confirm, k, min_ns, max_ns) - (int64_t)elapsed_ns;
+}
+
+extern "C" uint64_t gsim_push_pull_scale_ns(uint64_t interval_ns, uint32_t n) {
+  // [U] memberlist/util.go pushPullScale, threshold 32
+  if (n <= 32) return interval_ns;
+  double mult = ceil(log2((double)n) - log2(32.0)) + 1.0;
+  return (uint64_t)((int64_t)mult * (int64_t)interval_ns);
+}
+
+extern "C" uint32_t gsim_lamport_witness(uint32_t clock, uint32_t v) {
+  // [U] serf/lamport.go Witness: if v >= cur, cur = v + 1
+  return v < clock ? clock : v + 1u;
+}
+
+extern "C" uint32_t gsim_refute_incarnation(uint32_t cur, uint32_t accused) {
+  // [U] memberlist/state.go refute: inc = nextIncarnation(); if accused >= inc,
+  // inc = skipIncarnation(accused - inc + 1)
+  uint32_t inc = cur + 1u;
+  if (accused >= inc) inc += accused - inc + 1u;
+  return inc;
+}
+
+extern "C" void gsim_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  GsU4 r = gs_philox(key[0], key[1], ctr[0], ctr[1], ctr[2], ctr[3]);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  out[3] = r.w;
+}
+
+// ---------------------------------------------------------------------------
+// config presets
+// ---------------------------------------------------------------------------
+static const uint64_t MS = 1000000ull, SEC = 1000000000ull;
+
+extern "C" void gsim_config_default_lan(gsim_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(*c);
+  c->seed = 0x5EED0001ull;
+  c->capacity = 1024;
+  // [U] memberlist DefaultLANConfig, pinned by agent/config/runtime.go:1271-1336
+  c->probe_interval_ns = 1 * SEC;
+  c->probe_timeout_ns = 500 * MS;
+  c->gossip_interval_ns = 200 * MS;
+  c->gossip_to_the_dead_ns = 30 * SEC;
+  c->push_pull_interval_ns = 30 * SEC;
+  c->gossip_nodes = 3;
+  c->indirect_checks = 3;
+  c->retransmit_mult = 4;
+  c->suspicion_mult = 4;
+  c->suspicion_max_timeout_mult = 6;
+  c->awareness_max_multiplier = 8;
+  c->udp_buffer_size = 1400;
+  // [U] serf DefaultConfig with Consul's overrides: libserf/serf.go:19-36,
+  // agent/consul/config.go:622-623 (ReconnectTimeout 72h)
+  c->event_buffer = 512;
+  c->user_event_size_limit = 512;
+  c->leave_propagate_delay_ns = 3 * SEC;
+  c->broadcast_timeout_ns = 5 * SEC;
+  c->reap_interval_ns = 15 * SEC;
+  c->reconnect_timeout_ns = 72ull * 3600 * SEC;
+  c->tombstone_timeout_ns = 24ull * 3600 * SEC;
+  c->world_size = 1;
+  c->rank = 0;
+  c->device = -1;
+}
+
+extern "C" void gsim_config_default_wan(gsim_config* c) {
+  gsim_config_default_lan(c);
+  // [U] memberlist DefaultWANConfig, pinned by agent/config/runtime.go:1348-1413;
+  // gossip_nodes stays 3: agent/config/default.go:88-89 seeds gossip_wan from the LAN struct
+  c->probe_interval_ns = 5 * SEC;
+  c->probe_timeout_ns = 3 * SEC;
+  c->gossip_interval_ns = 500 * MS;
+  c->gossip_to_the_dead_ns = 60 * SEC;
+  c->push_pull_interval_ns = 60 * SEC;
+  c->suspicion_mult = 6;
+}
+
+extern "C" void gsim_config_consul_test(gsim_config* c) {
+  gsim_config_default_lan(c);
+  // agent/consul/server_test.go:221-237
+  c->probe_interval_ns = 100 * MS;
+  c->probe_timeout_ns = 50 * MS;
+  c->gossip_interval_ns = 100 * MS;
+  c->suspicion_mult = 2;
+}
+
+// ---------------------------------------------------------------------------
+// pool
+// ---------------------------------------------------------------------------
+struct RumorHost {
+  std::string name, payload;
+  int coalesce = 0;
+};
+struct Sched {
+  uint32_t tick, id, action;  // action 1 = shut down after Leave()
+};
+
+struct gsim_pool {
+  gsim_config cfg;
+  GsBackend* be = nullptr;
+  GsDev d;
+  GsGlobals g;
+  GsGlobals* g_dev = nullptr;
+  bool g_dirty = true;
+  bool counts_stale = true;
+  uint32_t now = 0;
+  uint64_t node_ticks = 0;
+  std::mutex mu;
+  RumorHost rh[GS_MAX_RUMORS];
+  std::vector<Sched> sched;
+  std::vector<void*> allocs;
+  GsRecount rc;
+  double last_ms = 0;
+  uint64_t last_launches = 0;
+  uint32_t events_dropped = 0;
+  std::string err;
+  uint64_t tick_ns = 0;
+  uint32_t leave_linger_base = 0;
+};
+
+static uint64_t gcd64(uint64_t a, uint64_t b) {
+  while (b) {
+    uint64_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+static uint32_t ceil_ticks(uint64_t ns, uint64_t tick) { return (uint32_t)((ns + tick - 1) / tick); }
+
+static int fail(gsim_pool* p, int code, const char* msg) {
+  p->err = msg ? msg : "";
+  if (code == GSIM_ERR_CUDA && p->be) p->err += std::string(": ") + p->be->last_error();
+  return code;
+}
+
+template <class T>
+static bool peek(gsim_pool* p, const T* col, size_t i, T* out) {
+  return p->be->d2h(out, col + i, sizeof(T));
+}
+template <class T>
+static bool poke(gsim_pool* p, T* col, size_t i, T v) {
+  return p->be->h2d(col + i, &v, sizeof(T));
+}
+
+// N-dependent scalars, recomputed whenever the member count changes (a11).
+static void recompute_tables(gsim_pool* p) {
+  GsGlobals& g = p->g;
+  const gsim_config& c = p->cfg;
+  const uint32_t n = g.n;
+  g.retransmit_limit = gsim_retransmit_limit(c.retransmit_mult, n);
+  if (g.retransmit_limit > 255u) g.retransmit_limit = 255u;
+  // [U] memberlist/state.go suspectNode: k = SuspicionMult - 2, 0 if n-2 < k
+  int k = (int)c.suspicion_mult - 2;
+  if ((int)n - 2 < k) k = 0;
+  if (k < 0) k = 0;
+  if (k > GS_K1MAX - 1) k = GS_K1MAX - 1;
+  g.sus_k = (uint32_t)k;
+  uint64_t min_ns = gsim_suspicion_timeout_ns(c.suspicion_mult, n, c.probe_interval_ns);
+  uint64_t max_ns = (uint64_t)c.suspicion_max_timeout_mult * min_ns;
+  for (uint32_t q = 0; q < GS_K1MAX; ++q) {
+    uint32_t cc = q > g.sus_k ? g.sus_k : q;
+    g.sus_ticks[q] = ceil_ticks(suspicion_total_ns(cc, g.sus_k, min_ns, max_ns), p->tick_ns);
+  }
+  uint32_t bits = 0;
+  while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+  if (bits < 2) bits = 2;
+  if (bits & 1u) ++bits;
+  g.perm_half_bits = bits / 2;
+  p->g_dirty = true;
+}
+
+static bool upload_globals(gsim_pool* p) {
+  if (!p->g_dirty) return true;
+  if (!p->be->h2d(p->g_dev, &p->g, sizeof(GsGlobals))) return false;
+  p->g_dirty = false;
+  return true;
+}
+
+static void rebuild_class_masks(gsim_pool* p) {
+  GsGlobals& g = p->g;
+  g.class_mask[0] = g.class_mask[1] = g.class_mask[2] = 0;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if ((g.active_mask >> r) & 1u) g.class_mask[g.rumors[r].qclass] |= 1u << r;
+  p->g_dirty = true;
+}
+
+template <class T>
+static bool alloc_col(gsim_pool* p, T** out, size_t count) {
+  void* q = p->be->alloc(count * sizeof(T));
+  if (!q) return false;
+  p->allocs.push_back(q);
+  *out = reinterpret_cast<T*>(q);
+  return true;
+}
+
+extern "C" int gsim_abi_version(void) { return GSIM_ABI_VERSION; }
+
+extern "C" const char* gsim_strerror(int code) {
+  switch (code) {
+    case GSIM_OK: return "ok";
+    case GSIM_ERR_INVALID: return "invalid argument";
+    case GSIM_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (libgsim has no CPU fallback)";
+    case GSIM_ERR_CUDA: return "CUDA error";
+    case GSIM_ERR_CAPACITY: return "capacity exhausted";
+    case GSIM_ERR_NOT_FOUND: return "not found";
+    case GSIM_ERR_STATE: return "illegal state";
+    case GSIM_ERR_TOO_LARGE: return "user event too large";
+    case GSIM_ERR_NOMEM: return "out of memory";
+  }
+  return "unknown error";
+}
+
+extern "C" const char* gsim_last_error(gsim_pool* p) { return p ? p->err.c_str() : ""; }
+
+static thread_local std::string g_create_err;
+
+extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
+  if (!cfg || !out || cfg->struct_size != sizeof(gsim_config)) return GSIM_ERR_INVALID;
+  if (cfg->capacity == 0 || cfg->n_initial > cfg->capacity) return GSIM_ERR_INVALID;
+  if (!cfg->probe_interval_ns || !cfg->probe_timeout_ns || !cfg->gossip_interval_ns)
+    return GSIM_ERR_INVALID;
+  if (cfg->probe_timeout_ns >= cfg->probe_interval_ns) return GSIM_ERR_INVALID;
+  if (cfg->world_size != 1 || cfg->rank != 0) return GSIM_ERR_INVALID;  // sharding: see DESIGN.md
+  uint64_t tick = cfg->tick_ns;
+  if (!tick) tick = gcd64(gcd64(cfg->probe_interval_ns, cfg->probe_timeout_ns), cfg->gossip_interval_ns);
+  if (cfg->probe_interval_ns % tick || cfg->probe_timeout_ns % tick || cfg->gossip_interval_ns % tick)
+    return GSIM_ERR_INVALID;
+  if (cfg->gossip_interval_ns / tick > 255 || cfg->awareness_max_multiplier < 1 ||
+      cfg->awareness_max_multiplier > 8 || cfg->gossip_nodes > 8 || cfg->indirect_checks > 8)
+    return GSIM_ERR_INVALID;
+
+  char errbuf[256] = {0};
+  GsBackend* be = GS_MAKE_BACKEND(cfg->device, errbuf, sizeof(errbuf));
+  if (!be) {
+    g_create_err = errbuf;
+    fprintf(stderr, "libgsim: %s\n", errbuf);
+    return GSIM_ERR_NO_DEVICE;
+  }
+  gsim_pool* p = new gsim_pool();
+  p->cfg = *cfg;
+  p->be = be;
+  p->tick_ns = tick;
+  memset(&p->d, 0, sizeof(p->d));
+  memset(&p->g, 0, sizeof(p->g));
+  memset(&p->rc, 0, sizeof(p->rc));
+  const size_t cap = cfg->capacity;
+  GsDev& d = p->d;
+  GsGlobals& g = p->g;
+  bool okk = true;
+  okk = okk && alloc_col(p, &d.key[0], cap) && alloc_col(p, &d.key[1], cap);
+  okk = okk && alloc_col(p, &d.inbox[0], cap) && alloc_col(p, &d.inbox[1], cap);
+  okk = okk && alloc_col(p, &d.due, cap) && alloc_col(p, &d.meta, cap);
+  okk = okk && alloc_col(p, &d.cursor, cap) && alloc_col(p, &d.pass, cap);
+  okk = okk && alloc_col(p, &d.probe_tgt, cap) && alloc_col(p, &d.probe_inc, cap);
+  okk = okk && alloc_col(p, &d.sus_start, cap) && alloc_col(p, &d.sus_from, cap * GS_K1MAX);
+  okk = okk && alloc_col(p, &d.acc, cap * GS_K1MAX * 2);
+  okk = okk && alloc_col(p, &d.change_tick, cap);
+  okk = okk && alloc_col(p, &d.ltime_member, cap) && alloc_col(p, &d.ltime_event, cap);
+  okk = okk && alloc_col(p, &d.event_min, cap);
+  okk = okk && alloc_col(p, &d.heard, cap) && alloc_col(p, &d.queued, cap);
+  okk = okk && alloc_col(p, &d.tx, cap * GS_MAX_RUMORS);
+  okk = okk && alloc_col(p, &d.stats, (size_t)GSIM_STAT_COUNT);
+  okk = okk && alloc_col(p, &d.heard_cnt, (size_t)32) && alloc_col(p, &d.conv_tick, (size_t)32);
+  okk = okk && alloc_col(p, &d.view_cnt, (size_t)4);
+  okk = okk && alloc_col(p, &d.crashed_alive, (size_t)1) && alloc_col(p, &d.crashed_dead_tick, (size_t)1);
+  uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
+  okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
+  okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
+  okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
+  if (!okk) {
+    g_create_err = be->last_error();
+    gsim_pool_destroy(p);
+    return GSIM_ERR_NOMEM;
+  }
+  // key = 0 means truth NONE for rows that were never created
+  okk = okk && be->fill32(d.key[0], 0, cap) && be->fill32(d.key[1], 0, cap);
+  okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
+  okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
+  okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
+  okk = okk && be->fill32(d.heard_cnt, 0, 32) && be->fill32(d.conv_tick, GS_EMPTY32, 32);
+  okk = okk && be->fill32(d.view_cnt, 0, 4) && be->fill32(d.crashed_alive, 0, 1);
+  okk = okk && be->fill32(d.crashed_dead_tick, GS_EMPTY32, 1);
+  okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
+
+  g.n = cfg->n_initial;
+  g.cap = cfg->capacity;
+  g.up_count = cfg->n_initial;
+  g.P = (uint32_t)(cfg->probe_interval_ns / tick);
+  g.T = (uint32_t)(cfg->probe_timeout_ns / tick);
+  g.GI = (uint32_t)(cfg->gossip_interval_ns / tick);
+  g.gossip_nodes = cfg->gossip_nodes;
+  g.indirect_checks = cfg->indirect_checks;
+  g.awareness_max = cfg->awareness_max_multiplier;
+  g.gtd_ticks = ceil_ticks(cfg->gossip_to_the_dead_ns, tick);
+  // [U] memberlist/state.go gossip(): bytesAvail = UDPBufferSize - compoundHeaderOverhead(2)
+  g.udp_avail = cfg->udp_buffer_size > 2 ? cfg->udp_buffer_size - 2 : 0;
+  g.disable_tcp = cfg->disable_tcp_pings;
+  g.loss_thr = (uint32_t)(((uint64_t)cfg->packet_loss_ppm << 32) / 1000000ull);
+  if (cfg->packet_loss_ppm >= 1000000u) g.loss_thr = 0xFFFFFFFFu;
+  g.event_buffer = cfg->event_buffer;
+  g.seed_lo = (uint32_t)cfg->seed;
+  g.seed_hi = (uint32_t)(cfg->seed >> 32);
+  g.flags = cfg->flags;
+  g.evlog_cap = evcap;
+  g.world = cfg->world_size;
+  g.rank = cfg->rank;
+  recompute_tables(p);
+  okk = okk && upload_globals(p);
+  okk = okk && be->init_rows(d, p->g_dev, g, 0, cfg->n_initial, 0);
+  if (!okk) {
+    g_create_err = be->last_error();
+    fprintf(stderr, "libgsim: pool init failed: %s\n", be->last_error());
+    gsim_pool_destroy(p);
+    return GSIM_ERR_CUDA;
+  }
+  *out = p;
+  return GSIM_OK;
+}
+
+extern "C" void gsim_pool_destroy(gsim_pool* p) {
+  if (!p) return;
+  if (p->be) {
+    p->be->sync();
+    for (void* q : p->allocs) p->be->release(q);
+    delete p->be;
+  }
+  delete p;
+}
+
+// ---- rumor slots --------------------------------------------------------------
+static bool do_recount(gsim_pool* p) {
+  if (!p->counts_stale) return true;
+  if (!upload_globals(p)) return false;
+  if (!p->be->recount(p->d, p->g_dev, p->g, p->now, &p->rc)) return false;
+  p->counts_stale = false;
+  return true;
+}
+
+static bool and_bit_columns(gsim_pool* p, uint32_t keep);
+
+static int retire_slot(gsim_pool* p, uint32_t slot) {
+  GsGlobals& g = p->g;
+  GsRumor& ru = g.rumors[slot];
+  if (ru.kind == GSIM_RUMOR_ALIVE) {
+    // fold into the base state: the subject becomes known to every non-isolated member
+    uint32_t k0, k1;
+    if (!peek(p, p->d.key[0], ru.subject, &k0) || !peek(p, p->d.key[1], ru.subject, &k1))
+      return GSIM_ERR_CUDA;
+    k0 &= ~(1u << 4);
+    k1 &= ~(1u << 4);
+    if (!poke(p, p->d.key[0], ru.subject, k0) || !poke(p, p->d.key[1], ru.subject, k1))
+      return GSIM_ERR_CUDA;
+  }
+  g.active_mask &= ~(1u << slot);
+  memset(&ru, 0, sizeof(ru));
+  p->rh[slot] = RumorHost();
+  rebuild_class_masks(p);
+  if (!and_bit_columns(p, ~(1u << slot))) return GSIM_ERR_CUDA;
+  if (!poke(p, p->d.heard_cnt, slot, 0u) || !poke(p, p->d.conv_tick, slot, GS_EMPTY32))
+    return GSIM_ERR_CUDA;
+  p->counts_stale = true;
+  return GSIM_OK;
+}
+
+// heard/queued/inbox bits of a freed slot must be zero before the slot is reused.
+static bool and_bit_columns(gsim_pool* p, uint32_t keep) {
+  // Rare control-plane operation: stream the three mask columns through the host.
+  const uint32_t n = p->g.n;
+  if (!n) return true;
+  std::vector<uint32_t> buf(n);
+  uint32_t* cols[4] = {p->d.heard, p->d.queued, p->d.inbox[0], p->d.inbox[1]};
+  for (int c = 0; c < 4; ++c) {
+    if (!p->be->d2h(buf.data(), cols[c], (size_t)n * 4)) return false;
+    bool changed = false;
+    for (uint32_t i = 0; i < n; ++i) {
+      uint32_t v = buf[i] & keep;
+      changed |= v != buf[i];
+      buf[i] = v;
+    }
+    if (changed && !p->be->h2d(cols[c], buf.data(), (size_t)n * 4)) return false;
+  }
+  return true;
+}
+
+// Retire finished membership rumors (alive / intents): every UP member has heard them and
+// nobody is retransmitting any more.  Runs at step boundaries only.
+static int auto_retire(gsim_pool* p) {
+  GsGlobals& g = p->g;
+  uint32_t cand = 0;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if (((g.active_mask >> r) & 1u) && g.rumors[r].kind != GSIM_RUMOR_USER_EVENT) cand |= 1u << r;
+  if (!cand) return GSIM_OK;
+  if (!do_recount(p)) return GSIM_ERR_CUDA;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+    if (!((cand >> r) & 1u)) continue;
+    if (p->rc.heard_cnt[r] == g.up_count && p->rc.queued_cnt[r] == 0) {
+      int rcode = retire_slot(p, r);
+      if (rcode) return rcode;
+    }
+  }
+  return GSIM_OK;
+}
+
+static int alloc_slot(gsim_pool* p, uint32_t* slot_out) {
+  GsGlobals& g = p->g;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+      if (!((g.active_mask >> r) & 1u)) {
+        *slot_out = r;
+        return GSIM_OK;
+      }
+    if (attempt == 0) {
+      int rc = auto_retire(p);
+      if (rc) return rc;
+    }
+  }
+  return GSIM_ERR_CAPACITY;
+}
+
+static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subject, uint32_t inc,
+                       uint32_t ltime, uint32_t origin, uint32_t size, uint32_t qclass) {
+  GsGlobals& g = p->g;
+  GsRumor& ru = g.rumors[slot];
+  ru.kind = kind;
+  ru.subject = subject;
+  ru.inc = inc;
+  ru.ltime = ltime;
+  ru.origin = origin;
+  ru.size = size;
+  ru.qclass = qclass;
+  ru.start_tick = p->now;
+  g.active_mask |= 1u << slot;
+  rebuild_class_masks(p);
+  // the origin holds it with transmits = 0
+  uint32_t h, q;
+  if (!peek(p, p->d.heard, origin, &h) || !peek(p, p->d.queued, origin, &q)) return GSIM_ERR_CUDA;
+  h |= 1u << slot;
+  q |= 1u << slot;
+  if (!poke(p, p->d.heard, origin, h) || !poke(p, p->d.queued, origin, q)) return GSIM_ERR_CUDA;
+  if (!poke(p, p->d.tx, (size_t)slot * g.cap + origin, (uint8_t)0)) return GSIM_ERR_CUDA;
+  if (!poke(p, p->d.heard_cnt, slot, 1u)) return GSIM_ERR_CUDA;
+  if (!poke(p, p->d.conv_tick, slot, g.up_count == 1u ? p->now : GS_EMPTY32)) return GSIM_ERR_CUDA;
+  p->counts_stale = true;
+  return GSIM_OK;
+}
+
+static void log_host_event(gsim_pool* p, uint32_t type, uint32_t subject, uint32_t observer,
+                           uint32_t ltime) {
+  uint32_t cur[2];
+  if (!p->be->d2h(cur, p->d.evlog_cursor, 8)) return;
+  if (cur[0] < p->g.evlog_cap) {
+    GsEventRec e = {p->now, type, subject, observer, ltime, 0u};
+    p->be->h2d(p->d.evlog + cur[0], &e, sizeof(e));
+    cur[0]++;
+  } else {
+    cur[1]++;
+  }
+  p->be->h2d(p->d.evlog_cursor, cur, 8);
+}
+
+// ---- membership operations -------------------------------------------------------
+extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint32_t* id_out) {
+  if (!p || !id_out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  GsGlobals& g = p->g;
+  if (g.n >= g.cap) return fail(p, GSIM_ERR_CAPACITY, "member capacity exhausted");
+  uint32_t slot;
+  int rc = alloc_slot(p, &slot);
+  if (rc) return fail(p, rc, "no free rumor slot for the member's alive broadcast");
+  const uint32_t id = g.n;
+  if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
+  if (!p->be->init_rows(p->d, p->g_dev, g, id, 1, p->now)) return fail(p, GSIM_ERR_CUDA, "init_rows");
+  // [U] memberlist.Create -> setAlive: incarnation 1, alive{} queued on the new member;
+  // pending: other members learn of it only through that rumor (aliveNode).
+  const uint32_t k = gs_key_make(1u, 1u, GS_RANK_ALIVE, GS_TRUTH_UP);
+  uint32_t m;
+  if (!peek(p, p->d.meta, id, &m)) return fail(p, GSIM_ERR_CUDA, "peek");
+  m |= GS_META_ISOLATED;
+  if (desc && (desc->flags & GSIM_MEMBER_WATCHED)) m |= GS_META_WATCHED;
+  if (!poke(p, p->d.key[0], id, k) || !poke(p, p->d.key[1], id, k) || !poke(p, p->d.meta, id, m))
+    return fail(p, GSIM_ERR_CUDA, "poke");
+  g.n += 1;
+  g.up_count += 1;
+  recompute_tables(p);
+  uint32_t size = desc && desc->alive_msg_size ? desc->alive_msg_size : 64u;
+  rc = start_rumor(p, slot, GSIM_RUMOR_ALIVE, id, 1u, 0u, id, size, 0u);
+  if (rc) return fail(p, rc, "start_rumor");
+  *id_out = id;
+  return GSIM_OK;
+}
+
+// One direction of a join push-pull: `dst` merges what `src` knows
+// ([U] memberlist.mergeState -> aliveNode; [U] serf/delegate.go MergeRemoteState).
+static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_old_events) {
+  GsGlobals& g = p->g;
+  uint32_t hs, hd, qd, lm_s, le_s, lm_d, le_d, emin, md;
+  if (!peek(p, p->d.heard, src, &hs) || !peek(p, p->d.heard, dst, &hd) ||
+      !peek(p, p->d.queued, dst, &qd) || !peek(p, p->d.ltime_member, src, &lm_s) ||
+      !peek(p, p->d.ltime_event, src, &le_s) || !peek(p, p->d.ltime_member, dst, &lm_d) ||
+      !peek(p, p->d.ltime_event, dst, &le_d) || !peek(p, p->d.event_min, dst, &emin) ||
+      !peek(p, p->d.meta, dst, &md))
+    return GSIM_ERR_CUDA;
+  // clocks: Witness(remote - 1)  ==  max(local, remote)
+  if (lm_s > lm_d) lm_d = lm_s;
+  if (le_s > le_d) le_d = le_s;
+  if (ignore_old_events && le_s > emin) emin = le_s;  // eventMinTime = pp.EventLTime
+  uint32_t fresh = hs & ~hd & g.active_mask;
+  uint32_t accepted = 0;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+    if (!((fresh >> r) & 1u)) continue;
+    const GsRumor& ru = g.rumors[r];
+    bool accept = true;
+    if (ru.kind == GSIM_RUMOR_USER_EVENT) {
+      if (ru.ltime >= le_d) le_d = ru.ltime + 1u;
+      if (ru.ltime < emin) accept = false;
+      else if (le_d > g.event_buffer && ru.ltime < le_d - g.event_buffer) accept = false;
+      if (accept && (md & GS_META_WATCHED)) log_host_event(p, GSIM_EVENT_USER, r, dst, ru.ltime);
+    } else if (ru.kind == GSIM_RUMOR_JOIN_INTENT || ru.kind == GSIM_RUMOR_LEAVE_INTENT) {
+      if (ru.ltime >= lm_d) lm_d = ru.ltime + 1u;
+    } else if (ru.kind == GSIM_RUMOR_ALIVE) {
+      if (md & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_JOIN, ru.subject, dst, 0u);
+    }
+    if (accept) {
+      accepted |= 1u << r;
+      if (!poke(p, p->d.tx, (size_t)r * g.cap + dst, (uint8_t)0)) return GSIM_ERR_CUDA;
+      uint32_t c;
+      if (!peek(p, p->d.heard_cnt, r, &c)) return GSIM_ERR_CUDA;
+      c += 1;
+      if (!poke(p, p->d.heard_cnt, r, c)) return GSIM_ERR_CUDA;
+      if (c == g.up_count) {
+        uint32_t ct;
+        if (!peek(p, p->d.conv_tick, r, &ct)) return GSIM_ERR_CUDA;
+        if (ct == GS_EMPTY32 && !poke(p, p->d.conv_tick, r, p->now)) return GSIM_ERR_CUDA;
+      }
+    }
+  }
+  hd |= accepted;
+  qd |= accepted;
+  if (!poke(p, p->d.heard, dst, hd) || !poke(p, p->d.queued, dst, qd) ||
+      !poke(p, p->d.ltime_member, dst, lm_d) || !poke(p, p->d.ltime_event, dst, le_d) ||
+      !poke(p, p->d.event_min, dst, emin))
+    return GSIM_ERR_CUDA;
+  p->counts_stale = true;
+  return GSIM_OK;
+}
+
+extern "C" int gsim_join(gsim_pool* p, uint32_t id, const uint32_t* seeds, size_t n_seeds,
+                         int ignore_old, int* n_ok) {
+  if (!p || (!seeds && n_seeds)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  GsGlobals& g = p->g;
+  if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t kid;
+  if (!peek(p, p->d.key[p->now & 1u], id, &kid)) return fail(p, GSIM_ERR_CUDA, "peek");
+  if (gs_key_truth(kid) != GS_TRUTH_UP) return fail(p, GSIM_ERR_STATE, "member is not running");
+  int okc = 0;
+  for (size_t s = 0; s < n_seeds; ++s) {
+    uint32_t sd = seeds[s];
+    if (sd >= g.n || sd == id) continue;
+    uint32_t ks;
+    if (!peek(p, p->d.key[p->now & 1u], sd, &ks)) return fail(p, GSIM_ERR_CUDA, "peek");
+    if (gs_key_truth(ks) != GS_TRUTH_UP) continue;  // unreachable seed: Join skips it
+    // push-pull in both directions; eventJoinIgnore applies to the joiner only
+    int rc = merge_remote(p, id, sd, ignore_old != 0);
+    if (!rc) rc = merge_remote(p, sd, id, false);
+    if (rc) return fail(p, rc, "merge");
+    uint32_t mi, ms;
+    if (!peek(p, p->d.meta, id, &mi) || !peek(p, p->d.meta, sd, &ms)) return fail(p, GSIM_ERR_CUDA, "peek");
+    uint32_t iso = mi & ms & GS_META_ISOLATED;
+    mi = (mi & ~GS_META_ISOLATED) | iso;
+    ms = (ms & ~GS_META_ISOLATED) | iso;
+    if (!poke(p, p->d.meta, id, mi) || !poke(p, p->d.meta, sd, ms)) return fail(p, GSIM_ERR_CUDA, "poke");
+    ++okc;
+  }
+  if (okc > 0) {
+    // [U] serf.Join -> broadcastJoin(clock.Time()): Witness(ltime), join intent queued
+    uint32_t lm;
+    if (!peek(p, p->d.ltime_member, id, &lm)) return fail(p, GSIM_ERR_CUDA, "peek");
+    uint32_t slot;
+    int rc = alloc_slot(p, &slot);
+    if (rc == GSIM_OK) {
+      rc = start_rumor(p, slot, GSIM_RUMOR_JOIN_INTENT, id, 0u, lm, id, 40u, 1u);
+      if (rc) return fail(p, rc, "start_rumor");
+    } else if (rc != GSIM_ERR_CAPACITY) {
+      return fail(p, rc, "alloc_slot");
+    }
+    if (!poke(p, p->d.ltime_member, id, lm + 1u)) return fail(p, GSIM_ERR_CUDA, "poke");
+  }
+  if (n_ok) *n_ok = okc;
+  return GSIM_OK;
+}
+
+static int set_truth(gsim_pool* p, uint32_t id, uint32_t truth) {
+  for (int b = 0; b < 2; ++b) {
+    uint32_t k;
+    if (!peek(p, p->d.key[b], id, &k)) return GSIM_ERR_CUDA;
+    k = (k & ~3u) | truth;
+    if (!poke(p, p->d.key[b], id, k)) return GSIM_ERR_CUDA;
+  }
+  return GSIM_OK;
+}
+
+static int refresh_after_truth_change(gsim_pool* p) {
+  p->counts_stale = true;
+  if (!do_recount(p)) return GSIM_ERR_CUDA;
+  GsGlobals& g = p->g;
+  g.up_count = p->rc.truth_cnt[GS_TRUTH_UP];
+  p->g_dirty = true;
+  if (!poke(p, p->d.crashed_alive, 0, p->rc.crashed_alive)) return GSIM_ERR_CUDA;
+  uint32_t cdt = GS_EMPTY32;
+  if (p->rc.crashed_alive == 0 && p->rc.truth_cnt[GS_TRUTH_CRASHED] > 0) cdt = p->now;
+  if (!poke(p, p->d.crashed_dead_tick, 0, cdt)) return GSIM_ERR_CUDA;
+  // heard counters are over UP members only
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+    if (!((g.active_mask >> r) & 1u)) continue;
+    if (!poke(p, p->d.heard_cnt, r, p->rc.heard_cnt[r])) return GSIM_ERR_CUDA;
+    if (p->rc.heard_cnt[r] == g.up_count) {
+      uint32_t ct;
+      if (!peek(p, p->d.conv_tick, r, &ct)) return GSIM_ERR_CUDA;
+      if (ct == GS_EMPTY32 && !poke(p, p->d.conv_tick, r, p->now)) return GSIM_ERR_CUDA;
+    }
+  }
+  return GSIM_OK;
+}
+
+extern "C" int gsim_crash_many(gsim_pool* p, const uint32_t* ids, size_t n) {
+  if (!p || (!ids && n)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  for (size_t x = 0; x < n; ++x) {
+    if (ids[x] >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+    uint32_t k;
+    if (!peek(p, p->d.key[p->now & 1u], ids[x], &k)) return fail(p, GSIM_ERR_CUDA, "peek");
+    if (gs_key_truth(k) != GS_TRUTH_UP) continue;
+    int rc = set_truth(p, ids[x], GS_TRUTH_CRASHED);
+    if (rc) return fail(p, rc, "set_truth");
+  }
+  int rc = refresh_after_truth_change(p);
+  return rc ? fail(p, rc, "recount") : GSIM_OK;
+}
+
+extern "C" int gsim_crash(gsim_pool* p, uint32_t id) { return gsim_crash_many(p, &id, 1); }
+
+extern "C" int gsim_crash_fraction(gsim_pool* p, uint32_t ppm, uint32_t salt, uint32_t* n_crashed) {
+  if (!p || ppm > 1000000u) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t thr = ppm >= 1000000u ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)ppm << 32) / 1000000ull);
+  uint32_t cnt = 0;
+  if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
+  if (!p->be->crash_fraction(p->d, p->g_dev, p->g, thr, salt, p->now, &cnt))
+    return fail(p, GSIM_ERR_CUDA, "crash_fraction");
+  if (n_crashed) *n_crashed = cnt;
+  int rc = refresh_after_truth_change(p);
+  return rc ? fail(p, rc, "recount") : GSIM_OK;
+}
+
+extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  GsGlobals& g = p->g;
+  if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t k, m;
+  if (!peek(p, p->d.key[p->now & 1u], id, &k) || !peek(p, p->d.meta, id, &m))
+    return fail(p, GSIM_ERR_CUDA, "peek");
+  if (gs_key_truth(k) != GS_TRUTH_UP || (m & GS_META_LEAVING))
+    return fail(p, GSIM_ERR_STATE, "member is not running or already leaving");
+  // [U] serf.Leave: leave intent with the member clock, then memberlist.Leave broadcasts
+  // dead{Node == From} which every receiver records as StateLeft.
+  uint32_t lm;
+  if (!peek(p, p->d.ltime_member, id, &lm)) return fail(p, GSIM_ERR_CUDA, "peek");
+  uint32_t slot;
+  int rc = alloc_slot(p, &slot);
+  if (rc == GSIM_OK) {
+    rc = start_rumor(p, slot, GSIM_RUMOR_LEAVE_INTENT, id, 0u, lm, id, 40u, 1u);
+    if (rc) return fail(p, rc, "start_rumor");
+  } else if (rc != GSIM_ERR_CAPACITY) {
+    return fail(p, rc, "alloc_slot");
+  }
+  if (!poke(p, p->d.ltime_member, id, lm + 1u)) return fail(p, GSIM_ERR_CUDA, "poke");
+  for (int b = 0; b < 2; ++b) {
+    uint32_t kk;
+    if (!peek(p, p->d.key[b], id, &kk)) return fail(p, GSIM_ERR_CUDA, "peek");
+    kk = gs_key_with_rank(kk, GS_RANK_LEFT);
+    if (!poke(p, p->d.key[b], id, kk)) return fail(p, GSIM_ERR_CUDA, "poke");
+  }
+  m |= GS_META_LEAVING;
+  if (!poke(p, p->d.meta, id, m) || !poke(p, p->d.change_tick, id, p->now))
+    return fail(p, GSIM_ERR_CUDA, "poke");
+  if (g.flags & GSIM_FLAG_LOG_GLOBAL_EVENTS) log_host_event(p, GSIM_EVENT_MEMBER_LEAVE, id, GS_EMPTY32, 0);
+  // the process lingers while its two broadcasts drain, then LeavePropagateDelay
+  uint32_t rounds = g.gossip_nodes ? (g.retransmit_limit + g.gossip_nodes - 1) / g.gossip_nodes : 0;
+  uint32_t drain = rounds * g.GI;
+  uint32_t bt = ceil_ticks(p->cfg.broadcast_timeout_ns, p->tick_ns);
+  if (drain > bt) drain = bt;
+  uint32_t linger = 2 * drain + ceil_ticks(p->cfg.leave_propagate_delay_ns, p->tick_ns);
+  Sched s = {p->now + linger, id, 1u};
+  p->sched.push_back(s);
+  p->counts_stale = true;
+  return GSIM_OK;
+}
+
+extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int prune) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (via >= p->g.n || target >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  // [U] serf.RemoveFailedNode: a forged leave intent turns Failed into Left
+  uint32_t any_truth = 0;
+  for (int b = 0; b < 2; ++b) {
+    uint32_t k;
+    if (!peek(p, p->d.key[b], target, &k)) return fail(p, GSIM_ERR_CUDA, "peek");
+    if (gs_key_rank(k) == GS_RANK_DEAD) k = gs_key_with_rank(k, GS_RANK_LEFT);
+    if (prune && gs_key_rank(k) == GS_RANK_LEFT && gs_key_truth(k) != GS_TRUTH_UP) k &= ~3u;
+    any_truth = gs_key_truth(k);
+    if (!poke(p, p->d.key[b], target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
+  }
+  (void)any_truth;
+  int rc = refresh_after_truth_change(p);
+  return rc ? fail(p, rc, "recount") : GSIM_OK;
+}
+
+static uint32_t msgpack_str_size(size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 256 ? 2 + n : 3 + n); }
+static uint32_t msgpack_uint_size(uint64_t v) {
+  return v < 128 ? 1 : v < 256 ? 2 : v < 65536 ? 3 : v < 4294967296ull ? 5 : 9;
+}
+
+extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size_t name_len,
+                               const void* payload, size_t payload_len, int coalesce,
+                               uint32_t* slot_out) {
+  if (!p || (!name && name_len) || (!payload && payload_len)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  GsGlobals& g = p->g;
+  if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  // [U] serf.UserEvent: size limit on name+payload (agent side: user_event.go:82-113)
+  if (name_len + payload_len > p->cfg.user_event_size_limit)
+    return fail(p, GSIM_ERR_TOO_LARGE, "user event exceeds UserEventSizeLimit");
+  uint32_t k, m;
+  if (!peek(p, p->d.key[p->now & 1u], id, &k) || !peek(p, p->d.meta, id, &m))
+    return fail(p, GSIM_ERR_CUDA, "peek");
+  if (gs_key_truth(k) != GS_TRUTH_UP) return fail(p, GSIM_ERR_STATE, "member is not running");
+  uint32_t le;
+  if (!peek(p, p->d.ltime_event, id, &le)) return fail(p, GSIM_ERR_CUDA, "peek");
+  std::string nm((const char*)name, name_len), pl((const char*)payload, payload_len);
+  // identical (LTime, Name, Payload) is the same event for serf's de-dup ring
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+    if (!((g.active_mask >> r) & 1u) || g.rumors[r].kind != GSIM_RUMOR_USER_EVENT) continue;
+    if (g.rumors[r].ltime == le && p->rh[r].name == nm && p->rh[r].payload == pl) {
+      if (!poke(p, p->d.ltime_event, id, le + 1u)) return fail(p, GSIM_ERR_CUDA, "poke");
+      if (slot_out) *slot_out = r;
+      return GSIM_OK;
+    }
+  }
+  uint32_t slot;
+  int rc = alloc_slot(p, &slot);
+  if (rc) return fail(p, rc, "no free rumor slot");
+  // msgpack size of messageUserEvent{LTime,Name,Payload,CC} + 1 type byte
+  uint32_t size = 1 + 1 + (6 + msgpack_uint_size(le)) + (5 + msgpack_str_size(name_len)) +
+                  (8 + msgpack_str_size(payload_len)) + (3 + 1);
+  rc = start_rumor(p, slot, GSIM_RUMOR_USER_EVENT, id, 0u, le, id, size, 2u);
+  if (rc) return fail(p, rc, "start_rumor");
+  p->rh[slot].name = nm;
+  p->rh[slot].payload = pl;
+  p->rh[slot].coalesce = coalesce;
+  if (!poke(p, p->d.ltime_event, id, le + 1u)) return fail(p, GSIM_ERR_CUDA, "poke");
+  if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_USER, slot, id, le);
+  if (slot_out) *slot_out = slot;
+  return GSIM_OK;
+}
+
+// ---- time -----------------------------------------------------------------------
+static int apply_sched(gsim_pool* p) {
+  bool any = false;
+  for (size_t x = 0; x < p->sched.size();) {
+    if (p->sched[x].tick <= p->now) {
+      if (p->sched[x].action == 1u) {
+        uint32_t k;
+        if (!peek(p, p->d.key[p->now & 1u], p->sched[x].id, &k)) return GSIM_ERR_CUDA;
+        if (gs_key_truth(k) == GS_TRUTH_UP) {
+          int rc = set_truth(p, p->sched[x].id, GS_TRUTH_GONE);
+          if (rc) return rc;
+          any = true;
+        }
+      }
+      p->sched.erase(p->sched.begin() + x);
+    } else {
+      ++x;
+    }
+  }
+  if (any) return refresh_after_truth_change(p);
+  return GSIM_OK;
+}
+
+static int step_locked(gsim_pool* p, uint32_t ticks) {
+  p->last_ms = 0;
+  p->last_launches = 0;
+  uint32_t left = ticks;
+  const bool use_graph = !(p->cfg.flags & GSIM_FLAG_NO_GRAPH);
+  while (left) {
+    int rc = apply_sched(p);
+    if (rc) return rc;
+    uint32_t chunk = left;
+    for (const Sched& s : p->sched)
+      if (s.tick > p->now && s.tick - p->now < chunk) chunk = s.tick - p->now;
+    if (!upload_globals(p)) return GSIM_ERR_CUDA;
+    if (!p->be->run_ticks(p->d, p->g_dev, p->g, p->now, chunk, use_graph, &p->last_ms,
+                          &p->last_launches))
+      return GSIM_ERR_CUDA;
+    p->now += chunk;
+    p->node_ticks += (uint64_t)chunk * p->g.n;
+    left -= chunk;
+    p->counts_stale = true;
+  }
+  int rc = apply_sched(p);
+  if (rc) return rc;
+  return auto_retire(p);
+}
+
+extern "C" int gsim_step(gsim_pool* p, uint32_t ticks) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int rc = step_locked(p, ticks);
+  return rc ? fail(p, rc, "step") : GSIM_OK;
+}
+
+extern "C" uint32_t gsim_now(gsim_pool* p) { return p ? p->now : 0; }
+
+extern "C" int gsim_run_until(gsim_pool* p, int predicate, uint32_t arg, uint32_t max_ticks,
+                              uint32_t check_every, uint32_t* tick_out) {
+  if (!p || !check_every) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (tick_out) *tick_out = GS_EMPTY32;
+  uint32_t done = 0;
+  double ms = 0;
+  uint64_t launches = 0;
+  for (;;) {
+    uint32_t result = GS_EMPTY32;
+    if (predicate == GSIM_PRED_RUMOR_CONVERGED) {
+      if (arg >= GS_MAX_RUMORS) return fail(p, GSIM_ERR_INVALID, "bad slot");
+      if (!peek(p, p->d.conv_tick, arg, &result)) return fail(p, GSIM_ERR_CUDA, "peek");
+    } else if (predicate == GSIM_PRED_ALL_RUMORS_CONVERGED) {
+      uint32_t ct[32];
+      if (!p->be->d2h(ct, p->d.conv_tick, sizeof(ct))) return fail(p, GSIM_ERR_CUDA, "d2h");
+      uint32_t mx = 0;
+      bool all = true;
+      for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+        if ((p->g.active_mask >> r) & 1u) {
+          if (ct[r] == GS_EMPTY32) all = false;
+          else if (ct[r] > mx) mx = ct[r];
+        }
+      if (all) result = mx;
+    } else if (predicate == GSIM_PRED_CRASHED_ALL_DEAD) {
+      if (!peek(p, p->d.crashed_dead_tick, 0, &result)) return fail(p, GSIM_ERR_CUDA, "peek");
+    } else {
+      return fail(p, GSIM_ERR_INVALID, "unknown predicate");
+    }
+    if (result != GS_EMPTY32) {
+      if (tick_out) *tick_out = result;
+      break;
+    }
+    if (done >= max_ticks) break;
+    uint32_t chunk = max_ticks - done < check_every ? max_ticks - done : check_every;
+    int rc = step_locked(p, chunk);
+    if (rc) return fail(p, rc, "step");
+    ms += p->last_ms;
+    launches += p->last_launches;
+    done += chunk;
+  }
+  p->last_ms = ms;
+  p->last_launches = launches;
+  return GSIM_OK;
+}
+
+// ---- observation ------------------------------------------------------------------
+static bool host_knows(const GsGlobals& g, uint32_t i, uint32_t c, uint32_t kc, uint32_t heard_i,
+                       uint32_t meta_i) {
+  if (c == i) return true;
+  if (!gs_key_pending(kc)) return !(meta_i & GS_META_ISOLATED);
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if (((g.active_mask >> r) & 1u) && g.rumors[r].kind == GSIM_RUMOR_ALIVE && g.rumors[r].subject == c)
+      return (heard_i >> r) & 1u;
+  return false;
+}
+
+static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, size_t cap, size_t* n) {
+  const GsGlobals& g = p->g;
+  if (observer >= g.n) return GSIM_ERR_NOT_FOUND;
+  std::vector<uint32_t> keys(g.n);
+  uint32_t heard, meta;
+  if (!p->be->d2h(keys.data(), p->d.key[p->now & 1u], (size_t)g.n * 4) ||
+      !peek(p, p->d.heard, observer, &heard) || !peek(p, p->d.meta, observer, &meta))
+    return GSIM_ERR_CUDA;
+  size_t cnt = 0;
+  for (uint32_t c = 0; c < g.n; ++c) {
+    uint32_t kc = keys[c];
+    if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
+    if (!host_knows(g, observer, c, kc, heard, meta)) continue;
+    if (out && cnt < cap) {
+      gsim_member& mm = out[cnt];
+      mm.id = c;
+      mm.incarnation = gs_key_inc(kc);
+      mm.rank = gs_key_rank(kc);
+      // memberlist suspect is still serf alive; dead -> failed; left -> left
+      mm.status = mm.rank == GS_RANK_DEAD   ? GSIM_STATUS_FAILED
+                  : mm.rank == GS_RANK_LEFT ? GSIM_STATUS_LEFT
+                                            : GSIM_STATUS_ALIVE;
+    }
+    ++cnt;
+  }
+  if (n) *n = cnt;
+  return GSIM_OK;
+}
+
+extern "C" int gsim_members(gsim_pool* p, uint32_t observer, gsim_member* out, size_t cap, size_t* n) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int rc = members_locked(p, observer, out, cap, n);
+  return rc ? fail(p, rc, "members") : GSIM_OK;
+}
+
+extern "C" int gsim_num_nodes(gsim_pool* p, uint32_t observer, uint32_t* n) {
+  if (!p || !n) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  size_t cnt = 0;
+  int rc = members_locked(p, observer, nullptr, 0, &cnt);
+  *n = (uint32_t)cnt;
+  return rc ? fail(p, rc, "num_nodes") : GSIM_OK;
+}
+
+extern "C" int gsim_poll_events(gsim_pool* p, gsim_event* out, size_t cap, size_t* n) {
+  if (!p || !n || (!out && cap)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t cur[2];
+  if (!p->be->d2h(cur, p->d.evlog_cursor, 8)) return fail(p, GSIM_ERR_CUDA, "d2h");
+  uint32_t have = cur[0] < p->g.evlog_cap ? cur[0] : p->g.evlog_cap;
+  std::vector<GsEventRec> ev(have);
+  if (have && !p->be->d2h(ev.data(), p->d.evlog, (size_t)have * sizeof(GsEventRec)))
+    return fail(p, GSIM_ERR_CUDA, "d2h");
+  // the device appends in scheduling order; canonical order is (tick, type, subject, observer)
+  std::sort(ev.begin(), ev.end(), [](const GsEventRec& a, const GsEventRec& b) {
+    if (a.tick != b.tick) return a.tick < b.tick;
+    if (a.type != b.type) return a.type < b.type;
+    if (a.subject != b.subject) return a.subject < b.subject;
+    return a.observer < b.observer;
+  });
+  size_t take = have < cap ? have : cap;
+  for (size_t x = 0; x < take; ++x) {
+    out[x].tick = ev[x].tick;
+    out[x].type = ev[x].type;
+    out[x].subject = ev[x].subject;
+    out[x].observer = ev[x].observer;
+    out[x].ltime = ev[x].ltime;
+    out[x].reserved = 0;
+  }
+  *n = take;
+  // keep what did not fit
+  uint32_t rest = have - (uint32_t)take;
+  if (rest && !p->be->h2d(p->d.evlog, ev.data() + take, (size_t)rest * sizeof(GsEventRec)))
+    return fail(p, GSIM_ERR_CUDA, "h2d");
+  p->events_dropped += cur[1];
+  uint32_t reset[2] = {rest, 0};
+  if (!p->be->h2d(p->d.evlog_cursor, reset, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
+  return GSIM_OK;
+}
+
+extern "C" int gsim_rumor_info_get(gsim_pool* p, uint32_t slot, gsim_rumor_info* out) {
+  if (!p || !out || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  const GsGlobals& g = p->g;
+  if (!((g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
+  if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
+  const GsRumor& ru = g.rumors[slot];
+  out->kind = ru.kind;
+  out->subject = ru.subject;
+  out->incarnation = ru.inc;
+  out->ltime = ru.ltime;
+  out->origin = ru.origin;
+  out->size_bytes = ru.size;
+  out->start_tick = ru.start_tick;
+  out->heard_count = p->rc.heard_cnt[slot];
+  out->queued_count = p->rc.queued_cnt[slot];
+  if (!peek(p, p->d.conv_tick, slot, &out->converged_tick)) return fail(p, GSIM_ERR_CUDA, "peek");
+  return GSIM_OK;
+}
+
+extern "C" int gsim_rumor_retire(gsim_pool* p, uint32_t slot) {
+  if (!p || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!((p->g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
+  if (p->g.rumors[slot].kind == GSIM_RUMOR_ALIVE) {
+    if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
+    if (p->rc.heard_cnt[slot] != p->g.up_count)
+      return fail(p, GSIM_ERR_STATE, "alive rumor has not reached every running member");
+  }
+  int rc = retire_slot(p, slot);
+  return rc ? fail(p, rc, "retire") : GSIM_OK;
+}
+
+extern "C" int gsim_user_event_get(gsim_pool* p, uint32_t slot, void* name, size_t name_cap,
+                                   size_t* name_len, void* payload, size_t payload_cap,
+                                   size_t* payload_len) {
+  if (!p || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!((p->g.active_mask >> slot) & 1u) || p->g.rumors[slot].kind != GSIM_RUMOR_USER_EVENT)
+    return fail(p, GSIM_ERR_NOT_FOUND, "not a user event slot");
+  const RumorHost& rh = p->rh[slot];
+  if (name_len) *name_len = rh.name.size();
+  if (payload_len) *payload_len = rh.payload.size();
+  if (name && name_cap) memcpy(name, rh.name.data(), std::min(name_cap, rh.name.size()));
+  if (payload && payload_cap) memcpy(payload, rh.payload.data(), std::min(payload_cap, rh.payload.size()));
+  return GSIM_OK;
+}
+
+extern "C" int gsim_stats_get(gsim_pool* p, gsim_stats* out) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  memset(out, 0, sizeof(*out));
+  if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
+  if (!p->be->d2h(out->counters, p->d.stats, sizeof(out->counters))) return fail(p, GSIM_ERR_CUDA, "d2h");
+  const GsGlobals& g = p->g;
+  out->node_ticks = p->node_ticks;
+  out->tick = p->now;
+  out->n_members = g.n;
+  out->n_up = p->rc.truth_cnt[GS_TRUTH_UP];
+  out->n_crashed = p->rc.truth_cnt[GS_TRUTH_CRASHED];
+  out->n_gone = p->rc.truth_cnt[GS_TRUTH_GONE];
+  out->n_view_alive = p->rc.rank_cnt[GS_RANK_ALIVE];
+  out->n_view_suspect = p->rc.rank_cnt[GS_RANK_SUSPECT];
+  out->n_view_dead = p->rc.rank_cnt[GS_RANK_DEAD];
+  out->n_view_left = p->rc.rank_cnt[GS_RANK_LEFT];
+  out->retransmit_limit = g.retransmit_limit;
+  out->suspicion_k = g.sus_k;
+  for (int q = 0; q < GS_K1MAX; ++q) out->suspicion_ticks[q] = g.sus_ticks[q];
+  out->probe_interval_ticks = g.P;
+  out->probe_timeout_ticks = g.T;
+  out->gossip_interval_ticks = g.GI;
+  uint32_t cur[2] = {0, 0};
+  p->be->d2h(cur, p->d.evlog_cursor, 8);
+  out->events_dropped = p->events_dropped + cur[1];
+  return GSIM_OK;
+}
+
+extern "C" int gsim_state_hash(gsim_pool* p, uint64_t out[4]) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
+  if (!p->be->state_hash(p->d, p->g_dev, p->g, p->now, out)) return fail(p, GSIM_ERR_CUDA, "hash");
+  // pool-wide scalars
+  uint64_t h = gs_mix64(0x243F6A8885A308D3ull, p->now);
+  h = gs_mix64(h, p->g.n);
+  h = gs_mix64(h, p->g.up_count);
+  h = gs_mix64(h, p->g.active_mask);
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if ((p->g.active_mask >> r) & 1u) {
+      const GsRumor& ru = p->g.rumors[r];
+      h = gs_mix64(h, ((uint64_t)r << 32) | ru.kind);
+      h = gs_mix64(h, ((uint64_t)ru.subject << 32) | ru.ltime);
+    }
+  uint64_t lanes[4];
+  gs_hash_lanes(h, lanes);
+  for (int q = 0; q < 4; ++q) out[q] += lanes[q];
+  return GSIM_OK;
+}
+
+extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_bytes, size_t* n_bytes) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  const GsDev& d = p->d;
+  const size_t cap = p->g.cap;
+  const void* src = nullptr;
+  size_t bytes = cap * 4;
+  switch (column) {
+    case GSIM_COL_KEY: src = d.key[p->now & 1u]; break;
+    case GSIM_COL_META: src = d.meta; break;
+    case GSIM_COL_DUE: src = d.due; break;
+    case GSIM_COL_CURSOR: src = d.cursor; break;
+    case GSIM_COL_PASS: src = d.pass; break;
+    case GSIM_COL_PROBE_TGT: src = d.probe_tgt; break;
+    case GSIM_COL_PROBE_INC: src = d.probe_inc; break;
+    case GSIM_COL_SUS_START: src = d.sus_start; break;
+    case GSIM_COL_SUS_FROM: src = d.sus_from; bytes = cap * 4 * GS_K1MAX; break;
+    case GSIM_COL_CHANGE_TICK: src = d.change_tick; break;
+    case GSIM_COL_LTIME_MEMBER: src = d.ltime_member; break;
+    case GSIM_COL_LTIME_EVENT: src = d.ltime_event; break;
+    case GSIM_COL_EVENT_MIN: src = d.event_min; break;
+    case GSIM_COL_HEARD: src = d.heard; break;
+    case GSIM_COL_QUEUED: src = d.queued; break;
+    case GSIM_COL_TX: src = d.tx; bytes = cap * GS_MAX_RUMORS; break;
+    case GSIM_COL_INBOX: src = d.inbox[p->now & 1u]; break;
+    default: return fail(p, GSIM_ERR_INVALID, "unknown column");
+  }
+  if (n_bytes) *n_bytes = bytes;
+  if (cap_bytes < bytes) return fail(p, GSIM_ERR_INVALID, "buffer too small");
+  if (!p->be->d2h(out, src, bytes)) return fail(p, GSIM_ERR_CUDA, "d2h");
+  if (column == GSIM_COL_META) {
+    uint32_t* mm = reinterpret_cast<uint32_t*>(out);
+    for (size_t i = 0; i < cap; ++i) mm[i] &= ~GS_META_DIRTY;  // implementation detail
+  }
+  return GSIM_OK;
+}
+
+// ---- checkpoint / resume ------------------------------------------------------------
+struct SnapCol {
+  void* ptr;
+  size_t bytes;
+};
+static std::vector<SnapCol> snap_cols(gsim_pool* p) {
+  const GsDev& d = p->d;
+  const size_t cap = p->g.cap;
+  std::vector<SnapCol> v;
+  auto add = [&](void* q, size_t b) { v.push_back(SnapCol{q, b}); };
+  add(d.key[0], cap * 4); add(d.key[1], cap * 4); add(d.inbox[0], cap * 4); add(d.inbox[1], cap * 4);
+  add(d.due, cap * 4); add(d.meta, cap * 4); add(d.cursor, cap * 4); add(d.pass, cap * 4);
+  add(d.probe_tgt, cap * 4); add(d.probe_inc, cap * 4); add(d.sus_start, cap * 4);
+  add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
+  add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
+  add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
+  add(d.stats, GSIM_STAT_COUNT * 8); add(d.heard_cnt, 32 * 4); add(d.conv_tick, 32 * 4);
+  add(d.crashed_alive, 4); add(d.crashed_dead_tick, 4);
+  return v;
+}
+struct SnapHeader {
+  uint64_t magic;
+  uint32_t version, cap;
+  uint32_t now, n_sched;
+  uint64_t node_ticks;
+  GsGlobals g;
+};
+static const uint64_t SNAP_MAGIC = 0x4753494D534E4150ull;  // "GSIMSNAP"
+
+static size_t snap_size(gsim_pool* p) {
+  size_t s = sizeof(SnapHeader) + p->sched.size() * sizeof(Sched);
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) s += 12 + p->rh[r].name.size() + p->rh[r].payload.size();
+  for (const SnapCol& c : snap_cols(p)) s += c.bytes;
+  return s;
+}
+
+extern "C" int gsim_snapshot_size(gsim_pool* p, size_t* n_bytes) {
+  if (!p || !n_bytes) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  *n_bytes = snap_size(p);
+  return GSIM_OK;
+}
+
+extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* n_bytes) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  size_t need = snap_size(p);
+  if (n_bytes) *n_bytes = need;
+  if (cap_bytes < need) return fail(p, GSIM_ERR_INVALID, "buffer too small");
+  uint8_t* w = reinterpret_cast<uint8_t*>(out);
+  SnapHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = SNAP_MAGIC;
+  h.version = 1;
+  h.cap = p->g.cap;
+  h.now = p->now;
+  h.n_sched = (uint32_t)p->sched.size();
+  h.node_ticks = p->node_ticks;
+  h.g = p->g;
+  memcpy(w, &h, sizeof(h));
+  w += sizeof(h);
+  if (!p->sched.empty()) memcpy(w, p->sched.data(), p->sched.size() * sizeof(Sched));
+  w += p->sched.size() * sizeof(Sched);
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+    uint32_t hdr[3] = {(uint32_t)p->rh[r].name.size(), (uint32_t)p->rh[r].payload.size(),
+                       (uint32_t)p->rh[r].coalesce};
+    memcpy(w, hdr, 12);
+    w += 12;
+    memcpy(w, p->rh[r].name.data(), hdr[0]);
+    w += hdr[0];
+    memcpy(w, p->rh[r].payload.data(), hdr[1]);
+    w += hdr[1];
+  }
+  for (const SnapCol& c : snap_cols(p)) {
+    if (!p->be->d2h(w, c.ptr, c.bytes)) return fail(p, GSIM_ERR_CUDA, "d2h");
+    w += c.bytes;
+  }
+  return GSIM_OK;
+}
+
+extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
+  if (!p || !blob || n_bytes < sizeof(SnapHeader)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  const uint8_t* r = reinterpret_cast<const uint8_t*>(blob);
+  const uint8_t* end = r + n_bytes;
+  SnapHeader h;
+  memcpy(&h, r, sizeof(h));
+  r += sizeof(h);
+  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap)
+    return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
+  if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
+  p->sched.resize(h.n_sched);
+  if (h.n_sched) memcpy(p->sched.data(), r, (size_t)h.n_sched * sizeof(Sched));
+  r += (size_t)h.n_sched * sizeof(Sched);
+  for (uint32_t x = 0; x < GS_MAX_RUMORS; ++x) {
+    if (end - r < 12) return fail(p, GSIM_ERR_INVALID, "truncated");
+    uint32_t hdr[3];
+    memcpy(hdr, r, 12);
+    r += 12;
+    if ((size_t)(end - r) < (size_t)hdr[0] + hdr[1]) return fail(p, GSIM_ERR_INVALID, "truncated");
+    p->rh[x].name.assign((const char*)r, hdr[0]);
+    r += hdr[0];
+    p->rh[x].payload.assign((const char*)r, hdr[1]);
+    r += hdr[1];
+    p->rh[x].coalesce = (int)hdr[2];
+  }
+  for (const SnapCol& c : snap_cols(p)) {
+    if ((size_t)(end - r) < c.bytes) return fail(p, GSIM_ERR_INVALID, "truncated");
+    if (!p->be->h2d(c.ptr, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+    r += c.bytes;
+  }
+  p->g = h.g;
+  p->now = h.now;
+  p->node_ticks = h.node_ticks;
+  p->g_dirty = true;
+  p->counts_stale = true;
+  if (!poke(p, p->d.tick_base, 0, p->now)) return fail(p, GSIM_ERR_CUDA, "poke");
+  uint32_t zero2[2] = {0, 0};
+  if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
+  return GSIM_OK;
+}
+
+// ---- measurement hooks ------------------------------------------------------------
+extern "C" int gsim_last_step_timing(gsim_pool* p, double* kernel_ms, uint64_t* launches) {
+  if (!p) return GSIM_ERR_INVALID;
+  if (kernel_ms) *kernel_ms = p->last_ms;
+  if (launches) *launches = p->last_launches;
+  return GSIM_OK;
+}
+
+extern "C" uint64_t gsim_launch_count(gsim_pool* p) { return p && p->be ? p->be->total_launches() : 0; }

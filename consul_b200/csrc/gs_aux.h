@@ -1,0 +1,101 @@
+// gs_aux.h — per-row bodies of the auxiliary kernels (row init, crash injection,
+// recount, state digest).  Same sharing arrangement as gs_row.h.
+#pragma once
+#include "gs_backend.h"
+#include "gs_row.h"
+
+// A converged member as serf.Create + a finished join leaves it ([U] memberlist.setAlive:
+// incarnation 1; [U] serf.Create: the three Lamport clocks incremented once).
+// Probe/gossip ticker phases mirror triggerFunc's random stagger ([U] state.go).
+GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t now) {
+  const size_t cap = g.cap;
+  GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, i, 0u, GS_PUR_PHASE, 0u);
+  const uint32_t pp = ph.x % g.P, gp = ph.y % g.GI;
+  const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
+  d.key[0][i] = k;
+  d.key[1][i] = k;
+  d.inbox[0][i] = 0u;
+  d.inbox[1][i] = 0u;
+  d.meta[i] = gp << GS_META_GPHASE_SHIFT;
+  d.due[i] = now + (pp + g.P - now % g.P) % g.P;  // first tick >= now congruent to the phase
+  d.cursor[i] = 0u;
+  d.pass[i] = 0u;
+  d.probe_tgt[i] = 0u;
+  d.probe_inc[i] = 0u;
+  d.sus_start[i] = 0u;
+  for (uint32_t q = 0; q < GS_K1MAX; ++q) {
+    d.sus_from[(size_t)q * cap + i] = GS_EMPTY32;
+    d.acc[(size_t)q * cap + i] = GS_EMPTY64;
+    d.acc[((size_t)GS_K1MAX + q) * cap + i] = GS_EMPTY64;
+  }
+  d.change_tick[i] = 0u;
+  d.ltime_member[i] = 1u;
+  d.ltime_event[i] = 1u;
+  d.event_min[i] = 0u;
+  d.heard[i] = 0u;
+  d.queued[i] = 0u;
+}
+
+// BASELINE config 3: crash every UP member whose Philox draw is below the threshold.
+GS_DEV bool gs_crash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t thr,
+                         uint32_t salt) {
+  uint32_t k = d.key[0][i];
+  if (gs_key_truth(k) != GS_TRUTH_UP) return false;
+  GsU4 r = gs_philox(g.seed_lo, g.seed_hi, i, salt, GS_PUR_CRASH, 0u);
+  if (r.x >= thr) return false;
+  k = (k & ~3u) | GS_TRUTH_CRASHED;
+  d.key[0][i] = k;
+  d.key[1][i] = (d.key[1][i] & ~3u) | GS_TRUTH_CRASHED;
+  return true;
+}
+
+// Canonical digest of one row: only fields that are semantically live are folded, so
+// that stale scratch in cold columns never matters (the oracle folds the same fields).
+GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t now) {
+  const uint32_t cur = now & 1u;  // buffer the next tick will read
+  const size_t cap = g.cap;
+  const uint32_t k = d.key[cur][i];
+  const uint32_t truth = gs_key_truth(k);
+  if (truth == GS_TRUTH_NONE) return 0ull;
+  const uint32_t m = d.meta[i] & ~GS_META_DIRTY;
+  const uint32_t rank = gs_key_rank(k);
+  const bool up = truth == GS_TRUTH_UP;
+  const bool probing = up && gs_meta_stage(m) != GS_STAGE_IDLE;
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  h = gs_mix64(h, i);
+  h = gs_mix64(h, k);
+  h = gs_mix64(h, m);
+  h = gs_mix64(h, up ? d.due[i] : 0u);
+  h = gs_mix64(h, d.cursor[i]);
+  h = gs_mix64(h, d.pass[i]);
+  h = gs_mix64(h, probing ? d.probe_tgt[i] : 0u);
+  h = gs_mix64(h, probing ? d.probe_inc[i] : 0u);
+  h = gs_mix64(h, rank == GS_RANK_SUSPECT ? d.sus_start[i] : 0u);
+  for (uint32_t q = 0; q < GS_K1MAX; ++q)
+    h = gs_mix64(h, rank == GS_RANK_SUSPECT ? d.sus_from[(size_t)q * cap + i] : 0u);
+  h = gs_mix64(h, rank >= GS_RANK_DEAD ? d.change_tick[i] : 0u);
+  h = gs_mix64(h, d.ltime_member[i]);
+  h = gs_mix64(h, d.ltime_event[i]);
+  h = gs_mix64(h, d.event_min[i]);
+  const uint32_t heard = d.heard[i] & g.active_mask;
+  h = gs_mix64(h, heard);
+  h = gs_mix64(h, d.queued[i] & g.active_mask);
+  const uint32_t inb = d.inbox[cur][i];
+  h = gs_mix64(h, inb & (g.active_mask | GS_ACC_BIT));
+  uint32_t hm = heard;
+  while (hm) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r = __ffs(hm) - 1;
+#else
+    uint32_t r = (uint32_t)__builtin_ctz(hm);
+#endif
+    hm &= hm - 1;
+    h = gs_mix64(h, (r << 8) | d.tx[(size_t)r * cap + i]);
+  }
+  if (inb & GS_ACC_BIT) {
+    const uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;
+    for (uint32_t s = 0; s < GS_K1MAX; ++s) h = gs_mix64(h, acc[(size_t)s * cap + i]);
+  }
+  return h;
+}
+

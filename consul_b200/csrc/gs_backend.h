@@ -1,0 +1,63 @@
+// gs_backend.h — the narrow device interface the host side of libgsim drives.
+// libgsim.so links exactly one implementation: the CUDA backend (gs_cuda.cu).  A second
+// implementation exists only under tests/hostemu/ (the same row function compiled by g++
+// and looped sequentially) so kernel logic can be debugged in a GPU-less container; it is
+// test infrastructure and is never linked into or loaded by the product library.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gs_core.h"
+
+struct GsRecount {
+  uint32_t heard_cnt[GS_MAX_RUMORS];
+  uint32_t queued_cnt[GS_MAX_RUMORS];
+  uint32_t truth_cnt[4];
+  uint32_t rank_cnt[4];
+  uint32_t crashed_alive;
+};
+
+class GsBackend {
+ public:
+  virtual ~GsBackend() {}
+  virtual const char* name() const = 0;
+  virtual void* alloc(size_t bytes) = 0;  // returns nullptr on failure
+  virtual void release(void* p) = 0;
+  virtual bool h2d(void* dst, const void* src, size_t bytes) = 0;
+  virtual bool d2h(void* dst, const void* src, size_t bytes) = 0;
+  virtual bool fill32(uint32_t* dst, uint32_t value, size_t count) = 0;
+  virtual bool fill8(uint8_t* dst, uint8_t value, size_t count) = 0;
+  // rows [first, first+count): converged members, inc=1, clocks=1, phases from Philox
+  virtual bool init_rows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t first,
+                         uint32_t count, uint32_t now) = 0;
+  // advance `nticks` ticks starting at tick t0 (tick_base on the device == t0 on entry and
+  // t0+nticks on exit).  kernel_ms accumulates CUDA-event time of the tick launches.
+  virtual bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0,
+                         uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches) = 0;
+  virtual bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g,
+                              uint32_t thr, uint32_t salt, uint32_t now, uint32_t* n_crashed) = 0;
+  virtual bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+                       GsRecount* out) = 0;
+  virtual bool state_hash(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+                          uint64_t out[4]) = 0;
+  virtual bool sync() = 0;
+  virtual const char* last_error() const = 0;
+  virtual uint64_t total_launches() const = 0;
+};
+
+// Implemented by gs_cuda.cu (product) — returns nullptr and fills err when no usable
+// sm_100-class device exists.  There is deliberately no CPU implementation in libgsim.
+GsBackend* gs_make_cuda_backend(int device, char* err, size_t err_cap);
+
+// ---- state digest shared by every implementation of state_hash -----------------
+GS_HD uint64_t gs_mix64(uint64_t h, uint64_t w) {
+  h = (h ^ w) * 0xff51afd7ed558ccdull;
+  h ^= h >> 32;
+  return h;
+}
+GS_HD void gs_hash_lanes(uint64_t h, uint64_t lanes[4]) {
+  lanes[0] = h;
+  lanes[1] = gs_mix64(h, 1);
+  lanes[2] = gs_mix64(h, 2);
+  lanes[3] = gs_mix64(h, 3);
+}

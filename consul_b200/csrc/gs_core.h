@@ -1,0 +1,236 @@
+// gs_core.h — state layout, packing helpers and counter-based RNG shared by the CUDA
+// kernels (gs_kernels.cu) and the host side of libgsim (gs_api.cpp).
+//
+// Data layout in HBM (SoA, one element per virtual member, index = member id):
+//   HOT, read by every row every tick (16 B / node-tick):
+//     key[2][N]   u32  double-buffered cluster view of the member as SUBJECT:
+//                      inc<<5 | pending<<4 | rank<<2 | truth     (a1, a6-a9 in SURVEY 8a)
+//     inbox[2][N] u32  per-arrival-tick mailbox: bit r = rumor r delivered, bit 31 =
+//                      accusation(s) pending in acc[][][]         (transport, §5)
+//     due[N]      u32  tick of the member's next probe action      (a2, a3)
+//     meta[N]     u32  awareness | probe stage | nack misses | dirty | flags | gossip phase
+//   COLD, touched only by rows that act in this tick:
+//     cursor/pass/probe_tgt/probe_inc   probe ring position and the in-flight probe
+//     sus_start, sus_from[K1][N]        Lifeguard suspicion record of the subject (a7)
+//     acc[2][K1][N] u64                 accusation mailbox, (~inc<<32 | from), kept as the
+//                                       K1 smallest by an atomicMin chain (commutative)
+//     change_tick                       tick the subject became Dead/Left
+//     ltime_member, ltime_event, event_min   serf Lamport clocks (a13)
+//     heard, queued (u32 masks), tx[R][N] u8 TransmitLimitedQueue per tracked rumor (a5)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GS_HD __host__ __device__ __forceinline__
+#else
+#define GS_HD inline
+#endif
+
+#define GS_MAX_RUMORS 31
+#define GS_K1MAX 5
+#define GS_ACC_BIT 0x80000000u
+#define GS_EMPTY32 0xFFFFFFFFu
+#define GS_EMPTY64 0xFFFFFFFFFFFFFFFFull
+#define GS_KR_MAX_TRIES 32u  // kRandomNodes tries = min(3n, 32); upstream: 3n
+#define GS_PROBE_SKIP_CAP 1024u
+
+// truth / rank values are the public GSIM_TRUTH_* / GSIM_RANK_* constants.
+enum { GS_TRUTH_NONE = 0, GS_TRUTH_UP = 1, GS_TRUTH_CRASHED = 2, GS_TRUTH_GONE = 3 };
+enum { GS_RANK_ALIVE = 0, GS_RANK_SUSPECT = 1, GS_RANK_DEAD = 2, GS_RANK_LEFT = 3 };
+enum { GS_STAGE_IDLE = 0, GS_STAGE_WAIT_T = 1, GS_STAGE_WAIT_P = 2 };
+
+// Philox counter "purpose" words.
+enum {
+  GS_PUR_PHASE = 1,
+  GS_PUR_PERM = 2,
+  GS_PUR_GOSSIP = 3,
+  GS_PUR_RELAY = 4,
+  GS_PUR_LOSS = 5,
+  GS_PUR_CRASH = 6
+};
+// Loss "kind" (folded into the counter) — one draw per simulated UDP packet.
+enum {
+  GS_LK_PING = 0,
+  GS_LK_ACK = 1,
+  GS_LK_INDREQ = 2,
+  GS_LK_INDPING = 3,
+  GS_LK_INDACK = 4,
+  GS_LK_INDFWD = 5,
+  GS_LK_NACK = 6,
+  GS_LK_GOSSIP = 7
+};
+
+// ---- key word -------------------------------------------------------------
+GS_HD uint32_t gs_key_make(uint32_t inc, uint32_t pending, uint32_t rank, uint32_t truth) {
+  return (inc << 5) | (pending << 4) | (rank << 2) | truth;
+}
+GS_HD uint32_t gs_key_truth(uint32_t k) { return k & 3u; }
+GS_HD uint32_t gs_key_rank(uint32_t k) { return (k >> 2) & 3u; }
+GS_HD uint32_t gs_key_pending(uint32_t k) { return (k >> 4) & 1u; }
+GS_HD uint32_t gs_key_inc(uint32_t k) { return k >> 5; }
+GS_HD uint32_t gs_key_with_rank(uint32_t k, uint32_t rank) { return (k & ~(3u << 2)) | (rank << 2); }
+GS_HD uint32_t gs_key_with_inc(uint32_t k, uint32_t inc) { return (k & 31u) | (inc << 5); }
+
+// ---- meta word ------------------------------------------------------------
+#define GS_META_AW_MASK 0x7u
+#define GS_META_STAGE_SHIFT 3
+#define GS_META_NMISS_SHIFT 5
+#define GS_META_DIRTY (1u << 8)
+#define GS_META_LEAVING (1u << 9)
+#define GS_META_WATCHED (1u << 10)
+#define GS_META_ISOLATED (1u << 11)  // created but has not completed a Join yet
+#define GS_META_GPHASE_SHIFT 16
+GS_HD uint32_t gs_meta_aw(uint32_t m) { return m & GS_META_AW_MASK; }
+GS_HD uint32_t gs_meta_stage(uint32_t m) { return (m >> GS_META_STAGE_SHIFT) & 3u; }
+GS_HD uint32_t gs_meta_nmiss(uint32_t m) { return (m >> GS_META_NMISS_SHIFT) & 7u; }
+GS_HD uint32_t gs_meta_gphase(uint32_t m) { return (m >> GS_META_GPHASE_SHIFT) & 0xFFu; }
+GS_HD uint32_t gs_meta_set_aw(uint32_t m, uint32_t aw) { return (m & ~GS_META_AW_MASK) | aw; }
+GS_HD uint32_t gs_meta_set_stage(uint32_t m, uint32_t s) {
+  return (m & ~(3u << GS_META_STAGE_SHIFT)) | (s << GS_META_STAGE_SHIFT);
+}
+GS_HD uint32_t gs_meta_set_nmiss(uint32_t m, uint32_t n) {
+  return (m & ~(7u << GS_META_NMISS_SHIFT)) | (n << GS_META_NMISS_SHIFT);
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter based: no RNG state in HBM ----
+GS_HD uint32_t gs_mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+struct GsU4 {
+  uint32_t x, y, z, w;
+};
+GS_HD GsU4 gs_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                     uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = gs_mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = gs_mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  GsU4 o;
+  o.x = c0;
+  o.y = c1;
+  o.z = c2;
+  o.w = c3;
+  return o;
+}
+GS_HD uint32_t gs_u4_get(const GsU4& v, uint32_t idx) {
+  return idx == 0 ? v.x : idx == 1 ? v.y : idx == 2 ? v.z : v.w;
+}
+
+// ---- probe ring: keyed Feistel permutation of [0, n) with cycle walking ------
+// Replaces the O(N)-per-member shuffled `nodes` slice ([U] memberlist/state.go
+// resetNodes/shuffleNodes): every member visits every peer exactly once per pass,
+// in a per-(member, pass) pseudo-random order, with O(1) state (cursor, pass).
+GS_HD uint32_t gs_feistel_round(uint32_t r, uint32_t k) {
+  uint32_t x = (r + k) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  return x;
+}
+GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t half_bits, const GsU4& rk) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  do {
+    uint32_t l = x >> half_bits, r = x & mask;
+    uint32_t t;
+    t = l ^ (gs_feistel_round(r, rk.x) & mask); l = r; r = t;
+    t = l ^ (gs_feistel_round(r, rk.y) & mask); l = r; r = t;
+    t = l ^ (gs_feistel_round(r, rk.z) & mask); l = r; r = t;
+    t = l ^ (gs_feistel_round(r, rk.w) & mask); l = r; r = t;
+    x = (l << half_bits) | r;
+  } while (x >= n);
+  return x;
+}
+
+// ---- tracked rumor table ------------------------------------------------------
+struct GsRumor {
+  uint32_t kind;     // GSIM_RUMOR_*
+  uint32_t subject;  // member id (ALIVE / intents) or origin (user event)
+  uint32_t inc;      // incarnation carried by an alive rumor
+  uint32_t ltime;    // Lamport time carried by serf messages
+  uint32_t origin;
+  uint32_t size;     // encoded message bytes (for the UDP budget)
+  uint32_t qclass;   // 0 memberlist queue, 1 serf intent queue, 2 serf event queue
+  uint32_t start_tick;
+};
+
+// Device-resident pool constants; rewritten by the host between steps only.
+struct GsGlobals {
+  uint32_t n;         // created member ids [0, n)
+  uint32_t cap;       // column stride
+  uint32_t up_count;  // members with truth == UP
+  uint32_t P, T, GI;  // probe interval, probe timeout, gossip interval (ticks)
+  uint32_t gossip_nodes, indirect_checks, awareness_max;
+  uint32_t retransmit_limit;
+  uint32_t sus_k;                // confirmations that shorten the timer
+  uint32_t sus_ticks[GS_K1MAX];  // timeout in ticks after c confirmations
+  uint32_t gtd_ticks;            // GossipToTheDeadTime
+  uint32_t udp_avail;            // UDPBufferSize - compoundHeaderOverhead
+  uint32_t disable_tcp;
+  uint32_t loss_thr;  // packet lost iff philox < loss_thr (0 = lossless fast path)
+  uint32_t event_buffer;
+  uint32_t seed_lo, seed_hi;
+  uint32_t active_mask;    // non-free rumor slots
+  uint32_t class_mask[3];  // rumor slots by queue class
+  uint32_t perm_half_bits;
+  uint32_t flags;
+  uint32_t evlog_cap;
+  uint32_t world, rank;
+  uint32_t pad0;
+  GsRumor rumors[GS_MAX_RUMORS];
+};
+
+struct GsEventRec {
+  uint32_t tick, type, subject, observer, ltime, reserved;
+};
+
+// Device column pointers.
+struct GsDev {
+  uint32_t* key[2];
+  uint32_t* inbox[2];
+  uint32_t* due;
+  uint32_t* meta;
+  uint32_t* cursor;
+  uint32_t* pass;
+  uint32_t* probe_tgt;
+  uint32_t* probe_inc;
+  uint32_t* sus_start;
+  uint32_t* sus_from;  // [GS_K1MAX][cap]
+  uint64_t* acc;       // [2][GS_K1MAX][cap]
+  uint32_t* change_tick;
+  uint32_t* ltime_member;
+  uint32_t* ltime_event;
+  uint32_t* event_min;
+  uint32_t* heard;
+  uint32_t* queued;
+  uint8_t* tx;  // [GS_MAX_RUMORS][cap]
+  // pool-wide device words
+  unsigned long long* stats;  // [GSIM_STAT_COUNT]
+  uint32_t* heard_cnt;        // [GS_MAX_RUMORS]
+  uint32_t* conv_tick;        // [GS_MAX_RUMORS]
+  uint32_t* view_cnt;         // [4] alive/suspect/dead/left transitions bookkeeping
+  uint32_t* crashed_alive;    // CRASHED members not yet Dead in the view
+  uint32_t* crashed_dead_tick;
+  GsEventRec* evlog;
+  uint32_t* evlog_cursor;  // [0]=written, [1]=dropped
+  uint32_t* tick_base;
+};
+
+// Per-row outputs that the launch wrapper reduces (warp/block aggregated atomics).
+#define GS_NSTAT 16
+struct GsRowOut {
+  uint32_t st[GS_NSTAT];
+  uint32_t new_heard;     // rumor bits accepted by this row in this tick
+  int32_t crashed_alive;  // delta of the "crashed but not yet dead" count
+};

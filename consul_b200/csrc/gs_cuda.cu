@@ -1,0 +1,370 @@
+// gs_cuda.cu — sm_100a kernels and the CUDA backend of libgsim.
+//
+// Kernels (all HBM/L2-bound integer work; no tensor cores by design — there is no dense
+// contraction anywhere on this path):
+//   gs_tick_kernel      one launch = one lock-step tick of every virtual member
+//                       (SURVEY §7 K1+K2 fused: emit and apply are separated by the
+//                       double-buffered mailbox instead of a grid barrier)
+//   gs_advance_kernel   bumps the device tick counter at the end of a CUDA-graph chunk
+//   gs_init_kernel, gs_crash_kernel, gs_recount_kernel, gs_hash_kernel   control plane
+//
+// Launch shape: 256 threads/CTA, one member per thread, consecutive members in a warp so
+// the four hot columns (key, inbox, due, meta) are read as four fully coalesced 128 B
+// requests per warp.  Ticks are chained inside a CUDA graph of GS_GRAPH_TICKS launches so
+// the ~2 us per-launch host cost is off the critical path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+
+#include "gs_aux.h"
+#include "gs_backend.h"
+
+#define GS_BLOCK 256
+#define GS_GRAPH_TICKS 64
+
+namespace {
+
+struct DevSink {
+  uint32_t* s_stat;
+  uint32_t* s_heard;
+  __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx], v); }
+  __device__ __forceinline__ void heard(uint32_t r) { atomicAdd(&s_heard[r], 1u); }
+  __device__ __forceinline__ void crashed_dead(const GsDev& d, uint32_t t) {
+    uint32_t old = atomicSub(d.crashed_alive, 1u);
+    if (old == 1u) *d.crashed_dead_tick = t;
+  }
+  __device__ __forceinline__ void log_event(const GsDev& d, const GsGlobals& g, uint32_t t,
+                                            uint32_t type, uint32_t subject, uint32_t observer,
+                                            uint32_t ltime) {
+    uint32_t pos = atomicAdd(&d.evlog_cursor[0], 1u);
+    if (pos < g.evlog_cap) {
+      GsEventRec e;
+      e.tick = t;
+      e.type = type;
+      e.subject = subject;
+      e.observer = observer;
+      e.ltime = ltime;
+      e.reserved = 0u;
+      d.evlog[pos] = e;
+    } else {
+      atomicAdd(&d.evlog_cursor[1], 1u);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
+  __shared__ uint32_t s_stat[GS_NSTAT];
+  __shared__ uint32_t s_heard[32];
+  const uint32_t tid = threadIdx.x;
+  if (tid < GS_NSTAT) s_stat[tid] = 0u;
+  if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  __syncthreads();
+  const GsGlobals& g = *gp;
+  const uint32_t t = *d.tick_base + k_off;
+  const uint32_t gslot = t % g.GI;
+  const uint32_t i = blockIdx.x * GS_BLOCK + tid;
+  DevSink sink{s_stat, s_heard};
+  if (i < g.n) gs_row_step(d, g, i, t, gslot, sink);
+  __syncthreads();
+  // one global atomic per counter per CTA, and only for CTAs that saw activity
+  if (tid < GS_NSTAT) {
+    uint32_t v = s_stat[tid];
+    if (v) atomicAdd(&d.stats[tid], (unsigned long long)v);
+  } else if (tid >= 32u && tid < 32u + GS_MAX_RUMORS) {
+    uint32_t r = tid - 32u, c = s_heard[r];
+    if (c) {
+      uint32_t old = atomicAdd(&d.heard_cnt[r], c);
+      if (old + c == g.up_count) d.conv_tick[r] = t;  // every UP member has heard rumor r
+    }
+  }
+}
+
+__global__ void gs_advance_kernel(uint32_t* tick_base, uint32_t k) { *tick_base += k; }
+
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_init_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t first, uint32_t count,
+                   uint32_t now) {
+  uint32_t x = blockIdx.x * GS_BLOCK + threadIdx.x;
+  if (x < count) gs_init_row(d, *gp, first + x, now);
+}
+
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_crash_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t thr, uint32_t salt,
+                    uint32_t* n_crashed) {
+  uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
+  bool c = false;
+  if (i < gp->n) c = gs_crash_row(d, *gp, i, thr, salt);
+  unsigned b = __ballot_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31u) == 0u && b) atomicAdd(n_crashed, (uint32_t)__popc(b));
+}
+
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_recount_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, GsRecount* out) {
+  __shared__ GsRecount s;
+  uint32_t* sw = reinterpret_cast<uint32_t*>(&s);
+  for (uint32_t x = threadIdx.x; x < sizeof(GsRecount) / 4; x += GS_BLOCK) sw[x] = 0u;
+  __syncthreads();
+  const GsGlobals& g = *gp;
+  uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
+  if (i < g.n) {
+    uint32_t k = d.key[now & 1u][i];
+    uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
+    atomicAdd(&s.truth_cnt[truth], 1u);
+    if (truth != GS_TRUTH_NONE) atomicAdd(&s.rank_cnt[rank], 1u);
+    if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) atomicAdd(&s.crashed_alive, 1u);
+    if (truth == GS_TRUTH_UP && g.active_mask) {
+      uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
+      while (h) {
+        uint32_t r = __ffs(h) - 1;
+        h &= h - 1;
+        atomicAdd(&s.heard_cnt[r], 1u);
+      }
+      while (q) {
+        uint32_t r = __ffs(q) - 1;
+        q &= q - 1;
+        atomicAdd(&s.queued_cnt[r], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+  for (uint32_t x = threadIdx.x; x < sizeof(GsRecount) / 4; x += GS_BLOCK)
+    if (sw[x]) atomicAdd(&ow[x], sw[x]);
+}
+
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_hash_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now,
+                   unsigned long long* out) {
+  __shared__ unsigned long long s[4];
+  if (threadIdx.x < 4) s[threadIdx.x] = 0ull;
+  __syncthreads();
+  uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
+  if (i < gp->n) {
+    uint64_t h = gs_hash_row(d, *gp, i, now);
+    if (h) {
+      uint64_t lanes[4];
+      gs_hash_lanes(h, lanes);
+      for (int q = 0; q < 4; ++q) atomicAdd(&s[q], (unsigned long long)lanes[q]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(&out[threadIdx.x], s[threadIdx.x]);
+}
+
+class CudaBackend : public GsBackend {
+ public:
+  explicit CudaBackend(int dev) : dev_(dev) {
+    err_[0] = 0;
+    cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
+    cudaEventCreate(&ev0_);
+    cudaEventCreate(&ev1_);
+    scratch_ = nullptr;
+    cudaMalloc(&scratch_, 4096);
+  }
+  ~CudaBackend() override {
+    cudaSetDevice(dev_);
+    for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    if (scratch_) cudaFree(scratch_);
+    cudaEventDestroy(ev0_);
+    cudaEventDestroy(ev1_);
+    cudaStreamDestroy(stream_);
+  }
+  const char* name() const override { return "cuda-sm_100a"; }
+  void* alloc(size_t bytes) override {
+    cudaSetDevice(dev_);
+    void* p = nullptr;
+    if (!ok(cudaMalloc(&p, bytes ? bytes : 4), "cudaMalloc")) return nullptr;
+    return p;
+  }
+  void release(void* p) override {
+    cudaSetDevice(dev_);
+    if (p) cudaFree(p);
+  }
+  bool h2d(void* dst, const void* src, size_t bytes) override {
+    cudaSetDevice(dev_);
+    return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_), "h2d") &&
+           ok(cudaStreamSynchronize(stream_), "h2d sync");
+  }
+  bool d2h(void* dst, const void* src, size_t bytes) override {
+    cudaSetDevice(dev_);
+    return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "d2h") &&
+           ok(cudaStreamSynchronize(stream_), "d2h sync");
+  }
+  bool fill32(uint32_t* dst, uint32_t value, size_t count) override {
+    cudaSetDevice(dev_);
+    if ((value & 0xFFu) == ((value >> 8) & 0xFFu) && (value & 0xFFFFu) == (value >> 16))
+      return ok(cudaMemsetAsync(dst, (int)(value & 0xFFu), count * 4, stream_), "memset");
+    return ok(cudaMemsetD32Async_(dst, value, count), "memset32");
+  }
+  bool fill8(uint8_t* dst, uint8_t value, size_t count) override {
+    cudaSetDevice(dev_);
+    return ok(cudaMemsetAsync(dst, value, count, stream_), "memset8");
+  }
+  bool init_rows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t first,
+                 uint32_t count, uint32_t now) override {
+    if (!count) return true;
+    cudaSetDevice(dev_);
+    gs_init_kernel<<<(count + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, first,
+                                                                                count, now);
+    ++launches_;
+    return ok(cudaGetLastError(), "init launch") && ok(cudaStreamSynchronize(stream_), "init");
+  }
+  bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0,
+                 uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches) override {
+    (void)t0;
+    if (!nticks || !g.n) {
+      if (nticks) {  // no members: just advance time
+        gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, nticks);
+        ++launches_;
+        return ok(cudaGetLastError(), "advance") && ok(cudaStreamSynchronize(stream_), "advance");
+      }
+      return true;
+    }
+    cudaSetDevice(dev_);
+    const uint32_t blocks = (g.n + GS_BLOCK - 1) / GS_BLOCK;
+    if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
+    uint32_t left = nticks;
+    if (use_graph && left >= GS_GRAPH_TICKS) {
+      cudaGraphExec_t ge = graph_for(d, g_dev, blocks);
+      if (!ge) return false;
+      while (left >= GS_GRAPH_TICKS) {
+        if (!ok(cudaGraphLaunch(ge, stream_), "graph launch")) return false;
+        left -= GS_GRAPH_TICKS;
+        launches_ += GS_GRAPH_TICKS + 1;
+      }
+    }
+    if (left) {
+      for (uint32_t k = 0; k < left; ++k)
+        gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+      gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
+      launches_ += left + 1;
+      if (!ok(cudaGetLastError(), "tick launch")) return false;
+    }
+    if (!ok(cudaEventRecord(ev1_, stream_), "event")) return false;
+    if (!ok(cudaStreamSynchronize(stream_), "tick sync")) return false;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0_, ev1_);
+    if (kernel_ms) *kernel_ms += ms;
+    if (launches) *launches += nticks;
+    return true;
+  }
+  bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t thr,
+                      uint32_t salt, uint32_t, uint32_t* n_crashed) override {
+    cudaSetDevice(dev_);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(scratch_);
+    if (!ok(cudaMemsetAsync(cnt, 0, 4, stream_), "memset")) return false;
+    if (g.n) {
+      gs_crash_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, thr,
+                                                                                 salt, cnt);
+      ++launches_;
+    }
+    return ok(cudaGetLastError(), "crash launch") && d2h(n_crashed, cnt, 4);
+  }
+  bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+               GsRecount* out) override {
+    cudaSetDevice(dev_);
+    GsRecount* dr = reinterpret_cast<GsRecount*>(scratch_);
+    if (!ok(cudaMemsetAsync(dr, 0, sizeof(GsRecount), stream_), "memset")) return false;
+    if (g.n) {
+      gs_recount_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, now,
+                                                                                   dr);
+      ++launches_;
+    }
+    return ok(cudaGetLastError(), "recount launch") && d2h(out, dr, sizeof(GsRecount));
+  }
+  bool state_hash(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+                  uint64_t out[4]) override {
+    cudaSetDevice(dev_);
+    unsigned long long* dh = reinterpret_cast<unsigned long long*>(scratch_);
+    if (!ok(cudaMemsetAsync(dh, 0, 32, stream_), "memset")) return false;
+    if (g.n) {
+      gs_hash_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, now, dh);
+      ++launches_;
+    }
+    return ok(cudaGetLastError(), "hash launch") && d2h(out, dh, 32);
+  }
+  bool sync() override {
+    cudaSetDevice(dev_);
+    return ok(cudaStreamSynchronize(stream_), "sync");
+  }
+  const char* last_error() const override { return err_; }
+  uint64_t total_launches() const override { return launches_; }
+
+ private:
+  cudaError_t cudaMemsetD32Async_(uint32_t* dst, uint32_t value, size_t count) {
+    // no runtime-API 32-bit memset: stage a small pattern buffer through the host
+    const size_t chunk = 1u << 16;
+    static thread_local uint32_t pat[1u << 16];
+    for (size_t x = 0; x < chunk; ++x) pat[x] = value;
+    for (size_t off = 0; off < count; off += chunk) {
+      size_t c = count - off < chunk ? count - off : chunk;
+      cudaError_t e = cudaMemcpyAsync(dst + off, pat, c * 4, cudaMemcpyHostToDevice, stream_);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(stream_);
+  }
+  cudaGraphExec_t graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks) {
+    auto it = graphs_.find(blocks);
+    if (it != graphs_.end()) return it->second;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture"))
+      return nullptr;
+    for (uint32_t k = 0; k < GS_GRAPH_TICKS; ++k)
+      gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+    gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
+    if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
+    if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
+      cudaGraphDestroy(graph);
+      return nullptr;
+    }
+    cudaGraphDestroy(graph);
+    graphs_[blocks] = ge;
+    return ge;
+  }
+  bool ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    snprintf(err_, sizeof(err_), "%s: %s", what, cudaGetErrorString(e));
+    return false;
+  }
+  int dev_;
+  cudaStream_t stream_;
+  cudaEvent_t ev0_, ev1_;
+  void* scratch_;
+  std::map<uint32_t, cudaGraphExec_t> graphs_;
+  uint64_t launches_ = 0;
+  char err_[256];
+};
+
+}  // namespace
+
+GsBackend* gs_make_cuda_backend(int device, char* err, size_t err_cap) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    snprintf(err, err_cap, "no CUDA device: %s (libgsim has no CPU fallback)",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= count) {
+    snprintf(err, err_cap, "CUDA device %d out of range (%d devices)", device, count);
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    snprintf(err, err_cap, "device %d is not sm_100-class (libgsim ships sm_100a SASS only)",
+             device);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    snprintf(err, err_cap, "cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  return new CudaBackend(device);
+}

@@ -1,0 +1,485 @@
+// gs_row.h — one virtual member's lock-step tick: the body of the sm_100a tick kernel.
+//
+// Reference functions restated here ([U] = hashicorp/memberlist v0.5.2 / serf v0.10.2,
+// un-vendored, /root/reference/go.mod:80,85; row numbers = SURVEY.md §8a):
+//   a2  schedule/probe/resetNodes       -> probe ring cursor over a keyed permutation
+//   a3  probeNode + handleIndirectPing  -> stages IDLE / WAIT_T / WAIT_P, pull-evaluated
+//   a4  gossip + kRandomNodes           -> gs_krandom + packet scatter (atomicOr)
+//   a5  TransmitLimitedQueue            -> queued mask + tx[r][i] counters, gs_select_packet
+//   a6-a9 alive/suspect/dead/refute     -> key transitions of the row owner
+//   a7  suspicion (Lifeguard)           -> sus_start/sus_from + timeout table
+//   a10 awareness                       -> meta bits 0..2
+//   a13 LamportClock.Witness            -> max(clock, v+1) on delivery
+//   a14 handleUserEvent                 -> event_min / event_buffer window checks
+//
+// Determinism: a tick reads only the snapshot written by earlier ticks (key[t&1],
+// inbox[t&1]) and its own row; everything a row sends is delivered through commutative
+// atomics (atomicOr on inbox[(t+1)&1], atomicMin chain on acc[(t+1)&1]) and consumed by
+// the receiving row in tick t+1.  Results do not depend on block scheduling.
+#pragma once
+#include "gs_core.h"
+
+#if defined(__CUDA_ARCH__)
+#define GS_DEV __device__ __forceinline__
+#define GS_ATOMIC_OR32(p, v) atomicOr((p), (v))
+#define GS_ATOMIC_MIN64(p, v) atomicMin((unsigned long long*)(p), (unsigned long long)(v))
+#else
+#define GS_DEV inline
+#define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
+static inline uint64_t gs_host_atomic_min64(uint64_t* p, uint64_t v) {
+  uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED,
+                                                 __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
+#define GS_ATOMIC_MIN64(p, v) gs_host_atomic_min64((uint64_t*)(p), (uint64_t)(v))
+#endif
+
+// Stat indices (mirror GSIM_STAT_* in include/gsim.h).
+enum {
+  GS_ST_PROBES = 0,
+  GS_ST_ACKS,
+  GS_ST_INDIRECT_PINGS,
+  GS_ST_NACKS,
+  GS_ST_PROBE_FAILURES,
+  GS_ST_SUSPECTS,
+  GS_ST_CONFIRMATIONS,
+  GS_ST_DEADS,
+  GS_ST_REFUTES,
+  GS_ST_GOSSIP_PACKETS,
+  GS_ST_RUMORS_SENT,
+  GS_ST_RUMORS_ACCEPTED,
+  GS_ST_RUMORS_DROPPED,
+  GS_ST_PACKETS_LOST,
+  GS_ST_ACTIVE_ROWS
+};
+
+// One simulated UDP packet is lost iff its Philox draw is below the threshold.
+template <class Sink>
+GS_DEV bool gs_lost(const GsGlobals& g, Sink& sink, uint32_t src, uint32_t dst, uint32_t t,
+                    uint32_t kind, uint32_t idx) {
+  if (g.loss_thr == 0u) return false;
+  GsU4 r = gs_philox(g.seed_lo, g.seed_hi, src, dst, t, GS_PUR_LOSS | (kind << 8) | (idx << 16));
+  bool lost = r.x < g.loss_thr;
+  if (lost) sink.stat(GS_ST_PACKETS_LOST, 1);
+  return lost;
+}
+
+// Does member i know member c exists?  Established members are known to everyone; a
+// pending joiner is known only to members that have heard its alive rumor.
+GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c, uint32_t kc,
+                     uint32_t heard_i, uint32_t meta_i) {
+  if (c == i) return true;
+  // a member that has not joined anyone yet knows nobody but itself and what it heard
+  if (!gs_key_pending(kc)) return !(meta_i & GS_META_ISOLATED);
+  uint32_t am = g.class_mask[0] & g.active_mask;
+  while (am) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r = __ffs(am) - 1;
+#else
+    uint32_t r = (uint32_t)__builtin_ctz(am);
+#endif
+    am &= am - 1;
+    if (g.rumors[r].kind == 1u /*ALIVE*/ && g.rumors[r].subject == c) return (heard_i >> r) & 1u;
+  }
+  (void)d;
+  return false;
+}
+
+// kRandomNodes ([U] memberlist/util.go): up to min(3n, 32) uniform draws `rand % n`,
+// rejecting excluded members and duplicates.  mode 0 = gossip targets (alive, suspect,
+// or dead for less than GossipToTheDeadTime), mode 1 = indirect-probe relays (alive only).
+GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t,
+                           uint32_t purpose, uint32_t k, uint32_t mode, uint32_t exclude2,
+                           uint32_t heard_i, uint32_t meta_i, uint32_t* out) {
+  const uint32_t n = g.n;
+  const uint32_t* keyc = d.key[t & 1u];
+  uint32_t tries = 3u * n;
+  if (tries > GS_KR_MAX_TRIES || n > 0x55555555u) tries = GS_KR_MAX_TRIES;
+  uint32_t cnt = 0;
+  GsU4 blk;
+  blk.x = blk.y = blk.z = blk.w = 0;
+  for (uint32_t dr = 0; dr < tries && cnt < k; ++dr) {
+    if ((dr & 3u) == 0u) blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, dr >> 2);
+    uint32_t c = gs_u4_get(blk, dr & 3u) % n;
+    if (c == i || c == exclude2) continue;
+    uint32_t kc = keyc[c];
+    if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
+    uint32_t rank = gs_key_rank(kc);
+    if (mode == 1u) {
+      if (rank != GS_RANK_ALIVE) continue;
+    } else {
+      if (rank == GS_RANK_LEFT) continue;
+      if (rank == GS_RANK_DEAD && (t - d.change_tick[c]) > g.gtd_ticks) continue;
+    }
+    if (!gs_knows(d, g, i, c, kc, heard_i, meta_i)) continue;
+    bool dup = false;
+    for (uint32_t q = 0; q < cnt; ++q) dup = dup || (out[q] == c);
+    if (dup) continue;
+    out[cnt++] = c;
+  }
+  return cnt;
+}
+
+// TransmitLimitedQueue.GetBroadcasts ([U] memberlist/queue.go) for one packet: walk the
+// member's queued rumors by (queue class, transmits asc, size desc, slot desc) and take
+// every message that still fits the UDP budget.  Class order = memberlist broadcasts,
+// then serf intents, then serf user events ([U] serf/delegate.go GetBroadcasts).
+GS_DEV uint32_t gs_select_packet(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t queued) {
+  uint32_t total = 0, qm = queued;
+  while (qm) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r = __ffs(qm) - 1;
+#else
+    uint32_t r = (uint32_t)__builtin_ctz(qm);
+#endif
+    qm &= qm - 1;
+    total += g.rumors[r].size + (g.rumors[r].qclass ? 3u : 2u);
+  }
+  if (total <= g.udp_avail) return queued;  // everything fits: the common case
+  uint32_t used = 0, mask = 0;
+  for (uint32_t cls = 0; cls < 3; ++cls) {
+    uint32_t cm = queued & g.class_mask[cls];
+    const uint32_t ovh = cls ? 3u : 2u;
+    while (cm) {
+      if (g.udp_avail <= used + ovh) break;
+      const uint32_t free_b = g.udp_avail - used - ovh;
+      uint32_t best = GS_EMPTY32, best_key = GS_EMPTY32, scan = cm;
+      while (scan) {
+#if defined(__CUDA_ARCH__)
+        uint32_t r = __ffs(scan) - 1;
+#else
+        uint32_t r = (uint32_t)__builtin_ctz(scan);
+#endif
+        scan &= scan - 1;
+        uint32_t sz = g.rumors[r].size;
+        if (sz > free_b) continue;
+        uint32_t tx = d.tx[(size_t)r * g.cap + i];
+        uint32_t key = (tx << 24) | ((0xFFFFu - (sz & 0xFFFFu)) << 8) | (31u - r);
+        if (key < best_key) {
+          best_key = key;
+          best = r;
+        }
+      }
+      if (best == GS_EMPTY32) break;
+      mask |= 1u << best;
+      cm &= ~(1u << best);
+      used += ovh + g.rumors[best].size;
+    }
+  }
+  return mask;
+}
+
+template <class Sink>
+GS_DEV void gs_log_event(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t t, uint32_t type,
+                         uint32_t subject, uint32_t observer, uint32_t ltime) {
+  sink.log_event(d, g, t, type, subject, observer, ltime);
+}
+
+// The tick of member i.  Returns nothing; all effects go to d.* and the sink.
+template <class Sink>
+GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t, uint32_t gslot,
+                        Sink& sink) {
+  const uint32_t cur = t & 1u, nxt = cur ^ 1u;
+  const uint32_t k0 = d.key[cur][i];
+  const uint32_t inb = d.inbox[cur][i];
+  const uint32_t m0 = d.meta[i];
+  const uint32_t due0 = d.due[i];
+  const uint32_t truth = gs_key_truth(k0);
+  if (truth == GS_TRUTH_NONE) return;
+
+  // ---- idle fast path: nothing arrived, nothing due, nothing queued ------------
+  const bool up = truth == GS_TRUTH_UP;
+  const bool gossip_slot = up && gslot == gs_meta_gphase(m0);  // gslot = t % GI
+  uint32_t queued = 0;
+  if (gossip_slot) queued = d.queued[i];
+  if (inb == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(m0 & GS_META_DIRTY) &&
+      !(up && due0 == t) && queued == 0u)
+    return;
+  sink.stat(GS_ST_ACTIVE_ROWS, 1);
+
+  uint32_t k = k0, m = m0, due = due0;
+  const size_t cap = g.cap;
+  uint32_t heard = 0;
+  bool heard_loaded = false;
+
+  // ---- A. consume the mailbox of this arrival tick ------------------------------
+  if (inb != 0u) {
+    d.inbox[cur][i] = 0u;
+    uint32_t rbits = inb & ~GS_ACC_BIT & g.active_mask;
+    if (rbits && up) {
+      heard = d.heard[i];
+      heard_loaded = true;
+      uint32_t fresh = rbits & ~heard;
+      uint32_t accepted = 0;
+      while (fresh) {
+#if defined(__CUDA_ARCH__)
+        uint32_t r = __ffs(fresh) - 1;
+#else
+        uint32_t r = (uint32_t)__builtin_ctz(fresh);
+#endif
+        fresh &= fresh - 1;
+        const GsRumor& ru = g.rumors[r];
+        bool accept = true;
+        if (ru.kind == 4u /*USER_EVENT*/) {
+          // [U] serf.handleUserEvent: Witness, then eventMinTime and buffer-window checks.
+          uint32_t c = d.ltime_event[i];
+          if (ru.ltime >= c) {
+            c = ru.ltime + 1u;
+            d.ltime_event[i] = c;
+          }
+          if (ru.ltime < d.event_min[i]) accept = false;
+          else if (c > g.event_buffer && ru.ltime < c - g.event_buffer) accept = false;
+          if (accept && (m & GS_META_WATCHED))
+            gs_log_event(d, g, sink, t, 5u /*EVENT_USER*/, r, i, ru.ltime);
+        } else if (ru.kind == 2u || ru.kind == 3u) {
+          // [U] serf.handleNodeJoinIntent / handleNodeLeaveIntent: clock.Witness(LTime).
+          uint32_t c = d.ltime_member[i];
+          if (ru.ltime >= c) d.ltime_member[i] = ru.ltime + 1u;
+        } else if (ru.kind == 1u) {
+          // [U] memberlist.aliveNode for a new node -> serf.handleNodeJoin -> EventMemberJoin.
+          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, 0u /*MEMBER_JOIN*/, ru.subject, i, 0u);
+        }
+        if (accept) {
+          accepted |= 1u << r;
+          d.tx[(size_t)r * cap + i] = 0;  // queued with transmits = 0
+          sink.heard(r);
+          sink.stat(GS_ST_RUMORS_ACCEPTED, 1);
+        } else {
+          sink.stat(GS_ST_RUMORS_DROPPED, 1);
+        }
+      }
+      if (accepted) {
+        heard |= accepted;
+        d.heard[i] = heard;
+        uint32_t q = d.queued[i] | accepted;
+        d.queued[i] = q;
+        if (gossip_slot) queued = q;
+      }
+    }
+    if (inb & GS_ACC_BIT) {
+      // [U] memberlist.suspectNode, subject side.  Entries are (~inc<<32 | from), sorted.
+      uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;
+      for (uint32_t s = 0; s < GS_K1MAX; ++s) {
+        uint64_t e = acc[(size_t)s * cap + i];
+        if (e == GS_EMPTY64) break;
+        acc[(size_t)s * cap + i] = GS_EMPTY64;
+        uint32_t e_inc = ~(uint32_t)(e >> 32), from = (uint32_t)e;
+        if (e_inc != gs_key_inc(k)) continue;  // older incarnation: ignored
+        uint32_t rank = gs_key_rank(k);
+        if (rank == GS_RANK_ALIVE) {
+          k = gs_key_with_rank(k, GS_RANK_SUSPECT);
+          d.sus_start[i] = t - 1u;  // the accuser started its timer when it sent
+          d.sus_from[i] = from;
+          for (uint32_t q = 1; q < GS_K1MAX; ++q) d.sus_from[(size_t)q * cap + i] = GS_EMPTY32;
+          sink.stat(GS_ST_SUSPECTS, 1);
+        } else if (rank == GS_RANK_SUSPECT) {
+          // suspicion.Confirm: distinct `from`, at most k confirmations are counted
+          for (uint32_t q = 0; q <= g.sus_k && q < GS_K1MAX; ++q) {
+            uint32_t f = d.sus_from[(size_t)q * cap + i];
+            if (f == from) break;
+            if (f == GS_EMPTY32) {
+              d.sus_from[(size_t)q * cap + i] = from;
+              sink.stat(GS_ST_CONFIRMATIONS, 1);
+              break;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- B. the member's own view transitions -------------------------------------
+  {
+    uint32_t rank = gs_key_rank(k);
+    if (up && !(m & GS_META_LEAVING) && (rank == GS_RANK_SUSPECT || rank == GS_RANK_DEAD)) {
+      // [U] memberlist.refute: bump past the accused incarnation, awareness +1,
+      // broadcast alive (instantly visible in the shared view).
+      uint32_t inc = gs_key_inc(k);
+      uint32_t accused = inc;
+      inc = inc + 1u;
+      if (accused >= inc) inc = accused + 1u;
+      k = gs_key_with_rank(gs_key_with_inc(k, inc), GS_RANK_ALIVE);
+      uint32_t aw = gs_meta_aw(m) + 1u;
+      if (aw > g.awareness_max - 1u) aw = g.awareness_max - 1u;
+      m = gs_meta_set_aw(m, aw);
+      sink.stat(GS_ST_REFUTES, 1);
+    } else if (rank == GS_RANK_SUSPECT) {
+      // [U] suspicion timer: fires at start + timeout(confirmations)
+      uint32_t c = 0;
+      for (uint32_t q = 1; q <= g.sus_k && q < GS_K1MAX; ++q)
+        c += d.sus_from[(size_t)q * cap + i] != GS_EMPTY32;
+      if (t - d.sus_start[i] >= g.sus_ticks[c]) {
+        k = gs_key_with_rank(k, GS_RANK_DEAD);  // [U] memberlist.deadNode
+        d.change_tick[i] = t;
+        sink.stat(GS_ST_DEADS, 1);
+        if (truth == GS_TRUTH_CRASHED) sink.crashed_dead(d, t);
+        if (g.flags & 1u) gs_log_event(d, g, sink, t, 2u /*MEMBER_FAILED*/, i, GS_EMPTY32, 0u);
+      }
+    }
+  }
+
+  if (up) {
+    // ---- C. failure detector: this member as prober ------------------------------
+    uint32_t stage = gs_meta_stage(m);
+    if (stage == GS_STAGE_WAIT_T && due == t) {
+      // ProbeTimeout elapsed without a direct ack: k indirect probes + TCP fallback.
+      if (!heard_loaded) {
+        heard = d.heard[i];
+        heard_loaded = true;
+      }
+      const uint32_t j = d.probe_tgt[i];
+      const uint32_t kj = d.key[cur][j];
+      const bool j_up = gs_key_truth(kj) == GS_TRUTH_UP;
+      uint32_t relays[8];
+      uint32_t kk = g.indirect_checks > 8u ? 8u : g.indirect_checks;
+      uint32_t nr = gs_krandom(d, g, i, t, GS_PUR_RELAY, kk, 1u, j, heard, m, relays);
+      bool success = false;
+      uint32_t nacks = 0;
+      for (uint32_t q = 0; q < nr; ++q) {
+        const uint32_t r = relays[q];
+        const bool r_up = gs_key_truth(d.key[cur][r]) == GS_TRUTH_UP;
+        sink.stat(GS_ST_INDIRECT_PINGS, 1);
+        if (!(r_up && !gs_lost(g, sink, i, r, t, GS_LK_INDREQ, q))) continue;  // no nack either
+        bool relay_acked = j_up && !gs_lost(g, sink, r, j, t, GS_LK_INDPING, q) &&
+                           !gs_lost(g, sink, j, r, t, GS_LK_INDACK, q);
+        if (relay_acked) {
+          if (!gs_lost(g, sink, r, i, t, GS_LK_INDFWD, q)) success = true;
+        } else if (!gs_lost(g, sink, r, i, t, GS_LK_NACK, q)) {
+          ++nacks;
+          sink.stat(GS_ST_NACKS, 1);
+        }
+      }
+      if (!g.disable_tcp && j_up) success = true;  // TCP fallback ping is reliable
+      const uint32_t t0 = t - g.T;
+      if (success) {
+        uint32_t aw = gs_meta_aw(m);
+        m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
+        m = gs_meta_set_stage(m, GS_STAGE_IDLE);
+        due = t0 + g.P;
+        sink.stat(GS_ST_ACKS, 1);
+      } else {
+        uint32_t miss = nr > 0u ? nr - nacks : 1u;
+        m = gs_meta_set_nmiss(gs_meta_set_stage(m, GS_STAGE_WAIT_P), miss);
+        due = t0 + g.P * (gs_meta_aw(m) + 1u);
+      }
+      stage = gs_meta_stage(m);
+    }
+    if (stage == GS_STAGE_WAIT_P && due == t) {
+      // probe deadline: awareness += missed nacks, then suspectNode(target)
+      uint32_t aw = gs_meta_aw(m) + gs_meta_nmiss(m);
+      if (aw > g.awareness_max - 1u) aw = g.awareness_max - 1u;
+      m = gs_meta_set_stage(gs_meta_set_aw(m, aw), GS_STAGE_IDLE);
+      const uint32_t j = d.probe_tgt[i];
+      const uint64_t e = ((uint64_t)(~d.probe_inc[i]) << 32) | (uint64_t)i;
+      uint64_t* acc = d.acc + (size_t)nxt * GS_K1MAX * cap;
+      uint64_t v = e;
+      for (uint32_t s = 0; s < GS_K1MAX; ++s) {
+        uint64_t old = GS_ATOMIC_MIN64(&acc[(size_t)s * cap + j], v);
+        if (old == v || old == GS_EMPTY64) break;
+        if (old > v) v = old;  // displaced a larger entry: carry it to the next slot
+      }
+      GS_ATOMIC_OR32(&d.inbox[nxt][j], GS_ACC_BIT);
+      sink.stat(GS_ST_PROBE_FAILURES, 1);
+      stage = GS_STAGE_IDLE;  // due == t: the buffered ticker fires immediately
+    }
+    if (stage == GS_STAGE_IDLE && due == t) {
+      // [U] memberlist.probe: next eligible entry of the ring, skipping self, unknown and
+      // dead/left members; a wrap re-keys the permutation (resetNodes + shuffle).
+      if (!heard_loaded) {
+        heard = d.heard[i];
+        heard_loaded = true;
+      }
+      uint32_t cursor = d.cursor[i], pass = d.pass[i];
+      const uint32_t n = g.n;
+      GsU4 rk = gs_philox(g.seed_lo, g.seed_hi, i, pass, GS_PUR_PERM, 0u);
+      uint32_t checked = 0, target = GS_EMPTY32, ktarget = 0;
+      const uint32_t limit = n < GS_PROBE_SKIP_CAP ? n : GS_PROBE_SKIP_CAP;
+      while (checked < limit) {
+        if (cursor >= n) {
+          cursor = 0;
+          ++pass;
+          ++checked;
+          rk = gs_philox(g.seed_lo, g.seed_hi, i, pass, GS_PUR_PERM, 0u);
+          continue;
+        }
+        uint32_t c = gs_perm(cursor, n, g.perm_half_bits, rk);
+        ++cursor;
+        uint32_t kc = d.key[cur][c];
+        uint32_t rank = gs_key_rank(kc);
+        if (c == i || gs_key_truth(kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD ||
+            rank == GS_RANK_LEFT || !gs_knows(d, g, i, c, kc, heard, m)) {
+          ++checked;
+          continue;
+        }
+        target = c;
+        ktarget = kc;
+        break;
+      }
+      d.cursor[i] = cursor;
+      d.pass[i] = pass;
+      if (target != GS_EMPTY32) {
+        sink.stat(GS_ST_PROBES, 1);
+        bool ok = gs_key_truth(ktarget) == GS_TRUTH_UP && !gs_lost(g, sink, i, target, t, GS_LK_PING, 0) &&
+                  !gs_lost(g, sink, target, i, t, GS_LK_ACK, 0);
+        if (ok) {
+          uint32_t aw = gs_meta_aw(m);
+          m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
+          due = t + g.P;
+          sink.stat(GS_ST_ACKS, 1);
+        } else {
+          m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
+          d.probe_tgt[i] = target;
+          d.probe_inc[i] = gs_key_inc(ktarget);
+          due = t + g.T;
+        }
+      } else {
+        due = t + g.P;
+      }
+    }
+
+    // ---- D. gossip: drain the broadcast queue to GossipNodes random peers ----------
+    if (gossip_slot && queued != 0u) {
+      if (!heard_loaded) {
+        heard = d.heard[i];
+        heard_loaded = true;
+      }
+      uint32_t peers[8];
+      uint32_t kk = g.gossip_nodes > 8u ? 8u : g.gossip_nodes;
+      uint32_t np = gs_krandom(d, g, i, t, GS_PUR_GOSSIP, kk, 0u, GS_EMPTY32, heard, m, peers);
+      const uint32_t q0 = queued;
+      for (uint32_t q = 0; q < np && queued != 0u; ++q) {
+        uint32_t pkt = gs_select_packet(d, g, i, queued);
+        if (pkt == 0u) break;
+        uint32_t pm = pkt;
+        while (pm) {
+#if defined(__CUDA_ARCH__)
+          uint32_t r = __ffs(pm) - 1;
+#else
+          uint32_t r = (uint32_t)__builtin_ctz(pm);
+#endif
+          pm &= pm - 1;
+          uint32_t tx = (uint32_t)d.tx[(size_t)r * cap + i] + 1u;
+          d.tx[(size_t)r * cap + i] = (uint8_t)tx;
+          if (tx >= g.retransmit_limit) queued &= ~(1u << r);  // broadcast finished
+          sink.stat(GS_ST_RUMORS_SENT, 1);
+        }
+        sink.stat(GS_ST_GOSSIP_PACKETS, 1);
+        if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q)) GS_ATOMIC_OR32(&d.inbox[nxt][peers[q]], pkt);
+      }
+      if (queued != q0) d.queued[i] = queued;
+    }
+  }
+
+  // ---- E. write back ------------------------------------------------------------
+  if (k != k0) {
+    d.key[nxt][i] = k;
+    m |= GS_META_DIRTY;  // the other buffer is stale for one more tick
+  } else if (m0 & GS_META_DIRTY) {
+    d.key[nxt][i] = k;
+    m &= ~GS_META_DIRTY;
+  }
+  if (m != m0) d.meta[i] = m;
+  if (due != due0) d.due[i] = due;
+}

@@ -1,0 +1,164 @@
+// hostemu_backend.cpp — TEST INFRASTRUCTURE ONLY.  Never linked into libgsim.so and never
+// loaded by the consul_b200 package.
+//
+// The tick kernel's per-row body (consul_b200/csrc/gs_row.h) is plain C++ between the
+// atomics macros, so it can be compiled by g++ and looped on the CPU.  That lets the
+// GPU-less development container run the kernel LOGIC against the oracle before any GPU
+// time is spent, and lets the tests execute rows in adversarial orders (reverse, strided)
+// to check that results do not depend on scheduling — the property that makes the
+// CUDA launch deterministic.  It is built into tests/hostemu/libgsim_hostemu.so together
+// with gs_api.cpp by `__graft_entry__.build()`; parity claims are made only for the CUDA
+// backend on a real B200 (tests marked `gpu`).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../consul_b200/csrc/gs_aux.h"
+#include "../../consul_b200/csrc/gs_backend.h"
+
+namespace {
+
+struct HostSink {
+  uint64_t* stats;
+  uint32_t* heard_cnt;
+  uint32_t local_heard[32];
+  void stat(int idx, uint32_t v) { stats[idx] += v; }
+  void heard(uint32_t r) { local_heard[r] += 1; }
+  void crashed_dead(const GsDev& d, uint32_t t) {
+    uint32_t old = (*d.crashed_alive)--;
+    if (old == 1u) *d.crashed_dead_tick = t;
+  }
+  void log_event(const GsDev& d, const GsGlobals& g, uint32_t t, uint32_t type, uint32_t subject,
+                 uint32_t observer, uint32_t ltime) {
+    uint32_t pos = d.evlog_cursor[0]++;
+    if (pos < g.evlog_cap) {
+      GsEventRec e = {t, type, subject, observer, ltime, 0u};
+      d.evlog[pos] = e;
+    } else {
+      d.evlog_cursor[1]++;
+    }
+  }
+};
+
+class HostEmuBackend : public GsBackend {
+ public:
+  HostEmuBackend() {
+    const char* o = getenv("GSIM_HOSTEMU_ORDER");
+    order_ = o ? atoi(o) : 0;
+    err_[0] = 0;
+  }
+  const char* name() const override { return "hostemu (tests only)"; }
+  void* alloc(size_t bytes) override { return calloc(1, bytes ? bytes : 4); }
+  void release(void* p) override { free(p); }
+  bool h2d(void* dst, const void* src, size_t bytes) override {
+    memcpy(dst, src, bytes);
+    return true;
+  }
+  bool d2h(void* dst, const void* src, size_t bytes) override {
+    memcpy(dst, src, bytes);
+    return true;
+  }
+  bool fill32(uint32_t* dst, uint32_t value, size_t count) override {
+    for (size_t i = 0; i < count; ++i) dst[i] = value;
+    return true;
+  }
+  bool fill8(uint8_t* dst, uint8_t value, size_t count) override {
+    memset(dst, value, count);
+    return true;
+  }
+  bool init_rows(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t first,
+                 uint32_t count, uint32_t now) override {
+    for (uint32_t x = 0; x < count; ++x) gs_init_row(d, g, first + x, now);
+    return true;
+  }
+  uint32_t row_at(uint32_t x, uint32_t n) const {
+    if (order_ == 1) return n - 1 - x;  // reverse
+    if (order_ == 2) {                  // odd rows first, then even rows
+      uint32_t odd = n / 2;
+      return x < odd ? 2 * x + 1 : 2 * (x - odd);
+    }
+    return x;
+  }
+  bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0,
+                 uint32_t nticks, bool, double*, uint64_t* launches) override {
+    const GsGlobals& g = *g_dev;  // the kernels read the device copy
+    for (uint32_t k = 0; k < nticks; ++k) {
+      const uint32_t t = *d.tick_base + k;
+      if (t != t0 + k) {
+        snprintf(err_, sizeof(err_), "tick_base out of sync");
+        return false;
+      }
+      const uint32_t gslot = t % g.GI;
+      HostSink sink;
+      sink.stats = reinterpret_cast<uint64_t*>(d.stats);
+      sink.heard_cnt = d.heard_cnt;
+      memset(sink.local_heard, 0, sizeof(sink.local_heard));
+      for (uint32_t x = 0; x < g.n; ++x) gs_row_step(d, g, row_at(x, g.n), t, gslot, sink);
+      for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+        uint32_t c = sink.local_heard[r];
+        if (c) {
+          uint32_t old = d.heard_cnt[r];
+          d.heard_cnt[r] = old + c;
+          if (old + c == g.up_count) d.conv_tick[r] = t;
+        }
+      }
+      ++launches_;
+    }
+    *d.tick_base += nticks;
+    ++launches_;
+    if (launches) *launches += nticks;
+    return true;
+  }
+  bool crash_fraction(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t thr,
+                      uint32_t salt, uint32_t, uint32_t* n_crashed) override {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < g.n; ++i) c += gs_crash_row(d, g, i, thr, salt) ? 1u : 0u;
+    *n_crashed = c;
+    return true;
+  }
+  bool recount(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now,
+               GsRecount* out) override {
+    memset(out, 0, sizeof(*out));
+    for (uint32_t i = 0; i < g.n; ++i) {
+      uint32_t k = d.key[now & 1u][i];
+      uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
+      out->truth_cnt[truth]++;
+      if (truth != GS_TRUTH_NONE) out->rank_cnt[rank]++;
+      if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) out->crashed_alive++;
+      if (truth == GS_TRUTH_UP) {
+        uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
+        for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
+          out->heard_cnt[r] += (h >> r) & 1u;
+          out->queued_cnt[r] += (q >> r) & 1u;
+        }
+      }
+    }
+    return true;
+  }
+  bool state_hash(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now,
+                  uint64_t out[4]) override {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (uint32_t i = 0; i < g.n; ++i) {
+      uint64_t h = gs_hash_row(d, g, i, now);
+      if (!h) continue;
+      uint64_t lanes[4];
+      gs_hash_lanes(h, lanes);
+      for (int q = 0; q < 4; ++q) out[q] += lanes[q];
+    }
+    return true;
+  }
+  bool sync() override { return true; }
+  const char* last_error() const override { return err_; }
+  uint64_t total_launches() const override { return launches_; }
+
+ private:
+  int order_;
+  uint64_t launches_ = 0;
+  char err_[128];
+};
+
+}  // namespace
+
+GsBackend* gs_make_hostemu_backend(int, char*, size_t) { return new HostEmuBackend(); }
