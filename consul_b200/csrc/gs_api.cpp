@@ -177,7 +177,7 @@ struct gsim_pool {
   uint32_t events_dropped = 0;
   std::string err;
   uint64_t tick_ns = 0;
-  uint32_t leave_linger_base = 0;
+  uint32_t n_established = 0;  // members folded into the base set (not pending)
 };
 
 static uint64_t gcd64(uint64_t a, uint64_t b) {
@@ -346,6 +346,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
 
   g.n = cfg->n_initial;
+  p->n_established = cfg->n_initial;
   g.cap = cfg->capacity;
   g.up_count = cfg->n_initial;
   g.P = (uint32_t)(cfg->probe_interval_ns / tick);
@@ -409,6 +410,7 @@ static int retire_slot(gsim_pool* p, uint32_t slot) {
     uint32_t k0, k1;
     if (!peek(p, p->d.key[0], ru.subject, &k0) || !peek(p, p->d.key[1], ru.subject, &k1))
       return GSIM_ERR_CUDA;
+    if (gs_key_pending(k0)) p->n_established += 1;
     k0 &= ~(1u << 4);
     k1 &= ~(1u << 4);
     if (!poke(p, p->d.key[0], ru.subject, k0) || !poke(p, p->d.key[1], ru.subject, k1))
@@ -456,6 +458,9 @@ static int auto_retire(gsim_pool* p) {
   if (!do_recount(p)) return GSIM_ERR_CUDA;
   for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
     if (!((cand >> r) & 1u)) continue;
+    // an alive rumor folds into the base set only when nobody still depends on having
+    // heard it individually (members that have not joined the base set yet)
+    if (g.rumors[r].kind == GSIM_RUMOR_ALIVE && p->rc.isolated_up != 0) continue;
     if (p->rc.heard_cnt[r] == g.up_count && p->rc.queued_cnt[r] == 0) {
       int rcode = retire_slot(p, r);
       if (rcode) return rcode;
@@ -538,7 +543,8 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   const uint32_t k = gs_key_make(1u, 1u, GS_RANK_ALIVE, GS_TRUTH_UP);
   uint32_t m;
   if (!peek(p, p->d.meta, id, &m)) return fail(p, GSIM_ERR_CUDA, "peek");
-  m |= GS_META_ISOLATED;
+  // it knows nobody yet; with an empty base set there is nothing it could be missing
+  if (p->n_established > 0) m |= GS_META_ISOLATED;
   if (desc && (desc->flags & GSIM_MEMBER_WATCHED)) m |= GS_META_WATCHED;
   if (!poke(p, p->d.key[0], id, k) || !poke(p, p->d.key[1], id, k) || !poke(p, p->d.meta, id, m))
     return fail(p, GSIM_ERR_CUDA, "poke");
@@ -771,7 +777,10 @@ extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int
     uint32_t k;
     if (!peek(p, p->d.key[b], target, &k)) return fail(p, GSIM_ERR_CUDA, "peek");
     if (gs_key_rank(k) == GS_RANK_DEAD) k = gs_key_with_rank(k, GS_RANK_LEFT);
-    if (prune && gs_key_rank(k) == GS_RANK_LEFT && gs_key_truth(k) != GS_TRUTH_UP) k &= ~3u;
+    if (prune && gs_key_rank(k) == GS_RANK_LEFT && gs_key_truth(k) != GS_TRUTH_UP && gs_key_truth(k) != GS_TRUTH_NONE) {
+      if (b == 0 && !gs_key_pending(k)) p->n_established -= 1;
+      k &= ~3u;
+    }
     any_truth = gs_key_truth(k);
     if (!poke(p, p->d.key[b], target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
   }
@@ -1049,7 +1058,7 @@ extern "C" int gsim_rumor_retire(gsim_pool* p, uint32_t slot) {
   if (!((p->g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
   if (p->g.rumors[slot].kind == GSIM_RUMOR_ALIVE) {
     if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
-    if (p->rc.heard_cnt[slot] != p->g.up_count)
+    if (p->rc.heard_cnt[slot] != p->g.up_count || p->rc.isolated_up != 0)
       return fail(p, GSIM_ERR_STATE, "alive rumor has not reached every running member");
   }
   int rc = retire_slot(p, slot);
@@ -1184,6 +1193,7 @@ struct SnapHeader {
   uint32_t version, cap;
   uint32_t now, n_sched;
   uint64_t node_ticks;
+  uint32_t n_established, pad;
   GsGlobals g;
 };
 static const uint64_t SNAP_MAGIC = 0x4753494D534E4150ull;  // "GSIMSNAP"
@@ -1217,6 +1227,7 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
   h.now = p->now;
   h.n_sched = (uint32_t)p->sched.size();
   h.node_ticks = p->node_ticks;
+  h.n_established = p->n_established;
   h.g = p->g;
   memcpy(w, &h, sizeof(h));
   w += sizeof(h);
@@ -1273,6 +1284,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   p->g = h.g;
   p->now = h.now;
   p->node_ticks = h.node_ticks;
+  p->n_established = h.n_established;
   p->g_dirty = true;
   p->counts_stale = true;
   if (!poke(p, p->d.tick_base, 0, p->now)) return fail(p, GSIM_ERR_CUDA, "poke");

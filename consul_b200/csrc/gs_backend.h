@@ -15,6 +15,7 @@ struct GsRecount {
   uint32_t truth_cnt[4];
   uint32_t rank_cnt[4];
   uint32_t crashed_alive;
+  uint32_t isolated_up;  // running members that have not joined the established set
 };
 
 class GsBackend {

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(GS_BLOCK)
     atomicAdd(&s.truth_cnt[truth], 1u);
     if (truth != GS_TRUTH_NONE) atomicAdd(&s.rank_cnt[rank], 1u);
     if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) atomicAdd(&s.crashed_alive, 1u);
+    if (truth == GS_TRUTH_UP && (d.meta[i] & GS_META_ISOLATED)) atomicAdd(&s.isolated_up, 1u);
     if (truth == GS_TRUTH_UP && g.active_mask) {
       uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
       while (h) {

@@ -194,9 +194,13 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const bool gossip_slot = up && gslot == gs_meta_gphase(m0);  // gslot = t % GI
   uint32_t queued = 0;
   if (gossip_slot) queued = d.queued[i];
-  if (inb == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(m0 & GS_META_DIRTY) &&
-      !(up && due0 == t) && queued == 0u)
+  if (inb == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(up && due0 == t) && queued == 0u) {
+    if (m0 & GS_META_DIRTY) {  // bring the other key buffer up to date, then idle
+      d.key[cur ^ 1u][i] = k0;
+      d.meta[i] = m0 & ~GS_META_DIRTY;
+    }
     return;
+  }
   sink.stat(GS_ST_ACTIVE_ROWS, 1);
 
   uint32_t k = k0, m = m0, due = due0;

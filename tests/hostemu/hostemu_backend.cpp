@@ -127,6 +127,7 @@ class HostEmuBackend : public GsBackend {
       out->truth_cnt[truth]++;
       if (truth != GS_TRUTH_NONE) out->rank_cnt[rank]++;
       if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) out->crashed_alive++;
+      if (truth == GS_TRUTH_UP && (d.meta[i] & GS_META_ISOLATED)) out->isolated_up++;
       if (truth == GS_TRUTH_UP) {
         uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
         for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {

@@ -1,0 +1,132 @@
+"""Parity tests proper: the sm_100a CUDA path, called through the C ABI, against the oracle on
+the same seeded inputs (bit-exact integer state), and size-independent properties at
+BASELINE.json's full sizes.  Run on a B200 with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import scenarios as sc
+from consul_b200.pool import (NEVER, PRED_ALL_RUMORS_CONVERGED, PRED_CRASHED_ALL_DEAD,
+                              PRED_RUMOR_CONVERGED, Pool, lan_config)
+from oracle_binding import OraclePool
+from parity import compare_pools
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def make(cuda_lib):
+    return lambda cfg: [Pool(cfg, cuda_lib), OraclePool(cfg, threads=0)]
+
+
+def test_c1_three_node_join(make, cuda_lib):
+    for seed in (1, 2, 3):
+        sc.c1_three_node_join(make, cuda_lib, seed)
+
+
+@pytest.mark.parametrize("n", [1, 3, 1000, 65536])
+def test_c2_join_cascade(make, cuda_lib, n):
+    sc.c2_join_cascade(make, cuda_lib, n)
+
+
+def test_c2_join_cascade_1m_three_seeds(make, cuda_lib):
+    """BASELINE config 2 at full size: ticks-to-convergence and the state digest equal the
+    oracle's for seeds 0x5EED0001..3."""
+    ticks = []
+    for seed in (0x5EED0001, 0x5EED0002, 0x5EED0003):
+        ticks.append(sc.c2_join_cascade(make, cuda_lib, 1_000_000, seed=seed, extra_ticks=32,
+                                        every=8, columns=(seed == 0x5EED0001)))
+    assert all(15 < t < 60 for t in ticks), ticks
+
+
+def test_c3_crash(make, cuda_lib):
+    sc.c3_crash(make, cuda_lib, 3000)
+    sc.c3_crash(make, cuda_lib, 100_000, every=100, columns=False)
+    sc.c3_crash(make, cuda_lib, 500, ppm=200000, cfg_fn=sc.consul_test_config, every=5)
+    sc.c3_crash(make, cuda_lib, 400, ppm=500000, cfg_fn=sc.wan_config, every=40)
+
+
+@pytest.mark.parametrize("n", [2, 5000, 300_000])
+def test_c4_user_event(make, cuda_lib, n):
+    sc.c4_user_event(make, cuda_lib, n, columns=n <= 5000)
+
+
+def test_leave_loss_budget_window(make, cuda_lib):
+    sc.leave_scenario(make, cuda_lib)
+    sc.lossy_scenario(make, cuda_lib)
+    sc.lossy_scenario(make, cuda_lib, n=200, loss_ppm=400000, seed=12, ticks=400, disable_tcp_pings=1)
+    sc.lossy_scenario(make, cuda_lib, n=50_000, loss_ppm=100000, seed=13, ticks=120)
+    sc.budget_scenario(make, cuda_lib)
+    sc.event_window_scenario(make, cuda_lib)
+
+
+def test_graph_and_plain_launches_agree(cuda_lib):
+    """CUDA-graph chunks (64 ticks) and one-by-one launches give the same state."""
+    out = []
+    for flags in (0, 2):
+        p = Pool(lan_config(cuda_lib, capacity=20001, n_initial=20000, seed=9, flags=flags), cuda_lib)
+        x = p.member_add()
+        p.join(x, [5])
+        p.crash_fraction(50000, 1)
+        p.step(333)
+        out.append((p.state_hash(), p.stats()))
+    assert out[0] == out[1]
+
+
+def test_determinism_and_snapshot(cuda_lib):
+    def run(restore_at=None):
+        p = Pool(lan_config(cuda_lib, capacity=50001, n_initial=50000, seed=77, packet_loss_ppm=50000), cuda_lib)
+        x = p.member_add()
+        p.join(x, [0])
+        p.user_event(3, b"evt", b"data", False)
+        p.crash_fraction(20000, 2)
+        p.step(100)
+        if restore_at is not None:
+            blob = p.snapshot()
+            p.step(57)                       # wander off, then come back
+            p.restore(blob)
+        p.step(200)
+        return p.state_hash(), p.stats()["deads"]
+    a, b, c = run(), run(), run(restore_at=100)
+    assert a == b, "two runs with the same seed differ"
+    assert a == c, "resume from a snapshot is not bit-exact"
+
+
+# ---- BASELINE full sizes: properties that need no oracle ---------------------------------
+
+def test_c3_full_size_properties(cuda_lib):
+    """4M members, ~10 % crashed at tick 0: every crashed member (and nobody else) is Dead
+    within the Lifeguard bound; min/max timers are the KAT values 265 / 1585 ticks."""
+    n = 4_000_000
+    p = Pool(lan_config(cuda_lib, capacity=n, n_initial=n, seed=0x5EED0001), cuda_lib)
+    crashed = p.crash_fraction(100000, 0)
+    assert abs(crashed - n // 10) < 5000
+    st = p.stats()
+    assert st["suspicion_ticks"][:3] == [1585, 752, 265] and st["retransmit_limit"] == 28
+    t = p.run_until(PRED_CRASHED_ALL_DEAD, 0, 2600, 64)
+    assert t != NEVER and 265 <= t <= 1585 + 400
+    s = p.stats()
+    assert s["deads"] == crashed and s["n_view_dead"] == crashed and s["refutes"] == 0
+    key = p.column("key")
+    truth, rank = key & 3, (key >> 2) & 3
+    assert np.array_equal(truth == 2, rank == 2)              # dead set == crashed set
+    change = p.column("change_tick")[truth == 2]
+    assert change.min() >= 265 and change.max() == t
+
+
+def test_c4_full_size_properties(cuda_lib):
+    """16 777 216 members, one user event from member 0: delivered to every member exactly
+    once, everyone's event clock witnessed it, retransmit budget 32 per member."""
+    n = 16_777_216
+    p = Pool(lan_config(cuda_lib, capacity=n, n_initial=n, seed=0x5EED0001), cuda_lib)
+    slot = p.user_event(0, b"deploy", bytes(32), False)
+    t = p.run_until(PRED_RUMOR_CONVERGED, slot, 400, 8)
+    assert t != NEVER and 20 < t < 80
+    info = p.rumor_info(slot)
+    assert info["heard_count"] == n
+    p.step(120)
+    s = p.stats()
+    assert s["rumors_accepted"] == n - 1                       # exactly once
+    assert s["retransmit_limit"] == 32 and s["rumors_sent"] == 32 * n
+    assert p.column("ltime_event").min() >= 2
+    tx = p.column("tx")[slot]
+    assert tx.min() == 32 and tx.max() == 32
