@@ -34,23 +34,25 @@ sys.path.insert(0, ROOT)
 N_MEMBERS = 1_000_000
 TICKS_PER_STEP = 2048
 SEED = 0x5EED0001
-N_HBM = 16_777_216          # secondary roofline point: hot columns (268 MB) exceed the 126 MB L2
+N_HBM = 67_108_864          # secondary roofline point: 268 MB mailbox column + cold columns exceed the 126 MB L2
 HBM_TICKS = 256
 
-# Algorithmic bytes: every member every tick reads its four hot words; the
-# event terms are the minimal useful bytes of the cold columns each action touches.
-B_ROW = 16.0        # key + inbox + due + meta
-B_QUEUED = 4.0      # queued mask, read on the member's own gossip ticks only (1/GI of ticks)
-B_PROBE = 24.0      # cursor r/w, pass, heard, target key gather, due write
-B_ACCEPT = 29.0     # inbox clear, heard r/w, queued r/w, tx init, clock witness
-B_PACKET = 16.0     # peer key gather, inbox atomic RMW, queued write-back share
+# Algorithmic bytes.  Every member every tick reads its 4-byte mailbox word;
+# tiles whose ticker phase can be due at this tick (2 of every P ticks) also read `due`.
+# Members that act pay for the cold columns they touch (useful bytes, not sectors).
+B_SCAN = 4.0        # inbox[t&1][i]
+B_DUE = 4.0         # due[i], on 2/P of the ticks
+B_ACTIVE = 24.0     # key, meta, due, queued reads; inbox clear; wake / write-back word
+B_PROBE = 12.0      # extra for a probe start: cursor r/w, pass, target key gather, due write
+B_ACCEPT = 21.0     # heard r/w, queued write, tx init, Lamport clock witness
+B_PACKET = 12.0     # peer key gather + mailbox atomic RMW
 B_RUMOR_TX = 2.0    # tx counter r/w per broadcast carried
 
 
-def algorithmic_bytes(d: dict, gossip_interval_ticks: int) -> float:
-    return (d["node_ticks"] * (B_ROW + B_QUEUED / gossip_interval_ticks) + d["probes"] * B_PROBE +
-            d["rumors_accepted"] * B_ACCEPT + d["gossip_packets"] * B_PACKET +
-            d["rumors_sent"] * B_RUMOR_TX)
+def algorithmic_bytes(d: dict, probe_interval_ticks: int) -> float:
+    return (d["node_ticks"] * (B_SCAN + B_DUE * 2.0 / probe_interval_ticks) +
+            d["active_rows"] * B_ACTIVE + d["probes"] * B_PROBE + d["rumors_accepted"] * B_ACCEPT +
+            d["gossip_packets"] * B_PACKET + d["rumors_sent"] * B_RUMOR_TX)
 
 
 def stat_delta(a: dict, b: dict) -> dict:
@@ -209,7 +211,7 @@ def main():
     total_steps = args.steps + args.warmup
     cfg = lan_config(capacity=n + 2 * total_steps + 4, n_initial=n, seed=SEED + rank, device=local_rank)
     pool = Pool(cfg)
-    gi = pool.stats()["gossip_interval_ticks"]
+    gi = pool.stats()["probe_interval_ticks"]  # P: the due column is read on 2/P of the ticks
 
     def step_resident():
         x = pool.member_add()
@@ -244,7 +246,7 @@ def main():
     pool.join(x, [0])
     t_join = pool.now
     slot_alive = None
-    for r in range(31):
+    for r in range(30):
         try:
             info = pool.rumor_info(r)
         except Exception:
@@ -311,7 +313,7 @@ def main():
                 "peak_source": peak_src, "bytes_per_launch": alg / max(1, tick_launches),
                 "launch_us": launch_us, "launches": tick_launches,
                 "bytes_per_node_tick": alg / max(1.0, d["node_ticks"]),
-                "note": "1M members: the 16 MB hot columns are L2-resident by construction (2048 dependent "
+                "note": "1M members: the hot columns (8 MB of mailboxes + due) are L2-resident by construction (2048 dependent "
                         "ticks over the same state); roofline_hbm below is the HBM-bound size"}
 
     roofline_hbm = None
@@ -328,7 +330,7 @@ def main():
         roofline_hbm = {"members": N_HBM, "ticks": HBM_TICKS, "achieved": algb / (ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": algb / (ms * 1e-3) / 1e9 / peak,
                         "launch_us": ms * 1e3 / nl, "node_ticks_per_s": db["node_ticks"] / (ms * 1e-3),
-                        "workload": "16,777,216 members, LAN steady state (BASELINE config 4 size on one GPU)"}
+                        "workload": f"{N_HBM:,} members, LAN steady state (4x BASELINE config 4 on one GPU; hot columns exceed L2)"}
         big.close()
 
     if rank != 0:

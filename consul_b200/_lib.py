@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(HERE, "libgsim.so")
 
-GSIM_MAX_RUMORS = 31
+GSIM_MAX_RUMORS = 30
 GSIM_MAX_SUSPICION_SLOTS = 5
 GSIM_STAT_COUNT = 16
 
@@ -47,7 +47,7 @@ class GsimConfig(C.Structure):
         ("reap_interval_ns", C.c_uint64), ("reconnect_timeout_ns", C.c_uint64),
         ("tombstone_timeout_ns", C.c_uint64),
         ("world_size", C.c_uint32), ("rank", C.c_uint32), ("device", C.c_int32),
-        ("event_log_capacity", C.c_uint32),
+        ("event_log_capacity", C.c_uint32), ("phase_group", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 

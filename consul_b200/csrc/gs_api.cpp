@@ -291,6 +291,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   if (cfg->gossip_interval_ns / tick > 255 || cfg->awareness_max_multiplier < 1 ||
       cfg->awareness_max_multiplier > 8 || cfg->gossip_nodes > 8 || cfg->indirect_checks > 8)
     return GSIM_ERR_INVALID;
+  const uint32_t phase_group = cfg->phase_group ? cfg->phase_group : GS_TILE;
+  if (phase_group != 1 && phase_group % GS_TILE != 0) return GSIM_ERR_INVALID;
 
   char errbuf[256] = {0};
   GsBackend* be = GS_MAKE_BACKEND(cfg->device, errbuf, sizeof(errbuf));
@@ -306,7 +308,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   memset(&p->d, 0, sizeof(p->d));
   memset(&p->g, 0, sizeof(p->g));
   memset(&p->rc, 0, sizeof(p->rc));
-  const size_t cap = cfg->capacity;
+  // column stride: padded to whole tiles so the tick kernel never needs a bounds check
+  const size_t cap = ((size_t)cfg->capacity + GS_TILE - 1) / GS_TILE * GS_TILE;
   GsDev& d = p->d;
   GsGlobals& g = p->g;
   bool okk = true;
@@ -329,6 +332,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
   okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
   okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
+  okk = okk && alloc_col(p, &d.phase_tab, cap / GS_TILE);
   okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
   if (!okk) {
     g_create_err = be->last_error();
@@ -338,6 +342,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   // key = 0 means truth NONE for rows that were never created
   okk = okk && be->fill32(d.key[0], 0, cap) && be->fill32(d.key[1], 0, cap);
   okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
+  okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
   okk = okk && be->fill32(d.heard_cnt, 0, 32) && be->fill32(d.conv_tick, GS_EMPTY32, 32);
@@ -347,7 +352,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
 
   g.n = cfg->n_initial;
   p->n_established = cfg->n_initial;
-  g.cap = cfg->capacity;
+  g.cap = (uint32_t)cap;
   g.up_count = cfg->n_initial;
   g.P = (uint32_t)(cfg->probe_interval_ns / tick);
   g.T = (uint32_t)(cfg->probe_timeout_ns / tick);
@@ -368,6 +373,19 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   g.evlog_cap = evcap;
   g.world = cfg->world_size;
   g.rank = cfg->rank;
+  g.phase_group = phase_group;
+  g.phase_gate = (phase_group % GS_TILE == 0 && g.P <= 255u) ? 1u : 0u;
+  {
+    // ticker phases per tile (what gs_init_row derives per member, tabulated for the gate)
+    std::vector<uint32_t> tab(cap / GS_TILE, 0u);
+    for (size_t tile = 0; tile < tab.size(); ++tile) {
+      uint32_t idx = (uint32_t)(tile * GS_TILE / phase_group);
+      GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, idx, 0u, GS_PUR_PHASE, 0u);
+      uint32_t pp = ph.x % g.P, gp = ph.y % g.GI;
+      tab[tile] = (pp & 0xFFu) | ((((pp + g.T) % g.P) & 0xFFu) << 8) | (gp << 16);
+    }
+    okk = okk && be->h2d(d.phase_tab, tab.data(), tab.size() * 4);
+  }
   recompute_tables(p);
   okk = okk && upload_globals(p);
   okk = okk && be->init_rows(d, p->g_dev, g, 0, cfg->n_initial, 0);
@@ -485,6 +503,15 @@ static int alloc_slot(gsim_pool* p, uint32_t* slot_out) {
   return GSIM_ERR_CAPACITY;
 }
 
+// A member whose broadcast queue became non-empty between ticks must be looked at by the
+// next tick: set the wake bit in the mailbox that tick will read.
+static bool post_wake(gsim_pool* p, uint32_t row) {
+  uint32_t* col = p->d.inbox[p->now & 1u];
+  uint32_t w;
+  if (!peek(p, col, row, &w)) return false;
+  return poke(p, col, row, w | GS_WAKE_BIT);
+}
+
 static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subject, uint32_t inc,
                        uint32_t ltime, uint32_t origin, uint32_t size, uint32_t qclass) {
   GsGlobals& g = p->g;
@@ -506,6 +533,7 @@ static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subj
   q |= 1u << slot;
   if (!poke(p, p->d.heard, origin, h) || !poke(p, p->d.queued, origin, q)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.tx, (size_t)slot * g.cap + origin, (uint8_t)0)) return GSIM_ERR_CUDA;
+  if (!post_wake(p, origin)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.heard_cnt, slot, 1u)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.conv_tick, slot, g.up_count == 1u ? p->now : GS_EMPTY32)) return GSIM_ERR_CUDA;
   p->counts_stale = true;
@@ -605,6 +633,7 @@ static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_ol
   }
   hd |= accepted;
   qd |= accepted;
+  if (accepted && !post_wake(p, dst)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.heard, dst, hd) || !poke(p, p->d.queued, dst, qd) ||
       !poke(p, p->d.ltime_member, dst, lm_d) || !poke(p, p->d.ltime_event, dst, le_d) ||
       !poke(p, p->d.event_min, dst, emin))
@@ -1158,12 +1187,25 @@ extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_
     case GSIM_COL_INBOX: src = d.inbox[p->now & 1u]; break;
     default: return fail(p, GSIM_ERR_INVALID, "unknown column");
   }
-  if (n_bytes) *n_bytes = bytes;
-  if (cap_bytes < bytes) return fail(p, GSIM_ERR_INVALID, "buffer too small");
-  if (!p->be->d2h(out, src, bytes)) return fail(p, GSIM_ERR_CUDA, "d2h");
+  // the caller sees rows of `capacity` elements; the device stride is padded to whole tiles
+  const size_t ucap = p->cfg.capacity;
+  const size_t planes = column == GSIM_COL_SUS_FROM ? GS_K1MAX : column == GSIM_COL_TX ? GS_MAX_RUMORS : 1;
+  const size_t elem = column == GSIM_COL_TX ? 1 : 4;
+  const size_t out_bytes = planes * ucap * elem;
+  (void)bytes;
+  if (n_bytes) *n_bytes = out_bytes;
+  if (cap_bytes < out_bytes) return fail(p, GSIM_ERR_INVALID, "buffer too small");
+  for (size_t q = 0; q < planes; ++q)
+    if (!p->be->d2h(reinterpret_cast<uint8_t*>(out) + q * ucap * elem,
+                    reinterpret_cast<const uint8_t*>(src) + q * cap * elem, ucap * elem))
+      return fail(p, GSIM_ERR_CUDA, "d2h");
   if (column == GSIM_COL_META) {
     uint32_t* mm = reinterpret_cast<uint32_t*>(out);
-    for (size_t i = 0; i < cap; ++i) mm[i] &= ~GS_META_DIRTY;  // implementation detail
+    for (size_t i = 0; i < ucap; ++i) mm[i] &= ~GS_META_DIRTY;  // implementation detail
+  }
+  if (column == GSIM_COL_INBOX) {
+    uint32_t* mm = reinterpret_cast<uint32_t*>(out);
+    for (size_t i = 0; i < ucap; ++i) mm[i] &= ~GS_WAKE_BIT;  // implementation detail
   }
   return GSIM_OK;
 }

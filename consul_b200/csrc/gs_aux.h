@@ -9,7 +9,9 @@
 // Probe/gossip ticker phases mirror triggerFunc's random stagger ([U] state.go).
 GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t now) {
   const size_t cap = g.cap;
-  GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, i, 0u, GS_PUR_PHASE, 0u);
+  // one stagger draw per phase group (default: per tile of 128 members, so that the
+  // failure-detector path is uniform per CTA); phase_group == 1 draws it per member
+  GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, i / g.phase_group, 0u, GS_PUR_PHASE, 0u);
   const uint32_t pp = ph.x % g.P, gp = ph.y % g.GI;
   const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
   d.key[0][i] = k;

@@ -26,9 +26,12 @@
 #define GS_HD inline
 #endif
 
-#define GS_MAX_RUMORS 31
+#define GS_MAX_RUMORS 30
 #define GS_K1MAX 5
-#define GS_ACC_BIT 0x80000000u
+#define GS_ACC_BIT 0x80000000u   // inbox: accusation(s) pending in acc[][][]
+#define GS_WAKE_BIT 0x40000000u  // inbox: "process this row" (self-posted or by the host)
+#define GS_TILE 128u             // rows per CTA; ticker phases are uniform per tile
+#define GS_NEVER 0xFFFFFFFFu
 #define GS_EMPTY32 0xFFFFFFFFu
 #define GS_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define GS_KR_MAX_TRIES 32u  // kRandomNodes tries = min(3n, 32); upstream: 3n
@@ -187,7 +190,8 @@ struct GsGlobals {
   uint32_t flags;
   uint32_t evlog_cap;
   uint32_t world, rank;
-  uint32_t pad0;
+  uint32_t phase_group;  // members per ticker-phase group (1 or a multiple of GS_TILE)
+  uint32_t phase_gate;   // 1: phase_tab is valid and whole tiles can skip the `due` column
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -215,6 +219,8 @@ struct GsDev {
   uint32_t* heard;
   uint32_t* queued;
   uint8_t* tx;  // [GS_MAX_RUMORS][cap]
+  // per tile of GS_TILE rows: probe phase | (probe phase + T) % P << 8 | gossip phase << 16
+  uint32_t* phase_tab;
   // pool-wide device words
   unsigned long long* stats;  // [GSIM_STAT_COUNT]
   uint32_t* heard_cnt;        // [GS_MAX_RUMORS]

@@ -54,20 +54,27 @@ struct DevSink {
   }
 };
 
-__global__ void __launch_bounds__(GS_BLOCK)
+// One CTA = one tile of GS_TILE (128) consecutive members, one member per thread.
+// Hot path per member per tick: ONE coalesced 4-byte load (its mailbox word); tiles whose
+// ticker phase matches this tick additionally read `due` (4 B).  Everything else is read
+// only by members that act.  A tile with no active member retires after one barrier.
+__global__ void __launch_bounds__(GS_TILE)
     gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
-  __syncthreads();
   const GsGlobals& g = *gp;
   const uint32_t t = *d.tick_base + k_off;
-  const uint32_t gslot = t % g.GI;
-  const uint32_t i = blockIdx.x * GS_BLOCK + tid;
+  const uint32_t i = blockIdx.x * GS_TILE + tid;  // columns are padded to a tile multiple
+  const uint32_t inb = d.inbox[t & 1u][i];
+  uint32_t due = GS_NEVER;
+  if (gs_tile_probe_gate(d, g, blockIdx.x, t % g.P)) due = d.due[i];
+  const bool active = inb != 0u || due == t;
+  if (!__syncthreads_or(active)) return;
   DevSink sink{s_stat, s_heard};
-  if (i < g.n) gs_row_step(d, g, i, t, gslot, sink);
+  if (active) gs_row_step(d, g, i, t, t % g.GI, inb, sink);
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {
@@ -225,7 +232,7 @@ class CudaBackend : public GsBackend {
       return true;
     }
     cudaSetDevice(dev_);
-    const uint32_t blocks = (g.n + GS_BLOCK - 1) / GS_BLOCK;
+    const uint32_t blocks = (g.n + GS_TILE - 1) / GS_TILE;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
     if (use_graph && left >= GS_GRAPH_TICKS) {
@@ -239,7 +246,7 @@ class CudaBackend : public GsBackend {
     }
     if (left) {
       for (uint32_t k = 0; k < left; ++k)
-        gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+        gs_tick_kernel<<<blocks, GS_TILE, 0, stream_>>>(d, g_dev, k);
       gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
       launches_ += left + 1;
       if (!ok(cudaGetLastError(), "tick launch")) return false;
@@ -315,7 +322,7 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture"))
       return nullptr;
     for (uint32_t k = 0; k < GS_GRAPH_TICKS; ++k)
-      gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+      gs_tick_kernel<<<blocks, GS_TILE, 0, stream_>>>(d, g_dev, k);
     gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {

@@ -69,10 +69,11 @@ GS_DEV bool gs_lost(const GsGlobals& g, Sink& sink, uint32_t src, uint32_t dst, 
 // Does member i know member c exists?  Established members are known to everyone; a
 // pending joiner is known only to members that have heard its alive rumor.
 GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c, uint32_t kc,
-                     uint32_t heard_i, uint32_t meta_i) {
+                     uint32_t meta_i) {
   if (c == i) return true;
   // a member that has not joined anyone yet knows nobody but itself and what it heard
   if (!gs_key_pending(kc)) return !(meta_i & GS_META_ISOLATED);
+  const uint32_t heard_i = d.heard[i];  // rare: only pending joiners reach this point
   uint32_t am = g.class_mask[0] & g.active_mask;
   while (am) {
 #if defined(__CUDA_ARCH__)
@@ -83,7 +84,6 @@ GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c,
     am &= am - 1;
     if (g.rumors[r].kind == 1u /*ALIVE*/ && g.rumors[r].subject == c) return (heard_i >> r) & 1u;
   }
-  (void)d;
   return false;
 }
 
@@ -92,7 +92,7 @@ GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c,
 // or dead for less than GossipToTheDeadTime), mode 1 = indirect-probe relays (alive only).
 GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t,
                            uint32_t purpose, uint32_t k, uint32_t mode, uint32_t exclude2,
-                           uint32_t heard_i, uint32_t meta_i, uint32_t* out) {
+                           uint32_t meta_i, uint32_t* out) {
   const uint32_t n = g.n;
   const uint32_t* keyc = d.key[t & 1u];
   uint32_t tries = 3u * n;
@@ -113,7 +113,7 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
       if (rank == GS_RANK_LEFT) continue;
       if (rank == GS_RANK_DEAD && (t - d.change_tick[c]) > g.gtd_ticks) continue;
     }
-    if (!gs_knows(d, g, i, c, kc, heard_i, meta_i)) continue;
+    if (!gs_knows(d, g, i, c, kc, meta_i)) continue;
     bool dup = false;
     for (uint32_t q = 0; q < cnt; ++q) dup = dup || (out[q] == c);
     if (dup) continue;
@@ -177,44 +177,53 @@ GS_DEV void gs_log_event(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_
   sink.log_event(d, g, t, type, subject, observer, ltime);
 }
 
-// The tick of member i.  Returns nothing; all effects go to d.* and the sink.
+// Tile-level gate: can any member of this tile have a probe action due at tick t?  A
+// member's `due` is always congruent to its ticker phase or to phase + ProbeTimeout
+// (mod ProbeInterval), and phases are uniform per tile, so 1 - 2/P of the tiles never
+// need to read the `due` column at all.
+GS_DEV bool gs_tile_probe_gate(const GsDev& d, const GsGlobals& g, uint32_t tile, uint32_t pslot) {
+  if (!g.phase_gate) return true;
+  const uint32_t tab = d.phase_tab[tile];
+  return (tab & 0xFFu) == pslot || ((tab >> 8) & 0xFFu) == pslot;
+}
+
+// The tick of member i, called only for rows that have mail (inb = inbox[t&1][i] != 0,
+// which includes the self-posted wake bit) or a probe action due (due[i] == t).
 template <class Sink>
 GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t, uint32_t gslot,
-                        Sink& sink) {
+                        uint32_t inb, Sink& sink) {
   const uint32_t cur = t & 1u, nxt = cur ^ 1u;
   const uint32_t k0 = d.key[cur][i];
-  const uint32_t inb = d.inbox[cur][i];
-  const uint32_t m0 = d.meta[i];
-  const uint32_t due0 = d.due[i];
   const uint32_t truth = gs_key_truth(k0);
   if (truth == GS_TRUTH_NONE) return;
-
-  // ---- idle fast path: nothing arrived, nothing due, nothing queued ------------
+  const uint32_t m0 = d.meta[i];
+  const uint32_t due0 = d.due[i];
   const bool up = truth == GS_TRUTH_UP;
   const bool gossip_slot = up && gslot == gs_meta_gphase(m0);  // gslot = t % GI
-  uint32_t queued = 0;
-  if (gossip_slot) queued = d.queued[i];
-  if (inb == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(up && due0 == t) && queued == 0u) {
-    if (m0 & GS_META_DIRTY) {  // bring the other key buffer up to date, then idle
-      d.key[cur ^ 1u][i] = k0;
+  uint32_t queued = up ? d.queued[i] : 0u;
+  if (inb != 0u) d.inbox[cur][i] = 0u;
+  sink.stat(GS_ST_ACTIVE_ROWS, 1);  // scheduling diagnostic: rows that left the 4-byte scan
+
+  // ---- nothing to do this tick (a wake that only keeps the row in the active set) ----
+  if ((inb & ~GS_WAKE_BIT) == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(up && due0 == t) &&
+      !(gossip_slot && queued != 0u)) {
+    if (m0 & GS_META_DIRTY) {  // bring the other key buffer up to date
+      d.key[nxt][i] = k0;
       d.meta[i] = m0 & ~GS_META_DIRTY;
     }
+    if (queued != 0u) GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
     return;
   }
-  sink.stat(GS_ST_ACTIVE_ROWS, 1);
 
   uint32_t k = k0, m = m0, due = due0;
   const size_t cap = g.cap;
   uint32_t heard = 0;
-  bool heard_loaded = false;
 
   // ---- A. consume the mailbox of this arrival tick ------------------------------
-  if (inb != 0u) {
-    d.inbox[cur][i] = 0u;
-    uint32_t rbits = inb & ~GS_ACC_BIT & g.active_mask;
+  if ((inb & ~GS_WAKE_BIT) != 0u) {
+    uint32_t rbits = inb & ~(GS_ACC_BIT | GS_WAKE_BIT) & g.active_mask;
     if (rbits && up) {
       heard = d.heard[i];
-      heard_loaded = true;
       uint32_t fresh = rbits & ~heard;
       uint32_t accepted = 0;
       while (fresh) {
@@ -255,11 +264,9 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
       }
       if (accepted) {
-        heard |= accepted;
-        d.heard[i] = heard;
-        uint32_t q = d.queued[i] | accepted;
-        d.queued[i] = q;
-        if (gossip_slot) queued = q;
+        d.heard[i] = heard | accepted;
+        queued |= accepted;
+        d.queued[i] = queued;
       }
     }
     if (inb & GS_ACC_BIT) {
@@ -329,16 +336,12 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
     uint32_t stage = gs_meta_stage(m);
     if (stage == GS_STAGE_WAIT_T && due == t) {
       // ProbeTimeout elapsed without a direct ack: k indirect probes + TCP fallback.
-      if (!heard_loaded) {
-        heard = d.heard[i];
-        heard_loaded = true;
-      }
       const uint32_t j = d.probe_tgt[i];
       const uint32_t kj = d.key[cur][j];
       const bool j_up = gs_key_truth(kj) == GS_TRUTH_UP;
       uint32_t relays[8];
       uint32_t kk = g.indirect_checks > 8u ? 8u : g.indirect_checks;
-      uint32_t nr = gs_krandom(d, g, i, t, GS_PUR_RELAY, kk, 1u, j, heard, m, relays);
+      uint32_t nr = gs_krandom(d, g, i, t, GS_PUR_RELAY, kk, 1u, j, m, relays);
       bool success = false;
       uint32_t nacks = 0;
       for (uint32_t q = 0; q < nr; ++q) {
@@ -391,10 +394,6 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
     if (stage == GS_STAGE_IDLE && due == t) {
       // [U] memberlist.probe: next eligible entry of the ring, skipping self, unknown and
       // dead/left members; a wrap re-keys the permutation (resetNodes + shuffle).
-      if (!heard_loaded) {
-        heard = d.heard[i];
-        heard_loaded = true;
-      }
       uint32_t cursor = d.cursor[i], pass = d.pass[i];
       const uint32_t n = g.n;
       GsU4 rk = gs_philox(g.seed_lo, g.seed_hi, i, pass, GS_PUR_PERM, 0u);
@@ -413,7 +412,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         uint32_t kc = d.key[cur][c];
         uint32_t rank = gs_key_rank(kc);
         if (c == i || gs_key_truth(kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD ||
-            rank == GS_RANK_LEFT || !gs_knows(d, g, i, c, kc, heard, m)) {
+            rank == GS_RANK_LEFT || !gs_knows(d, g, i, c, kc, m)) {
           ++checked;
           continue;
         }
@@ -445,13 +444,9 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
 
     // ---- D. gossip: drain the broadcast queue to GossipNodes random peers ----------
     if (gossip_slot && queued != 0u) {
-      if (!heard_loaded) {
-        heard = d.heard[i];
-        heard_loaded = true;
-      }
       uint32_t peers[8];
       uint32_t kk = g.gossip_nodes > 8u ? 8u : g.gossip_nodes;
-      uint32_t np = gs_krandom(d, g, i, t, GS_PUR_GOSSIP, kk, 0u, GS_EMPTY32, heard, m, peers);
+      uint32_t np = gs_krandom(d, g, i, t, GS_PUR_GOSSIP, kk, 0u, GS_EMPTY32, m, peers);
       const uint32_t q0 = queued;
       for (uint32_t q = 0; q < np && queued != 0u; ++q) {
         uint32_t pkt = gs_select_packet(d, g, i, queued);
@@ -486,4 +481,8 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   }
   if (m != m0) d.meta[i] = m;
   if (due != due0) d.due[i] = due;
+  // stay in the active set while something time-driven is pending: a running suspicion
+  // timer, a stale key buffer, or a non-empty broadcast queue
+  if (gs_key_rank(k) == GS_RANK_SUSPECT || (m & GS_META_DIRTY) || queued != 0u)
+    GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
 }

@@ -76,7 +76,7 @@ extern "C" {
 #define GSIM_RUMOR_JOIN_INTENT 2  /* serf messageJoin{LTime,Node}                     */
 #define GSIM_RUMOR_LEAVE_INTENT 3 /* serf messageLeave{LTime,Node}                    */
 #define GSIM_RUMOR_USER_EVENT 4   /* serf messageUserEvent{LTime,Name,Payload,CC}     */
-#define GSIM_MAX_RUMORS 31        /* bit 31 of the inbox word flags accusations       */
+#define GSIM_MAX_RUMORS 30        /* inbox bits 0..29; bit 30 = wake, bit 31 = accusations */
 #define GSIM_MAX_SUSPICION_SLOTS 5 /* k+1 with k = SuspicionMult-2 <= 4               */
 
 typedef struct gsim_pool gsim_pool;
@@ -124,6 +124,12 @@ typedef struct gsim_config {
   uint32_t rank;
   int32_t device; /* CUDA device ordinal, -1 = current */
   uint32_t event_log_capacity; /* device event ring entries (0 = default 65536) */
+  /* Ticker stagger granularity: members [g*phase_group, (g+1)*phase_group) share one random
+   * probe/gossip phase ([U] state.go triggerFunc draws it per agent).  0 = default 128, which
+   * makes the failure-detector path uniform per 128-thread CTA; 1 = per-member phases (small
+   * clusters, no CTA-level gating).  Must be 1 or a multiple of 128. */
+  uint32_t phase_group;
+  uint32_t reserved0;
 } gsim_config;
 
 #define GSIM_FLAG_LOG_GLOBAL_EVENTS 1u /* log Failed/Left/Join transitions of every member */

@@ -342,7 +342,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
   if (!inbox && !accused && me.v.rank == GSIM_RANK_ALIVE && !(up && me.due == t) &&
       !(my_gossip_tick && me.queued))
     return;
-  ta.c[GSIM_STAT_ACTIVE_ROWS]++;
+  // (GSIM_STAT_ACTIVE_ROWS is a scheduling diagnostic of the CUDA implementation; not modelled)
 
   // -- deliveries ------------------------------------------------------------------------
   if (up) {
@@ -812,7 +812,8 @@ void* oracle_create(const gsim_config* cfg, int threads) {
     me.v.truth = GSIM_TRUTH_UP;
     me.v.rank = GSIM_RANK_ALIVE;
     me.v.inc = 1;
-    Rand4 ph = philox4x32_10(cfg->seed, i, 0, PUR_PHASE, 0);  // ticker stagger
+    // ticker stagger ([U] state.go triggerFunc), drawn once per phase group of members
+    Rand4 ph = philox4x32_10(cfg->seed, i / (cfg->phase_group ? cfg->phase_group : 128), 0, PUR_PHASE, 0);
     me.due = ph.v[0] % o->P;
     me.gossip_phase = ph.v[1] % o->GI;
     o->pub[i] = me.v;
@@ -841,7 +842,7 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   me.v.pending = 1;
   me.isolated = o.established > 0;  // with an empty base set there is nothing to be missing
   me.watched = desc && (desc->flags & GSIM_MEMBER_WATCHED);
-  Rand4 ph = philox4x32_10(o.cfg.seed, id, 0, PUR_PHASE, 0);
+  Rand4 ph = philox4x32_10(o.cfg.seed, id / (o.cfg.phase_group ? o.cfg.phase_group : 128), 0, PUR_PHASE, 0);
   uint32_t pp = ph.v[0] % o.P;
   me.due = o.now + (pp + o.P - o.now % o.P) % o.P;
   me.gossip_phase = ph.v[1] % o.GI;

@@ -95,7 +95,16 @@ class HostEmuBackend : public GsBackend {
       sink.stats = reinterpret_cast<uint64_t*>(d.stats);
       sink.heard_cnt = d.heard_cnt;
       memset(sink.local_heard, 0, sizeof(sink.local_heard));
-      for (uint32_t x = 0; x < g.n; ++x) gs_row_step(d, g, row_at(x, g.n), t, gslot, sink);
+      // same activity test as gs_tick_kernel: mailbox word, plus `due` only for tiles whose
+      // ticker phase can be due at this tick
+      const uint32_t pslot = t % g.P;
+      for (uint32_t x = 0; x < g.n; ++x) {
+        const uint32_t i = row_at(x, g.n);
+        const uint32_t inb = d.inbox[t & 1u][i];
+        uint32_t due = GS_NEVER;
+        if (gs_tile_probe_gate(d, g, i / GS_TILE, pslot)) due = d.due[i];
+        if (inb != 0u || due == t) gs_row_step(d, g, i, t, gslot, inb, sink);
+      }
       for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
         uint32_t c = sink.local_heard[r];
         if (c) {

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from consul_b200._lib import GSIM_MAX_RUMORS
 from consul_b200.pool import GsimError
 
 ACC_BIT = 0x80000000
@@ -10,7 +11,7 @@ ACC_BIT = 0x80000000
 
 def active_mask(pool) -> int:
     m = 0
-    for r in range(31):
+    for r in range(GSIM_MAX_RUMORS):
         try:
             pool.rumor_info(r)
             m |= 1 << r
@@ -21,7 +22,8 @@ def active_mask(pool) -> int:
 
 def compare_stats(a, b, where=""):
     sa, sb = a.stats(), b.stats()
-    diffs = {k: (sa[k], sb[k]) for k in sa if sa[k] != sb[k]}
+    # active_rows is a scheduling diagnostic of the CUDA implementation, not simulation state
+    diffs = {k: (sa[k], sb[k]) for k in sa if sa[k] != sb[k] and k != "active_rows"}
     assert not diffs, f"stats differ {where}: {diffs}"
 
 
@@ -69,7 +71,7 @@ def compare_columns(a, b, where=""):
     eq("queued", transform=lambda v: v & act)
     eq("inbox", truth != 0, transform=lambda v: v & (act | ACC_BIT))
     heard = col["heard"][0][:n] & act
-    bits = ((heard[None, :] >> np.arange(31, dtype=np.uint32)[:, None]) & 1).astype(bool)
+    bits = ((heard[None, :] >> np.arange(GSIM_MAX_RUMORS, dtype=np.uint32)[:, None]) & 1).astype(bool)
     eq("tx", bits)
 
 

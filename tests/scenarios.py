@@ -33,7 +33,7 @@ def step_compare(pools, ticks, every, where, columns=True):
 
 def c1_three_node_join(make, lib, seed=1):
     """3 agents, s2 and s3 join s1 (server_test.go:704-705), then s3 crashes (":725")."""
-    cfg = consul_test_config(lib, capacity=8, n_initial=0, seed=seed, flags=1)
+    cfg = consul_test_config(lib, capacity=8, n_initial=0, seed=seed, flags=1, phase_group=1)
     pools = make(cfg)
     ids = [both(pools, lambda p: p.member_add(watched=True)) for _ in range(3)]
     assert ids == [0, 1, 2]
