@@ -58,23 +58,96 @@ struct DevSink {
 // Hot path per member per tick: ONE coalesced 4-byte load (its mailbox word); tiles whose
 // ticker phase matches this tick additionally read `due` (4 B).  Everything else is read
 // only by members that act.  A tile with no active member retires after one barrier.
-__global__ void __launch_bounds__(GS_TILE)
+struct TileWords {
+  uint32_t inb[4], due[4];
+};
+
+__device__ __forceinline__ void gs_load_tile(const GsDev& d, const GsGlobals& g, uint32_t tile,
+                                             uint32_t lane, uint32_t cur, uint32_t pslot,
+                                             TileWords& w) {
+  const uint32_t base = tile * GS_TILE + lane;  // columns are padded to a tile multiple
+  const bool gate = gs_tile_probe_gate(d, g, tile, pslot);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) w.inb[u] = d.inbox[cur][base + 32u * u];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) w.due[u] = gate ? d.due[base + 32u * u] : GS_NEVER;
+}
+
+// Persistent, warp-centric tick.  A warp owns whole tiles of 128 consecutive members
+// (4 members per lane, each a coalesced 128-byte request) and walks them with a stride of
+// the total warp count, prefetching the next tile's words while it works on the current
+// one.  Hot path per member per tick: ONE 4-byte mailbox word; tiles whose ticker phase
+// can be due at this tick additionally read `due`.  Members that act are handled in two
+// tiers: the staged probe fast path (gs_fast_*), then the generic gs_row_step.
+__global__ void __launch_bounds__(GS_BLOCK)
     gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  __syncthreads();
   const GsGlobals& g = *gp;
   const uint32_t t = *d.tick_base + k_off;
-  const uint32_t i = blockIdx.x * GS_TILE + tid;  // columns are padded to a tile multiple
-  const uint32_t inb = d.inbox[t & 1u][i];
-  uint32_t due = GS_NEVER;
-  if (gs_tile_probe_gate(d, g, blockIdx.x, t % g.P)) due = d.due[i];
-  const bool active = inb != 0u || due == t;
-  if (!__syncthreads_or(active)) return;
+  const uint32_t cur = t & 1u, pslot = t % g.P, gslot = t % g.GI;
+  const uint32_t lane = tid & 31u;
+  const uint32_t n_tiles = (g.n + GS_TILE - 1u) / GS_TILE;
+  const uint32_t n_warps = gridDim.x * (GS_BLOCK / 32u);
   DevSink sink{s_stat, s_heard};
-  if (active) gs_row_step(d, g, i, t, t % g.GI, inb, sink);
+  uint32_t tile = blockIdx.x * (GS_BLOCK / 32u) + (tid >> 5);
+  TileWords w;
+  if (tile < n_tiles) gs_load_tile(d, g, tile, lane, cur, pslot, w);
+  while (tile < n_tiles) {
+    const uint32_t next = tile + n_warps;
+    TileWords wn;
+    if (next < n_tiles) gs_load_tile(d, g, next, lane, cur, pslot, wn);  // prefetch
+    bool act[4], cand[4];
+    bool any_act = false, any_cand = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool due_now = w.due[u] == t;
+      act[u] = w.inb[u] != 0u || due_now;
+      cand[u] = w.inb[u] == 0u && due_now;  // empty mailbox + ticker fired: probe fast path
+      any_act |= act[u];
+      any_cand |= cand[u];
+    }
+    if (__any_sync(0xFFFFFFFFu, any_act)) {
+      const uint32_t base = tile * GS_TILE + lane;
+      if (__any_sync(0xFFFFFFFFu, any_cand)) {
+        GsFastProbe f[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cand[u]) gs_fast_load(d, cur, base + 32u * u, f[u]);  // stage A: own columns
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cand[u]) cand[u] = gs_fast_target(d, g, cur, base + 32u * u, f[u]);  // B: gathers
+        uint32_t n_probe = 0, n_ack = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          bool acked = false;
+          const bool done = cand[u] && gs_fast_finish(d, g, base + 32u * u, t, f[u], &acked);  // C
+          if (done) act[u] = false;
+          n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
+          n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
+        }
+        if (lane == 0u && n_probe) {
+          atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
+          atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
+          if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
+        }
+      }
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const bool a = u == 0 ? act[0] : u == 1 ? act[1] : u == 2 ? act[2] : act[3];
+        if (__any_sync(0xFFFFFFFFu, a)) {
+          const uint32_t inb = u == 0 ? w.inb[0] : u == 1 ? w.inb[1] : u == 2 ? w.inb[2] : w.inb[3];
+          if (a) gs_row_step(d, g, base + 32u * u, t, gslot, inb, sink);
+        }
+      }
+    }
+    w = wn;
+    tile = next;
+  }
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {
@@ -169,6 +242,11 @@ class CudaBackend : public GsBackend {
     cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
     cudaEventCreate(&ev0_);
     cudaEventCreate(&ev1_);
+    int sms = 148, occ = 4;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel, GS_BLOCK, 0) != cudaSuccess || occ < 1)
+      occ = 4;
+    full_grid_ = (uint32_t)(sms * occ);
     scratch_ = nullptr;
     cudaMalloc(&scratch_, 4096);
   }
@@ -232,7 +310,11 @@ class CudaBackend : public GsBackend {
       return true;
     }
     cudaSetDevice(dev_);
-    const uint32_t blocks = (g.n + GS_TILE - 1) / GS_TILE;
+    // persistent launch: one warp per tile up to a full machine (SMs x resident CTAs)
+    const uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
+    const uint32_t warps_per_block = GS_BLOCK / 32;
+    uint32_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
+    if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
     if (use_graph && left >= GS_GRAPH_TICKS) {
@@ -246,7 +328,7 @@ class CudaBackend : public GsBackend {
     }
     if (left) {
       for (uint32_t k = 0; k < left; ++k)
-        gs_tick_kernel<<<blocks, GS_TILE, 0, stream_>>>(d, g_dev, k);
+        gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
       gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
       launches_ += left + 1;
       if (!ok(cudaGetLastError(), "tick launch")) return false;
@@ -322,7 +404,7 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture"))
       return nullptr;
     for (uint32_t k = 0; k < GS_GRAPH_TICKS; ++k)
-      gs_tick_kernel<<<blocks, GS_TILE, 0, stream_>>>(d, g_dev, k);
+      gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
     gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
@@ -342,6 +424,7 @@ class CudaBackend : public GsBackend {
   cudaStream_t stream_;
   cudaEvent_t ev0_, ev1_;
   void* scratch_;
+  uint32_t full_grid_ = 592;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   uint64_t launches_ = 0;
   char err_[256];

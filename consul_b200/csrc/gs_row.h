@@ -486,3 +486,62 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   if (gs_key_rank(k) == GS_RANK_SUSPECT || (m & GS_META_DIRTY) || queued != 0u)
     GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
 }
+
+// ---------------------------------------------------------------------------------------
+// Staged fast path for the steady-state case of [U] memberlist.probe/probeNode: a member
+// with an empty mailbox whose probe ticker fires, whose ring cursor does not wrap and whose
+// next ring entry is an established, non-dead peer.  The three stages let the tick kernel
+// batch the memory phases of several members (A: own columns, B: target gather, C: commit)
+// so a warp pays two dependent latencies per tile instead of five per member.  Any member
+// that does not qualify falls back to gs_row_step, which must produce identical results;
+// the fast path performs no write before stage C has accepted the member.
+// ---------------------------------------------------------------------------------------
+struct GsFastProbe {
+  uint32_t k, m, cursor, pass, c, kc;
+};
+
+GS_DEV void gs_fast_load(const GsDev& d, uint32_t cur, uint32_t i, GsFastProbe& f) {
+  f.k = d.key[cur][i];
+  f.m = d.meta[i];
+  f.cursor = d.cursor[i];
+  f.pass = d.pass[i];
+}
+
+GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uint32_t i,
+                           GsFastProbe& f) {
+  if (g.loss_thr != 0u) return false;
+  if (gs_key_truth(f.k) != GS_TRUTH_UP || gs_key_rank(f.k) != GS_RANK_ALIVE) return false;
+  if (gs_meta_stage(f.m) != GS_STAGE_IDLE || (f.m & (GS_META_DIRTY | GS_META_ISOLATED))) return false;
+  if (f.cursor >= g.n) return false;  // ring wrap: re-key in the generic path
+  GsU4 rk = gs_philox(g.seed_lo, g.seed_hi, i, f.pass, GS_PUR_PERM, 0u);
+  f.c = gs_perm(f.cursor, g.n, g.perm_half_bits, rk);
+  if (f.c == i) return false;
+  f.kc = d.key[cur][f.c];
+  return true;
+}
+
+// Returns true when the member was fully handled; *acked tells whether the direct probe
+// succeeded (stats: PROBES +1, ACKS +acked, ACTIVE_ROWS +1 are added by the caller).
+GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t,
+                           const GsFastProbe& f, bool* acked) {
+  const uint32_t rank = gs_key_rank(f.kc);
+  if (gs_key_truth(f.kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD || rank == GS_RANK_LEFT ||
+      gs_key_pending(f.kc))
+    return false;  // ring entry must be skipped or needs the heard mask: generic path
+  uint32_t m = f.m;
+  if (gs_key_truth(f.kc) == GS_TRUTH_UP) {
+    const uint32_t aw = gs_meta_aw(m);
+    m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
+    d.due[i] = t + g.P;
+    *acked = true;
+  } else {
+    m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
+    d.probe_tgt[i] = f.c;
+    d.probe_inc[i] = gs_key_inc(f.kc);
+    d.due[i] = t + g.T;
+    *acked = false;
+  }
+  d.cursor[i] = f.cursor + 1u;
+  if (m != f.m) d.meta[i] = m;
+  return true;
+}

@@ -103,7 +103,19 @@ class HostEmuBackend : public GsBackend {
         const uint32_t inb = d.inbox[t & 1u][i];
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(d, g, i / GS_TILE, pslot)) due = d.due[i];
-        if (inb != 0u || due == t) gs_row_step(d, g, i, t, gslot, inb, sink);
+        if (!(inb != 0u || due == t)) continue;
+        if (inb == 0u && !getenv("GSIM_HOSTEMU_NO_FAST")) {  // same two tiers as the kernel
+          GsFastProbe f;
+          bool acked = false;
+          gs_fast_load(d, t & 1u, i, f);
+          if (gs_fast_target(d, g, t & 1u, i, f) && gs_fast_finish(d, g, i, t, f, &acked)) {
+            sink.stat(GS_ST_PROBES, 1);
+            sink.stat(GS_ST_ACTIVE_ROWS, 1);
+            if (acked) sink.stat(GS_ST_ACKS, 1);
+            continue;
+          }
+        }
+        gs_row_step(d, g, i, t, gslot, inb, sink);
       }
       for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
         uint32_t c = sink.local_heard[r];
