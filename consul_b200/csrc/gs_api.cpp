@@ -292,7 +292,9 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       cfg->awareness_max_multiplier > 8 || cfg->gossip_nodes > 8 || cfg->indirect_checks > 8)
     return GSIM_ERR_INVALID;
   const uint32_t phase_group = cfg->phase_group ? cfg->phase_group : GS_TILE;
-  if (phase_group != 1 && phase_group % GS_TILE != 0) return GSIM_ERR_INVALID;
+  // 1 (per member) or 128 * 2^k (whole tiles)
+  if (phase_group != 1 && (phase_group % GS_TILE != 0 || ((phase_group / GS_TILE) & (phase_group / GS_TILE - 1)) != 0))
+    return GSIM_ERR_INVALID;
 
   char errbuf[256] = {0};
   GsBackend* be = GS_MAKE_BACKEND(cfg->device, errbuf, sizeof(errbuf));
@@ -332,7 +334,6 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
   okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
   okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
-  okk = okk && alloc_col(p, &d.phase_tab, cap / GS_TILE);
   okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
   if (!okk) {
     g_create_err = be->last_error();
@@ -374,17 +375,13 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   g.world = cfg->world_size;
   g.rank = cfg->rank;
   g.phase_group = phase_group;
-  g.phase_gate = (phase_group % GS_TILE == 0 && g.P <= 255u) ? 1u : 0u;
+  g.phase_gate = (phase_group % GS_TILE == 0) ? 1u : 0u;
+  g.phase_shift = 0;
+  while (g.phase_gate && (GS_TILE << g.phase_shift) < phase_group) g.phase_shift++;
   {
-    // ticker phases per tile (what gs_init_row derives per member, tabulated for the gate)
-    std::vector<uint32_t> tab(cap / GS_TILE, 0u);
-    for (size_t tile = 0; tile < tab.size(); ++tile) {
-      uint32_t idx = (uint32_t)(tile * GS_TILE / phase_group);
-      GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, idx, 0u, GS_PUR_PHASE, 0u);
-      uint32_t pp = ph.x % g.P, gp = ph.y % g.GI;
-      tab[tile] = (pp & 0xFFu) | ((((pp + g.T) % g.P) & 0xFFu) << 8) | (gp << 16);
-    }
-    okk = okk && be->h2d(d.phase_tab, tab.data(), tab.size() * 4);
+    const uint32_t rot = gs_phase_rot(g.seed_lo, g.seed_hi);
+    g.rot_p = rot % g.P;
+    g.rot_g = (rot >> 16) % g.GI;
   }
   recompute_tables(p);
   okk = okk && upload_globals(p);

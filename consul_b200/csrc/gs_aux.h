@@ -11,8 +11,8 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const size_t cap = g.cap;
   // one stagger draw per phase group (default: per tile of 128 members, so that the
   // failure-detector path is uniform per CTA); phase_group == 1 draws it per member
-  GsU4 ph = gs_philox(g.seed_lo, g.seed_hi, i / g.phase_group, 0u, GS_PUR_PHASE, 0u);
-  const uint32_t pp = ph.x % g.P, gp = ph.y % g.GI;
+  const uint32_t group = i / g.phase_group;
+  const uint32_t pp = gs_probe_phase(g.rot_p, group, g.P), gp = gs_gossip_phase(g.rot_g, group, g.P, g.GI);
   const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
   d.key[0][i] = k;
   d.key[1][i] = k;

@@ -127,6 +127,31 @@ GS_HD GsU4 gs_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_
   o.w = c3;
   return o;
 }
+// ---- ticker stagger ([U] memberlist/state.go triggerFunc: rand % interval per agent) ----
+// The stagger only has to spread the tickers evenly over their interval, so phases are
+// dealt round-robin over consecutive phase groups, rotated by a seed-derived offset:
+//   probe phase  = (group + rot_p) mod P,   gossip phase = (group / P + rot_g) mod GI.
+// Any run of consecutive tiles then holds every phase equally often, which is what lets the
+// tick kernel give each warp a contiguous chunk of tiles with a perfectly balanced number of
+// probing tiles — no work stealing, no atomics.
+GS_HD uint32_t gs_fmix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+GS_HD uint32_t gs_phase_rot(uint32_t seed_lo, uint32_t seed_hi) {
+  return gs_fmix32(seed_lo * 0x9E3779B1u + seed_hi);
+}
+GS_HD uint32_t gs_probe_phase(uint32_t rot_p, uint32_t group, uint32_t P) {
+  return (group % P + rot_p) % P;
+}
+GS_HD uint32_t gs_gossip_phase(uint32_t rot_g, uint32_t group, uint32_t P, uint32_t GI) {
+  return ((group / P) % GI + rot_g) % GI;
+}
+
 GS_HD uint32_t gs_u4_get(const GsU4& v, uint32_t idx) {
   return idx == 0 ? v.x : idx == 1 ? v.y : idx == 2 ? v.z : v.w;
 }
@@ -141,6 +166,15 @@ GS_HD uint32_t gs_feistel_round(uint32_t r, uint32_t k) {
   x *= 0x85EBCA77u;
   x ^= x >> 13;
   return x;
+}
+// Round keys of one (member, pass) ring: two murmur finalisers, two cheap combinations.
+GS_HD GsU4 gs_perm_keys(uint32_t seed_lo, uint32_t seed_hi, uint32_t member, uint32_t pass) {
+  GsU4 k;
+  k.x = gs_fmix32(member * 0x9E3779B1u + pass * 0x85EBCA77u + seed_lo);
+  k.y = gs_fmix32(k.x ^ seed_hi ^ 0xC2B2AE3Du);
+  k.z = k.x * 0x9E3779B1u + k.y;
+  k.w = (k.y * 0x85EBCA77u) ^ k.x;
+  return k;
 }
 GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t half_bits, const GsU4& rk) {
   const uint32_t mask = (1u << half_bits) - 1u;
@@ -191,7 +225,10 @@ struct GsGlobals {
   uint32_t evlog_cap;
   uint32_t world, rank;
   uint32_t phase_group;  // members per ticker-phase group (1 or a multiple of GS_TILE)
-  uint32_t phase_gate;   // 1: phase_tab is valid and whole tiles can skip the `due` column
+  uint32_t phase_gate;   // 1: phases are uniform per tile, whole tiles can skip the `due` column
+  uint32_t phase_shift;  // phase_group == GS_TILE << phase_shift when phase_gate
+  uint32_t rot_p, rot_g; // seed-derived rotation of the probe / gossip phases
+  uint32_t pad1;
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -219,8 +256,6 @@ struct GsDev {
   uint32_t* heard;
   uint32_t* queued;
   uint8_t* tx;  // [GS_MAX_RUMORS][cap]
-  // per tile of GS_TILE rows: probe phase | (probe phase + T) % P << 8 | gossip phase << 16
-  uint32_t* phase_tab;
   // pool-wide device words
   unsigned long long* stats;  // [GSIM_STAT_COUNT]
   uint32_t* heard_cnt;        // [GS_MAX_RUMORS]

@@ -14,6 +14,7 @@
 // the ~2 us per-launch host cost is off the critical path.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -54,70 +55,113 @@ struct DevSink {
   }
 };
 
-// One CTA = one tile of GS_TILE (128) consecutive members, one member per thread.
-// Hot path per member per tick: ONE coalesced 4-byte load (its mailbox word); tiles whose
-// ticker phase matches this tick additionally read `due` (4 B).  Everything else is read
-// only by members that act.  A tile with no active member retires after one barrier.
-struct TileWords {
-  uint32_t inb[4], due[4];
-};
+#ifndef GS_MIN_BLOCKS
+#define GS_MIN_BLOCKS 3
+#endif
+#define GS_STAGES 4                  // cp.async pipeline depth of the scan (tiles in flight per warp)
+#define GS_WARPS (GS_BLOCK / 32)
 
-__device__ __forceinline__ void gs_load_tile(const GsDev& d, const GsGlobals& g, uint32_t tile,
-                                             uint32_t lane, uint32_t cur, uint32_t pslot,
-                                             TileWords& w) {
-  const uint32_t base = tile * GS_TILE + lane;  // columns are padded to a tile multiple
-  const bool gate = gs_tile_probe_gate(d, g, tile, pslot);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) w.inb[u] = d.inbox[cur][base + 32u * u];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) w.due[u] = gate ? d.due[base + 32u * u] : GS_NEVER;
+// Asynchronous 16-byte global -> shared copy (LDGSTS.128, L2 only): the scan words of the
+// tiles ahead are in flight without holding registers or stalling the warp.
+__device__ __forceinline__ void gs_cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void gs_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void gs_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Persistent, warp-centric tick.  A warp owns whole tiles of 128 consecutive members
-// (4 members per lane, each a coalesced 128-byte request) and walks them with a stride of
-// the total warp count, prefetching the next tile's words while it works on the current
-// one.  Hot path per member per tick: ONE 4-byte mailbox word; tiles whose ticker phase
-// can be due at this tick additionally read `due`.  Members that act are handled in two
-// tiers: the staged probe fast path (gs_fast_*), then the generic gs_row_step.
-__global__ void __launch_bounds__(GS_BLOCK)
+// Persistent, warp-centric tick.  Every warp owns a CONTIGUOUS chunk of tiles (128 members
+// each); because ticker phases are dealt round-robin over tiles, every chunk holds the same
+// number of probing tiles (+-1) at every tick, so the static split is balanced.
+//   Scan: each lane moves the mailbox words of 4 members (16 B; a tile is one 512-byte
+// request) into a per-warp shared-memory ring with cp.async, GS_STAGES-1 tiles ahead; tiles
+// whose ticker phase can be due at this tick also bring their `due` words.  An idle tile
+// costs ~40 warp instructions and 4 bytes per member.
+//   Work: a tile with activity is re-read from shared memory one member per lane (coalesced
+// column accesses).  The four 32-member groups of a probing tile go through the staged fast
+// path together — own columns, target gathers and commits are each issued for all four
+// before the first is consumed — so the tile pays two dependent memory latencies, not eight.
+// Whatever the fast path declines goes to the generic gs_row_step.
+__global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
+  __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
+  __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  // Programmatic dependent launch: let the next tick's grid start launching now; it blocks in
+  // its own griddepcontrol.wait until this grid has completed and flushed.  Everything above
+  // this line touches no global memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const GsGlobals& g = *gp;
   const uint32_t t = *d.tick_base + k_off;
-  const uint32_t cur = t & 1u, pslot = t % g.P, gslot = t % g.GI;
-  const uint32_t lane = tid & 31u;
+  const uint32_t cur = t & 1u, P = g.P, pslot = t % P, gslot = t % g.GI;
+  const uint32_t pslot_t = (t + P - g.T % P) % P;
+  const uint32_t lane = tid & 31u, wib = tid >> 5;
   const uint32_t n_tiles = (g.n + GS_TILE - 1u) / GS_TILE;
-  const uint32_t n_warps = gridDim.x * (GS_BLOCK / 32u);
+  const uint32_t n_warps = gridDim.x * GS_WARPS;
+  const uint32_t chunk = (n_tiles + n_warps - 1u) / n_warps;
+  const uint32_t wid = blockIdx.x * GS_WARPS + wib;
+  const uint32_t t_begin = wid * chunk < n_tiles ? wid * chunk : n_tiles;
+  const uint32_t t_end = t_begin + chunk < n_tiles ? t_begin + chunk : n_tiles;
+  const uint32_t* __restrict__ inbox_cur = d.inbox[cur];
+  const bool gated = g.phase_gate != 0u;
+  const uint32_t shift = g.phase_shift;
   DevSink sink{s_stat, s_heard};
-  uint32_t tile = blockIdx.x * (GS_BLOCK / 32u) + (tid >> 5);
-  TileWords w;
-  if (tile < n_tiles) gs_load_tile(d, g, tile, lane, cur, pslot, w);
-  while (tile < n_tiles) {
-    const uint32_t next = tile + n_warps;
-    TileWords wn;
-    if (next < n_tiles) gs_load_tile(d, g, next, lane, cur, pslot, wn);  // prefetch
-    bool act[4], cand[4];
-    bool any_act = false, any_cand = false;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool due_now = w.due[u] == t;
-      act[u] = w.inb[u] != 0u || due_now;
-      cand[u] = w.inb[u] == 0u && due_now;  // empty mailbox + ticker fired: probe fast path
-      any_act |= act[u];
-      any_cand |= cand[u];
+
+  uint32_t tq = t_begin;  // next tile to issue
+  auto issue = [&](uint32_t st) {
+    if (tq < t_end) {
+      const size_t off = (size_t)tq * GS_TILE + lane * 4u;  // columns are padded to whole tiles
+      gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
+      bool gate = true;
+      if (gated) {
+        const uint32_t pp = gs_probe_phase(g.rot_p, tq >> shift, P);
+        gate = pp == pslot || pp == pslot_t;
+      }
+      if (gate) {
+        gs_cp_async16(&s_due[st][wib][lane * 4u], d.due + off);
+      } else {
+        *reinterpret_cast<uint4*>(&s_due[st][wib][lane * 4u]) = make_uint4(GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER);
+      }
     }
-    if (__any_sync(0xFFFFFFFFu, any_act)) {
+    ++tq;
+    gs_cp_async_commit();
+  };
+#pragma unroll
+  for (uint32_t q = 0; q < GS_STAGES - 1; ++q) issue(q);
+  uint32_t st = 0;
+  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+    issue((st + GS_STAGES - 1u) % GS_STAGES);
+    gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
+    const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
+    const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
+    const bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
+    if (__any_sync(0xFFFFFFFFu, mine)) {
+      __syncwarp();  // other lanes' copies are now visible: re-read one member per lane
       const uint32_t base = tile * GS_TILE + lane;
+      bool act[4], cand[4];
+      bool any_cand = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w = s_inb[st][wib][u * 32 + lane];
+        const bool due_now = s_due[st][wib][u * 32 + lane] == t;
+        act[u] = w != 0u || due_now;
+        cand[u] = w == 0u && due_now;  // empty mailbox + ticker fired
+        any_cand |= cand[u];
+      }
       if (__any_sync(0xFFFFFFFFu, any_cand)) {
         GsFastProbe f[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (cand[u]) gs_fast_load(d, cur, base + 32u * u, f[u]);  // stage A: own columns
+          if (cand[u]) gs_fast_load(d, cur, base + 32u * u, f[u]);               // A: own columns
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (cand[u]) cand[u] = gs_fast_target(d, g, cur, base + 32u * u, f[u]);  // B: gathers
@@ -140,13 +184,12 @@ __global__ void __launch_bounds__(GS_BLOCK)
       for (int u = 0; u < 4; ++u) {
         const bool a = u == 0 ? act[0] : u == 1 ? act[1] : u == 2 ? act[2] : act[3];
         if (__any_sync(0xFFFFFFFFu, a)) {
-          const uint32_t inb = u == 0 ? w.inb[0] : u == 1 ? w.inb[1] : u == 2 ? w.inb[2] : w.inb[3];
-          if (a) gs_row_step(d, g, base + 32u * u, t, gslot, inb, sink);
+          if (a) gs_row_step(d, g, base + 32u * u, t, gslot, s_inb[st][wib][u * 32 + lane], sink);
         }
       }
+      __syncwarp();  // everyone is done with this stage before it is refilled
     }
-    w = wn;
-    tile = next;
+    st = (st + 1u) % GS_STAGES;
   }
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
@@ -235,6 +278,23 @@ __global__ void __launch_bounds__(GS_BLOCK)
   if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(&out[threadIdx.x], s[threadIdx.x]);
 }
 
+// Tick launches use programmatic stream serialization (PDL) so consecutive ticks overlap
+// launch latency and prologue with the previous tick's tail.
+static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const GsDev& d,
+                                  const GsGlobals* g_dev, uint32_t k, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(GS_BLOCK);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gs_tick_kernel, d, g_dev, k);
+}
+
 class CudaBackend : public GsBackend {
  public:
   explicit CudaBackend(int dev) : dev_(dev) {
@@ -310,7 +370,7 @@ class CudaBackend : public GsBackend {
       return true;
     }
     cudaSetDevice(dev_);
-    // persistent launch: one warp per tile up to a full machine (SMs x resident CTAs)
+    // persistent launch: one warp per 128-member tile up to a full machine (SMs x resident CTAs)
     const uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
     const uint32_t warps_per_block = GS_BLOCK / 32;
     uint32_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
@@ -328,7 +388,7 @@ class CudaBackend : public GsBackend {
     }
     if (left) {
       for (uint32_t k = 0; k < left; ++k)
-        gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+        if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_), "tick launch")) return false;
       gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
       launches_ += left + 1;
       if (!ok(cudaGetLastError(), "tick launch")) return false;
@@ -404,7 +464,12 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture"))
       return nullptr;
     for (uint32_t k = 0; k < GS_GRAPH_TICKS; ++k)
-      gs_tick_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, k);
+      if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_), "tick capture")) {
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(stream_, &dead);
+        if (dead) cudaGraphDestroy(dead);
+        return nullptr;
+      }
     gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
@@ -425,6 +490,7 @@ class CudaBackend : public GsBackend {
   cudaEvent_t ev0_, ev1_;
   void* scratch_;
   uint32_t full_grid_ = 592;
+  bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   uint64_t launches_ = 0;
   char err_[256];

@@ -181,10 +181,12 @@ GS_DEV void gs_log_event(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_
 // member's `due` is always congruent to its ticker phase or to phase + ProbeTimeout
 // (mod ProbeInterval), and phases are uniform per tile, so 1 - 2/P of the tiles never
 // need to read the `due` column at all.
-GS_DEV bool gs_tile_probe_gate(const GsDev& d, const GsGlobals& g, uint32_t tile, uint32_t pslot) {
+// pslot = t % P; pslot_t = (t - T) % P, i.e. the phase whose ProbeTimeout stage is due now.
+GS_DEV bool gs_tile_probe_gate(const GsGlobals& g, uint32_t tile, uint32_t pslot, uint32_t pslot_t) {
   if (!g.phase_gate) return true;
-  const uint32_t tab = d.phase_tab[tile];
-  return (tab & 0xFFu) == pslot || ((tab >> 8) & 0xFFu) == pslot;
+  const uint32_t group = tile >> g.phase_shift;  // phase_group = 128 << phase_shift
+  const uint32_t pp = gs_probe_phase(g.rot_p, group, g.P);
+  return pp == pslot || pp == pslot_t;
 }
 
 // The tick of member i, called only for rows that have mail (inb = inbox[t&1][i] != 0,
@@ -396,7 +398,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       // dead/left members; a wrap re-keys the permutation (resetNodes + shuffle).
       uint32_t cursor = d.cursor[i], pass = d.pass[i];
       const uint32_t n = g.n;
-      GsU4 rk = gs_philox(g.seed_lo, g.seed_hi, i, pass, GS_PUR_PERM, 0u);
+      GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, pass);
       uint32_t checked = 0, target = GS_EMPTY32, ktarget = 0;
       const uint32_t limit = n < GS_PROBE_SKIP_CAP ? n : GS_PROBE_SKIP_CAP;
       while (checked < limit) {
@@ -404,7 +406,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           cursor = 0;
           ++pass;
           ++checked;
-          rk = gs_philox(g.seed_lo, g.seed_hi, i, pass, GS_PUR_PERM, 0u);
+          rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, pass);
           continue;
         }
         uint32_t c = gs_perm(cursor, n, g.perm_half_bits, rk);
@@ -513,7 +515,7 @@ GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uin
   if (gs_key_truth(f.k) != GS_TRUTH_UP || gs_key_rank(f.k) != GS_RANK_ALIVE) return false;
   if (gs_meta_stage(f.m) != GS_STAGE_IDLE || (f.m & (GS_META_DIRTY | GS_META_ISOLATED))) return false;
   if (f.cursor >= g.n) return false;  // ring wrap: re-key in the generic path
-  GsU4 rk = gs_philox(g.seed_lo, g.seed_hi, i, f.pass, GS_PUR_PERM, 0u);
+  GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, f.pass);
   f.c = gs_perm(f.cursor, g.n, g.perm_half_bits, rk);
   if (f.c == i) return false;
   f.kc = d.key[cur][f.c];

@@ -76,6 +76,30 @@ Rand4 philox4x32_10(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32
   return r;
 }
 
+// ---- ticker stagger: one draw per phase group ([U] state.go triggerFunc: rand % interval) ----
+// murmur3's 32-bit finaliser over (seed, group); multiply-high maps it onto [0, interval).
+uint32_t murmur_fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+struct Stagger {
+  uint32_t probe, gossip;
+};
+// Phases are dealt round-robin over consecutive phase groups, rotated by a seed-derived offset:
+// group g probes at ticks = g + rot (mod P) and gossips at ticks = g / P + rot' (mod GI).
+Stagger stagger_of(uint64_t seed, uint32_t member, uint32_t phase_group, uint32_t P, uint32_t GI) {
+  uint64_t group = member / (phase_group ? phase_group : 128);
+  uint32_t rot = murmur_fmix32((uint32_t)seed * 0x9E3779B1u + (uint32_t)(seed >> 32));
+  Stagger s;
+  s.probe = (uint32_t)((group + rot % P) % P);
+  s.gossip = (uint32_t)((group / P + (rot >> 16) % GI) % GI);
+  return s;
+}
+
 // ---- upstream scalar formulas ---------------------------------------------------------
 // [U] memberlist/util.go retransmitLimit
 uint32_t retransmit_limit(uint32_t mult, uint32_t n) {
@@ -216,6 +240,17 @@ void retune(Oracle& o) {
   bits = std::max(bits, 2u);
   bits += bits & 1;
   o.perm_half_bits = bits / 2;
+}
+
+// The four Feistel round keys of one (member, pass) probe ring.
+Rand4 ring_keys(uint64_t seed, uint32_t member, uint32_t pass) {
+  const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+  Rand4 k;
+  k.v[0] = murmur_fmix32(member * 0x9E3779B1u + pass * 0x85EBCA77u + lo);
+  k.v[1] = murmur_fmix32(k.v[0] ^ hi ^ 0xC2B2AE3Du);
+  k.v[2] = k.v[0] * 0x9E3779B1u + k.v[1];
+  k.v[3] = (k.v[1] * 0x85EBCA77u) ^ k.v[0];
+  return k;
 }
 
 // Feistel permutation of [0,n) with cycle walking — the probe ring of one (member, pass).
@@ -463,7 +498,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     if (me.stage == ST_IDLE && me.due == t) {
       // [U] memberlist.probe: walk the ring to the next probe-able member
       const uint32_t n = (uint32_t)o.m.size();
-      Rand4 keys = philox4x32_10(o.cfg.seed, i, me.pass, PUR_PERM, 0);
+      Rand4 keys = ring_keys(o.cfg.seed, i, me.pass);
       uint32_t checked = 0, target = NONE32;
       const uint32_t cap = std::min(n, PROBE_SKIP_CAP);
       while (checked < cap) {
@@ -471,7 +506,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
           me.cursor = 0;
           me.pass++;
           checked++;
-          keys = philox4x32_10(o.cfg.seed, i, me.pass, PUR_PERM, 0);
+          keys = ring_keys(o.cfg.seed, i, me.pass);
           continue;
         }
         uint32_t c = ring_entry(o, me.cursor++, n, keys);
@@ -813,9 +848,9 @@ void* oracle_create(const gsim_config* cfg, int threads) {
     me.v.rank = GSIM_RANK_ALIVE;
     me.v.inc = 1;
     // ticker stagger ([U] state.go triggerFunc), drawn once per phase group of members
-    Rand4 ph = philox4x32_10(cfg->seed, i / (cfg->phase_group ? cfg->phase_group : 128), 0, PUR_PHASE, 0);
-    me.due = ph.v[0] % o->P;
-    me.gossip_phase = ph.v[1] % o->GI;
+    Stagger ph = stagger_of(cfg->seed, i, cfg->phase_group, o->P, o->GI);
+    me.due = ph.probe;
+    me.gossip_phase = ph.gossip;
     o->pub[i] = me.v;
   }
   retune(*o);
@@ -842,10 +877,9 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   me.v.pending = 1;
   me.isolated = o.established > 0;  // with an empty base set there is nothing to be missing
   me.watched = desc && (desc->flags & GSIM_MEMBER_WATCHED);
-  Rand4 ph = philox4x32_10(o.cfg.seed, id / (o.cfg.phase_group ? o.cfg.phase_group : 128), 0, PUR_PHASE, 0);
-  uint32_t pp = ph.v[0] % o.P;
-  me.due = o.now + (pp + o.P - o.now % o.P) % o.P;
-  me.gossip_phase = ph.v[1] % o.GI;
+  Stagger ph = stagger_of(o.cfg.seed, id, o.cfg.phase_group, o.P, o.GI);
+  me.due = o.now + (ph.probe + o.P - o.now % o.P) % o.P;  // first tick >= now on its phase
+  me.gossip_phase = ph.gossip;
   publish(o, id);
   o.up_count++;
   retune(o);

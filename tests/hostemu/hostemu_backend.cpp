@@ -102,7 +102,7 @@ class HostEmuBackend : public GsBackend {
         const uint32_t i = row_at(x, g.n);
         const uint32_t inb = d.inbox[t & 1u][i];
         uint32_t due = GS_NEVER;
-        if (gs_tile_probe_gate(d, g, i / GS_TILE, pslot)) due = d.due[i];
+        if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
         if (!(inb != 0u || due == t)) continue;
         if (inb == 0u && !getenv("GSIM_HOSTEMU_NO_FAST")) {  // same two tiers as the kernel
           GsFastProbe f;
