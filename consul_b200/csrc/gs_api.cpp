@@ -556,7 +556,7 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   if (!p || !id_out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
   GsGlobals& g = p->g;
-  if (g.n >= g.cap) return fail(p, GSIM_ERR_CAPACITY, "member capacity exhausted");
+  if (g.n >= p->cfg.capacity) return fail(p, GSIM_ERR_CAPACITY, "member capacity exhausted");
   uint32_t slot;
   int rc = alloc_slot(p, &slot);
   if (rc) return fail(p, rc, "no free rumor slot for the member's alive broadcast");

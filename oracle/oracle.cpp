@@ -156,7 +156,6 @@ struct Member {
   uint32_t ltime_member = 1, ltime_event = 1, event_min = 0;
   uint32_t heard = 0, queued = 0;
   uint8_t tx[GSIM_MAX_RUMORS];
-  uint32_t inbox = 0;  // rumor bits arriving at the tick about to run
   Member() {
     memset(tx, 0, sizeof(tx));
     for (int i = 0; i < MAX_SUS; ++i) sus_from[i] = NONE32;
@@ -206,7 +205,8 @@ struct Oracle {
   std::vector<Member> m;
   std::vector<View> pub;                 // published views (state at the start of the tick)
   std::vector<uint32_t> pub_change_tick; // published change ticks
-  std::vector<uint32_t> next_inbox;      // rumor bits that arrive next tick
+  std::vector<uint32_t> inbox[2];        // rumor bits by arrival-tick parity (bit 31: accused)
+  std::vector<uint32_t> wake;            // 0 = look every tick, else the only tick worth a look
   std::vector<Accusation> arriving;      // accusations that arrive at the tick about to run
   Rumor rumor[GSIM_MAX_RUMORS];
   uint32_t active = 0;
@@ -360,6 +360,16 @@ void log_event(const Oracle& o, Tally& ta, uint32_t t, uint32_t type, uint32_t s
   ta.events.push_back(e);
 }
 
+// When does this member next need a look if no mail arrives?  0 = every tick (a running
+// suspicion timer, a refutation, a non-empty broadcast queue), NONE32 = never.
+uint32_t wake_of(const Member& me) {
+  if (me.v.truth == GSIM_TRUTH_NONE) return NONE32;
+  const bool up = me.v.truth == GSIM_TRUTH_UP;
+  if (me.v.rank == GSIM_RANK_SUSPECT) return 0;
+  if (up && (me.v.rank != GSIM_RANK_ALIVE || me.queued)) return 0;
+  return up ? me.due : NONE32;
+}
+
 // One member, one tick.
 void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
   Member& me = o.m[i];
@@ -367,12 +377,16 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
   const bool up = me.v.truth == GSIM_TRUTH_UP;
   const View before = me.v;
   const bool my_gossip_tick = up && (t % o.GI) == me.gossip_phase;
-  const uint32_t inbox = me.inbox;
-  me.inbox = 0;
-  // accusations addressed to me (the arriving list is sorted by subject)
-  auto lo = std::lower_bound(o.arriving.begin(), o.arriving.end(), i,
-                             [](const Accusation& a, uint32_t s) { return a.subject < s; });
-  const bool accused = lo != o.arriving.end() && lo->subject == i;
+  const uint32_t word = o.inbox[t & 1][i];
+  o.inbox[t & 1][i] = 0;
+  const uint32_t inbox = word & 0x7FFFFFFFu;
+  // accusations addressed to me (bit 31 was set when they were handed over; the arriving
+  // list is sorted by subject)
+  const bool accused = (word >> 31) != 0;
+  auto lo = o.arriving.end();
+  if (accused)
+    lo = std::lower_bound(o.arriving.begin(), o.arriving.end(), i,
+                          [](const Accusation& a, uint32_t s) { return a.subject < s; });
 
   if (!inbox && !accused && me.v.rank == GSIM_RANK_ALIVE && !(up && me.due == t) &&
       !(my_gossip_tick && me.queued))
@@ -552,7 +566,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
         }
         ta.c[GSIM_STAT_GOSSIP_PACKETS]++;
         if (!packet_lost(o, ta, i, peers[q], t, LK_GOSSIP, q))
-          __atomic_fetch_or(&o.next_inbox[peers[q]], packet, __ATOMIC_RELAXED);
+          __atomic_fetch_or(&o.inbox[(t + 1) & 1][peers[q]], packet, __ATOMIC_RELAXED);
       }
     }
   }
@@ -563,11 +577,6 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
 void run_tick(Oracle& o) {
   const uint32_t t = o.now;
   const uint32_t n = (uint32_t)o.m.size();
-  // hand over the mailboxes filled during the previous tick
-  for (uint32_t i = 0; i < n; ++i) {
-    o.m[i].inbox = o.next_inbox[i];
-    o.next_inbox[i] = 0;
-  }
   std::sort(o.arriving.begin(), o.arriving.end(), [](const Accusation& a, const Accusation& b) {
     if (a.subject != b.subject) return a.subject < b.subject;
     if (a.inc != b.inc) return a.inc > b.inc;
@@ -578,16 +587,29 @@ void run_tick(Oracle& o) {
                                  return a.subject == b.subject && a.inc == b.inc && a.from == b.from;
                                }),
                    o.arriving.end());
+  for (const Accusation& a : o.arriving) o.inbox[t & 1][a.subject] |= 0x80000000u;
+  // Members with no mail whose only scheduled action lies at another tick cannot do anything
+  // (this is exactly the idle test at the top of member_tick, evaluated from two flat arrays).
+  const uint32_t* mail = o.inbox[t & 1].data();
+  uint32_t* wake = o.wake.data();
   std::vector<Tally> tallies((size_t)o.threads);
 #ifdef _OPENMP
 #pragma omp parallel num_threads(o.threads)
   {
     Tally& ta = tallies[(size_t)omp_get_thread_num()];
 #pragma omp for schedule(static)
-    for (int64_t i = 0; i < (int64_t)n; ++i) member_tick(o, (uint32_t)i, t, ta);
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      if (mail[i] == 0 && wake[i] != 0 && wake[i] != t) continue;
+      member_tick(o, (uint32_t)i, t, ta);
+      wake[i] = wake_of(o.m[(size_t)i]);
+    }
   }
 #else
-  for (uint32_t i = 0; i < n; ++i) member_tick(o, i, t, tallies[0]);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (mail[i] == 0 && wake[i] != 0 && wake[i] != t) continue;
+    member_tick(o, i, t, tallies[0]);
+    wake[i] = wake_of(o.m[i]);
+  }
 #endif
   // end of tick: publish, count, hand accusations to the next tick
   o.arriving.clear();
@@ -672,7 +694,8 @@ void retire(Oracle& o, uint32_t slot) {
     me.heard &= ~(1u << slot);
     me.queued &= ~(1u << slot);
   }
-  for (uint32_t& w : o.next_inbox) w &= ~(1u << slot);
+  for (int b = 0; b < 2; ++b)
+    for (uint32_t& w : o.inbox[b]) w &= ~(1u << slot);
 }
 
 void auto_retire(Oracle& o) {
@@ -776,6 +799,10 @@ void apply_shutdowns(Oracle& o) {
 void step(Oracle& o, uint32_t ticks) {
   for (uint32_t k = 0; k < ticks; ++k) {
     apply_shutdowns(o);
+    if (k == 0 || o.wake.size() != o.m.size()) {  // between-tick operations may have changed anyone
+      o.wake.resize(o.m.size());
+      for (size_t i = 0; i < o.m.size(); ++i) o.wake[i] = wake_of(o.m[i]);
+    }
     run_tick(o);
   }
   apply_shutdowns(o);
@@ -839,7 +866,8 @@ void* oracle_create(const gsim_config* cfg, int threads) {
   o->m.resize(cfg->n_initial);
   o->pub.resize(cfg->n_initial);
   o->pub_change_tick.assign(cfg->n_initial, 0);
-  o->next_inbox.assign(cfg->n_initial, 0);
+  o->inbox[0].assign(cfg->n_initial, 0);
+  o->inbox[1].assign(cfg->n_initial, 0);
   o->up_count = cfg->n_initial;
   o->established = cfg->n_initial;
   for (uint32_t i = 0; i < cfg->n_initial; ++i) {
@@ -869,7 +897,8 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   o.m.emplace_back();
   o.pub.emplace_back();
   o.pub_change_tick.push_back(0);
-  o.next_inbox.push_back(0);
+  o.inbox[0].push_back(0);
+  o.inbox[1].push_back(0);
   Member& me = o.m.back();
   me.v.truth = GSIM_TRUTH_UP;
   me.v.rank = GSIM_RANK_ALIVE;
@@ -1182,7 +1211,7 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
     x = mix(x, heard);
     x = mix(x, me.queued & o.active);
     bool has_acc = ap < acc.size() && acc[ap].subject == i;
-    uint32_t inb = (o.next_inbox[i] & o.active) | (has_acc ? 0x80000000u : 0);
+    uint32_t inb = (o.inbox[o.now & 1][i] & o.active) | (has_acc ? 0x80000000u : 0);
     x = mix(x, inb);
     for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
       if ((heard >> r) & 1) x = mix(x, (r << 8) | me.tx[r]);
@@ -1245,7 +1274,7 @@ int oracle_column_read(void* h, int column, void* out, size_t cap_bytes, size_t*
       case GSIM_COL_TX:
         for (int r = 0; r < GSIM_MAX_RUMORS; ++r) b[(size_t)r * cap + i] = me.tx[r];
         break;
-      case GSIM_COL_INBOX: w[i] = o.next_inbox[i]; break;
+      case GSIM_COL_INBOX: w[i] = o.inbox[o.now & 1][i] & 0x7FFFFFFFu; break;
       default: return GSIM_ERR_INVALID;
     }
   }
