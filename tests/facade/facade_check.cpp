@@ -1,0 +1,174 @@
+// facade_check.cpp — the reference's own gossip tests, replayed against the C++ serf facade
+// (include/gsim_serf.hpp) over the C ABI.  Linked twice by tests/test_facade.py: against the
+// host emulation (CPU suite) and against libgsim.so (GPU suite).
+//
+//   TestServer_JoinLAN            agent/consul/server_test.go:509-529
+//   TestServer_LANReap (shape)    agent/consul/server_test.go:666-733
+//   TestAgent_ForceLeave          agent/agent_endpoint_test.go:2524-2566
+//   TestClientServer_UserEvent    agent/consul/client_test.go:756-835
+//   TestAgent_Leave               agent/agent_endpoint_test.go:2447
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+
+#include "../../include/gsim_serf.hpp"
+
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                        \
+    }                                                                      \
+  } while (0)
+
+using namespace serf;
+
+static int count_status(Serf& s, int status) {
+  int n = 0;
+  for (auto& m : s.Members()) n += m.Status == status;
+  return n;
+}
+
+// retry.Run (sdk/testutil/retry/retryer.go:18-20: 7 s / 25 ms) in simulated time
+template <class F>
+static bool eventually(Pool& p, uint32_t max_ticks, F f) {
+  for (uint32_t t = 0; t < max_ticks; ++t) {
+    if (f()) return true;
+    p.Step(1);
+  }
+  return f();
+}
+
+static gsim_config test_cfg() {
+  gsim_config c = Pool::TestConfig();
+  c.capacity = 16;
+  c.n_initial = 0;
+  c.seed = 42;
+  c.flags = GSIM_FLAG_LOG_GLOBAL_EVENTS;
+  return c;
+}
+
+static void test_join_lan() {
+  Pool pool(test_cfg());
+  Config c1, c2;
+  c1.NodeName = "s1";
+  c1.Tags = {{"role", "consul"}, {"dc", "dc1"}};
+  c2.NodeName = "s2";
+  c2.Tags = {{"role", "consul"}, {"dc", "dc1"}};
+  auto s1 = Serf::Create(pool, c1);
+  auto s2 = Serf::Create(pool, c2);
+  CHECK(s1->Members().size() == 1 && s2->Members().size() == 1);
+  CHECK(s2->Join({"s1/127.0.0.1:8301"}, true) == 1);
+  CHECK(eventually(pool, 140, [&] { return s1->Members().size() == 2 && s2->Members().size() == 2; }));
+  CHECK(s1->LocalMember().Name == "s1" && s1->LocalMember().Status == StatusAlive);
+  CHECK(s1->Members()[1].Tags.at("role") == "consul");
+  bool threw = false;
+  try {
+    s2->Join({"nosuch/127.0.0.1:1"}, true);
+  } catch (const Error&) {
+    threw = true;
+  }
+  CHECK(threw);
+  threw = false;
+  try {
+    Serf::Create(pool, c1);  // node name conflict
+  } catch (const Error&) {
+    threw = true;
+  }
+  CHECK(threw);
+  std::puts("PASS TestServer_JoinLAN");
+}
+
+static void test_lan_reap_and_force_leave() {
+  Pool pool(test_cfg());
+  std::deque<Event> ch1;
+  Config c1, c2, c3;
+  c1.NodeName = "s1";
+  c1.EventCh = &ch1;
+  c2.NodeName = "s2";
+  c3.NodeName = "s3";
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2), s3 = Serf::Create(pool, c3);
+  s2->Join({"s1/x"}, true);
+  s3->Join({"s1/x"}, true);
+  CHECK(eventually(pool, 140, [&] { return s1->NumNodes() == 3 && s2->NumNodes() == 3 && s3->NumNodes() == 3; }));
+  s3->Shutdown();  // crash without Leave
+  CHECK(eventually(pool, 400, [&] { return count_status(*s1, StatusFailed) == 1 && count_status(*s2, StatusFailed) == 1; }));
+  CHECK(count_status(*s1, StatusAlive) == 2);
+  pool.PumpEvents();
+  std::set<std::string> joined;
+  bool failed_seen = false;
+  for (auto& e : ch1) {
+    if (e.Type == EventMemberJoin) joined.insert(e.Members[0].Name);
+    if (e.Type == EventMemberFailed && e.Members[0].Name == "s3") failed_seen = true;
+  }
+  CHECK(joined.count("s2") && joined.count("s3") && failed_seen);
+  s1->RemoveFailedNode("s3");  // Failed -> Left
+  CHECK(count_status(*s2, StatusLeft) == 1 && count_status(*s2, StatusFailed) == 0);
+  s1->RemoveFailedNodePrune("s3");  // erased (EventMemberReap in serf)
+  CHECK(s1->Members().size() == 2);
+  std::puts("PASS TestServer_LANReap / TestAgent_ForceLeave");
+}
+
+static void test_user_event() {
+  Pool pool(test_cfg());
+  std::deque<Event> chs, chc;
+  Config cs, cc;
+  cs.NodeName = "server";
+  cs.EventCh = &chs;
+  cc.NodeName = "client";
+  cc.EventCh = &chc;
+  auto srv = Serf::Create(pool, cs), cli = Serf::Create(pool, cc);
+  cli->Join({"server/x"}, true);
+  CHECK(eventually(pool, 140, [&] { return srv->NumNodes() == 2 && cli->NumNodes() == 2; }));
+  srv->UserEvent("consul:event:foo", "bar", false);
+  pool.Step(60);
+  pool.PumpEvents();
+  int got_s = 0, got_c = 0;
+  for (auto& e : chs) got_s += e.Type == EventUser && e.Name == "consul:event:foo" && e.Payload == "bar";
+  for (auto& e : chc) got_c += e.Type == EventUser && e.Name == "consul:event:foo" && e.Payload == "bar";
+  CHECK(got_s == 1 && got_c == 1);  // exactly once on both
+  bool threw = false;
+  try {
+    srv->UserEvent(std::string(400, 'n'), std::string(400, 'p'), false);  // > UserEventSizeLimit
+  } catch (const Error& e) {
+    threw = e.code == GSIM_ERR_TOO_LARGE;
+  }
+  CHECK(threw);
+  std::puts("PASS TestClientServer_UserEvent");
+}
+
+static void test_leave() {
+  gsim_config c = Pool::DefaultLANConfig();
+  c.capacity = 64;
+  c.n_initial = 40;
+  Pool pool(c);
+  Config ca;
+  ca.NodeName = "a1";
+  auto a = Serf::Create(pool, ca);
+  // the 40 pre-converged members are anonymous; join through member 0 by id name
+  int rc = 0;
+  uint32_t seed = 0;
+  int n_ok = 0;
+  rc = gsim_join(pool.handle(), a->id(), &seed, 1, 1, &n_ok);
+  CHECK(rc == 0 && n_ok == 1);
+  CHECK(eventually(pool, 200, [&] { return a->NumNodes() == 41; }));
+  a->Leave();
+  CHECK(a->LocalMember().Status == StatusLeft);
+  pool.Step(300);
+  CHECK(a->Stats().at("left") == "1");
+  std::puts("PASS TestAgent_Leave");
+}
+
+int main() {
+  try {
+    test_join_lan();
+    test_lan_reap_and_force_leave();
+    test_user_event();
+    test_leave();
+  } catch (const Error& e) {
+    std::fprintf(stderr, "gsim error %d: %s\n", e.code, e.what());
+    return 2;
+  }
+  std::puts("ALL PASS");
+  return 0;
+}
