@@ -115,7 +115,7 @@ def run_reference(args, rank: int, world: int):
     ge.build()
     from consul_b200.pool import lan_config
     from oracle_binding import OraclePool
-    ticks = 64          # bounded sample of the 2048-tick step: join cascade + first steady ticks
+    ticks = 256         # bounded sample of the 2048-tick step: join cascade + first steady ticks
     cfg = lan_config(capacity=N_MEMBERS + args.steps + args.warmup + 2, n_initial=N_MEMBERS, seed=SEED)
     o = OraclePool(cfg, threads=0)
     conv = []

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/gsim.h"
@@ -178,6 +179,16 @@ struct gsim_pool {
   std::string err;
   uint64_t tick_ns = 0;
   uint32_t n_established = 0;  // members folded into the base set (not pending)
+  // sharded (multi-GPU) pools: DESIGN.md §7
+  bool sharded = false;
+  uint32_t world = 1, rank = 0;
+  size_t rows_per_rank = 0;
+  uint8_t* pages = nullptr;  // page column: rank r's pool-wide words at pages + r*GS_PAGE_BYTES
+  int shard_fd = -1;
+  uint32_t attached = 1;     // ranks whose memory is mapped here (including this one)
+  bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
+  uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
+  GsXbar xb;
 };
 
 static uint64_t gcd64(uint64_t a, uint64_t b) {
@@ -234,10 +245,82 @@ static void recompute_tables(gsim_pool* p) {
 
 static bool upload_globals(gsim_pool* p) {
   if (!p->g_dirty) return true;
-  if (!p->be->h2d(p->g_dev, &p->g, sizeof(GsGlobals))) return false;
+  if (p->sharded) {
+    // the controller (rank 0) writes every rank's device copy; only `rank` differs
+    for (uint32_t r = 0; r < p->world; ++r) {
+      GsGlobals tmp = p->g;
+      tmp.rank = r;
+      if (!p->be->h2d(p->pages + (size_t)r * GS_PAGE_BYTES + GS_PG_GLOBALS, &tmp, sizeof(GsGlobals))) return false;
+    }
+  } else if (!p->be->h2d(p->g_dev, &p->g, sizeof(GsGlobals))) {
+    return false;
+  }
   p->g_dirty = false;
   return true;
 }
+
+// ---- sharded pools: the controller protocol ---------------------------------------------------
+// Every rank calls every API function in the same order.  Rank 0 (the controller) executes the
+// host-side operation — all device pokes go through the unified address space, to whichever GPU
+// owns the row — then publishes the resulting host state (GsGlobals incl. the rumor table, clock,
+// schedule, return code, small out-parameters) in a blob in its page and enters the device
+// barrier; the other ranks enter the barrier, read the blob and adopt the state.
+struct BlobHdr {
+  int32_t rc;
+  uint32_t now, n_established, n_sched, out_bytes, pad;
+  uint64_t node_ticks;
+};
+
+template <class F>
+static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
+  if (!p->sharded) return f();
+  const uint32_t slot = p->call_seq++ & 1u;
+  uint8_t* blob_dev = p->pages + GS_PG_BLOB + (size_t)slot * GS_BLOB_BYTES;  // in rank 0's page
+  std::vector<uint8_t> blob(GS_BLOB_BYTES, 0);
+  BlobHdr h;
+  memset(&h, 0, sizeof(h));
+  if (p->rank == 0) {
+    h.rc = f();
+    if (p->g_dirty && !upload_globals(p)) h.rc = h.rc ? h.rc : GSIM_ERR_CUDA;
+    h.now = p->now;
+    h.n_established = p->n_established;
+    h.n_sched = (uint32_t)p->sched.size();
+    h.out_bytes = (uint32_t)(out ? out_bytes : 0);
+    h.node_ticks = p->node_ticks;
+    uint8_t* w = blob.data();
+    memcpy(w, &h, sizeof(h)); w += sizeof(h);
+    memcpy(w, &p->g, sizeof(GsGlobals)); w += sizeof(GsGlobals);
+    if (h.n_sched) memcpy(w, p->sched.data(), h.n_sched * sizeof(Sched));
+    w += h.n_sched * sizeof(Sched);
+    if (h.out_bytes) memcpy(w, out, h.out_bytes);
+    w += h.out_bytes;
+    if ((size_t)(w - blob.data()) > GS_BLOB_BYTES) return fail(p, GSIM_ERR_INVALID, "state blob overflow");
+    if (!p->be->h2d(blob_dev, blob.data(), (size_t)(w - blob.data()))) return fail(p, GSIM_ERR_CUDA, "blob h2d");
+    if (!p->be->xbar_host(p->xb)) return fail(p, GSIM_ERR_CUDA, "barrier");
+    return h.rc;
+  }
+  if (!p->be->xbar_host(p->xb)) return fail(p, GSIM_ERR_CUDA, "barrier");
+  if (!p->be->d2h(blob.data(), blob_dev, GS_BLOB_BYTES)) return fail(p, GSIM_ERR_CUDA, "blob d2h");
+  const uint8_t* r = blob.data();
+  memcpy(&h, r, sizeof(h)); r += sizeof(h);
+  memcpy(&p->g, r, sizeof(GsGlobals)); r += sizeof(GsGlobals);
+  p->g.rank = p->rank;
+  p->sched.resize(h.n_sched);
+  if (h.n_sched) memcpy(p->sched.data(), r, h.n_sched * sizeof(Sched));
+  r += h.n_sched * sizeof(Sched);
+  if (out && h.out_bytes == out_bytes && out_bytes) memcpy(out, r, out_bytes);
+  p->now = h.now;
+  p->n_established = h.n_established;
+  p->node_ticks = h.node_ticks;
+  p->g_dirty = false;
+  p->counts_stale = true;
+  if (h.rc) p->err = "controller reported an error";
+  return h.rc;
+}
+
+#define GS_CONTROLLER_ONLY(p)                                                                        \
+  if ((p)->sharded && (p)->rank != 0)                                                                \
+    return fail((p), GSIM_ERR_STATE, "bulk observation of a sharded pool is served by rank 0 only")
 
 static void rebuild_class_masks(gsim_pool* p) {
   GsGlobals& g = p->g;
@@ -254,6 +337,31 @@ static bool alloc_col(gsim_pool* p, T** out, size_t count) {
   p->allocs.push_back(q);
   *out = reinterpret_cast<T*>(q);
   return true;
+}
+
+// Device-side initial state: empty columns, zeroed counters, the converged initial members.
+// On a sharded pool this runs on rank 0 only and reaches every GPU through the unified columns.
+static int init_device_state(gsim_pool* p) {
+  GsBackend* be = p->be;
+  GsDev& d = p->d;
+  GsGlobals& g = p->g;
+  const size_t cap = g.cap;
+  bool okk = true;
+  // key = 0 means truth NONE for rows that were never created
+  okk = okk && be->fill32(d.key[0], 0, cap) && be->fill32(d.key[1], 0, cap);
+  okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
+  okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
+  okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
+  okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
+  okk = okk && be->fill32(d.heard_cnt, 0, 32) && be->fill32(d.conv_tick, GS_EMPTY32, 32);
+  okk = okk && be->fill32(d.view_cnt, 0, 4) && be->fill32(d.crashed_alive, 0, 1);
+  okk = okk && be->fill32(d.crashed_dead_tick, GS_EMPTY32, 1);
+  okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
+
+  p->g_dirty = true;
+  okk = okk && upload_globals(p);
+  okk = okk && be->init_rows(d, p->g_dev, g, 0, p->cfg.n_initial, 0);
+  return okk ? GSIM_OK : GSIM_ERR_CUDA;
 }
 
 extern "C" int gsim_abi_version(void) { return GSIM_ABI_VERSION; }
@@ -283,7 +391,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   if (!cfg->probe_interval_ns || !cfg->probe_timeout_ns || !cfg->gossip_interval_ns)
     return GSIM_ERR_INVALID;
   if (cfg->probe_timeout_ns >= cfg->probe_interval_ns) return GSIM_ERR_INVALID;
-  if (cfg->world_size != 1 || cfg->rank != 0) return GSIM_ERR_INVALID;  // sharding: see DESIGN.md
+  if (cfg->world_size < 1 || cfg->world_size > GS_MAX_WORLD || cfg->rank >= cfg->world_size) return GSIM_ERR_INVALID;
+  const bool sharded = cfg->world_size > 1;
   uint64_t tick = cfg->tick_ns;
   if (!tick) tick = gcd64(gcd64(cfg->probe_interval_ns, cfg->probe_timeout_ns), cfg->gossip_interval_ns);
   if (cfg->probe_interval_ns % tick || cfg->probe_timeout_ns % tick || cfg->gossip_interval_ns % tick)
@@ -311,45 +420,92 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   memset(&p->g, 0, sizeof(p->g));
   memset(&p->rc, 0, sizeof(p->rc));
   // column stride: padded to whole tiles so the tick kernel never needs a bounds check
-  const size_t cap = ((size_t)cfg->capacity + GS_TILE - 1) / GS_TILE * GS_TILE;
+  size_t cap = ((size_t)cfg->capacity + GS_TILE - 1) / GS_TILE * GS_TILE;
   GsDev& d = p->d;
   GsGlobals& g = p->g;
+  if (sharded) {
+    // one virtual address range per column, physically sharded over the GPUs (gs_vmm.h);
+    // rows per rank is a multiple of the 2 MB mapping granularity so byte columns align too
+    if (!be->shard_begin(cfg->world_size, cfg->rank)) {
+      g_create_err = be->last_error();
+      fprintf(stderr, "libgsim: sharded pools unavailable: %s\n", be->last_error());
+      gsim_pool_destroy(p);
+      return GSIM_ERR_CUDA;
+    }
+    const size_t gran = be->shard_granularity();
+    size_t per = ((size_t)cfg->capacity + cfg->world_size - 1) / cfg->world_size;
+    per = (per + gran - 1) / gran * gran;
+    p->sharded = true;
+    p->world = cfg->world_size;
+    p->rank = cfg->rank;
+    p->rows_per_rank = per;
+    p->ready = false;
+    cap = per * cfg->world_size;
+  }
+  const size_t per_rank = p->rows_per_rank;
+  auto acol = [&](auto** out, size_t planes) -> bool {
+    typedef typename std::remove_pointer<typename std::remove_pointer<decltype(out)>::type>::type T;
+    if (!sharded) return alloc_col(p, out, cap * planes);
+    void* q = be->shard_alloc(per_rank * sizeof(T), planes);
+    *out = reinterpret_cast<T*>(q);
+    return q != nullptr;
+  };
   bool okk = true;
-  okk = okk && alloc_col(p, &d.key[0], cap) && alloc_col(p, &d.key[1], cap);
-  okk = okk && alloc_col(p, &d.inbox[0], cap) && alloc_col(p, &d.inbox[1], cap);
-  okk = okk && alloc_col(p, &d.due, cap) && alloc_col(p, &d.meta, cap);
-  okk = okk && alloc_col(p, &d.cursor, cap) && alloc_col(p, &d.pass, cap);
-  okk = okk && alloc_col(p, &d.probe_tgt, cap) && alloc_col(p, &d.probe_inc, cap);
-  okk = okk && alloc_col(p, &d.sus_start, cap) && alloc_col(p, &d.sus_from, cap * GS_K1MAX);
-  okk = okk && alloc_col(p, &d.acc, cap * GS_K1MAX * 2);
-  okk = okk && alloc_col(p, &d.change_tick, cap);
-  okk = okk && alloc_col(p, &d.ltime_member, cap) && alloc_col(p, &d.ltime_event, cap);
-  okk = okk && alloc_col(p, &d.event_min, cap);
-  okk = okk && alloc_col(p, &d.heard, cap) && alloc_col(p, &d.queued, cap);
-  okk = okk && alloc_col(p, &d.tx, cap * GS_MAX_RUMORS);
-  okk = okk && alloc_col(p, &d.stats, (size_t)GSIM_STAT_COUNT);
-  okk = okk && alloc_col(p, &d.heard_cnt, (size_t)32) && alloc_col(p, &d.conv_tick, (size_t)32);
-  okk = okk && alloc_col(p, &d.view_cnt, (size_t)4);
-  okk = okk && alloc_col(p, &d.crashed_alive, (size_t)1) && alloc_col(p, &d.crashed_dead_tick, (size_t)1);
+  okk = okk && acol(&d.key[0], 1) && acol(&d.key[1], 1);
+  okk = okk && acol(&d.inbox[0], 1) && acol(&d.inbox[1], 1);
+  okk = okk && acol(&d.due, 1) && acol(&d.meta, 1);
+  okk = okk && acol(&d.cursor, 1) && acol(&d.pass, 1);
+  okk = okk && acol(&d.probe_tgt, 1) && acol(&d.probe_inc, 1);
+  okk = okk && acol(&d.sus_start, 1) && acol(&d.sus_from, GS_K1MAX);
+  okk = okk && acol(&d.acc, GS_K1MAX * 2);
+  okk = okk && acol(&d.change_tick, 1);
+  okk = okk && acol(&d.ltime_member, 1) && acol(&d.ltime_event, 1);
+  okk = okk && acol(&d.event_min, 1);
+  okk = okk && acol(&d.heard, 1) && acol(&d.queued, 1);
+  okk = okk && acol(&d.tx, GS_MAX_RUMORS);
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
-  okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
-  okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
-  okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
+  if (!sharded) {
+    okk = okk && alloc_col(p, &d.stats, (size_t)GSIM_STAT_COUNT);
+    okk = okk && alloc_col(p, &d.heard_cnt, (size_t)32) && alloc_col(p, &d.conv_tick, (size_t)32);
+    okk = okk && alloc_col(p, &d.view_cnt, (size_t)4);
+    okk = okk && alloc_col(p, &d.crashed_alive, (size_t)1) && alloc_col(p, &d.crashed_dead_tick, (size_t)1);
+    okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
+    okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
+    okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
+  } else if (okk) {
+    // pool-wide words: one 2 MB page per rank; counters and the event log live in rank 0's
+    p->pages = reinterpret_cast<uint8_t*>(be->shard_alloc(GS_PAGE_BYTES, 1));
+    okk = p->pages != nullptr && be->shard_commit(&p->shard_fd);
+    if (okk) {
+      uint8_t* page0 = p->pages;
+      uint8_t* mine = p->pages + (size_t)p->rank * GS_PAGE_BYTES;
+      d.stats = reinterpret_cast<unsigned long long*>(page0 + GS_PG_STATS);
+      d.heard_cnt = reinterpret_cast<uint32_t*>(page0 + GS_PG_HEARD_CNT);
+      d.conv_tick = reinterpret_cast<uint32_t*>(page0 + GS_PG_CONV_TICK);
+      d.view_cnt = reinterpret_cast<uint32_t*>(page0 + GS_PG_VIEW_CNT);
+      d.crashed_alive = reinterpret_cast<uint32_t*>(page0 + GS_PG_CRASHED_ALIVE);
+      d.crashed_dead_tick = reinterpret_cast<uint32_t*>(page0 + GS_PG_CRASHED_DEAD_TICK);
+      d.evlog_cursor = reinterpret_cast<uint32_t*>(page0 + GS_PG_EVLOG_CURSOR);
+      d.evlog = reinterpret_cast<GsEventRec*>(page0 + GS_PG_EVLOG);
+      const uint32_t room = (GS_PAGE_BYTES - GS_PG_EVLOG) / (uint32_t)sizeof(GsEventRec);
+      if (evcap > room) evcap = room;
+      d.tick_base = reinterpret_cast<uint32_t*>(mine + GS_PG_TICK_BASE);
+      p->g_dev = reinterpret_cast<GsGlobals*>(mine + GS_PG_GLOBALS);
+      for (uint32_t r = 0; r < GS_MAX_WORLD; ++r)
+        p->xb.flags[r] = reinterpret_cast<uint32_t*>(p->pages + (size_t)(r < p->world ? r : 0) * GS_PAGE_BYTES + GS_PG_XBAR_FLAGS);
+      p->xb.epoch = reinterpret_cast<uint32_t*>(mine + GS_PG_XBAR_EPOCH);
+      p->xb.rank = p->rank;
+      p->xb.world = p->world;
+      // peers write barrier flags into this page as soon as they have mapped it: zero it now
+      okk = be->fill8(mine, 0, GS_PAGE_BYTES) && be->sync();
+    }
+  }
   if (!okk) {
     g_create_err = be->last_error();
+    fprintf(stderr, "libgsim: allocation failed: %s\n", be->last_error());
     gsim_pool_destroy(p);
     return GSIM_ERR_NOMEM;
   }
-  // key = 0 means truth NONE for rows that were never created
-  okk = okk && be->fill32(d.key[0], 0, cap) && be->fill32(d.key[1], 0, cap);
-  okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
-  okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
-  okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
-  okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
-  okk = okk && be->fill32(d.heard_cnt, 0, 32) && be->fill32(d.conv_tick, GS_EMPTY32, 32);
-  okk = okk && be->fill32(d.view_cnt, 0, 4) && be->fill32(d.crashed_alive, 0, 1);
-  okk = okk && be->fill32(d.crashed_dead_tick, GS_EMPTY32, 1);
-  okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
 
   g.n = cfg->n_initial;
   p->n_established = cfg->n_initial;
@@ -383,16 +539,43 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     g.rot_p = rot % g.P;
     g.rot_g = (rot >> 16) % g.GI;
   }
+  g.rows_per_rank = (uint32_t)p->rows_per_rank;
   recompute_tables(p);
-  okk = okk && upload_globals(p);
-  okk = okk && be->init_rows(d, p->g_dev, g, 0, cfg->n_initial, 0);
-  if (!okk) {
+  if (!sharded && init_device_state(p) != GSIM_OK) {  // sharded pools: gsim_shard_ready
     g_create_err = be->last_error();
     fprintf(stderr, "libgsim: pool init failed: %s\n", be->last_error());
     gsim_pool_destroy(p);
     return GSIM_ERR_CUDA;
   }
   *out = p;
+  return GSIM_OK;
+}
+
+// ---- sharded pools: wiring the ranks together ------------------------------------------------------
+extern "C" int gsim_shard_export_fd(gsim_pool* p, int* fd_out) {
+  if (!p || !fd_out || !p->sharded) return GSIM_ERR_INVALID;
+  *fd_out = p->shard_fd;
+  return GSIM_OK;
+}
+
+extern "C" int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, int fd) {
+  if (!p || !p->sharded || p->ready) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!p->be->shard_attach(peer_rank, fd)) return fail(p, GSIM_ERR_CUDA, "shard_attach");
+  p->attached += 1;
+  return GSIM_OK;
+}
+
+extern "C" int gsim_shard_ready(gsim_pool* p) {
+  if (!p) return GSIM_ERR_INVALID;
+  if (!p->sharded) return GSIM_OK;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->ready) return GSIM_OK;
+  if (p->attached != p->world) return fail(p, GSIM_ERR_STATE, "not every peer rank has been attached");
+  if (!p->be->xbar_host(p->xb)) return fail(p, GSIM_ERR_CUDA, "barrier");  // every page is mapped and zeroed
+  int rc = controller_call(p, nullptr, 0, [&]() -> int { return init_device_state(p); });
+  if (rc) return fail(p, rc, "init");
+  p->ready = true;
   return GSIM_OK;
 }
 
@@ -555,6 +738,7 @@ static void log_host_event(gsim_pool* p, uint32_t type, uint32_t subject, uint32
 extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint32_t* id_out) {
   if (!p || !id_out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, id_out, sizeof(uint32_t), [&]() -> int {
   GsGlobals& g = p->g;
   if (g.n >= p->cfg.capacity) return fail(p, GSIM_ERR_CAPACITY, "member capacity exhausted");
   uint32_t slot;
@@ -581,6 +765,7 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   if (rc) return fail(p, rc, "start_rumor");
   *id_out = id;
   return GSIM_OK;
+  });
 }
 
 // One direction of a join push-pull: `dst` merges what `src` knows
@@ -643,6 +828,9 @@ extern "C" int gsim_join(gsim_pool* p, uint32_t id, const uint32_t* seeds, size_
                          int ignore_old, int* n_ok) {
   if (!p || (!seeds && n_seeds)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  int n_ok_local = 0;
+  if (!n_ok) n_ok = &n_ok_local;
+  return controller_call(p, n_ok, sizeof(int), [&]() -> int {
   GsGlobals& g = p->g;
   if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
   uint32_t kid;
@@ -683,6 +871,7 @@ extern "C" int gsim_join(gsim_pool* p, uint32_t id, const uint32_t* seeds, size_
   }
   if (n_ok) *n_ok = okc;
   return GSIM_OK;
+  });
 }
 
 static int set_truth(gsim_pool* p, uint32_t id, uint32_t truth) {
@@ -721,6 +910,7 @@ static int refresh_after_truth_change(gsim_pool* p) {
 extern "C" int gsim_crash_many(gsim_pool* p, const uint32_t* ids, size_t n) {
   if (!p || (!ids && n)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
   for (size_t x = 0; x < n; ++x) {
     if (ids[x] >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
     uint32_t k;
@@ -731,6 +921,7 @@ extern "C" int gsim_crash_many(gsim_pool* p, const uint32_t* ids, size_t n) {
   }
   int rc = refresh_after_truth_change(p);
   return rc ? fail(p, rc, "recount") : GSIM_OK;
+  });
 }
 
 extern "C" int gsim_crash(gsim_pool* p, uint32_t id) { return gsim_crash_many(p, &id, 1); }
@@ -738,6 +929,9 @@ extern "C" int gsim_crash(gsim_pool* p, uint32_t id) { return gsim_crash_many(p,
 extern "C" int gsim_crash_fraction(gsim_pool* p, uint32_t ppm, uint32_t salt, uint32_t* n_crashed) {
   if (!p || ppm > 1000000u) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t n_crashed_local = 0;
+  if (!n_crashed) n_crashed = &n_crashed_local;
+  return controller_call(p, n_crashed, sizeof(uint32_t), [&]() -> int {
   uint32_t thr = ppm >= 1000000u ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)ppm << 32) / 1000000ull);
   uint32_t cnt = 0;
   if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
@@ -746,11 +940,13 @@ extern "C" int gsim_crash_fraction(gsim_pool* p, uint32_t ppm, uint32_t salt, ui
   if (n_crashed) *n_crashed = cnt;
   int rc = refresh_after_truth_change(p);
   return rc ? fail(p, rc, "recount") : GSIM_OK;
+  });
 }
 
 extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
   if (!p) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
   GsGlobals& g = p->g;
   if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
   uint32_t k, m;
@@ -791,11 +987,13 @@ extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
   p->sched.push_back(s);
   p->counts_stale = true;
   return GSIM_OK;
+  });
 }
 
 extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int prune) {
   if (!p) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
   if (via >= p->g.n || target >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
   // [U] serf.RemoveFailedNode: a forged leave intent turns Failed into Left
   uint32_t any_truth = 0;
@@ -813,6 +1011,7 @@ extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int
   (void)any_truth;
   int rc = refresh_after_truth_change(p);
   return rc ? fail(p, rc, "recount") : GSIM_OK;
+  });
 }
 
 static uint32_t msgpack_str_size(size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 256 ? 2 + n : 3 + n); }
@@ -825,6 +1024,9 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
                                uint32_t* slot_out) {
   if (!p || (!name && name_len) || (!payload && payload_len)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t slot_local = 0;
+  if (!slot_out) slot_out = &slot_local;
+  return controller_call(p, slot_out, sizeof(uint32_t), [&]() -> int {
   GsGlobals& g = p->g;
   if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
   // [U] serf.UserEvent: size limit on name+payload (agent side: user_event.go:82-113)
@@ -861,6 +1063,7 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
   if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_USER, slot, id, le);
   if (slot_out) *slot_out = slot;
   return GSIM_OK;
+  });
 }
 
 // ---- time -----------------------------------------------------------------------
@@ -886,29 +1089,38 @@ static int apply_sched(gsim_pool* p) {
   return GSIM_OK;
 }
 
+// Advance `ticks` ticks.  On a sharded pool every rank runs this together: the host-side parts
+// (scheduled shutdowns, globals upload, rumor retirement) are controller calls, the tick kernels
+// run on every rank with a device barrier after each tick.
 static int step_locked(gsim_pool* p, uint32_t ticks) {
+  if (!p->ready) return GSIM_ERR_STATE;
   p->last_ms = 0;
   p->last_launches = 0;
   uint32_t left = ticks;
   const bool use_graph = !(p->cfg.flags & GSIM_FLAG_NO_GRAPH);
   while (left) {
-    int rc = apply_sched(p);
+    int rc = controller_call(p, nullptr, 0, [&]() -> int {
+      int r = apply_sched(p);
+      if (r) return r;
+      return upload_globals(p) ? GSIM_OK : GSIM_ERR_CUDA;
+    });
     if (rc) return rc;
     uint32_t chunk = left;
     for (const Sched& s : p->sched)
       if (s.tick > p->now && s.tick - p->now < chunk) chunk = s.tick - p->now;
-    if (!upload_globals(p)) return GSIM_ERR_CUDA;
     if (!p->be->run_ticks(p->d, p->g_dev, p->g, p->now, chunk, use_graph, &p->last_ms,
-                          &p->last_launches))
+                          &p->last_launches, p->sharded ? &p->xb : nullptr))
       return GSIM_ERR_CUDA;
     p->now += chunk;
     p->node_ticks += (uint64_t)chunk * p->g.n;
     left -= chunk;
     p->counts_stale = true;
   }
-  int rc = apply_sched(p);
-  if (rc) return rc;
-  return auto_retire(p);
+  return controller_call(p, nullptr, 0, [&]() -> int {
+    int r = apply_sched(p);
+    if (r) return r;
+    return auto_retire(p);
+  });
 }
 
 extern "C" int gsim_step(gsim_pool* p, uint32_t ticks) {
@@ -1009,6 +1221,7 @@ static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, siz
 extern "C" int gsim_members(gsim_pool* p, uint32_t observer, gsim_member* out, size_t cap, size_t* n) {
   if (!p) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   int rc = members_locked(p, observer, out, cap, n);
   return rc ? fail(p, rc, "members") : GSIM_OK;
 }
@@ -1016,15 +1229,18 @@ extern "C" int gsim_members(gsim_pool* p, uint32_t observer, gsim_member* out, s
 extern "C" int gsim_num_nodes(gsim_pool* p, uint32_t observer, uint32_t* n) {
   if (!p || !n) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, n, sizeof(uint32_t), [&]() -> int {
   size_t cnt = 0;
   int rc = members_locked(p, observer, nullptr, 0, &cnt);
   *n = (uint32_t)cnt;
   return rc ? fail(p, rc, "num_nodes") : GSIM_OK;
+  });
 }
 
 extern "C" int gsim_poll_events(gsim_pool* p, gsim_event* out, size_t cap, size_t* n) {
   if (!p || !n || (!out && cap)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   uint32_t cur[2];
   if (!p->be->d2h(cur, p->d.evlog_cursor, 8)) return fail(p, GSIM_ERR_CUDA, "d2h");
   uint32_t have = cur[0] < p->g.evlog_cap ? cur[0] : p->g.evlog_cap;
@@ -1061,6 +1277,7 @@ extern "C" int gsim_poll_events(gsim_pool* p, gsim_event* out, size_t cap, size_
 extern "C" int gsim_rumor_info_get(gsim_pool* p, uint32_t slot, gsim_rumor_info* out) {
   if (!p || !out || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, out, sizeof(gsim_rumor_info), [&]() -> int {
   const GsGlobals& g = p->g;
   if (!((g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
   if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
@@ -1076,11 +1293,13 @@ extern "C" int gsim_rumor_info_get(gsim_pool* p, uint32_t slot, gsim_rumor_info*
   out->queued_count = p->rc.queued_cnt[slot];
   if (!peek(p, p->d.conv_tick, slot, &out->converged_tick)) return fail(p, GSIM_ERR_CUDA, "peek");
   return GSIM_OK;
+  });
 }
 
 extern "C" int gsim_rumor_retire(gsim_pool* p, uint32_t slot) {
   if (!p || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
   if (!((p->g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
   if (p->g.rumors[slot].kind == GSIM_RUMOR_ALIVE) {
     if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
@@ -1089,6 +1308,7 @@ extern "C" int gsim_rumor_retire(gsim_pool* p, uint32_t slot) {
   }
   int rc = retire_slot(p, slot);
   return rc ? fail(p, rc, "retire") : GSIM_OK;
+  });
 }
 
 extern "C" int gsim_user_event_get(gsim_pool* p, uint32_t slot, void* name, size_t name_cap,
@@ -1096,6 +1316,7 @@ extern "C" int gsim_user_event_get(gsim_pool* p, uint32_t slot, void* name, size
                                    size_t* payload_len) {
   if (!p || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   if (!((p->g.active_mask >> slot) & 1u) || p->g.rumors[slot].kind != GSIM_RUMOR_USER_EVENT)
     return fail(p, GSIM_ERR_NOT_FOUND, "not a user event slot");
   const RumorHost& rh = p->rh[slot];
@@ -1109,6 +1330,7 @@ extern "C" int gsim_user_event_get(gsim_pool* p, uint32_t slot, void* name, size
 extern "C" int gsim_stats_get(gsim_pool* p, gsim_stats* out) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, out, sizeof(gsim_stats), [&]() -> int {
   memset(out, 0, sizeof(*out));
   if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
   if (!p->be->d2h(out->counters, p->d.stats, sizeof(out->counters))) return fail(p, GSIM_ERR_CUDA, "d2h");
@@ -1133,11 +1355,13 @@ extern "C" int gsim_stats_get(gsim_pool* p, gsim_stats* out) {
   p->be->d2h(cur, p->d.evlog_cursor, 8);
   out->events_dropped = p->events_dropped + cur[1];
   return GSIM_OK;
+  });
 }
 
 extern "C" int gsim_state_hash(gsim_pool* p, uint64_t out[4]) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, out, 4 * sizeof(uint64_t), [&]() -> int {
   if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
   if (!p->be->state_hash(p->d, p->g_dev, p->g, p->now, out)) return fail(p, GSIM_ERR_CUDA, "hash");
   // pool-wide scalars
@@ -1155,11 +1379,13 @@ extern "C" int gsim_state_hash(gsim_pool* p, uint64_t out[4]) {
   gs_hash_lanes(h, lanes);
   for (int q = 0; q < 4; ++q) out[q] += lanes[q];
   return GSIM_OK;
+  });
 }
 
 extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_bytes, size_t* n_bytes) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   const GsDev& d = p->d;
   const size_t cap = p->g.cap;
   const void* src = nullptr;
@@ -1247,6 +1473,7 @@ static size_t snap_size(gsim_pool* p) {
 extern "C" int gsim_snapshot_size(gsim_pool* p, size_t* n_bytes) {
   if (!p || !n_bytes) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   *n_bytes = snap_size(p);
   return GSIM_OK;
 }
@@ -1254,6 +1481,7 @@ extern "C" int gsim_snapshot_size(gsim_pool* p, size_t* n_bytes) {
 extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* n_bytes) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
   size_t need = snap_size(p);
   if (n_bytes) *n_bytes = need;
   if (cap_bytes < need) return fail(p, GSIM_ERR_INVALID, "buffer too small");
@@ -1292,6 +1520,7 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
 extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   if (!p || !blob || n_bytes < sizeof(SnapHeader)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
   const uint8_t* r = reinterpret_cast<const uint8_t*>(blob);
   const uint8_t* end = r + n_bytes;
   SnapHeader h;
@@ -1330,6 +1559,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   uint32_t zero2[2] = {0, 0};
   if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
   return GSIM_OK;
+  });
 }
 
 // ---- measurement hooks ------------------------------------------------------------

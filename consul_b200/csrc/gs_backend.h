@@ -34,7 +34,15 @@ class GsBackend {
   // advance `nticks` ticks starting at tick t0 (tick_base on the device == t0 on entry and
   // t0+nticks on exit).  kernel_ms accumulates CUDA-event time of the tick launches.
   virtual bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0,
-                         uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches) = 0;
+                         uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches,
+                         const GsXbar* xbar = nullptr) = 0;
+  // ---- sharded (multi-GPU) pools, see gs_vmm.h; unsupported by default ------------------------
+  virtual bool shard_begin(uint32_t, uint32_t) { return false; }
+  virtual size_t shard_granularity() { return 0; }
+  virtual void* shard_alloc(size_t /*slice_bytes*/, size_t /*planes*/) { return nullptr; }
+  virtual bool shard_commit(int* /*fd_out*/) { return false; }
+  virtual bool shard_attach(uint32_t /*peer*/, int /*fd*/) { return false; }
+  virtual bool xbar_host(const GsXbar&) { return false; }  // arrive, wait for every rank, sync
   virtual bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g,
                               uint32_t thr, uint32_t salt, uint32_t now, uint32_t* n_crashed) = 0;
   virtual bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,

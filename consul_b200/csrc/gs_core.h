@@ -228,7 +228,7 @@ struct GsGlobals {
   uint32_t phase_gate;   // 1: phases are uniform per tile, whole tiles can skip the `due` column
   uint32_t phase_shift;  // phase_group == GS_TILE << phase_shift when phase_gate
   uint32_t rot_p, rot_g; // seed-derived rotation of the probe / gossip phases
-  uint32_t pad1;
+  uint32_t rows_per_rank; // sharded pools: rank r owns members [r*rows_per_rank, (r+1)*rows_per_rank)
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -274,4 +274,35 @@ struct GsRowOut {
   uint32_t st[GS_NSTAT];
   uint32_t new_heard;     // rumor bits accepted by this row in this tick
   int32_t crashed_alive;  // delta of the "crashed but not yet dead" count
+};
+
+// ---- multi-GPU (sharded) pools: DESIGN.md §7, gs_vmm.h ---------------------------------------
+// Every rank has one 2 MB "page" of pool-wide words in its own HBM, mapped by all ranks.
+// Counters and the event log live in rank 0's page (the other ranks update them with
+// remote atomics over NVLink); tick_base, the device copy of GsGlobals and the barrier flags
+// are per rank.
+#define GS_PAGE_BYTES (2u << 20)
+#define GS_PG_STATS 0u
+#define GS_PG_HEARD_CNT 256u
+#define GS_PG_CONV_TICK 512u
+#define GS_PG_VIEW_CNT 768u
+#define GS_PG_CRASHED_ALIVE 800u
+#define GS_PG_CRASHED_DEAD_TICK 804u
+#define GS_PG_EVLOG_CURSOR 808u
+#define GS_PG_TICK_BASE 816u
+#define GS_PG_XBAR_EPOCH 820u
+#define GS_PG_XBAR_FLAGS 832u
+#define GS_PG_GLOBALS 1024u
+#define GS_PG_SCRATCH 8192u
+#define GS_PG_BLOB 16384u      // 2 slots of GS_BLOB_BYTES
+#define GS_BLOB_BYTES 32768u
+#define GS_PG_EVLOG 131072u
+#define GS_MAX_WORLD 8
+
+// Cross-GPU barrier between ticks: rank r stores its epoch into slot r of every rank's flag
+// array (st.release.sys over NVLink) and spins on its own array until all slots caught up.
+struct GsXbar {
+  uint32_t* flags[GS_MAX_WORLD];  // flags[r] = rank r's array of GS_MAX_WORLD words
+  uint32_t* epoch;                // this rank's last completed epoch
+  uint32_t rank, world;
 };

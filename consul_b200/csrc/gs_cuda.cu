@@ -21,6 +21,7 @@
 
 #include "gs_aux.h"
 #include "gs_backend.h"
+#include "gs_vmm.h"
 
 #define GS_BLOCK 256
 #define GS_GRAPH_TICKS 64
@@ -105,12 +106,18 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   const uint32_t cur = t & 1u, P = g.P, pslot = t % P, gslot = t % g.GI;
   const uint32_t pslot_t = (t + P - g.T % P) % P;
   const uint32_t lane = tid & 31u, wib = tid >> 5;
-  const uint32_t n_tiles = (g.n + GS_TILE - 1u) / GS_TILE;
+  // this rank's tiles: everything on one GPU, a contiguous range of members when sharded
+  uint32_t tile_lo = 0, tile_hi = (g.n + GS_TILE - 1u) / GS_TILE;
+  if (g.world > 1u) {
+    const uint32_t per = g.rows_per_rank / GS_TILE;
+    tile_lo = g.rank * per < tile_hi ? g.rank * per : tile_hi;
+    tile_hi = tile_lo + per < tile_hi ? tile_lo + per : tile_hi;
+  }
   const uint32_t n_warps = gridDim.x * GS_WARPS;
-  const uint32_t chunk = (n_tiles + n_warps - 1u) / n_warps;
+  const uint32_t chunk = (tile_hi - tile_lo + n_warps - 1u) / n_warps;
   const uint32_t wid = blockIdx.x * GS_WARPS + wib;
-  const uint32_t t_begin = wid * chunk < n_tiles ? wid * chunk : n_tiles;
-  const uint32_t t_end = t_begin + chunk < n_tiles ? t_begin + chunk : n_tiles;
+  const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
+  const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
   const uint32_t* __restrict__ inbox_cur = d.inbox[cur];
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
@@ -206,6 +213,27 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 }
 
 __global__ void gs_advance_kernel(uint32_t* tick_base, uint32_t k) { *tick_base += k; }
+
+// Cross-GPU barrier (sharded pools).  One warp: lane r publishes this rank's new epoch into
+// slot `rank` of rank r's flag array (release, system scope, over NVLink) and then spins on
+// slot r of its own array until rank r has published the same epoch.  Everything the preceding
+// tick kernel wrote — including remote atomics into peers' mailboxes — happens-before the
+// release, so a rank that leaves the barrier sees every delivery addressed to it.
+__global__ void gs_xbar_kernel(GsXbar xb) {
+  const uint32_t lane = threadIdx.x;
+  const uint32_t e = *xb.epoch + 1u;
+  __threadfence_system();
+  if (lane < xb.world) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xb.flags[lane] + xb.rank), "r"(e) : "memory");
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(xb.flags[xb.rank] + lane) : "memory");
+    } while ((int32_t)(v - e) < 0);
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (lane == 0) *xb.epoch = e;
+}
 
 __global__ void __launch_bounds__(GS_BLOCK)
     gs_init_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t first, uint32_t count,
@@ -313,6 +341,7 @@ class CudaBackend : public GsBackend {
   ~CudaBackend() override {
     cudaSetDevice(dev_);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    if (sharded_) vmm_.destroy();
     if (scratch_) cudaFree(scratch_);
     cudaEventDestroy(ev0_);
     cudaEventDestroy(ev1_);
@@ -327,7 +356,7 @@ class CudaBackend : public GsBackend {
   }
   void release(void* p) override {
     cudaSetDevice(dev_);
-    if (p) cudaFree(p);
+    if (p && !sharded_) cudaFree(p);
   }
   bool h2d(void* dst, const void* src, size_t bytes) override {
     cudaSetDevice(dev_);
@@ -359,7 +388,8 @@ class CudaBackend : public GsBackend {
     return ok(cudaGetLastError(), "init launch") && ok(cudaStreamSynchronize(stream_), "init");
   }
   bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0,
-                 uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches) override {
+                 uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches,
+                 const GsXbar* xbar) override {
     (void)t0;
     if (!nticks || !g.n) {
       if (nticks) {  // no members: just advance time
@@ -371,14 +401,15 @@ class CudaBackend : public GsBackend {
     }
     cudaSetDevice(dev_);
     // persistent launch: one warp per 128-member tile up to a full machine (SMs x resident CTAs)
-    const uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
+    uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
+    if (g.world > 1 && tiles > g.rows_per_rank / GS_TILE) tiles = g.rows_per_rank / GS_TILE;
     const uint32_t warps_per_block = GS_BLOCK / 32;
     uint32_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
     if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
     if (use_graph && left >= GS_GRAPH_TICKS) {
-      cudaGraphExec_t ge = graph_for(d, g_dev, blocks);
+      cudaGraphExec_t ge = graph_for(d, g_dev, blocks, xbar);
       if (!ge) return false;
       while (left >= GS_GRAPH_TICKS) {
         if (!ok(cudaGraphLaunch(ge, stream_), "graph launch")) return false;
@@ -387,8 +418,10 @@ class CudaBackend : public GsBackend {
       }
     }
     if (left) {
-      for (uint32_t k = 0; k < left; ++k)
-        if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_), "tick launch")) return false;
+      for (uint32_t k = 0; k < left; ++k) {
+        if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_ && !xbar), "tick launch")) return false;
+        if (xbar) gs_xbar_kernel<<<1, 32, 0, stream_>>>(*xbar);
+      }
       gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
       launches_ += left + 1;
       if (!ok(cudaGetLastError(), "tick launch")) return false;
@@ -436,6 +469,41 @@ class CudaBackend : public GsBackend {
     }
     return ok(cudaGetLastError(), "hash launch") && d2h(out, dh, 32);
   }
+  // ---- sharded pools -----------------------------------------------------------------------
+  bool shard_begin(uint32_t world, uint32_t rank) override {
+    cudaSetDevice(dev_);
+    cudaFree(0);  // make sure the primary context exists before driver-API calls
+    sharded_ = vmm_.init(dev_, world, rank, err_, sizeof(err_));
+    return sharded_;
+  }
+  size_t shard_granularity() override { return vmm_.granularity(); }
+  void* shard_alloc(size_t slice_bytes, size_t planes) override {
+    void* q = vmm_.reserve(slice_bytes, planes);
+    if (!q) snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
+    return q;
+  }
+  bool shard_commit(int* fd_out) override {
+    if (!vmm_.commit()) {
+      snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
+      return false;
+    }
+    *fd_out = vmm_.export_fd();
+    return true;
+  }
+  bool shard_attach(uint32_t peer, int fd) override {
+    cudaSetDevice(dev_);
+    if (!vmm_.attach(peer, fd)) {
+      snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
+      return false;
+    }
+    return true;
+  }
+  bool xbar_host(const GsXbar& xb) override {
+    cudaSetDevice(dev_);
+    gs_xbar_kernel<<<1, 32, 0, stream_>>>(xb);
+    ++launches_;
+    return ok(cudaGetLastError(), "xbar launch") && ok(cudaStreamSynchronize(stream_), "xbar");
+  }
   bool sync() override {
     cudaSetDevice(dev_);
     return ok(cudaStreamSynchronize(stream_), "sync");
@@ -456,7 +524,7 @@ class CudaBackend : public GsBackend {
     }
     return cudaStreamSynchronize(stream_);
   }
-  cudaGraphExec_t graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks) {
+  cudaGraphExec_t graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks, const GsXbar* xbar) {
     auto it = graphs_.find(blocks);
     if (it != graphs_.end()) return it->second;
     cudaGraph_t graph = nullptr;
@@ -464,12 +532,13 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture"))
       return nullptr;
     for (uint32_t k = 0; k < GS_GRAPH_TICKS; ++k)
-      if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_), "tick capture")) {
+      if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_ && !xbar), "tick capture")) {
         cudaGraph_t dead = nullptr;
         cudaStreamEndCapture(stream_, &dead);
         if (dead) cudaGraphDestroy(dead);
         return nullptr;
       }
+      if (xbar) gs_xbar_kernel<<<1, 32, 0, stream_>>>(*xbar);
     gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
@@ -490,6 +559,8 @@ class CudaBackend : public GsBackend {
   cudaEvent_t ev0_, ev1_;
   void* scratch_;
   uint32_t full_grid_ = 592;
+  GsVmm vmm_;
+  bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   uint64_t launches_ = 0;

@@ -310,6 +310,17 @@ int gsim_snapshot_size(gsim_pool* p, size_t* n_bytes);
 int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* n_bytes);
 int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes);
 
+/* ---- sharded pools: one process per GPU, cfg.world_size > 1 ----
+ * Every rank creates the pool with the same config except `rank`/`device`, exchanges the file
+ * descriptor of its physical shard with every other rank (SCM_RIGHTS or pidfd_getfd), attaches
+ * the peers' descriptors and calls gsim_shard_ready.  After that EVERY rank must issue the same
+ * API calls in the same order: rank 0 executes the host-side operation, the others adopt its
+ * result; gsim_step runs the tick kernels on all ranks with a device barrier per tick.  Bulk
+ * observation (members, column_read, poll_events, snapshot, user_event_get) is served by rank 0. */
+int gsim_shard_export_fd(gsim_pool* p, int* fd_out);
+int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, int fd);
+int gsim_shard_ready(gsim_pool* p);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------- */
 /* Device time of the tick kernels of the last gsim_step, measured with CUDA events
  * on the launching stream: total ms and number of tick launches. */

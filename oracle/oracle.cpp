@@ -207,6 +207,7 @@ struct Oracle {
   std::vector<uint32_t> pub_change_tick; // published change ticks
   std::vector<uint32_t> inbox[2];        // rumor bits by arrival-tick parity (bit 31: accused)
   std::vector<uint32_t> wake;            // 0 = look every tick, else the only tick worth a look
+  std::vector<Tally> tallies;            // per-thread accumulators, reused every tick
   std::vector<Accusation> arriving;      // accusations that arrive at the tick about to run
   Rumor rumor[GSIM_MAX_RUMORS];
   uint32_t active = 0;
@@ -297,10 +298,25 @@ bool knows(const Oracle& o, uint32_t i, const Member& me, uint32_t c) {
   return slot >= 0 && ((me.heard >> slot) & 1);
 }
 
+// up to 8 member ids without touching the heap (kRandomNodes never returns more)
+struct Picks {
+  uint32_t v[8];
+  uint32_t n = 0;
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  uint32_t operator[](size_t q) const { return v[q]; }
+  bool has(uint32_t c) const {
+    for (uint32_t q = 0; q < n; ++q)
+      if (v[q] == c) return true;
+    return false;
+  }
+  void push_back(uint32_t c) { v[n++] = c; }
+};
+
 // [U] memberlist/util.go kRandomNodes
-std::vector<uint32_t> k_random(const Oracle& o, uint32_t i, const Member& me, uint32_t t, uint32_t purpose,
+Picks k_random(const Oracle& o, uint32_t i, const Member& me, uint32_t t, uint32_t purpose,
                                uint32_t k, bool relays, uint32_t also_exclude) {
-  std::vector<uint32_t> out;
+  Picks out;
   const uint32_t n = (uint32_t)o.m.size();
   uint64_t tries = std::min<uint64_t>(3ull * n, KRANDOM_MAX_TRIES);
   Rand4 block = {{0, 0, 0, 0}};
@@ -318,7 +334,7 @@ std::vector<uint32_t> k_random(const Oracle& o, uint32_t i, const Member& me, ui
       if (vc.rank == GSIM_RANK_DEAD && t - o.pub_change_tick[c] > o.gtd) continue;
     }
     if (!knows(o, i, me, c)) continue;
-    if (std::find(out.begin(), out.end(), c) != out.end()) continue;
+    if (out.has(c)) continue;
     out.push_back(c);
   }
   return out;
@@ -329,14 +345,13 @@ uint32_t pick_packet(const Oracle& o, const Member& me) {
   struct Item {
     uint32_t cls, tx, size, slot;
   };
-  std::vector<Item> items;
   uint32_t total = 0;
   for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
-    if ((me.queued >> r) & 1) {
-      items.push_back({o.rumor[r].qclass, me.tx[r], o.rumor[r].size, r});
-      total += o.rumor[r].size + (o.rumor[r].qclass ? 3 : 2);
-    }
-  if (total <= o.udp_avail) return me.queued;
+    if ((me.queued >> r) & 1) total += o.rumor[r].size + (o.rumor[r].qclass ? 3 : 2);
+  if (total <= o.udp_avail) return me.queued;  // everything fits in one packet
+  std::vector<Item> items;
+  for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
+    if ((me.queued >> r) & 1) items.push_back({o.rumor[r].qclass, me.tx[r], o.rumor[r].size, r});
   std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
     if (a.cls != b.cls) return a.cls < b.cls;      // memberlist, then intents, then events
     if (a.tx != b.tx) return a.tx < b.tx;          // fewest transmits first
@@ -473,7 +488,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     if (me.stage == ST_WAIT_TIMEOUT && me.due == t) {
       const uint32_t j = me.probe_target;
       const bool target_up = o.pub[j].truth == GSIM_TRUTH_UP;
-      std::vector<uint32_t> relays = k_random(o, i, me, t, PUR_RELAY, std::min<uint32_t>(8, o.cfg.indirect_checks), true, j);
+      Picks relays = k_random(o, i, me, t, PUR_RELAY, std::min<uint32_t>(8, o.cfg.indirect_checks), true, j);
       bool success = false;
       uint32_t nacks = 0;
       for (uint32_t q = 0; q < relays.size(); ++q) {
@@ -554,7 +569,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
 
     // -- dissemination ([U] memberlist.gossip) --------------------------------------------------
     if (my_gossip_tick && me.queued) {
-      std::vector<uint32_t> peers = k_random(o, i, me, t, PUR_GOSSIP, std::min<uint32_t>(8, o.cfg.gossip_nodes), false, NONE32);
+      Picks peers = k_random(o, i, me, t, PUR_GOSSIP, std::min<uint32_t>(8, o.cfg.gossip_nodes), false, NONE32);
       for (uint32_t q = 0; q < peers.size() && me.queued; ++q) {
         uint32_t packet = pick_packet(o, me);
         if (!packet) break;
@@ -592,7 +607,9 @@ void run_tick(Oracle& o) {
   // (this is exactly the idle test at the top of member_tick, evaluated from two flat arrays).
   const uint32_t* mail = o.inbox[t & 1].data();
   uint32_t* wake = o.wake.data();
-  std::vector<Tally> tallies((size_t)o.threads);
+  std::vector<Tally>& tallies = o.tallies;
+  tallies.resize((size_t)o.threads);
+  for (Tally& ta : tallies) ta.clear();
 #ifdef _OPENMP
 #pragma omp parallel num_threads(o.threads)
   {

@@ -82,7 +82,7 @@ class HostEmuBackend : public GsBackend {
     return x;
   }
   bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0,
-                 uint32_t nticks, bool, double*, uint64_t* launches) override {
+                 uint32_t nticks, bool, double*, uint64_t* launches, const GsXbar*) override {
     const GsGlobals& g = *g_dev;  // the kernels read the device copy
     for (uint32_t k = 0; k < nticks; ++k) {
       const uint32_t t = *d.tick_base + k;
