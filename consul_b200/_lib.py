@@ -127,8 +127,8 @@ SIGNATURES = [
     ("gsim_snapshot_size", _i32, [_P, C.POINTER(_sz)]),
     ("gsim_snapshot", _i32, [_P, _P, _sz, C.POINTER(_sz)]),
     ("gsim_restore", _i32, [_P, _P, _sz]),
-    ("gsim_shard_export_fd", _i32, [_P, C.POINTER(_i32)]),
-    ("gsim_shard_attach", _i32, [_P, _u32, _i32]),
+    ("gsim_shard_export_fds", _i32, [_P, C.POINTER(_i32), _sz, C.POINTER(_sz)]),
+    ("gsim_shard_attach", _i32, [_P, _u32, C.POINTER(_i32), _sz]),
     ("gsim_shard_ready", _i32, [_P]),
     ("gsim_last_step_timing", _i32, [_P, C.POINTER(C.c_double), C.POINTER(_u64)]),
     ("gsim_launch_count", _u64, [_P]),

@@ -184,7 +184,8 @@ struct gsim_pool {
   uint32_t world = 1, rank = 0;
   size_t rows_per_rank = 0;
   uint8_t* pages = nullptr;  // page column: rank r's pool-wide words at pages + r*GS_PAGE_BYTES
-  int shard_fd = -1;
+  const int* shard_fds = nullptr;  // one exported descriptor per column slice
+  size_t n_shard_fds = 0;
   uint32_t attached = 1;     // ranks whose memory is mapped here (including this one)
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
@@ -475,7 +476,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   } else if (okk) {
     // pool-wide words: one 2 MB page per rank; counters and the event log live in rank 0's
     p->pages = reinterpret_cast<uint8_t*>(be->shard_alloc(GS_PAGE_BYTES, 1));
-    okk = p->pages != nullptr && be->shard_commit(&p->shard_fd);
+    okk = p->pages != nullptr && be->shard_commit(&p->shard_fds, &p->n_shard_fds);
     if (okk) {
       uint8_t* page0 = p->pages;
       uint8_t* mine = p->pages + (size_t)p->rank * GS_PAGE_BYTES;
@@ -552,16 +553,20 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
 }
 
 // ---- sharded pools: wiring the ranks together ------------------------------------------------------
-extern "C" int gsim_shard_export_fd(gsim_pool* p, int* fd_out) {
-  if (!p || !fd_out || !p->sharded) return GSIM_ERR_INVALID;
-  *fd_out = p->shard_fd;
+extern "C" int gsim_shard_export_fds(gsim_pool* p, int* fds, size_t cap, size_t* n) {
+  if (!p || !n || !p->sharded) return GSIM_ERR_INVALID;
+  *n = p->n_shard_fds;
+  if (fds) {
+    if (cap < p->n_shard_fds) return GSIM_ERR_INVALID;
+    memcpy(fds, p->shard_fds, p->n_shard_fds * sizeof(int));
+  }
   return GSIM_OK;
 }
 
-extern "C" int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, int fd) {
-  if (!p || !p->sharded || p->ready) return GSIM_ERR_INVALID;
+extern "C" int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, const int* fds, size_t n) {
+  if (!p || !p->sharded || p->ready || !fds) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
-  if (!p->be->shard_attach(peer_rank, fd)) return fail(p, GSIM_ERR_CUDA, "shard_attach");
+  if (!p->be->shard_attach(peer_rank, fds, n)) return fail(p, GSIM_ERR_CUDA, "shard_attach");
   p->attached += 1;
   return GSIM_OK;
 }

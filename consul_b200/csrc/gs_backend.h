@@ -40,8 +40,8 @@ class GsBackend {
   virtual bool shard_begin(uint32_t, uint32_t) { return false; }
   virtual size_t shard_granularity() { return 0; }
   virtual void* shard_alloc(size_t /*slice_bytes*/, size_t /*planes*/) { return nullptr; }
-  virtual bool shard_commit(int* /*fd_out*/) { return false; }
-  virtual bool shard_attach(uint32_t /*peer*/, int /*fd*/) { return false; }
+  virtual bool shard_commit(const int** /*fds*/, size_t* /*n*/) { return false; }
+  virtual bool shard_attach(uint32_t /*peer*/, const int* /*fds*/, size_t /*n*/) { return false; }
   virtual bool xbar_host(const GsXbar&) { return false; }  // arrive, wait for every rank, sync
   virtual bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g,
                               uint32_t thr, uint32_t salt, uint32_t now, uint32_t* n_crashed) = 0;

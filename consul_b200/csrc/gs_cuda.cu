@@ -482,17 +482,18 @@ class CudaBackend : public GsBackend {
     if (!q) snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
     return q;
   }
-  bool shard_commit(int* fd_out) override {
+  bool shard_commit(const int** fds, size_t* n) override {
     if (!vmm_.commit()) {
       snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
       return false;
     }
-    *fd_out = vmm_.export_fd();
+    *fds = vmm_.export_fds().data();
+    *n = vmm_.export_fds().size();
     return true;
   }
-  bool shard_attach(uint32_t peer, int fd) override {
+  bool shard_attach(uint32_t peer, const int* fds, size_t n) override {
     cudaSetDevice(dev_);
-    if (!vmm_.attach(peer, fd)) {
+    if (!vmm_.attach(peer, fds, n)) {
       snprintf(err_, sizeof(err_), "%s", vmm_.last_error());
       return false;
     }

@@ -27,7 +27,7 @@ bool GsVmm::init(int device, uint32_t world, uint32_t rank, char* err, size_t er
   device_ = device;
   world_ = world;
   rank_ = rank;
-  handles_.assign(world, 0);
+  handles_.assign(world, std::vector<CUmemGenericAllocationHandle>());
   bool ok = sym("cuGetErrorString", &cuGetErrorString_) &&
             sym("cuMemGetAllocationGranularity", &cuMemGetAllocationGranularity_) &&
             sym("cuMemAddressReserve", &cuMemAddressReserve_) && sym("cuMemAddressFree", &cuMemAddressFree_) &&
@@ -58,33 +58,35 @@ void* GsVmm::reserve(size_t slice_bytes, size_t planes) {
   GsVmmColumn c;
   c.slice_bytes = slice_bytes;
   c.planes = planes;
-  c.chunk_off = chunk_bytes_;
+  c.first_slice = n_slices_;
   CUresult rc = cuMemAddressReserve_(&c.va, slice_bytes * planes * world_, gran_, 0, 0);
   if (rc != CUDA_SUCCESS) {
     fail("cuMemAddressReserve", rc);
     return nullptr;
   }
-  chunk_bytes_ += slice_bytes * planes;
+  n_slices_ += planes;
   cols_.push_back(c);
   return reinterpret_cast<void*>(c.va);
 }
 
-bool GsVmm::map_rank(uint32_t r, CUmemGenericAllocationHandle h) {
+bool GsVmm::map_slice(uint32_t r, size_t slice, CUmemGenericAllocationHandle h) {
   CUmemAccessDesc acc;
   memset(&acc, 0, sizeof(acc));
   acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
   acc.location.id = device_;
   acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
   for (const GsVmmColumn& c : cols_) {
-    for (size_t p = 0; p < c.planes; ++p) {
-      CUdeviceptr at = c.va + (p * world_ + r) * c.slice_bytes;
-      CUresult rc = cuMemMap_(at, c.slice_bytes, c.chunk_off + p * c.slice_bytes, h, 0);
-      if (rc != CUDA_SUCCESS) return fail("cuMemMap", rc);
-      rc = cuMemSetAccess_(at, c.slice_bytes, &acc, 1);
-      if (rc != CUDA_SUCCESS) return fail("cuMemSetAccess", rc);
-    }
+    if (slice < c.first_slice || slice >= c.first_slice + c.planes) continue;
+    const size_t p = slice - c.first_slice;
+    CUdeviceptr at = c.va + (p * world_ + r) * c.slice_bytes;
+    CUresult rc = cuMemMap_(at, c.slice_bytes, 0, h, 0);
+    if (rc != CUDA_SUCCESS) return fail("cuMemMap", rc);
+    rc = cuMemSetAccess_(at, c.slice_bytes, &acc, 1);
+    if (rc != CUDA_SUCCESS) return fail("cuMemSetAccess", rc);
+    return true;
   }
-  return true;
+  snprintf(err_, sizeof(err_), "slice %zu does not exist", slice);
+  return false;
 }
 
 bool GsVmm::commit() {
@@ -94,43 +96,57 @@ bool GsVmm::commit() {
   prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
   prop.location.id = device_;
   prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
-  CUmemGenericAllocationHandle h = 0;
-  CUresult rc = cuMemCreate_(&h, chunk_bytes_, &prop, 0);
-  if (rc != CUDA_SUCCESS) return fail("cuMemCreate", rc);
-  handles_[rank_] = h;
-  int fd = -1;
-  rc = cuMemExportToShareableHandle_(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
-  if (rc != CUDA_SUCCESS) return fail("cuMemExportToShareableHandle", rc);
-  fd_ = fd;
-  return map_rank(rank_, h);
+  handles_[rank_].assign(n_slices_, 0);
+  fds_.assign(n_slices_, -1);
+  for (const GsVmmColumn& c : cols_) {
+    for (size_t p = 0; p < c.planes; ++p) {
+      const size_t k = c.first_slice + p;
+      CUmemGenericAllocationHandle h = 0;
+      CUresult rc = cuMemCreate_(&h, c.slice_bytes, &prop, 0);
+      if (rc != CUDA_SUCCESS) return fail("cuMemCreate", rc);
+      handles_[rank_][k] = h;
+      int fd = -1;
+      rc = cuMemExportToShareableHandle_(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+      if (rc != CUDA_SUCCESS) return fail("cuMemExportToShareableHandle", rc);
+      fds_[k] = fd;
+      if (!map_slice(rank_, k, h)) return false;
+    }
+  }
+  return true;
 }
 
-bool GsVmm::attach(uint32_t peer, int fd) {
-  if (peer >= world_ || peer == rank_ || handles_[peer]) {
-    snprintf(err_, sizeof(err_), "bad peer rank %u", peer);
+bool GsVmm::attach(uint32_t peer, const int* fds, size_t n) {
+  if (peer >= world_ || peer == rank_ || !handles_[peer].empty() || n != n_slices_) {
+    snprintf(err_, sizeof(err_), "bad attach: peer %u, %zu descriptors (expected %zu)", peer, n, n_slices_);
     return false;
   }
-  CUmemGenericAllocationHandle h = 0;
-  CUresult rc = cuMemImportFromShareableHandle_(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
-  if (rc != CUDA_SUCCESS) return fail("cuMemImportFromShareableHandle", rc);
-  handles_[peer] = h;
-  return map_rank(peer, h);
+  handles_[peer].assign(n_slices_, 0);
+  for (size_t k = 0; k < n; ++k) {
+    CUmemGenericAllocationHandle h = 0;
+    CUresult rc = cuMemImportFromShareableHandle_(&h, (void*)(uintptr_t)fds[k], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (rc != CUDA_SUCCESS) return fail("cuMemImportFromShareableHandle", rc);
+    handles_[peer][k] = h;
+    if (!map_slice(peer, k, h)) return false;
+  }
+  return true;
 }
 
 void GsVmm::destroy() {
   for (const GsVmmColumn& c : cols_) {
     for (uint32_t r = 0; r < world_; ++r) {
-      if (!handles_[r]) continue;
-      for (size_t p = 0; p < c.planes; ++p) cuMemUnmap_(c.va + (p * world_ + r) * c.slice_bytes, c.slice_bytes);
+      if (handles_[r].empty()) continue;
+      for (size_t p = 0; p < c.planes; ++p)
+        if (handles_[r][c.first_slice + p]) cuMemUnmap_(c.va + (p * world_ + r) * c.slice_bytes, c.slice_bytes);
     }
     cuMemAddressFree_(c.va, c.slice_bytes * c.planes * world_);
   }
   cols_.clear();
-  for (auto& h : handles_)
-    if (h) {
-      cuMemRelease_(h);
-      h = 0;
-    }
-  if (fd_ >= 0) close(fd_);
-  fd_ = -1;
+  for (auto& hv : handles_) {
+    for (auto& h : hv)
+      if (h) cuMemRelease_(h);
+    hv.clear();
+  }
+  for (int& fd : fds_)
+    if (fd >= 0) close(fd);
+  fds_.clear();
 }

@@ -4,9 +4,10 @@
 // CUDA virtual-memory reservation of planes * world * slice bytes; the slice (plane p, rank r)
 // is backed by rank r's HBM and mapped at the same offset in every process, so device code
 // indexes a column by global member id exactly as on one GPU and the hardware routes the access
-// to local HBM or over NVLink.  Each rank creates ONE physical allocation holding all its
-// slices, exports it as a POSIX file descriptor, and maps the other ranks' allocations after
-// importing their descriptors.  The driver API is reached through cudaGetDriverEntryPoint so
+// to local HBM or over NVLink.  cuMemMap cannot map a sub-range of a physical allocation
+// (its offset argument must be zero), so every (column, plane) slice is its own physical
+// allocation: each rank exports one POSIX file descriptor per slice and maps the other ranks'
+// slices after importing their descriptors.  The driver API is reached through cudaGetDriverEntryPoint so
 // libgsim.so has no link-time dependency on libcuda (it must still load on GPU-less hosts).
 #pragma once
 #include <cuda.h>
@@ -20,7 +21,7 @@ struct GsVmmColumn {
   CUdeviceptr va = 0;
   size_t slice_bytes = 0;  // bytes of one (plane, rank) slice: a multiple of the granularity
   size_t planes = 0;
-  size_t chunk_off = 0;    // offset of (plane 0, this rank) inside a rank's physical chunk
+  size_t first_slice = 0;  // index of (plane 0) in the per-rank slice list
 };
 
 class GsVmm {
@@ -29,25 +30,25 @@ class GsVmm {
   size_t granularity() const { return gran_; }
   // reserve the address range of one column (all planes, all ranks); returns its base pointer
   void* reserve(size_t slice_bytes, size_t planes);
-  // create this rank's physical chunk (all columns reserved so far), map its own slices
+  // create and map this rank's slices of every column reserved so far
   bool commit();
-  int export_fd() const { return fd_; }
-  bool attach(uint32_t peer, int fd);  // import a peer's chunk and map its slices
+  const std::vector<int>& export_fds() const { return fds_; }
+  bool attach(uint32_t peer, const int* fds, size_t n);  // import and map a peer's slices
   void destroy();
   const char* last_error() const { return err_; }
 
  private:
-  bool map_rank(uint32_t r, CUmemGenericAllocationHandle h);
+  bool map_slice(uint32_t r, size_t slice, CUmemGenericAllocationHandle h);
   bool fail(const char* what, CUresult rc);
   template <class T>
   bool sym(const char* name, T* out);
 
   int device_ = 0;
   uint32_t world_ = 1, rank_ = 0;
-  size_t gran_ = 0, chunk_bytes_ = 0;
-  int fd_ = -1;
+  size_t gran_ = 0, n_slices_ = 0;
+  std::vector<int> fds_;  // this rank's exported descriptors, one per slice
   std::vector<GsVmmColumn> cols_;
-  std::vector<CUmemGenericAllocationHandle> handles_;  // [world], 0 = not attached
+  std::vector<std::vector<CUmemGenericAllocationHandle>> handles_;  // [world][slice], 0 = not mapped
   char err_[256] = {0};
 
   // driver entry points

@@ -16,8 +16,8 @@ from .pool import GsimError, Pool
 _POOL_SEQ = 0
 
 
-def _exchange_fds(my_fd: int, rank: int, world: int, tag: str) -> dict:
-    """Hand this rank's shard descriptor to every peer (SCM_RIGHTS over abstract unix sockets)."""
+def _exchange_fds(my_fds: list, rank: int, world: int, tag: str) -> dict:
+    """Hand this rank's slice descriptors to every peer (SCM_RIGHTS over abstract unix sockets)."""
     import torch.distributed as dist
     name = lambda r: "\0gsim-%s-%d" % (tag, r)  # noqa: E731  (abstract namespace: no files)
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
@@ -29,13 +29,13 @@ def _exchange_fds(my_fd: int, rank: int, world: int, tag: str) -> dict:
             continue
         c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
         c.connect(name(peer))
-        socket.send_fds(c, [struct.pack("I", rank)], [my_fd])
+        socket.send_fds(c, [struct.pack("I", rank)], list(my_fds))
         c.close()
     got = {}
     for _ in range(world - 1):
         conn, _ = srv.accept()
-        msg, fds, _, _ = socket.recv_fds(conn, 4, 1)
-        got[struct.unpack("I", msg)[0]] = fds[0]
+        msg, fds, _, _ = socket.recv_fds(conn, 4, 250)
+        got[struct.unpack("I", msg)[0]] = list(fds)
         conn.close()
     srv.close()
     dist.barrier()
@@ -56,14 +56,18 @@ class ShardedPool(Pool):
         cfg.world_size, cfg.rank = world, rank
         super().__init__(cfg, lib)
         self.rank, self.world = rank, world
-        fd = C.c_int()
-        self._ck(self.lib.gsim_shard_export_fd(self.h, C.byref(fd)))
+        n = C.c_size_t()
+        self._ck(self.lib.gsim_shard_export_fds(self.h, None, 0, C.byref(n)))
+        mine = (C.c_int * n.value)()
+        self._ck(self.lib.gsim_shard_export_fds(self.h, mine, n.value, C.byref(n)))
         tag = "%s-%d" % (os.environ.get("MASTER_PORT", "0"), _POOL_SEQ)
         _POOL_SEQ += 1
-        peers = _exchange_fds(fd.value, rank, world, tag)
-        for peer, pfd in sorted(peers.items()):
-            self._ck(self.lib.gsim_shard_attach(self.h, peer, pfd))
-            os.close(pfd)
+        peers = _exchange_fds(list(mine), rank, world, tag)
+        for peer, pfds in sorted(peers.items()):
+            arr = (C.c_int * len(pfds))(*pfds)
+            self._ck(self.lib.gsim_shard_attach(self.h, peer, arr, len(pfds)))
+            for f in pfds:
+                os.close(f)
         self._ck(self.lib.gsim_shard_ready(self.h))
 
     def close(self):

@@ -312,13 +312,13 @@ int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes);
 
 /* ---- sharded pools: one process per GPU, cfg.world_size > 1 ----
  * Every rank creates the pool with the same config except `rank`/`device`, exchanges the file
- * descriptor of its physical shard with every other rank (SCM_RIGHTS or pidfd_getfd), attaches
+ * descriptors of its physical column slices with every other rank (SCM_RIGHTS or pidfd_getfd), attaches
  * the peers' descriptors and calls gsim_shard_ready.  After that EVERY rank must issue the same
  * API calls in the same order: rank 0 executes the host-side operation, the others adopt its
  * result; gsim_step runs the tick kernels on all ranks with a device barrier per tick.  Bulk
  * observation (members, column_read, poll_events, snapshot, user_event_get) is served by rank 0. */
-int gsim_shard_export_fd(gsim_pool* p, int* fd_out);
-int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, int fd);
+int gsim_shard_export_fds(gsim_pool* p, int* fds, size_t cap, size_t* n); /* one per column slice */
+int gsim_shard_attach(gsim_pool* p, uint32_t peer_rank, const int* fds, size_t n);
 int gsim_shard_ready(gsim_pool* p);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------- */
