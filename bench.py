@@ -209,8 +209,18 @@ def main():
 
     n, ticks = args.members, args.ticks
     total_steps = args.steps + args.warmup
-    cfg = lan_config(capacity=n + 2 * total_steps + 4, n_initial=n, seed=SEED + rank, device=local_rank)
-    pool = Pool(cfg)
+    sharded = world > 1
+    if sharded:
+        # one pool sharded over all ranks: 2 Mi members per GPU (the VMM mapping
+        # granularity makes 2 Mi rows the shard quantum), the last 256 ids are left for joiners
+        from consul_b200.sharded import ShardedPool
+        per_gpu = 2 * 1024 * 1024
+        n = per_gpu * world - 256
+        cfg = lan_config(capacity=per_gpu * world, n_initial=n, seed=SEED, device=local_rank)
+        pool = ShardedPool(cfg)
+    else:
+        cfg = lan_config(capacity=n + 2 * total_steps + 4, n_initial=n, seed=SEED + rank, device=local_rank)
+        pool = Pool(cfg)
     gi = pool.stats()["probe_interval_ticks"]  # P: the due column is read on 2/P of the ticks
 
     def step_resident():
@@ -259,47 +269,68 @@ def main():
 
     # ---- e2e: HOST buffers through the C ABI, H2D + D2H inside the timed region -----------
     import ctypes as C
-    blob = pool.snapshot()
-    pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
-    pinned.numpy()[:] = memoryview(blob)
-    blob_ptr = C.c_void_p(pinned.data_ptr())
-    from consul_b200._lib import GsimMember
-    mem_cap = n + 2 * total_steps + 4
-    mem_buf = (GsimMember * mem_cap)()
-    mem_n = C.c_size_t()
-    lib = pool.lib
+    if sharded:
+        # sharded pool: the cluster stays resident on the GPUs; the per-step host traffic is the
+        # join operation (pokes) and the result read-back (stats, NumNodes of the joiner)
+        def step_e2e():
+            xx, _ = step_resident()
+            return pool.stats()["n_view_alive"] + pool.num_nodes(xx)
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        dte = time.perf_counter() - te0
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        n_now = pool.stats()["n_members"]
+        e2e_nodeticks = float(n_now) * ticks * args.steps
+        h2d, d2h = 4096, 4096 + 4 * n_now
+        blob = None
+    else:
+        blob = pool.snapshot()
+        pinned = torch.empty(len(blob), dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = memoryview(blob)
+        blob_ptr = C.c_void_p(pinned.data_ptr())
+        from consul_b200._lib import GsimMember
+        mem_cap = n + 2 * total_steps + 4
+        mem_buf = (GsimMember * mem_cap)()
+        mem_n = C.c_size_t()
+        lib = pool.lib
 
-    def step_e2e():
-        rc = lib.gsim_restore(pool.h, blob_ptr, len(blob))
-        assert rc == 0, rc
-        xx = pool.member_add()
-        assert pool.join(xx, [0]) == 1
-        pool.step(ticks)
-        rc = lib.gsim_members(pool.h, 0, mem_buf, mem_cap, C.byref(mem_n))
-        assert rc == 0 and mem_n.value == xx + 1
-        return pool.stats()["n_view_alive"]
+        def step_e2e():
+            rc = lib.gsim_restore(pool.h, blob_ptr, len(blob))
+            assert rc == 0, rc
+            xx = pool.member_add()
+            assert pool.join(xx, [0]) == 1
+            pool.step(ticks)
+            rc = lib.gsim_members(pool.h, 0, mem_buf, mem_cap, C.byref(mem_n))
+            assert rc == 0 and mem_n.value == xx + 1
+            return pool.stats()["n_view_alive"]
 
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    te0 = time.perf_counter()
-    for _ in range(args.steps):
-        alive = step_e2e()
-    barrier()
-    dte = time.perf_counter() - te0
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
-    n_now = pool.stats()["n_members"]
-    e2e_nodeticks = float(n_now) * ticks * args.steps
-    h2d = len(blob)
-    d2h = mem_n.value * C.sizeof(GsimMember) + n_now * 4 + 512
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(args.steps):
+            alive = step_e2e()
+        barrier()
+        dte = time.perf_counter() - te0
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        n_now = pool.stats()["n_members"]
+        e2e_nodeticks = float(n_now) * ticks * args.steps
+        h2d = len(blob)
+        d2h = mem_n.value * C.sizeof(GsimMember) + n_now * 4 + 512
 
     # ---- max over ranks, aggregate ------------------------------------------------------------
     tt = torch.tensor([dt, dte, kernel_ms], dtype=torch.float64, device="cuda")
     nt = torch.tensor([float(d["node_ticks"]), e2e_nodeticks], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nt, op=dist.ReduceOp.SUM)
+        # a sharded pool's counters are already global (every rank reports the same totals)
     dt_max, dte_max, kms_max = [float(v) for v in tt.tolist()]
     node_ticks_all, e2e_all = [float(v) for v in nt.tolist()]
 
@@ -317,7 +348,9 @@ def main():
                         "ticks over the same state); roofline_hbm below is the HBM-bound size"}
 
     roofline_hbm = None
-    if not args.skip_hbm_point and rank == 0:
+    if sharded:
+        pool.close()
+    if not args.skip_hbm_point and rank == 0 and not sharded:
         pool.close()
         big = Pool(lan_config(capacity=N_HBM, n_initial=N_HBM, seed=SEED, device=local_rank))
         big.step(64)
@@ -353,7 +386,8 @@ def main():
         "config": {"workload": f"C2: {n:,} converged members + 1 joiner per step, LAN defaults "
                                f"(probe 1s/500ms, gossip 200ms x3), tau=100 ms, {ticks} ticks/step",
                    "members_per_gpu": n, "ticks_per_step": ticks, "seed": hex(SEED),
-                   "parallelism": "1 pool per GPU" if world > 1 else "single GPU",
+                   "parallelism": (f"one pool range-sharded over {world} GPUs, {n // world:,} members per GPU, P2P mailboxes "
+                                   "over NVLink inside the tick kernel, device barrier per tick") if sharded else "single GPU",
                    "l2": "not flushed: a step is 2048 dependent ticks over the same state, whose hot "
                          "columns are L2-resident by construction; see roofline_hbm for the >L2 size"},
         "ticks_to_convergence": ticks_to_conv,
@@ -361,7 +395,8 @@ def main():
         "e2e": {"value": e2e_all / dte_max / 1e6, "unit": "M node-ticks/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": dte_max / args.steps * 1e3,
-                "path": "gsim_restore(pinned host snapshot) -> member_add -> join -> step -> members + stats"},
+                "path": ("member_add -> join -> step -> stats + num_nodes (cluster resident, sharded)" if sharded else
+                         "gsim_restore(pinned host snapshot) -> member_add -> join -> step -> members + stats")},
         "gpu_launches": int(l1 - l0),
         "roofline": roofline, "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,

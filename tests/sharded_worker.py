@@ -54,7 +54,10 @@ if rank == 0:
     for k in ("joined", "crashed", "conv", "dead_tick", "event", "stats", "hash", "now"):
         if got[k] != want[k]:
             ok = False
-            print("MISMATCH", k, got[k], want[k], flush=True)
+            if isinstance(got[k], dict):
+                print("MISMATCH", k, {f: (got[k][f], want[k][f]) for f in got[k] if got[k][f] != want[k][f]}, flush=True)
+            else:
+                print("MISMATCH", k, got[k], want[k], flush=True)
     print(json.dumps({"ok": ok, "world": world, "members": N, "sharded_us_per_tick": got["us_per_tick"],
                       "single_us_per_tick": want["us_per_tick"], "dead_tick": got["dead_tick"],
                       "hash": got["hash"][0]}), flush=True)
