@@ -12,6 +12,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <vector>
 
@@ -24,15 +26,15 @@ struct HostSink {
   uint64_t* stats;
   uint32_t* heard_cnt;
   uint32_t local_heard[32];
-  void stat(int idx, uint32_t v) { stats[idx] += v; }
+  void stat(int idx, uint32_t v) { __atomic_fetch_add(&stats[idx], (uint64_t)v, __ATOMIC_RELAXED); }
   void heard(uint32_t r) { local_heard[r] += 1; }
   void crashed_dead(const GsDev& d, uint32_t t) {
-    uint32_t old = (*d.crashed_alive)--;
+    uint32_t old = __atomic_fetch_sub(d.crashed_alive, 1u, __ATOMIC_RELAXED);
     if (old == 1u) *d.crashed_dead_tick = t;
   }
   void log_event(const GsDev& d, const GsGlobals& g, uint32_t t, uint32_t type, uint32_t subject,
                  uint32_t observer, uint32_t ltime) {
-    uint32_t pos = d.evlog_cursor[0]++;
+    uint32_t pos = __atomic_fetch_add(&d.evlog_cursor[0], 1u, __ATOMIC_RELAXED);
     if (pos < g.evlog_cap) {
       GsEventRec e = {t, type, subject, observer, ltime, 0u};
       d.evlog[pos] = e;
@@ -51,7 +53,9 @@ class HostEmuBackend : public GsBackend {
   }
   const char* name() const override { return "hostemu (tests only)"; }
   void* alloc(size_t bytes) override { return calloc(1, bytes ? bytes : 4); }
-  void release(void* p) override { free(p); }
+  void release(void* p) override {
+    if (!sharded_) free(p);
+  }
   bool h2d(void* dst, const void* src, size_t bytes) override {
     memcpy(dst, src, bytes);
     return true;
@@ -82,7 +86,7 @@ class HostEmuBackend : public GsBackend {
     return x;
   }
   bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0,
-                 uint32_t nticks, bool, double*, uint64_t* launches, const GsXbar*) override {
+                 uint32_t nticks, bool, double*, uint64_t* launches, const GsXbar* xbar) override {
     const GsGlobals& g = *g_dev;  // the kernels read the device copy
     for (uint32_t k = 0; k < nticks; ++k) {
       const uint32_t t = *d.tick_base + k;
@@ -98,8 +102,14 @@ class HostEmuBackend : public GsBackend {
       // same activity test as gs_tick_kernel: mailbox word, plus `due` only for tiles whose
       // ticker phase can be due at this tick
       const uint32_t pslot = t % g.P;
-      for (uint32_t x = 0; x < g.n; ++x) {
-        const uint32_t i = row_at(x, g.n);
+      // this rank's members: everything, or its contiguous range on a sharded pool
+      uint32_t lo = 0, hi = g.n;
+      if (g.world > 1u) {
+        lo = g.rank * g.rows_per_rank < g.n ? g.rank * g.rows_per_rank : g.n;
+        hi = lo + g.rows_per_rank < g.n ? lo + g.rows_per_rank : g.n;
+      }
+      for (uint32_t x = 0; x < hi - lo; ++x) {
+        const uint32_t i = lo + row_at(x, hi - lo);
         const uint32_t inb = d.inbox[t & 1u][i];
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
@@ -120,12 +130,12 @@ class HostEmuBackend : public GsBackend {
       for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
         uint32_t c = sink.local_heard[r];
         if (c) {
-          uint32_t old = d.heard_cnt[r];
-          d.heard_cnt[r] = old + c;
+          uint32_t old = __atomic_fetch_add(&d.heard_cnt[r], c, __ATOMIC_RELAXED);
           if (old + c == g.up_count) d.conv_tick[r] = t;
         }
       }
       ++launches_;
+      if (xbar) xbar_host(*xbar);
     }
     *d.tick_base += nticks;
     ++launches_;
@@ -171,6 +181,62 @@ class HostEmuBackend : public GsBackend {
     }
     return true;
   }
+  // ---- sharded pools on the host: the same layout as gs_vmm.h with memfd + mmap(MAP_FIXED) ----
+  // standing in for cuMemCreate + cuMemMap, so the controller protocol, the descriptor
+  // exchange and the per-tick barrier can be tested with 2 gloo processes on a GPU-less box.
+  struct Col {
+    uint8_t* va;
+    size_t slice_bytes, planes, first_slice;
+  };
+  bool shard_begin(uint32_t world, uint32_t rank) override {
+    world_ = world;
+    rank_ = rank;
+    sharded_ = true;
+    return true;
+  }
+  size_t shard_granularity() override { return 4096; }
+  void* shard_alloc(size_t slice_bytes, size_t planes) override {
+    void* va = mmap(nullptr, slice_bytes * planes * world_, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (va == MAP_FAILED) return nullptr;
+    cols_.push_back(Col{(uint8_t*)va, slice_bytes, planes, n_slices_});
+    n_slices_ += planes;
+    return va;
+  }
+  bool map_slice(uint32_t r, size_t k, int fd) {
+    for (const Col& c : cols_) {
+      if (k < c.first_slice || k >= c.first_slice + c.planes) continue;
+      uint8_t* at = c.va + ((k - c.first_slice) * world_ + r) * c.slice_bytes;
+      return mmap(at, c.slice_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0) != MAP_FAILED;
+    }
+    return false;
+  }
+  bool shard_commit(const int** fds, size_t* n) override {
+    fds_.assign(n_slices_, -1);
+    for (const Col& c : cols_)
+      for (size_t p = 0; p < c.planes; ++p) {
+        int fd = memfd_create("gsim-hostemu-slice", 0);
+        if (fd < 0 || ftruncate(fd, (off_t)c.slice_bytes) != 0) return false;
+        fds_[c.first_slice + p] = fd;
+        if (!map_slice(rank_, c.first_slice + p, fd)) return false;
+      }
+    *fds = fds_.data();
+    *n = fds_.size();
+    return true;
+  }
+  bool shard_attach(uint32_t peer, const int* fds, size_t n) override {
+    if (n != n_slices_ || peer >= world_ || peer == rank_) return false;
+    for (size_t k = 0; k < n; ++k)
+      if (!map_slice(peer, k, fds[k])) return false;
+    return true;
+  }
+  bool xbar_host(const GsXbar& xb) override {
+    const uint32_t e = *xb.epoch + 1u;
+    for (uint32_t r = 0; r < xb.world; ++r) __atomic_store_n(&xb.flags[r][xb.rank], e, __ATOMIC_RELEASE);
+    for (uint32_t r = 0; r < xb.world; ++r)
+      while ((int32_t)(__atomic_load_n(&xb.flags[xb.rank][r], __ATOMIC_ACQUIRE) - e) < 0) usleep(20);
+    *xb.epoch = e;
+    return true;
+  }
   bool sync() override { return true; }
   const char* last_error() const override { return err_; }
   uint64_t total_launches() const override { return launches_; }
@@ -178,6 +244,11 @@ class HostEmuBackend : public GsBackend {
  private:
   int order_;
   uint64_t launches_ = 0;
+  bool sharded_ = false;
+  uint32_t world_ = 1, rank_ = 0;
+  size_t n_slices_ = 0;
+  std::vector<Col> cols_;
+  std::vector<int> fds_;
   char err_[128];
 };
 
