@@ -23,6 +23,9 @@
 #define GS_DEV __device__ __forceinline__
 #define GS_ATOMIC_OR32(p, v) atomicOr((p), (v))
 #define GS_ATOMIC_MIN64(p, v) atomicMin((unsigned long long*)(p), (unsigned long long)(v))
+// Reads of OTHER members' columns go to L2 (ld.global.cg): on a sharded pool the line may live
+// on another GPU, and an L1 copy of a peer line is not something to rely on across ticks.
+#define GS_LD_OTHER(p) __ldcg(p)
 #else
 #define GS_DEV inline
 #define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
@@ -34,6 +37,7 @@ static inline uint64_t gs_host_atomic_min64(uint64_t* p, uint64_t v) {
   return old;
 }
 #define GS_ATOMIC_MIN64(p, v) gs_host_atomic_min64((uint64_t*)(p), (uint64_t)(v))
+#define GS_LD_OTHER(p) (*(p))
 #endif
 
 // Stat indices (mirror GSIM_STAT_* in include/gsim.h).
@@ -104,14 +108,14 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
     if ((dr & 3u) == 0u) blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, dr >> 2);
     uint32_t c = gs_u4_get(blk, dr & 3u) % n;
     if (c == i || c == exclude2) continue;
-    uint32_t kc = keyc[c];
+    uint32_t kc = GS_LD_OTHER(&keyc[c]);
     if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
     uint32_t rank = gs_key_rank(kc);
     if (mode == 1u) {
       if (rank != GS_RANK_ALIVE) continue;
     } else {
       if (rank == GS_RANK_LEFT) continue;
-      if (rank == GS_RANK_DEAD && (t - d.change_tick[c]) > g.gtd_ticks) continue;
+      if (rank == GS_RANK_DEAD && (t - GS_LD_OTHER(&d.change_tick[c])) > g.gtd_ticks) continue;
     }
     if (!gs_knows(d, g, i, c, kc, meta_i)) continue;
     bool dup = false;
@@ -339,7 +343,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
     if (stage == GS_STAGE_WAIT_T && due == t) {
       // ProbeTimeout elapsed without a direct ack: k indirect probes + TCP fallback.
       const uint32_t j = d.probe_tgt[i];
-      const uint32_t kj = d.key[cur][j];
+      const uint32_t kj = GS_LD_OTHER(&d.key[cur][j]);
       const bool j_up = gs_key_truth(kj) == GS_TRUTH_UP;
       uint32_t relays[8];
       uint32_t kk = g.indirect_checks > 8u ? 8u : g.indirect_checks;
@@ -348,7 +352,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       uint32_t nacks = 0;
       for (uint32_t q = 0; q < nr; ++q) {
         const uint32_t r = relays[q];
-        const bool r_up = gs_key_truth(d.key[cur][r]) == GS_TRUTH_UP;
+        const bool r_up = gs_key_truth(GS_LD_OTHER(&d.key[cur][r])) == GS_TRUTH_UP;
         sink.stat(GS_ST_INDIRECT_PINGS, 1);
         if (!(r_up && !gs_lost(g, sink, i, r, t, GS_LK_INDREQ, q))) continue;  // no nack either
         bool relay_acked = j_up && !gs_lost(g, sink, r, j, t, GS_LK_INDPING, q) &&
@@ -411,7 +415,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
         uint32_t c = gs_perm(cursor, n, g.perm_half_bits, rk);
         ++cursor;
-        uint32_t kc = d.key[cur][c];
+        uint32_t kc = GS_LD_OTHER(&d.key[cur][c]);
         uint32_t rank = gs_key_rank(kc);
         if (c == i || gs_key_truth(kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD ||
             rank == GS_RANK_LEFT || !gs_knows(d, g, i, c, kc, m)) {
@@ -518,7 +522,7 @@ GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uin
   GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, f.pass);
   f.c = gs_perm(f.cursor, g.n, g.perm_half_bits, rk);
   if (f.c == i) return false;
-  f.kc = d.key[cur][f.c];
+  f.kc = GS_LD_OTHER(&d.key[cur][f.c]);
   return true;
 }
 
