@@ -412,7 +412,11 @@ class CudaBackend : public GsBackend {
     if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
-    if (use_graph && left >= GS_GRAPH_TICKS) {
+    // Sharded pools launch tick by tick.  Inside a CUDA graph the tick/barrier chain showed
+    // mailbox deliveries from the peer GPU being consumed 2-6 ticks late on B200 (state digest
+    // diverges from the single-GPU run; profiles/README.md, "multi-GPU"); with stream launches the
+    // same kernels are bit-exact, so the graph path stays off until that is understood.
+    if (use_graph && !xbar && left >= GS_GRAPH_TICKS) {
       cudaGraphExec_t ge = graph_for(d, g_dev, blocks, xbar);
       if (!ge) return false;
       while (left >= GS_GRAPH_TICKS) {

@@ -21,11 +21,29 @@
 
 #if defined(__CUDA_ARCH__)
 #define GS_DEV __device__ __forceinline__
-#define GS_ATOMIC_OR32(p, v) atomicOr((p), (v))
-#define GS_ATOMIC_MIN64(p, v) atomicMin((unsigned long long*)(p), (unsigned long long)(v))
+// Mailbox deliveries may target a row on another GPU (sharded pools).  They are issued as
+// system-scope FETCHING atomics: a fire-and-forget reduction over NVLink can still be in flight
+// when its kernel retires, a fetching atomic has been performed at the owner once it returns.
+__device__ __forceinline__ uint32_t gs_atomic_or_sys(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.global.sys.or.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint64_t gs_atomic_min_sys(uint64_t* p, uint64_t v) {
+  unsigned long long old;
+  asm volatile("atom.global.sys.min.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"((unsigned long long)v) : "memory");
+  return old;
+}
+#define GS_ATOMIC_OR32(p, v) gs_atomic_or_sys((p), (v))
+#define GS_ATOMIC_MIN64(p, v) gs_atomic_min_sys((uint64_t*)(p), (uint64_t)(v))
 // Reads of OTHER members' columns go to L2 (ld.global.cg): on a sharded pool the line may live
 // on another GPU, and an L1 copy of a peer line is not something to rely on across ticks.
-#define GS_LD_OTHER(p) __ldcg(p)
+__device__ __forceinline__ uint32_t gs_ld_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#define GS_LD_OTHER(p) gs_ld_sys(p)
 #else
 #define GS_DEV inline
 #define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)

@@ -28,7 +28,11 @@ def script(p):
     slot = p.user_event(3, b"deploy", b"x" * 32, False)
     out["crashed"] = p.crash_fraction(20000, 1)
     t0 = time.perf_counter()
-    p.step(192)
+    if os.environ.get("GSIM_SHARD_STEP1"):      # debug: a host-level barrier around every tick
+        for _ in range(192):
+            p.step(1)
+    else:
+        p.step(192)
     out["wall_s_192"] = time.perf_counter() - t0
     out["us_per_tick"] = p.last_step_timing()[0] * 1e3 / 192
     out["conv"] = p.run_until(PRED_ALL_RUMORS_CONVERGED, 0, 64, 8)
