@@ -340,6 +340,21 @@ static bool alloc_col(gsim_pool* p, T** out, size_t count) {
   return true;
 }
 
+// Sharded pools: every rank's progress words say "all ticks < now are done" (controller only).
+static bool reset_tick_flags(gsim_pool* p) {
+  if (!p->sharded) return true;
+  uint32_t words[GS_MAX_WORLD];
+  for (uint32_t r = 0; r < GS_MAX_WORLD; ++r) words[r] = p->now;
+  const uint32_t zero = 0;
+  for (uint32_t r = 0; r < p->world; ++r) {
+    uint8_t* page = p->pages + (size_t)r * GS_PAGE_BYTES;
+    if (!p->be->h2d(page + GS_PG_TICK_FLAGS, words, sizeof(words))) return false;
+    if (!p->be->h2d(page + GS_PG_DONE_CTR, &zero, 4)) return false;
+    if (!p->be->h2d(page + GS_PG_TICK_BASE, &p->now, 4)) return false;
+  }
+  return true;
+}
+
 // Device-side initial state: empty columns, zeroed counters, the converged initial members.
 // On a sharded pool this runs on rank 0 only and reaches every GPU through the unified columns.
 static int init_device_state(gsim_pool* p) {
@@ -361,6 +376,7 @@ static int init_device_state(gsim_pool* p) {
 
   p->g_dirty = true;
   okk = okk && upload_globals(p);
+  okk = okk && reset_tick_flags(p);
   okk = okk && be->init_rows(d, p->g_dev, g, 0, p->cfg.n_initial, 0);
   return okk ? GSIM_OK : GSIM_ERR_CUDA;
 }
@@ -494,6 +510,9 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       p->g_dev = reinterpret_cast<GsGlobals*>(mine + GS_PG_GLOBALS);
       for (uint32_t r = 0; r < GS_MAX_WORLD; ++r)
         p->xb.flags[r] = reinterpret_cast<uint32_t*>(p->pages + (size_t)(r < p->world ? r : 0) * GS_PAGE_BYTES + GS_PG_XBAR_FLAGS);
+      for (uint32_t r = 0; r < GS_MAX_WORLD; ++r)
+        d.tick_flags[r] = reinterpret_cast<uint32_t*>(p->pages + (size_t)(r < p->world ? r : 0) * GS_PAGE_BYTES + GS_PG_TICK_FLAGS);
+      d.done_ctr = reinterpret_cast<uint32_t*>(mine + GS_PG_DONE_CTR);
       p->xb.epoch = reinterpret_cast<uint32_t*>(mine + GS_PG_XBAR_EPOCH);
       p->xb.rank = p->rank;
       p->xb.world = p->world;
@@ -1560,7 +1579,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   p->n_established = h.n_established;
   p->g_dirty = true;
   p->counts_stale = true;
-  if (!poke(p, p->d.tick_base, 0, p->now)) return fail(p, GSIM_ERR_CUDA, "poke");
+  if (!poke(p, p->d.tick_base, 0, p->now) || !reset_tick_flags(p)) return fail(p, GSIM_ERR_CUDA, "poke");
   uint32_t zero2[2] = {0, 0};
   if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
   return GSIM_OK;

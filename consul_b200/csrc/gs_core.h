@@ -27,6 +27,7 @@
 #endif
 
 #define GS_MAX_RUMORS 30
+#define GS_MAX_WORLD_ 8
 #define GS_K1MAX 5
 #define GS_ACC_BIT 0x80000000u   // inbox: accusation(s) pending in acc[][][]
 #define GS_WAKE_BIT 0x40000000u  // inbox: "process this row" (self-posted or by the host)
@@ -266,6 +267,9 @@ struct GsDev {
   GsEventRec* evlog;
   uint32_t* evlog_cursor;  // [0]=written, [1]=dropped
   uint32_t* tick_base;
+  // sharded pools: inter-tick barrier state (gs_tick_kernel); null on single-GPU pools
+  uint32_t* tick_flags[GS_MAX_WORLD_];  // tick_flags[r] = rank r's array of per-rank progress words
+  uint32_t* done_ctr;
 };
 
 // Per-row outputs that the launch wrapper reduces (warp/block aggregated atomics).
@@ -292,6 +296,8 @@ struct GsRowOut {
 #define GS_PG_TICK_BASE 816u
 #define GS_PG_XBAR_EPOCH 820u
 #define GS_PG_XBAR_FLAGS 832u
+#define GS_PG_TICK_FLAGS 896u   // [GS_MAX_WORLD] "rank r has completed every tick < value"
+#define GS_PG_DONE_CTR 960u     // CTAs of this rank that have finished the current tick
 #define GS_PG_GLOBALS 1024u
 #define GS_PG_SCRATCH 8192u
 #define GS_PG_BLOB 16384u      // 2 slots of GS_BLOB_BYTES

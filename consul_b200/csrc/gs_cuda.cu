@@ -103,6 +103,18 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   __syncthreads();
   const GsGlobals& g = *gp;
   const uint32_t t = *d.tick_base + k_off;
+  if (g.world > 1u) {
+    // Sharded pool, acquire side of the inter-tick barrier: tick t may start once every rank has
+    // published "all ticks < t done" in this rank's progress array (written by the peers over
+    // NVLink with st.release.sys at the end of their previous tick, see the end of this kernel).
+    if (tid < g.world) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(d.tick_flags[g.rank] + tid) : "memory");
+      } while ((int32_t)(v - t) < 0);
+    }
+    __syncthreads();
+  }
   const uint32_t cur = t & 1u, P = g.P, pslot = t % P, gslot = t % g.GI;
   const uint32_t pslot_t = (t + P - g.T % P) % P;
   const uint32_t lane = tid & 31u, wib = tid >> 5;
@@ -127,7 +139,15 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   auto issue = [&](uint32_t st) {
     if (tq < t_end) {
       const size_t off = (size_t)tq * GS_TILE + lane * 4u;  // columns are padded to whole tiles
-      gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
+      if (g.world > 1u) {
+        // sharded pool: this mailbox word is written by other GPUs; read it at system scope
+        uint4 v;
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(inbox_cur + off) : "memory");
+        *reinterpret_cast<uint4*>(&s_inb[st][wib][lane * 4u]) = v;
+      } else {
+        gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
+      }
       bool gate = true;
       if (gated) {
         const uint32_t pp = gs_probe_phase(g.rot_p, tq >> shift, P);
@@ -212,6 +232,25 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     if (c) {
       uint32_t old = atomicAdd(&d.heard_cnt[r], c);
       if (old + c == g.up_count) d.conv_tick[r] = t;  // every UP member has heard rumor r
+    }
+  }
+  if (g.world > 1u) {
+    // Release side of the inter-tick barrier.  Every thread fenced at system scope above, so
+    // its mailbox clears, key updates and remote deliveries are performed; CTAs count in with
+    // a device-scope atomic and the last one publishes t+1 to every rank.  The chain
+    // (write -> fence.sys -> bar -> atomic ... atomic -> fence.sys -> st.release.sys) does not
+    // rely on kernel boundaries, which is what makes it safe inside a CUDA graph.
+    __syncthreads();
+    if (tid == 0u) {
+      __threadfence_system();
+      const uint32_t arrived = atomicAdd(d.done_ctr, 1u);
+      if (arrived == gridDim.x - 1u) {
+        __threadfence_system();
+        *d.done_ctr = 0u;
+        __threadfence_system();
+        for (uint32_t r = 0; r < g.world; ++r)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(d.tick_flags[r] + g.rank), "r"(t + 1u) : "memory");
+      }
     }
   }
 }
@@ -412,11 +451,7 @@ class CudaBackend : public GsBackend {
     if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
-    // Sharded pools launch tick by tick.  Inside a CUDA graph the tick/barrier chain showed
-    // mailbox deliveries from the peer GPU being consumed 2-6 ticks late on B200 (state digest
-    // diverges from the single-GPU run; profiles/README.md, "multi-GPU"); with stream launches the
-    // same kernels are bit-exact, so the graph path stays off until that is understood.
-    if (use_graph && !xbar && left >= GS_GRAPH_TICKS) {
+    if (use_graph && (!xbar || !no_shard_graph_) && left >= GS_GRAPH_TICKS) {
       cudaGraphExec_t ge = graph_for(d, g_dev, blocks, xbar);
       if (!ge) return false;
       while (left >= GS_GRAPH_TICKS) {
@@ -428,7 +463,6 @@ class CudaBackend : public GsBackend {
     if (left) {
       for (uint32_t k = 0; k < left; ++k) {
         if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_ && !xbar), "tick launch")) return false;
-        if (xbar) gs_xbar_kernel<<<1, 32, 0, stream_>>>(*xbar);
       }
       gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
       launches_ += left + 1;
@@ -547,7 +581,7 @@ class CudaBackend : public GsBackend {
         if (dead) cudaGraphDestroy(dead);
         return nullptr;
       }
-      if (xbar) gs_xbar_kernel<<<1, 32, 0, stream_>>>(*xbar);
+
     gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
@@ -571,6 +605,7 @@ class CudaBackend : public GsBackend {
   GsVmm vmm_;
   bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
+  bool no_shard_graph_ = getenv("GSIM_NO_SHARD_GRAPH") != nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   uint64_t launches_ = 0;
   char err_[256];

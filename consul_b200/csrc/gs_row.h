@@ -43,7 +43,13 @@ __device__ __forceinline__ uint32_t gs_ld_sys(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t gs_ld_sys64(const uint64_t* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 #define GS_LD_OTHER(p) gs_ld_sys(p)
+#define GS_LD_OTHER64(p) gs_ld_sys64(p)
 #else
 #define GS_DEV inline
 #define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
@@ -56,6 +62,7 @@ static inline uint64_t gs_host_atomic_min64(uint64_t* p, uint64_t v) {
 }
 #define GS_ATOMIC_MIN64(p, v) gs_host_atomic_min64((uint64_t*)(p), (uint64_t)(v))
 #define GS_LD_OTHER(p) (*(p))
+#define GS_LD_OTHER64(p) (*(p))
 #endif
 
 // Stat indices (mirror GSIM_STAT_* in include/gsim.h).
@@ -297,7 +304,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       // [U] memberlist.suspectNode, subject side.  Entries are (~inc<<32 | from), sorted.
       uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;
       for (uint32_t s = 0; s < GS_K1MAX; ++s) {
-        uint64_t e = acc[(size_t)s * cap + i];
+        uint64_t e = GS_LD_OTHER64(&acc[(size_t)s * cap + i]);  // written by accusers anywhere
         if (e == GS_EMPTY64) break;
         acc[(size_t)s * cap + i] = GS_EMPTY64;
         uint32_t e_inc = ~(uint32_t)(e >> 32), from = (uint32_t)e;
