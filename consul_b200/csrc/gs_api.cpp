@@ -217,6 +217,14 @@ static bool poke(gsim_pool* p, T* col, size_t i, T v) {
   return p->be->h2d(col + i, &v, sizeof(T));
 }
 
+// Host-side write of a member's key word: every replica on a sharded pool.
+static bool poke_key(gsim_pool* p, uint32_t buf, uint32_t i, uint32_t k) {
+  if (!p->sharded) return poke(p, p->d.key[buf], i, k);
+  for (uint32_t r = 0; r < p->world; ++r)
+    if (!poke(p, p->d.key_rep[buf], (size_t)r * p->g.key_stride + i, k)) return false;
+  return true;
+}
+
 // N-dependent scalars, recomputed whenever the member count changes (a11).
 static void recompute_tables(gsim_pool* p) {
   GsGlobals& g = p->g;
@@ -364,7 +372,8 @@ static int init_device_state(gsim_pool* p) {
   const size_t cap = g.cap;
   bool okk = true;
   // key = 0 means truth NONE for rows that were never created
-  okk = okk && be->fill32(d.key[0], 0, cap) && be->fill32(d.key[1], 0, cap);
+  const size_t key_words = p->sharded ? (size_t)g.key_stride * p->world : cap;
+  okk = okk && be->fill32(d.key_rep[0], 0, key_words) && be->fill32(d.key_rep[1], 0, key_words);
   okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
@@ -468,7 +477,21 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     return q != nullptr;
   };
   bool okk = true;
-  okk = okk && acol(&d.key[0], 1) && acol(&d.key[1], 1);
+  if (!sharded) {
+    okk = okk && alloc_col(p, &d.key[0], cap) && alloc_col(p, &d.key[1], cap);
+    d.key_rep[0] = d.key[0];
+    d.key_rep[1] = d.key[1];
+  } else {
+    // one full replica of the key column per rank (gathers stay local; writers update all)
+    const size_t gran = be->shard_granularity();
+    const size_t rep_bytes = (cap * 4 + gran - 1) / gran * gran;
+    g.key_stride = (uint32_t)(rep_bytes / 4);
+    for (int b = 0; b < 2 && okk; ++b) {
+      d.key_rep[b] = reinterpret_cast<uint32_t*>(be->shard_alloc(rep_bytes, 1));
+      okk = d.key_rep[b] != nullptr;
+      d.key[b] = okk ? d.key_rep[b] + (size_t)cfg->rank * g.key_stride : nullptr;
+    }
+  }
   okk = okk && acol(&d.inbox[0], 1) && acol(&d.inbox[1], 1);
   okk = okk && acol(&d.due, 1) && acol(&d.meta, 1);
   okk = okk && acol(&d.cursor, 1) && acol(&d.pass, 1);
@@ -496,7 +519,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     if (okk) {
       uint8_t* page0 = p->pages;
       uint8_t* mine = p->pages + (size_t)p->rank * GS_PAGE_BYTES;
-      d.stats = reinterpret_cast<unsigned long long*>(page0 + GS_PG_STATS);
+      d.stats = reinterpret_cast<unsigned long long*>(mine + GS_PG_STATS);  // per rank, summed on read
       d.heard_cnt = reinterpret_cast<uint32_t*>(page0 + GS_PG_HEARD_CNT);
       d.conv_tick = reinterpret_cast<uint32_t*>(page0 + GS_PG_CONV_TICK);
       d.view_cnt = reinterpret_cast<uint32_t*>(page0 + GS_PG_VIEW_CNT);
@@ -635,7 +658,7 @@ static int retire_slot(gsim_pool* p, uint32_t slot) {
     if (gs_key_pending(k0)) p->n_established += 1;
     k0 &= ~(1u << 4);
     k1 &= ~(1u << 4);
-    if (!poke(p, p->d.key[0], ru.subject, k0) || !poke(p, p->d.key[1], ru.subject, k1))
+    if (!poke_key(p, 0, ru.subject, k0) || !poke_key(p, 1, ru.subject, k1))
       return GSIM_ERR_CUDA;
   }
   g.active_mask &= ~(1u << slot);
@@ -779,7 +802,7 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   // it knows nobody yet; with an empty base set there is nothing it could be missing
   if (p->n_established > 0) m |= GS_META_ISOLATED;
   if (desc && (desc->flags & GSIM_MEMBER_WATCHED)) m |= GS_META_WATCHED;
-  if (!poke(p, p->d.key[0], id, k) || !poke(p, p->d.key[1], id, k) || !poke(p, p->d.meta, id, m))
+  if (!poke_key(p, 0, id, k) || !poke_key(p, 1, id, k) || !poke(p, p->d.meta, id, m))
     return fail(p, GSIM_ERR_CUDA, "poke");
   g.n += 1;
   g.up_count += 1;
@@ -903,7 +926,7 @@ static int set_truth(gsim_pool* p, uint32_t id, uint32_t truth) {
     uint32_t k;
     if (!peek(p, p->d.key[b], id, &k)) return GSIM_ERR_CUDA;
     k = (k & ~3u) | truth;
-    if (!poke(p, p->d.key[b], id, k)) return GSIM_ERR_CUDA;
+    if (!poke_key(p, b, id, k)) return GSIM_ERR_CUDA;
   }
   return GSIM_OK;
 }
@@ -995,7 +1018,7 @@ extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
     uint32_t kk;
     if (!peek(p, p->d.key[b], id, &kk)) return fail(p, GSIM_ERR_CUDA, "peek");
     kk = gs_key_with_rank(kk, GS_RANK_LEFT);
-    if (!poke(p, p->d.key[b], id, kk)) return fail(p, GSIM_ERR_CUDA, "poke");
+    if (!poke_key(p, b, id, kk)) return fail(p, GSIM_ERR_CUDA, "poke");
   }
   m |= GS_META_LEAVING;
   if (!poke(p, p->d.meta, id, m) || !poke(p, p->d.change_tick, id, p->now))
@@ -1030,7 +1053,7 @@ extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int
       k &= ~3u;
     }
     any_truth = gs_key_truth(k);
-    if (!poke(p, p->d.key[b], target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
+    if (!poke_key(p, b, target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
   }
   (void)any_truth;
   int rc = refresh_after_truth_change(p);
@@ -1357,7 +1380,17 @@ extern "C" int gsim_stats_get(gsim_pool* p, gsim_stats* out) {
   return controller_call(p, out, sizeof(gsim_stats), [&]() -> int {
   memset(out, 0, sizeof(*out));
   if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
-  if (!p->be->d2h(out->counters, p->d.stats, sizeof(out->counters))) return fail(p, GSIM_ERR_CUDA, "d2h");
+  if (!p->sharded) {
+    if (!p->be->d2h(out->counters, p->d.stats, sizeof(out->counters))) return fail(p, GSIM_ERR_CUDA, "d2h");
+  } else {
+    // message counters are accumulated per rank (no cross-GPU atomics in the tick): sum the pages
+    for (uint32_t r = 0; r < p->world; ++r) {
+      uint64_t part[GSIM_STAT_COUNT];
+      if (!p->be->d2h(part, p->pages + (size_t)r * GS_PAGE_BYTES + GS_PG_STATS, sizeof(part)))
+        return fail(p, GSIM_ERR_CUDA, "d2h");
+      for (int q = 0; q < GSIM_STAT_COUNT; ++q) out->counters[q] += part[q];
+    }
+  }
   const GsGlobals& g = p->g;
   out->node_ticks = p->node_ticks;
   out->tick = p->now;
@@ -1571,6 +1604,18 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   for (const SnapCol& c : snap_cols(p)) {
     if ((size_t)(end - r) < c.bytes) return fail(p, GSIM_ERR_INVALID, "truncated");
     if (!p->be->h2d(c.ptr, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+    if (p->sharded && (c.ptr == p->d.key[0] || c.ptr == p->d.key[1])) {
+      // the key column is replicated per rank: restore every replica
+      uint32_t* rep0 = c.ptr == p->d.key[0] ? p->d.key_rep[0] : p->d.key_rep[1];
+      for (uint32_t q = 0; q < p->world; ++q)
+        if (!p->be->h2d(rep0 + (size_t)q * p->g.key_stride, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+    }
+    if (p->sharded && c.ptr == (void*)p->d.stats) {
+      // counters restore into rank 0's page; the other ranks' partial sums restart at zero
+      std::vector<uint8_t> zeros(c.bytes, 0);
+      for (uint32_t q = 1; q < p->world; ++q)
+        if (!p->be->h2d(p->pages + (size_t)q * GS_PAGE_BYTES + GS_PG_STATS, zeros.data(), c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+    }
     r += c.bytes;
   }
   p->g = h.g;

@@ -14,8 +14,8 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const uint32_t group = i / g.phase_group;
   const uint32_t pp = gs_probe_phase(g.rot_p, group, g.P), gp = gs_gossip_phase(g.rot_g, group, g.P, g.GI);
   const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
-  d.key[0][i] = k;
-  d.key[1][i] = k;
+  gs_key_store(d, g, 0u, i, k);
+  gs_key_store(d, g, 1u, i, k);
   d.inbox[0][i] = 0u;
   d.inbox[1][i] = 0u;
   d.meta[i] = gp << GS_META_GPHASE_SHIFT;
@@ -46,8 +46,8 @@ GS_DEV bool gs_crash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_
   GsU4 r = gs_philox(g.seed_lo, g.seed_hi, i, salt, GS_PUR_CRASH, 0u);
   if (r.x >= thr) return false;
   k = (k & ~3u) | GS_TRUTH_CRASHED;
-  d.key[0][i] = k;
-  d.key[1][i] = (d.key[1][i] & ~3u) | GS_TRUTH_CRASHED;
+  gs_key_store(d, g, 0u, i, k);
+  gs_key_store(d, g, 1u, i, (d.key[1][i] & ~3u) | GS_TRUTH_CRASHED);
   return true;
 }
 

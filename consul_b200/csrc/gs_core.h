@@ -230,6 +230,7 @@ struct GsGlobals {
   uint32_t phase_shift;  // phase_group == GS_TILE << phase_shift when phase_gate
   uint32_t rot_p, rot_g; // seed-derived rotation of the probe / gossip phases
   uint32_t rows_per_rank; // sharded pools: rank r owns members [r*rows_per_rank, (r+1)*rows_per_rank)
+  uint32_t key_stride;    // sharded pools: elements between the per-rank replicas of the key column
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -239,7 +240,8 @@ struct GsEventRec {
 
 // Device column pointers.
 struct GsDev {
-  uint32_t* key[2];
+  uint32_t* key[2];      // the key column this rank READS (its own replica when sharded)
+  uint32_t* key_rep[2];  // replica 0; replica r at + r*key_stride.  Writers update every replica.
   uint32_t* inbox[2];
   uint32_t* due;
   uint32_t* meta;

@@ -136,10 +136,11 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   DevSink sink{s_stat, s_heard};
 
   uint32_t tq = t_begin;  // next tile to issue
+  bool did_work = false;  // this thread touched global state (needs the closing fence when sharded)
   auto issue = [&](uint32_t st) {
     if (tq < t_end) {
       const size_t off = (size_t)tq * GS_TILE + lane * 4u;  // columns are padded to whole tiles
-      if (g.world > 1u) {
+      if (g.world > 1u && (g.flags & 4u)) {  // GSIM_FLAG_SHARD_SYNC_SCAN (debug)
         // sharded pool: this mailbox word is written by other GPUs; read it at system scope
         uint4 v;
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
     const bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
     if (__any_sync(0xFFFFFFFFu, mine)) {
+      did_work = true;
       __syncwarp();  // other lanes' copies are now visible: re-read one member per lane
       const uint32_t base = tile * GS_TILE + lane;
       bool act[4], cand[4];
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // Sharded pools: mailbox deliveries to other GPUs are fire-and-forget reductions over NVLink;
   // a system-scope fence by the issuing thread is what guarantees they have been performed at
   // the owner before this rank can signal the inter-tick barrier.
-  if (g.world > 1u) __threadfence_system();
+  if (g.world > 1u && did_work) __threadfence_system();
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {

@@ -48,7 +48,7 @@ __device__ __forceinline__ uint64_t gs_ld_sys64(const uint64_t* p) {
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-#define GS_LD_OTHER(p) gs_ld_sys(p)
+#define GS_LD_OTHER(p) __ldcg(p)
 #define GS_LD_OTHER64(p) gs_ld_sys64(p)
 #else
 #define GS_DEV inline
@@ -83,6 +83,18 @@ enum {
   GS_ST_PACKETS_LOST,
   GS_ST_ACTIVE_ROWS
 };
+
+// The key column is the one column every member reads about every other member (probe targets,
+// gossip peers, relays).  On a sharded pool each GPU keeps a full replica so those gathers stay
+// in local HBM; a key changes rarely (suspect, dead, refute, join), and whoever changes it
+// writes all replicas (remote stores over NVLink, ordered by the closing fence.sys).
+GS_DEV void gs_key_store(const GsDev& d, const GsGlobals& g, uint32_t buf, uint32_t i, uint32_t k) {
+  if (g.world <= 1u) {
+    d.key[buf][i] = k;
+    return;
+  }
+  for (uint32_t r = 0; r < g.world; ++r) d.key_rep[buf][(size_t)r * g.key_stride + i] = k;
+}
 
 // One simulated UDP packet is lost iff its Philox draw is below the threshold.
 template <class Sink>
@@ -239,7 +251,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   if ((inb & ~GS_WAKE_BIT) == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(up && due0 == t) &&
       !(gossip_slot && queued != 0u)) {
     if (m0 & GS_META_DIRTY) {  // bring the other key buffer up to date
-      d.key[nxt][i] = k0;
+      gs_key_store(d, g, nxt, i, k0);
       d.meta[i] = m0 & ~GS_META_DIRTY;
     }
     if (queued != 0u) GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
@@ -504,10 +516,10 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
 
   // ---- E. write back ------------------------------------------------------------
   if (k != k0) {
-    d.key[nxt][i] = k;
+    gs_key_store(d, g, nxt, i, k);
     m |= GS_META_DIRTY;  // the other buffer is stale for one more tick
   } else if (m0 & GS_META_DIRTY) {
-    d.key[nxt][i] = k;
+    gs_key_store(d, g, nxt, i, k);
     m &= ~GS_META_DIRTY;
   }
   if (m != m0) d.meta[i] = m;

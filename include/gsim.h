@@ -134,6 +134,7 @@ typedef struct gsim_config {
 
 #define GSIM_FLAG_LOG_GLOBAL_EVENTS 1u /* log Failed/Left/Join transitions of every member */
 #define GSIM_FLAG_NO_GRAPH 2u          /* launch tick kernels one by one (debug/profiling)  */
+#define GSIM_FLAG_SHARD_SYNC_SCAN 4u   /* sharded pools: scan mailboxes with ld.relaxed.sys (debug) */
 
 /* Preset defaults.  LAN/WAN: [U] memberlist DefaultLANConfig/DefaultWANConfig as
  * pinned by agent/config/runtime.go:1271-1413 with Consul's overrides

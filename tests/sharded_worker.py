@@ -46,7 +46,7 @@ def script(p):
     return out
 
 
-cfg = lan_config(capacity=N, n_initial=N - 8, seed=SEED, device=local)
+cfg = lan_config(capacity=N, n_initial=N - 8, seed=SEED, device=local, flags=int(os.environ.get("GSIM_FLAGS", "0")))
 sp = ShardedPool(cfg)
 got = script(sp)
 sp.close()
