@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     // Sharded pool, acquire side of the inter-tick barrier: tick t may start once every rank has
     // published "all ticks < t done" in this rank's progress array (written by the peers over
     // NVLink with st.release.sys at the end of their previous tick, see the end of this kernel).
-    if (tid < g.world) {
+    if (tid < g.world && !(g.flags & 16u)) {  // flag 16: timing experiment only (no wait)
       uint32_t v;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(d.tick_flags[g.rank] + tid) : "memory");
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // Sharded pools: mailbox deliveries to other GPUs are fire-and-forget reductions over NVLink;
   // a system-scope fence by the issuing thread is what guarantees they have been performed at
   // the owner before this rank can signal the inter-tick barrier.
-  if (g.world > 1u && did_work) __threadfence_system();
+  if (g.world > 1u && did_work && !(g.flags & 8u)) __threadfence_system();  // flag 8: timing experiment only
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {
@@ -607,7 +607,9 @@ class CudaBackend : public GsBackend {
   GsVmm vmm_;
   bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
-  bool no_shard_graph_ = getenv("GSIM_NO_SHARD_GRAPH") != nullptr;
+  // sharded pools: stream launches measured faster than graph replay (21 vs 28 us/tick at 2 Mi
+  // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
+  bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   uint64_t launches_ = 0;
   char err_[256];

@@ -34,8 +34,11 @@ __device__ __forceinline__ uint64_t gs_atomic_min_sys(uint64_t* p, uint64_t v) {
   asm volatile("atom.global.sys.min.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"((unsigned long long)v) : "memory");
   return old;
 }
-#define GS_ATOMIC_OR32(p, v) gs_atomic_or_sys((p), (v))
-#define GS_ATOMIC_MIN64(p, v) gs_atomic_min_sys((uint64_t*)(p), (uint64_t)(v))
+// (`g` is the GsGlobals in scope at every use: single-GPU pools keep the cheap device-scope forms)
+#define GS_ATOMIC_OR32(p, v) (g.world > 1u ? gs_atomic_or_sys((p), (v)) : atomicOr((p), (v)))
+#define GS_ATOMIC_MIN64(p, v)                                                    \
+  (g.world > 1u ? gs_atomic_min_sys((uint64_t*)(p), (uint64_t)(v))               \
+                : (uint64_t)atomicMin((unsigned long long*)(p), (unsigned long long)(v)))
 // Reads of OTHER members' columns go to L2 (ld.global.cg): on a sharded pool the line may live
 // on another GPU, and an L1 copy of a peer line is not something to rely on across ticks.
 __device__ __forceinline__ uint32_t gs_ld_sys(const uint32_t* p) {

@@ -9,7 +9,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for per_mi in [int(x) for x in os.environ.get("GSIM_PER_MI", "2,8").split(",")]:
     n = per_mi * 1024 * 1024 * world
-    for flags in (0, 2):
+    for flags in [int(x) for x in os.environ.get("GSIM_FLAGS_LIST", "0,2").split(",")]:
         p = ShardedPool(lan_config(capacity=n, n_initial=n, seed=0x5EED0001, device=local, flags=flags))
         p.step(64)
         best = 1e9
