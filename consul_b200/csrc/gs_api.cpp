@@ -382,6 +382,7 @@ static int init_device_state(gsim_pool* p) {
   okk = okk && be->fill32(d.view_cnt, 0, 4) && be->fill32(d.crashed_alive, 0, 1);
   okk = okk && be->fill32(d.crashed_dead_tick, GS_EMPTY32, 1);
   okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
+  if (!p->sharded) okk = okk && be->fill32(d.done_ctr, 0, 1);
 
   p->g_dirty = true;
   okk = okk && upload_globals(p);
@@ -511,6 +512,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     okk = okk && alloc_col(p, &d.crashed_alive, (size_t)1) && alloc_col(p, &d.crashed_dead_tick, (size_t)1);
     okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
     okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
+    okk = okk && alloc_col(p, &d.done_ctr, (size_t)1);  // grid barrier of multi-tick launches
     okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
   } else if (okk) {
     // pool-wide words: one 2 MB page per rank; counters and the event log live in rank 0's

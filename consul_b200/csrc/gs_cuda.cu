@@ -87,7 +87,7 @@ __device__ __forceinline__ void gs_cp_async_wait() {
 // before the first is consumed — so the tile pays two dependent memory latencies, not eight.
 // Whatever the fast path declines goes to the generic gs_row_step.
 __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
-    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
+    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
@@ -102,7 +102,12 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const GsGlobals& g = *gp;
-  const uint32_t t = *d.tick_base + k_off;
+  const uint32_t t_first = *d.tick_base + k_off;
+  // n_ticks > 1 (single-GPU pools): several ticks in one launch, separated by a grid barrier —
+  // the per-launch gap is most of a tick at 1 M members.  All CTAs are co-resident (persistent
+  // grid, cooperative launch).
+  for (uint32_t kk = 0; kk < n_ticks; ++kk) {
+  const uint32_t t = t_first + kk;
   if (g.world > 1u) {
     // Sharded pool, acquire side of the inter-tick barrier: tick t may start once every rank has
     // published "all ticks < t done" in this rank's progress array (written by the peers over
@@ -255,9 +260,32 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       }
     }
   }
+  if (kk + 1u < n_ticks) {
+    // Grid barrier between ticks of one launch: every thread's writes are fenced (which also
+    // drops this SM's L1), CTAs count in on a monotonic counter and wait for the whole grid.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0u) {
+      const uint32_t target = (kk + 1u) * gridDim.x;
+      __threadfence();
+      atomicAdd(d.done_ctr, 1u);
+      uint32_t v, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(d.done_ctr) : "memory");
+      } while (v < target && ++spins < (1u << 26));  // bounded: a bug must not hang the device
+    }
+    __syncthreads();
+    if (tid < GS_NSTAT) s_stat[tid] = 0u;
+    if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+    __syncthreads();
+  }
+  }  // for kk
 }
 
-__global__ void gs_advance_kernel(uint32_t* tick_base, uint32_t k) { *tick_base += k; }
+__global__ void gs_advance_kernel(uint32_t* tick_base, uint32_t k, uint32_t* done_ctr) {
+  *tick_base += k;
+  if (done_ctr) *done_ctr = 0u;
+}
 
 // Cross-GPU barrier (sharded pools).  One warp: lane r publishes this rank's new epoch into
 // slot `rank` of rank r's flag array (release, system scope, over NVLink) and then spins on
@@ -365,7 +393,16 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gs_tick_kernel, d, g_dev, k);
+  return cudaLaunchKernelEx(&cfg, gs_tick_kernel, d, g_dev, k, 1u);
+}
+
+// Several ticks in one cooperative launch (single-GPU pools).
+static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const GsDev& d,
+                                   const GsGlobals* g_dev, uint32_t n_ticks) {
+  GsDev dd = d;
+  uint32_t k0 = 0;
+  void* args[] = {(void*)&dd, (void*)&g_dev, (void*)&k0, (void*)&n_ticks};
+  return cudaLaunchCooperativeKernel((const void*)gs_tick_kernel, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
 }
 
 class CudaBackend : public GsBackend {
@@ -438,7 +475,7 @@ class CudaBackend : public GsBackend {
     (void)t0;
     if (!nticks || !g.n) {
       if (nticks) {  // no members: just advance time
-        gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, nticks);
+        gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, nticks, nullptr);
         ++launches_;
         return ok(cudaGetLastError(), "advance") && ok(cudaStreamSynchronize(stream_), "advance");
       }
@@ -453,6 +490,16 @@ class CudaBackend : public GsBackend {
     if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
+    if (use_graph && !xbar && g.world <= 1u && multi_tick_ && d.done_ctr && left > 1u) {
+      // one cooperative launch for the whole chunk (bounded to keep any single launch short)
+      while (left) {
+        const uint32_t c = left > 4096u ? 4096u : left;
+        if (!ok(gs_launch_multi(blocks, stream_, d, g_dev, c), "multi-tick launch")) return false;
+        gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, c, d.done_ctr);
+        launches_ += 2;
+        left -= c;
+      }
+    }
     if (use_graph && (!xbar || !no_shard_graph_) && left >= GS_GRAPH_TICKS) {
       cudaGraphExec_t ge = graph_for(d, g_dev, blocks, xbar);
       if (!ge) return false;
@@ -466,7 +513,7 @@ class CudaBackend : public GsBackend {
       for (uint32_t k = 0; k < left; ++k) {
         if (!ok(gs_launch_tick(blocks, stream_, d, g_dev, k, pdl_ && !xbar), "tick launch")) return false;
       }
-      gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left);
+      gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, left, nullptr);
       launches_ += left + 1;
       if (!ok(cudaGetLastError(), "tick launch")) return false;
     }
@@ -584,7 +631,7 @@ class CudaBackend : public GsBackend {
         return nullptr;
       }
 
-    gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS);
+    gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, GS_GRAPH_TICKS, nullptr);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture")) return nullptr;
     if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
       cudaGraphDestroy(graph);
@@ -607,6 +654,7 @@ class CudaBackend : public GsBackend {
   GsVmm vmm_;
   bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
+  bool multi_tick_ = getenv("GSIM_MULTI_TICK") != nullptr;
   // sharded pools: stream launches measured faster than graph replay (21 vs 28 us/tick at 2 Mi
   // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
   bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;
