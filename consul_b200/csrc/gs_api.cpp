@@ -676,22 +676,7 @@ static int retire_slot(gsim_pool* p, uint32_t slot) {
 
 // heard/queued/inbox bits of a freed slot must be zero before the slot is reused.
 static bool and_bit_columns(gsim_pool* p, uint32_t keep) {
-  // Rare control-plane operation: stream the three mask columns through the host.
-  const uint32_t n = p->g.n;
-  if (!n) return true;
-  std::vector<uint32_t> buf(n);
-  uint32_t* cols[4] = {p->d.heard, p->d.queued, p->d.inbox[0], p->d.inbox[1]};
-  for (int c = 0; c < 4; ++c) {
-    if (!p->be->d2h(buf.data(), cols[c], (size_t)n * 4)) return false;
-    bool changed = false;
-    for (uint32_t i = 0; i < n; ++i) {
-      uint32_t v = buf[i] & keep;
-      changed |= v != buf[i];
-      buf[i] = v;
-    }
-    if (changed && !p->be->h2d(cols[c], buf.data(), (size_t)n * 4)) return false;
-  }
-  return true;
+  return p->be->and_columns(p->d, p->g, keep);
 }
 
 // Retire finished membership rumors (alive / intents): every UP member has heard them and

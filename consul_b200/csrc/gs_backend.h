@@ -49,6 +49,8 @@ class GsBackend {
                        GsRecount* out) = 0;
   virtual bool state_hash(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
                           uint64_t out[4]) = 0;
+  // clear rumor bits outside `keep` in the heard / queued / mailbox columns (slot retirement)
+  virtual bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) = 0;
   virtual bool sync() = 0;
   virtual const char* last_error() const = 0;
   virtual uint64_t total_launches() const = 0;

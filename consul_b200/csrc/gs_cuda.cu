@@ -405,6 +405,20 @@ static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const G
   return cudaLaunchCooperativeKernel((const void*)gs_tick_kernel, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
 }
 
+__global__ void __launch_bounds__(GS_BLOCK) gs_and_kernel(GsDev d, uint32_t n, uint32_t keep) {
+  const uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v;
+  v = d.heard[i];
+  if (v & ~keep) d.heard[i] = v & keep;
+  v = d.queued[i];
+  if (v & ~keep) d.queued[i] = v & keep;
+  v = d.inbox[0][i];
+  if (v & ~keep) d.inbox[0][i] = v & keep;
+  v = d.inbox[1][i];
+  if (v & ~keep) d.inbox[1][i] = v & keep;
+}
+
 class CudaBackend : public GsBackend {
  public:
   explicit CudaBackend(int dev) : dev_(dev) {
@@ -595,6 +609,13 @@ class CudaBackend : public GsBackend {
     gs_xbar_kernel<<<1, 32, 0, stream_>>>(xb);
     ++launches_;
     return ok(cudaGetLastError(), "xbar launch") && ok(cudaStreamSynchronize(stream_), "xbar");
+  }
+  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) override {
+    cudaSetDevice(dev_);
+    if (!g.n) return true;
+    gs_and_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g.n, keep);
+    ++launches_;
+    return ok(cudaGetLastError(), "and launch") && ok(cudaStreamSynchronize(stream_), "and");
   }
   bool sync() override {
     cudaSetDevice(dev_);

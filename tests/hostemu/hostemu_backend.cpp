@@ -237,6 +237,15 @@ class HostEmuBackend : public GsBackend {
     *xb.epoch = e;
     return true;
   }
+  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) override {
+    for (uint32_t i = 0; i < g.n; ++i) {
+      d.heard[i] &= keep;
+      d.queued[i] &= keep;
+      d.inbox[0][i] &= keep;
+      d.inbox[1][i] &= keep;
+    }
+    return true;
+  }
   bool sync() override { return true; }
   const char* last_error() const override { return err_; }
   uint64_t total_launches() const override { return launches_; }
