@@ -49,6 +49,13 @@ B_PACKET = 12.0     # peer key gather + mailbox atomic RMW
 B_RUMOR_TX = 2.0    # tx counter r/w per broadcast carried
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gs_tick_kernel launch in LAN steady state,
+# from the `ncu --set full` captures committed as profiles/r1h_1m_raw.csv and r1h_64m_raw.csv
+# (tools/prof_target.py --members N --nograph).  They belong to the workload, not to this run.
+TRAFFIC_1M_BYTES = 10.73e6       # 1 M members: the hot columns sit in L2, DRAM sees ~11 B/member
+TRAFFIC_64M_BYTES = 1.208e9      # 64 Mi members: 18.0 B/member against 8.9 B algorithmic
+
+
 def algorithmic_bytes(d: dict, probe_interval_ticks: int) -> float:
     return (d["node_ticks"] * (B_SCAN + B_DUE * 2.0 / probe_interval_ticks) +
             d["active_rows"] * B_ACTIVE + d["probes"] * B_PROBE + d["rumors_accepted"] * B_ACCEPT +
@@ -340,7 +347,8 @@ def main():
     launch_us = kernel_ms * 1e3 / max(1, tick_launches)
     achieved = alg / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "gs_tick_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": TRAFFIC_1M_BYTES if (not sharded and n == N_MEMBERS) else None,
                 "peak_source": peak_src, "bytes_per_launch": alg / max(1, tick_launches),
                 "launch_us": launch_us, "launches": tick_launches,
                 "bytes_per_node_tick": alg / max(1.0, d["node_ticks"]),
@@ -363,6 +371,7 @@ def main():
         roofline_hbm = {"members": N_HBM, "ticks": HBM_TICKS, "achieved": algb / (ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": algb / (ms * 1e-3) / 1e9 / peak,
                         "launch_us": ms * 1e3 / nl, "node_ticks_per_s": db["node_ticks"] / (ms * 1e-3),
+                        "traffic": TRAFFIC_64M_BYTES, "bytes_per_launch": algb / nl,
                         "workload": f"{N_HBM:,} members, LAN steady state (4x BASELINE config 4 on one GPU; hot columns exceed L2)"}
         big.close()
 
