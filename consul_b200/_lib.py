@@ -47,7 +47,7 @@ class GsimConfig(C.Structure):
         ("reap_interval_ns", C.c_uint64), ("reconnect_timeout_ns", C.c_uint64),
         ("tombstone_timeout_ns", C.c_uint64),
         ("world_size", C.c_uint32), ("rank", C.c_uint32), ("device", C.c_int32),
-        ("event_log_capacity", C.c_uint32), ("phase_group", C.c_uint32), ("reserved0", C.c_uint32),
+        ("event_log_capacity", C.c_uint32), ("phase_group", C.c_uint32), ("mailbox_depth", C.c_uint32),
     ]
 
 
@@ -112,6 +112,9 @@ SIGNATURES = [
     ("gsim_crash_fraction", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("gsim_force_leave", _i32, [_P, _u32, _u32, _i32]),
     ("gsim_user_event", _i32, [_P, _u32, C.c_char_p, _sz, C.c_char_p, _sz, _i32, C.POINTER(_u32)]),
+    ("gsim_rumor_inject", _i32, [_P, _u32, _u32, C.POINTER(_i32)]),
+    ("gsim_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
+    ("gsim_member_watch", _i32, [_P, _u32, _i32]),
     ("gsim_step", _i32, [_P, _u32]),
     ("gsim_run_until", _i32, [_P, _i32, _u32, _u32, _u32, C.POINTER(_u32)]),
     ("gsim_now", _u32, [_P]),

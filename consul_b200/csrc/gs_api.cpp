@@ -374,7 +374,7 @@ static int init_device_state(gsim_pool* p) {
   // key = 0 means truth NONE for rows that were never created
   const size_t key_words = p->sharded ? (size_t)g.key_stride * p->world : cap;
   okk = okk && be->fill32(d.key_rep[0], 0, key_words) && be->fill32(d.key_rep[1], 0, key_words);
-  okk = okk && be->fill32(d.inbox[0], 0, cap) && be->fill32(d.inbox[1], 0, cap);
+  for (uint32_t s = 0; s <= g.ring_mask; ++s) okk = okk && be->fill32(d.inbox[s], 0, cap);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
@@ -410,6 +410,8 @@ extern "C" const char* gsim_strerror(int code) {
 
 extern "C" const char* gsim_last_error(gsim_pool* p) { return p ? p->err.c_str() : ""; }
 
+static_assert(GS_PG_GLOBALS + sizeof(GsGlobals) <= GS_PG_SCRATCH, "GsGlobals outgrew its page slot");
+static_assert(sizeof(BlobHdr) + sizeof(GsGlobals) + 4096 <= GS_BLOB_BYTES, "state blob too small");
 static thread_local std::string g_create_err;
 
 extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
@@ -431,6 +433,9 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   // 1 (per member) or 128 * 2^k (whole tiles)
   if (phase_group != 1 && (phase_group % GS_TILE != 0 || ((phase_group / GS_TILE) & (phase_group / GS_TILE - 1)) != 0))
     return GSIM_ERR_INVALID;
+  // mailbox ring: 2 arrival slots unless the pool is going to carry a latency matrix
+  const uint32_t ring_depth = cfg->mailbox_depth ? cfg->mailbox_depth : 2u;
+  if (ring_depth < 2 || ring_depth > GS_RING_MAX || (ring_depth & (ring_depth - 1u)) != 0) return GSIM_ERR_INVALID;
 
   char errbuf[256] = {0};
   GsBackend* be = GS_MAKE_BACKEND(cfg->device, errbuf, sizeof(errbuf));
@@ -493,7 +498,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       d.key[b] = okk ? d.key_rep[b] + (size_t)cfg->rank * g.key_stride : nullptr;
     }
   }
-  okk = okk && acol(&d.inbox[0], 1) && acol(&d.inbox[1], 1);
+  g.ring_mask = ring_depth - 1u;
+  for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && acol(&d.inbox[s], 1);
   okk = okk && acol(&d.due, 1) && acol(&d.meta, 1);
   okk = okk && acol(&d.cursor, 1) && acol(&d.pass, 1);
   okk = okk && acol(&d.probe_tgt, 1) && acol(&d.probe_inc, 1);
@@ -720,7 +726,7 @@ static int alloc_slot(gsim_pool* p, uint32_t* slot_out) {
 // A member whose broadcast queue became non-empty between ticks must be looked at by the
 // next tick: set the wake bit in the mailbox that tick will read.
 static bool post_wake(gsim_pool* p, uint32_t row) {
-  uint32_t* col = p->d.inbox[p->now & 1u];
+  uint32_t* col = p->d.inbox[p->now & p->g.ring_mask];
   uint32_t w;
   if (!peek(p, col, row, &w)) return false;
   return poke(p, col, row, w | GS_WAKE_BIT);
@@ -1100,6 +1106,91 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
   });
 }
 
+// Out-of-band delivery of a tracked broadcast to one member: what arrival by gossip would do, but
+// now and by name.  BASELINE config 5's bridge members use it to re-fire an event they delivered
+// in one WAN pool into the other (models ForwardRPC, agent/consul/internal_endpoint.go:839).
+extern "C" int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* accepted_out) {
+  if (!p || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  int acc_local = 0;
+  if (!accepted_out) accepted_out = &acc_local;
+  return controller_call(p, accepted_out, sizeof(int), [&]() -> int {
+  GsGlobals& g = p->g;
+  *accepted_out = 0;
+  if (!((g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
+  if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t k, m, h, q, le, lm, emin;
+  if (!peek(p, p->d.key[p->now & 1u], id, &k) || !peek(p, p->d.meta, id, &m) ||
+      !peek(p, p->d.heard, id, &h) || !peek(p, p->d.queued, id, &q) ||
+      !peek(p, p->d.ltime_event, id, &le) || !peek(p, p->d.ltime_member, id, &lm) ||
+      !peek(p, p->d.event_min, id, &emin))
+    return fail(p, GSIM_ERR_CUDA, "peek");
+  if (gs_key_truth(k) != GS_TRUTH_UP) return fail(p, GSIM_ERR_STATE, "member is not running");
+  if ((h >> slot) & 1u) return GSIM_OK;  // already delivered: serf's de-dup ring drops it
+  const GsRumor& ru = g.rumors[slot];
+  bool accept = true;
+  if (ru.kind == GSIM_RUMOR_USER_EVENT) {
+    if (ru.ltime >= le) le = ru.ltime + 1u;
+    if (ru.ltime < emin) accept = false;
+    else if (le > g.event_buffer && ru.ltime < le - g.event_buffer) accept = false;
+    if (accept && (m & GS_META_WATCHED)) log_host_event(p, GSIM_EVENT_USER, slot, id, ru.ltime);
+    if (!poke(p, p->d.ltime_event, id, le)) return fail(p, GSIM_ERR_CUDA, "poke");
+  } else if (ru.kind == GSIM_RUMOR_JOIN_INTENT || ru.kind == GSIM_RUMOR_LEAVE_INTENT) {
+    if (ru.ltime >= lm) lm = ru.ltime + 1u;
+    if (!poke(p, p->d.ltime_member, id, lm)) return fail(p, GSIM_ERR_CUDA, "poke");
+  } else if (ru.kind == GSIM_RUMOR_ALIVE) {
+    if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_JOIN, ru.subject, id, 0u);
+  }
+  if (!accept) return GSIM_OK;
+  uint32_t c, ct;
+  if (!poke(p, p->d.heard, id, h | (1u << slot)) || !poke(p, p->d.queued, id, q | (1u << slot)) ||
+      !poke(p, p->d.tx, (size_t)slot * g.cap + id, (uint8_t)0) || !post_wake(p, id) ||
+      !peek(p, p->d.heard_cnt, slot, &c) || !poke(p, p->d.heard_cnt, slot, c + 1u) ||
+      !peek(p, p->d.conv_tick, slot, &ct))
+    return fail(p, GSIM_ERR_CUDA, "poke");
+  if (c + 1u == g.up_count && ct == GS_EMPTY32 && !poke(p, p->d.conv_tick, slot, p->now))
+    return fail(p, GSIM_ERR_CUDA, "poke");
+  p->counts_stale = true;
+  *accepted_out = 1;
+  return GSIM_OK;
+  });
+}
+
+// Turn event logging for one member on or off after creation (gsim_member_desc.flags does it at
+// creation): the EventCh of that agent, polled through gsim_poll_events.
+extern "C" int gsim_member_watch(gsim_pool* p, uint32_t id, int on) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
+  if (id >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t m;
+  if (!peek(p, p->d.meta, id, &m)) return fail(p, GSIM_ERR_CUDA, "peek");
+  m = on ? (m | GS_META_WATCHED) : (m & ~GS_META_WATCHED);
+  if (!poke(p, p->d.meta, id, m)) return fail(p, GSIM_ERR_CUDA, "poke");
+  return GSIM_OK;
+  });
+}
+
+// WAN latency pools (BASELINE config 5): n_dcs synthetic datacenters, member i
+// lives in datacenter (i / 128) % n_dcs; a packet from datacenter a to b takes lat[a*n_dcs+b]
+// ticks (>= 1; 1 is the latency every packet has on a pool without a matrix).
+extern "C" int gsim_latency_set(gsim_pool* p, uint32_t n_dcs, const uint8_t* lat_ticks) {
+  if (!p || n_dcs > GS_MAX_DCS || (n_dcs && !lat_ticks)) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
+  GsGlobals& g = p->g;
+  for (uint32_t x = 0; x < n_dcs * n_dcs; ++x)
+    if (lat_ticks[x] < 1u || lat_ticks[x] > g.ring_mask)
+      return fail(p, GSIM_ERR_INVALID, "latency must be in [1, mailbox_depth - 1] ticks");
+  memset(g.lat, 0, sizeof(g.lat));
+  for (uint32_t a = 0; a < n_dcs; ++a)
+    for (uint32_t b = 0; b < n_dcs; ++b) g.lat[a * GS_MAX_DCS + b] = (uint8_t)(lat_ticks[a * n_dcs + b] - 1u);
+  g.n_dcs = n_dcs;
+  p->g_dirty = true;
+  return GSIM_OK;
+  });
+}
+
 // ---- time -----------------------------------------------------------------------
 static int apply_sched(gsim_pool* p) {
   bool any = false;
@@ -1451,7 +1542,7 @@ extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_
     case GSIM_COL_HEARD: src = d.heard; break;
     case GSIM_COL_QUEUED: src = d.queued; break;
     case GSIM_COL_TX: src = d.tx; bytes = cap * GS_MAX_RUMORS; break;
-    case GSIM_COL_INBOX: src = d.inbox[p->now & 1u]; break;
+    case GSIM_COL_INBOX: src = d.inbox[p->now & p->g.ring_mask]; break;
     default: return fail(p, GSIM_ERR_INVALID, "unknown column");
   }
   // the caller sees rows of `capacity` elements; the device stride is padded to whole tiles
@@ -1487,7 +1578,8 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   const size_t cap = p->g.cap;
   std::vector<SnapCol> v;
   auto add = [&](void* q, size_t b) { v.push_back(SnapCol{q, b}); };
-  add(d.key[0], cap * 4); add(d.key[1], cap * 4); add(d.inbox[0], cap * 4); add(d.inbox[1], cap * 4);
+  add(d.key[0], cap * 4); add(d.key[1], cap * 4);
+  for (uint32_t s = 0; s <= p->g.ring_mask; ++s) add(d.inbox[s], cap * 4);
   add(d.due, cap * 4); add(d.meta, cap * 4); add(d.cursor, cap * 4); add(d.pass, cap * 4);
   add(d.probe_tgt, cap * 4); add(d.probe_inc, cap * 4); add(d.sus_start, cap * 4);
   add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
@@ -1570,7 +1662,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   SnapHeader h;
   memcpy(&h, r, sizeof(h));
   r += sizeof(h);
-  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap)
+  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask)
     return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
   if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
   p->sched.resize(h.n_sched);

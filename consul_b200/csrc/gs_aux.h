@@ -16,8 +16,7 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
   gs_key_store(d, g, 0u, i, k);
   gs_key_store(d, g, 1u, i, k);
-  d.inbox[0][i] = 0u;
-  d.inbox[1][i] = 0u;
+  for (uint32_t s = 0; s <= g.ring_mask; ++s) d.inbox[s][i] = 0u;
   d.meta[i] = gp << GS_META_GPHASE_SHIFT;
   d.due[i] = now + (pp + g.P - now % g.P) % g.P;  // first tick >= now congruent to the phase
   d.cursor[i] = 0u;
@@ -82,8 +81,11 @@ GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint
   const uint32_t heard = d.heard[i] & g.active_mask;
   h = gs_mix64(h, heard);
   h = gs_mix64(h, d.queued[i] & g.active_mask);
-  const uint32_t inb = d.inbox[cur][i];
+  const uint32_t inb = d.inbox[now & g.ring_mask][i];
   h = gs_mix64(h, inb & (g.active_mask | GS_ACC_BIT));
+  // latency pools: packets still in flight, by ticks until arrival (slot now-1 was just consumed)
+  for (uint32_t s = 1; s < g.ring_mask; ++s)
+    h = gs_mix64(h, d.inbox[(now + s) & g.ring_mask][i] & g.active_mask);
   uint32_t hm = heard;
   while (hm) {
 #if defined(__CUDA_ARCH__)

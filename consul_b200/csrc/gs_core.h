@@ -29,6 +29,8 @@
 #define GS_MAX_RUMORS 30
 #define GS_MAX_WORLD_ 8
 #define GS_K1MAX 5
+#define GS_RING_MAX 8            // deepest mailbox ring (WAN latency pools): latency <= GS_RING_MAX - 1
+#define GS_MAX_DCS 64u           // synthetic datacenters of a latency pool (BASELINE config 5)
 #define GS_ACC_BIT 0x80000000u   // inbox: accusation(s) pending in acc[][][]
 #define GS_WAKE_BIT 0x40000000u  // inbox: "process this row" (self-posted or by the host)
 #define GS_TILE 128u             // rows per CTA; ticker phases are uniform per tile
@@ -231,6 +233,12 @@ struct GsGlobals {
   uint32_t rot_p, rot_g; // seed-derived rotation of the probe / gossip phases
   uint32_t rows_per_rank; // sharded pools: rank r owns members [r*rows_per_rank, (r+1)*rows_per_rank)
   uint32_t key_stride;    // sharded pools: elements between the per-rank replicas of the key column
+  // WAN latency pools (BASELINE config 5).  A packet sent at tick t from a member
+  // of datacenter a to one of datacenter b arrives at tick t + 1 + lat[a][b]; mailboxes are a
+  // ring of ring_mask + 1 arrival slots.  n_dcs == 0: every packet arrives at t + 1.
+  uint32_t ring_mask;     // mailbox ring depth - 1 (depth is a power of two, 2 by default)
+  uint32_t n_dcs;         // datacenter of member i = (i / GS_TILE) % n_dcs
+  uint8_t lat[GS_MAX_DCS * GS_MAX_DCS];  // EXTRA one-way latency in ticks (matrix entry - 1)
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -242,7 +250,7 @@ struct GsEventRec {
 struct GsDev {
   uint32_t* key[2];      // the key column this rank READS (its own replica when sharded)
   uint32_t* key_rep[2];  // replica 0; replica r at + r*key_stride.  Writers update every replica.
-  uint32_t* inbox[2];
+  uint32_t* inbox[GS_RING_MAX];  // arrival-tick ring; slots >= ring depth are null
   uint32_t* due;
   uint32_t* meta;
   uint32_t* cursor;

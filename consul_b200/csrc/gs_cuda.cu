@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   const uint32_t wid = blockIdx.x * GS_WARPS + wib;
   const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
   const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
-  const uint32_t* __restrict__ inbox_cur = d.inbox[cur];
+  const uint32_t* __restrict__ inbox_cur = d.inbox[t & g.ring_mask];  // this tick's arrival slot
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
   DevSink sink{s_stat, s_heard};
@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(GS_BLOCK) gs_and_kernel(GsDev d, uint32_t n, u
   if (v & ~keep) d.heard[i] = v & keep;
   v = d.queued[i];
   if (v & ~keep) d.queued[i] = v & keep;
-  v = d.inbox[0][i];
-  if (v & ~keep) d.inbox[0][i] = v & keep;
-  v = d.inbox[1][i];
-  if (v & ~keep) d.inbox[1][i] = v & keep;
+  for (uint32_t s = 0; s < GS_RING_MAX && d.inbox[s] != nullptr; ++s) {
+    v = d.inbox[s][i];
+    if (v & ~keep) d.inbox[s][i] = v & keep;
+  }
 }
 
 class CudaBackend : public GsBackend {

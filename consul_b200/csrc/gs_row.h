@@ -99,6 +99,23 @@ GS_DEV void gs_key_store(const GsDev& d, const GsGlobals& g, uint32_t buf, uint3
   for (uint32_t r = 0; r < g.world; ++r) d.key_rep[buf][(size_t)r * g.key_stride + i] = k;
 }
 
+// WAN latency pools (BASELINE config 5): EXTRA one-way latency in ticks from src to dst on top
+// of the one tick every packet takes; 0 everywhere on a pool without datacenters.  An all-zero
+// matrix is indistinguishable from n_dcs == 0 (tests/test_latency_cpu.py).
+GS_DEV uint32_t gs_extra(const GsGlobals& g, uint32_t src, uint32_t dst) {
+  if (g.n_dcs == 0u) return 0u;
+  return g.lat[((src / GS_TILE) % g.n_dcs) * GS_MAX_DCS + (dst / GS_TILE) % g.n_dcs];
+}
+
+// Same draw as gs_lost without touching the counters: re-evaluates, at the ProbeTimeout stage,
+// whether the direct ping/ack of the probe started at t0 were lost (late acks, latency pools).
+GS_DEV bool gs_lost_quiet(const GsGlobals& g, uint32_t src, uint32_t dst, uint32_t t, uint32_t kind,
+                          uint32_t idx) {
+  if (g.loss_thr == 0u) return false;
+  GsU4 r = gs_philox(g.seed_lo, g.seed_hi, src, dst, t, GS_PUR_LOSS | (kind << 8) | (idx << 16));
+  return r.x < g.loss_thr;
+}
+
 // One simulated UDP packet is lost iff its Philox draw is below the threshold.
 template <class Sink>
 GS_DEV bool gs_lost(const GsGlobals& g, Sink& sink, uint32_t src, uint32_t dst, uint32_t t,
@@ -238,7 +255,8 @@ GS_DEV bool gs_tile_probe_gate(const GsGlobals& g, uint32_t tile, uint32_t pslot
 template <class Sink>
 GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t, uint32_t gslot,
                         uint32_t inb, Sink& sink) {
-  const uint32_t cur = t & 1u, nxt = cur ^ 1u;
+  const uint32_t cur = t & 1u, nxt = cur ^ 1u;                            // key / acc buffers
+  const uint32_t icur = t & g.ring_mask, inxt = (t + 1u) & g.ring_mask;  // mailbox ring slots
   const uint32_t k0 = d.key[cur][i];
   const uint32_t truth = gs_key_truth(k0);
   if (truth == GS_TRUTH_NONE) return;
@@ -247,7 +265,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const bool up = truth == GS_TRUTH_UP;
   const bool gossip_slot = up && gslot == gs_meta_gphase(m0);  // gslot = t % GI
   uint32_t queued = up ? d.queued[i] : 0u;
-  if (inb != 0u) d.inbox[cur][i] = 0u;
+  if (inb != 0u) d.inbox[icur][i] = 0u;
   sink.stat(GS_ST_ACTIVE_ROWS, 1);  // scheduling diagnostic: rows that left the 4-byte scan
 
   // ---- nothing to do this tick (a wake that only keeps the row in the active set) ----
@@ -257,7 +275,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       gs_key_store(d, g, nxt, i, k0);
       d.meta[i] = m0 & ~GS_META_DIRTY;
     }
-    if (queued != 0u) GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
+    if (queued != 0u) GS_ATOMIC_OR32(&d.inbox[inxt][i], GS_WAKE_BIT);
     return;
   }
 
@@ -390,22 +408,33 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       uint32_t nr = gs_krandom(d, g, i, t, GS_PUR_RELAY, kk, 1u, j, m, relays);
       bool success = false;
       uint32_t nacks = 0;
+      // Latency pools: whatever comes back must arrive before the probe deadline, i.e. within
+      // `budget` ticks of extra latency from now (t0 + P*(awareness+1) - (t0 + T)).
+      const uint32_t budget = g.P * (gs_meta_aw(m) + 1u) - g.T;
       for (uint32_t q = 0; q < nr; ++q) {
         const uint32_t r = relays[q];
         const bool r_up = gs_key_truth(GS_LD_OTHER(&d.key[cur][r])) == GS_TRUTH_UP;
         sink.stat(GS_ST_INDIRECT_PINGS, 1);
         if (!(r_up && !gs_lost(g, sink, i, r, t, GS_LK_INDREQ, q))) continue;  // no nack either
+        const uint32_t via = gs_extra(g, i, r) + gs_extra(g, r, i);
+        const uint32_t rtt_rj = gs_extra(g, r, j) + gs_extra(g, j, r);
+        // the relay waits ProbeTimeout for the target's ack, then answers with a nack
         bool relay_acked = j_up && !gs_lost(g, sink, r, j, t, GS_LK_INDPING, q) &&
-                           !gs_lost(g, sink, j, r, t, GS_LK_INDACK, q);
+                           !gs_lost(g, sink, j, r, t, GS_LK_INDACK, q) && rtt_rj <= g.T;
         if (relay_acked) {
-          if (!gs_lost(g, sink, r, i, t, GS_LK_INDFWD, q)) success = true;
-        } else if (!gs_lost(g, sink, r, i, t, GS_LK_NACK, q)) {
+          if (!gs_lost(g, sink, r, i, t, GS_LK_INDFWD, q) && via + rtt_rj <= budget) success = true;
+        } else if (!gs_lost(g, sink, r, i, t, GS_LK_NACK, q) && via <= budget) {
           ++nacks;
           sink.stat(GS_ST_NACKS, 1);
         }
       }
-      if (!g.disable_tcp && j_up) success = true;  // TCP fallback ping is reliable
       const uint32_t t0 = t - g.T;
+      const uint32_t rtt_ij = gs_extra(g, i, j) + gs_extra(g, j, i);
+      if (!g.disable_tcp && j_up && rtt_ij <= budget) success = true;  // TCP fallback ping is reliable
+      // a direct ack that was merely slower than ProbeTimeout still counts until the deadline
+      if (g.n_dcs != 0u && j_up && rtt_ij > g.T && rtt_ij <= budget + g.T &&
+          !gs_lost_quiet(g, i, j, t0, GS_LK_PING, 0) && !gs_lost_quiet(g, j, i, t0, GS_LK_ACK, 0))
+        success = true;
       if (success) {
         uint32_t aw = gs_meta_aw(m);
         m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
@@ -433,7 +462,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         if (old == v || old == GS_EMPTY64) break;
         if (old > v) v = old;  // displaced a larger entry: carry it to the next slot
       }
-      GS_ATOMIC_OR32(&d.inbox[nxt][j], GS_ACC_BIT);
+      GS_ATOMIC_OR32(&d.inbox[inxt][j], GS_ACC_BIT);
       sink.stat(GS_ST_PROBE_FAILURES, 1);
       stage = GS_STAGE_IDLE;  // due == t: the buffered ticker fires immediately
     }
@@ -471,7 +500,8 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       if (target != GS_EMPTY32) {
         sink.stat(GS_ST_PROBES, 1);
         bool ok = gs_key_truth(ktarget) == GS_TRUTH_UP && !gs_lost(g, sink, i, target, t, GS_LK_PING, 0) &&
-                  !gs_lost(g, sink, target, i, t, GS_LK_ACK, 0);
+                  !gs_lost(g, sink, target, i, t, GS_LK_ACK, 0) &&
+                  gs_extra(g, i, target) + gs_extra(g, target, i) <= g.T;  // ack within ProbeTimeout
         if (ok) {
           uint32_t aw = gs_meta_aw(m);
           m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
@@ -511,7 +541,8 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           sink.stat(GS_ST_RUMORS_SENT, 1);
         }
         sink.stat(GS_ST_GOSSIP_PACKETS, 1);
-        if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q)) GS_ATOMIC_OR32(&d.inbox[nxt][peers[q]], pkt);
+        if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q))
+          GS_ATOMIC_OR32(&d.inbox[(t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask][peers[q]], pkt);
       }
       if (queued != q0) d.queued[i] = queued;
     }
@@ -530,7 +561,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   // stay in the active set while something time-driven is pending: a running suspicion
   // timer, a stale key buffer, or a non-empty broadcast queue
   if (gs_key_rank(k) == GS_RANK_SUSPECT || (m & GS_META_DIRTY) || queued != 0u)
-    GS_ATOMIC_OR32(&d.inbox[nxt][i], GS_WAKE_BIT);
+    GS_ATOMIC_OR32(&d.inbox[inxt][i], GS_WAKE_BIT);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -575,7 +606,7 @@ GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
       gs_key_pending(f.kc))
     return false;  // ring entry must be skipped or needs the heard mask: generic path
   uint32_t m = f.m;
-  if (gs_key_truth(f.kc) == GS_TRUTH_UP) {
+  if (gs_key_truth(f.kc) == GS_TRUTH_UP && gs_extra(g, i, f.c) + gs_extra(g, f.c, i) <= g.T) {
     const uint32_t aw = gs_meta_aw(m);
     m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
     d.due[i] = t + g.P;

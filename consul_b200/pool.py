@@ -136,6 +136,24 @@ class Pool:
                                           int(coalesce), C.byref(out)))
         return out.value
 
+    def rumor_inject(self, slot: int, member: int) -> bool:
+        """Out-of-band delivery of tracked broadcast `slot` to `member` (WAN bridges)."""
+        out = C.c_int()
+        self._ck(self.lib.gsim_rumor_inject(self.h, slot, member, C.byref(out)))
+        return bool(out.value)
+
+    def member_watch(self, member: int, on: bool = True):
+        self._ck(self.lib.gsim_member_watch(self.h, member, int(on)))
+
+    def latency_set(self, lat):
+        """lat: square matrix (n_dcs x n_dcs) of one-way latencies in ticks (>= 1), or None."""
+        if lat is None:
+            self._ck(self.lib.gsim_latency_set(self.h, 0, None))
+            return
+        m = np.ascontiguousarray(lat, dtype=np.uint8)
+        assert m.ndim == 2 and m.shape[0] == m.shape[1]
+        self._ck(self.lib.gsim_latency_set(self.h, m.shape[0], m.ctypes.data_as(C.POINTER(C.c_uint8))))
+
     # -- time ---------------------------------------------------------------------
     def step(self, ticks: int = 1):
         self._ck(self.lib.gsim_step(self.h, ticks))

@@ -129,7 +129,9 @@ typedef struct gsim_config {
    * makes the failure-detector path uniform per 128-thread CTA; 1 = per-member phases (small
    * clusters, no CTA-level gating).  Must be 1 or a multiple of 128. */
   uint32_t phase_group;
-  uint32_t reserved0;
+  /* Mailbox ring depth: arrival slots per member (power of two, 2..8; 0 = 2).  A pool that will
+   * carry a latency matrix (gsim_latency_set) needs depth > the largest one-way latency. */
+  uint32_t mailbox_depth;
 } gsim_config;
 
 #define GSIM_FLAG_LOG_GLOBAL_EVENTS 1u /* log Failed/Left/Join transitions of every member */
@@ -195,6 +197,27 @@ int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int prune);
  * internal_endpoint.go:862, leader.go:150).  slot_out = tracked rumor slot. */
 int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size_t name_len,
                     const void* payload, size_t payload_len, int coalesce, uint32_t* slot_out);
+
+/* Out-of-band delivery of tracked broadcast `slot` to member `id`, exactly as if a gossip packet
+ * carrying it had just arrived (Lamport witness, de-dup, event-window checks, re-queue with
+ * transmits = 0).  BASELINE config 5: bridge members re-fire an event they delivered in one WAN
+ * pool into the other pool (the ForwardRPC of agent/consul/internal_endpoint.go:839).
+ * *accepted = 1 when the member had not heard it and took it. */
+int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* accepted);
+
+/* Event logging of one member on/off after creation (that agent's EventCh; see
+ * gsim_member_desc.flags / GSIM_MEMBER_WATCHED and gsim_poll_events). */
+int gsim_member_watch(gsim_pool* p, uint32_t id, int on);
+
+/* WAN latency (BASELINE config 5; Consul's WAN pool wiring: agent/consul/server_serf.go:187-213,
+ * agent/consul/wanfed/wanfed.go:36-40).  Members are grouped into n_dcs (<= 64) synthetic
+ * datacenters, member i in datacenter (i / 128) % n_dcs.  lat_ticks[a * n_dcs + b] = one-way
+ * latency in ticks of a packet from datacenter a to datacenter b, 1 <= latency < mailbox_depth
+ * (1 = the tick every packet takes on a pool without a matrix, so an all-ones matrix changes
+ * nothing).  Applies to gossip packets and to probe round trips: an ack slower than ProbeTimeout
+ * sends the prober into the indirect/TCP stage, where it still counts until the probe deadline.
+ * n_dcs = 0 removes the matrix.  Callable between steps; packets in flight keep their slots. */
+int gsim_latency_set(gsim_pool* p, uint32_t n_dcs, const uint8_t* lat_ticks);
 
 /* ---- time ---------------------------------------------------------------- */
 int gsim_step(gsim_pool* p, uint32_t ticks);

@@ -205,7 +205,12 @@ struct Oracle {
   std::vector<Member> m;
   std::vector<View> pub;                 // published views (state at the start of the tick)
   std::vector<uint32_t> pub_change_tick; // published change ticks
-  std::vector<uint32_t> inbox[2];        // rumor bits by arrival-tick parity (bit 31: accused)
+  static const uint32_t RING = 8;        // arrival slots kept per member (one-way latency <= 7 ticks)
+  std::vector<uint32_t> inbox[RING];     // rumor bits by arrival tick mod RING (bit 31: accused)
+  // WAN pools (BASELINE config 5): one-way latency in ticks between synthetic datacenters;
+  // member i lives in datacenter (i / 128) % n_dcs.  n_dcs == 0: one tick everywhere.
+  uint32_t n_dcs = 0;
+  uint8_t latency[64][64];
   std::vector<uint32_t> wake;            // 0 = look every tick, else the only tick worth a look
   std::vector<Tally> tallies;            // per-thread accumulators, reused every tick
   std::vector<Accusation> arriving;      // accusations that arrive at the tick about to run
@@ -283,6 +288,20 @@ bool packet_lost(const Oracle& o, Tally& ta, uint32_t src, uint32_t dst, uint32_
   }
   return false;
 }
+
+bool packet_lost_silently(const Oracle& o, uint32_t src, uint32_t dst, uint32_t t, uint32_t kind, uint32_t idx) {
+  if (!o.loss_thr) return false;
+  return philox4x32_10(o.cfg.seed, src, dst, t, PUR_LOSS | (kind << 8) | (idx << 16)).v[0] < o.loss_thr;
+}
+
+// one-way latency of a packet in ticks (>= 1)
+uint32_t one_way(const Oracle& o, uint32_t src, uint32_t dst) {
+  if (!o.n_dcs) return 1;
+  return o.latency[(src / 128) % o.n_dcs][(dst / 128) % o.n_dcs];
+}
+// Round trip beyond the two ticks the lock-step model does not charge to a probe: probes are
+// evaluated within their tick, so only latency above one tick per direction delays an ack.
+uint32_t round_trip(const Oracle& o, uint32_t a, uint32_t b) { return one_way(o, a, b) + one_way(o, b, a) - 2; }
 
 int alive_slot_of(const Oracle& o, uint32_t subject) {
   for (int r = 0; r < GSIM_MAX_RUMORS; ++r)
@@ -392,8 +411,8 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
   const bool up = me.v.truth == GSIM_TRUTH_UP;
   const View before = me.v;
   const bool my_gossip_tick = up && (t % o.GI) == me.gossip_phase;
-  const uint32_t word = o.inbox[t & 1][i];
-  o.inbox[t & 1][i] = 0;
+  const uint32_t word = o.inbox[t % Oracle::RING][i];
+  o.inbox[t % Oracle::RING][i] = 0;
   const uint32_t inbox = word & 0x7FFFFFFFu;
   // accusations addressed to me (bit 31 was set when they were handed over; the arriving
   // list is sorted by subject)
@@ -491,22 +510,33 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
       Picks relays = k_random(o, i, me, t, PUR_RELAY, std::min<uint32_t>(8, o.cfg.indirect_checks), true, j);
       bool success = false;
       uint32_t nacks = 0;
+      const uint32_t started = t - o.T;
+      // ticks left until the probe deadline (started + P * (awareness + 1)); on a WAN pool an
+      // answer only counts if its extra latency fits in them
+      const uint32_t left = started + o.P * (me.awareness + 1u) - t;
       for (uint32_t q = 0; q < relays.size(); ++q) {
         uint32_t r = relays[q];
         ta.c[GSIM_STAT_INDIRECT_PINGS]++;
         if (o.pub[r].truth != GSIM_TRUTH_UP) continue;                  // relay is down
         if (packet_lost(o, ta, i, r, t, LK_INDREQ, q)) continue;        // request lost
+        const uint32_t to_relay_and_back = round_trip(o, i, r);
+        const uint32_t relay_to_target = round_trip(o, r, j);
+        // the relay gives the target ProbeTimeout to ack, then reports a nack
         bool acked = target_up && !packet_lost(o, ta, r, j, t, LK_INDPING, q) &&
-                     !packet_lost(o, ta, j, r, t, LK_INDACK, q);
+                     !packet_lost(o, ta, j, r, t, LK_INDACK, q) && relay_to_target <= o.T;
         if (acked) {
-          if (!packet_lost(o, ta, r, i, t, LK_INDFWD, q)) success = true;
-        } else if (!packet_lost(o, ta, r, i, t, LK_NACK, q)) {
+          if (!packet_lost(o, ta, r, i, t, LK_INDFWD, q) && to_relay_and_back + relay_to_target <= left) success = true;
+        } else if (!packet_lost(o, ta, r, i, t, LK_NACK, q) && to_relay_and_back <= left) {
           nacks++;
           ta.c[GSIM_STAT_NACKS]++;
         }
       }
-      if (!o.cfg.disable_tcp_pings && target_up) success = true;  // TCP fallback
-      const uint32_t started = t - o.T;
+      const uint32_t direct = round_trip(o, i, j);
+      if (!o.cfg.disable_tcp_pings && target_up && direct <= left) success = true;  // TCP fallback
+      // the direct ack may simply have been slower than ProbeTimeout: it counts until the deadline
+      if (o.n_dcs && target_up && direct > o.T && started + direct <= t + left &&
+          !packet_lost_silently(o, i, j, started, LK_PING, 0) && !packet_lost_silently(o, j, i, started, LK_ACK, 0))
+        success = true;
       if (success) {
         if (me.awareness) me.awareness--;
         me.stage = ST_IDLE;
@@ -553,7 +583,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
       } else {
         ta.c[GSIM_STAT_PROBES]++;
         bool acked = o.pub[target].truth == GSIM_TRUTH_UP && !packet_lost(o, ta, i, target, t, LK_PING, 0) &&
-                     !packet_lost(o, ta, target, i, t, LK_ACK, 0);
+                     !packet_lost(o, ta, target, i, t, LK_ACK, 0) && round_trip(o, i, target) <= o.T;
         if (acked) {
           if (me.awareness) me.awareness--;
           me.due = t + o.P;
@@ -581,7 +611,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
         }
         ta.c[GSIM_STAT_GOSSIP_PACKETS]++;
         if (!packet_lost(o, ta, i, peers[q], t, LK_GOSSIP, q))
-          __atomic_fetch_or(&o.inbox[(t + 1) & 1][peers[q]], packet, __ATOMIC_RELAXED);
+          __atomic_fetch_or(&o.inbox[(t + one_way(o, i, peers[q])) % Oracle::RING][peers[q]], packet, __ATOMIC_RELAXED);
       }
     }
   }
@@ -602,10 +632,10 @@ void run_tick(Oracle& o) {
                                  return a.subject == b.subject && a.inc == b.inc && a.from == b.from;
                                }),
                    o.arriving.end());
-  for (const Accusation& a : o.arriving) o.inbox[t & 1][a.subject] |= 0x80000000u;
+  for (const Accusation& a : o.arriving) o.inbox[t % Oracle::RING][a.subject] |= 0x80000000u;
   // Members with no mail whose only scheduled action lies at another tick cannot do anything
   // (this is exactly the idle test at the top of member_tick, evaluated from two flat arrays).
-  const uint32_t* mail = o.inbox[t & 1].data();
+  const uint32_t* mail = o.inbox[t % Oracle::RING].data();
   uint32_t* wake = o.wake.data();
   std::vector<Tally>& tallies = o.tallies;
   tallies.resize((size_t)o.threads);
@@ -711,7 +741,7 @@ void retire(Oracle& o, uint32_t slot) {
     me.heard &= ~(1u << slot);
     me.queued &= ~(1u << slot);
   }
-  for (int b = 0; b < 2; ++b)
+  for (uint32_t b = 0; b < Oracle::RING; ++b)
     for (uint32_t& w : o.inbox[b]) w &= ~(1u << slot);
 }
 
@@ -883,8 +913,8 @@ void* oracle_create(const gsim_config* cfg, int threads) {
   o->m.resize(cfg->n_initial);
   o->pub.resize(cfg->n_initial);
   o->pub_change_tick.assign(cfg->n_initial, 0);
-  o->inbox[0].assign(cfg->n_initial, 0);
-  o->inbox[1].assign(cfg->n_initial, 0);
+  for (uint32_t b = 0; b < Oracle::RING; ++b) o->inbox[b].assign(cfg->n_initial, 0);
+  memset(o->latency, 1, sizeof(o->latency));
   o->up_count = cfg->n_initial;
   o->established = cfg->n_initial;
   for (uint32_t i = 0; i < cfg->n_initial; ++i) {
@@ -914,8 +944,7 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   o.m.emplace_back();
   o.pub.emplace_back();
   o.pub_change_tick.push_back(0);
-  o.inbox[0].push_back(0);
-  o.inbox[1].push_back(0);
+  for (uint32_t b = 0; b < Oracle::RING; ++b) o.inbox[b].push_back(0);
   Member& me = o.m.back();
   me.v.truth = GSIM_TRUTH_UP;
   me.v.rank = GSIM_RANK_ALIVE;
@@ -1050,6 +1079,54 @@ int oracle_user_event(void* h, uint32_t id, const void* name, size_t nl, const v
   o.m[id].ltime_event = lt + 1;
   if (o.m[id].watched) host_event(o, GSIM_EVENT_USER, (uint32_t)slot, id, lt);
   if (slot_out) *slot_out = (uint32_t)slot;
+  return GSIM_OK;
+}
+
+// Out-of-band delivery of a tracked broadcast to one member (WAN bridge re-fire, config 5).
+int oracle_rumor_inject(void* h, uint32_t slot, uint32_t id, int* accepted) {
+  Oracle& o = *(Oracle*)h;
+  if (accepted) *accepted = 0;
+  if (slot >= GSIM_MAX_RUMORS || !((o.active >> slot) & 1)) return GSIM_ERR_NOT_FOUND;
+  if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
+  Member& me = o.m[id];
+  if (me.v.truth != GSIM_TRUTH_UP) return GSIM_ERR_STATE;
+  if ((me.heard >> slot) & 1) return GSIM_OK;
+  Rumor& ru = o.rumor[slot];
+  if (ru.kind == GSIM_RUMOR_USER_EVENT) {
+    me.ltime_event = lamport_witness(me.ltime_event, ru.ltime);
+    if (ru.ltime < me.event_min) return GSIM_OK;
+    if (me.ltime_event > o.cfg.event_buffer && ru.ltime < me.ltime_event - o.cfg.event_buffer) return GSIM_OK;
+    if (me.watched) host_event(o, GSIM_EVENT_USER, slot, id, ru.ltime);
+  } else if (ru.kind == GSIM_RUMOR_JOIN_INTENT || ru.kind == GSIM_RUMOR_LEAVE_INTENT) {
+    me.ltime_member = lamport_witness(me.ltime_member, ru.ltime);
+  } else if (ru.kind == GSIM_RUMOR_ALIVE) {
+    if (me.watched) host_event(o, GSIM_EVENT_MEMBER_JOIN, ru.subject, id, 0);
+  }
+  me.heard |= 1u << slot;
+  me.queued |= 1u << slot;
+  me.tx[slot] = 0;
+  ru.heard_count++;
+  if (ru.heard_count == o.up_count && ru.converged_tick == NONE32) ru.converged_tick = o.now;
+  if (accepted) *accepted = 1;
+  return GSIM_OK;
+}
+
+int oracle_member_watch(void* h, uint32_t id, int on) {
+  Oracle& o = *(Oracle*)h;
+  if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
+  o.m[id].watched = on != 0;
+  return GSIM_OK;
+}
+
+int oracle_latency_set(void* h, uint32_t n_dcs, const uint8_t* lat) {
+  Oracle& o = *(Oracle*)h;
+  if (n_dcs > 64) return GSIM_ERR_INVALID;
+  const uint32_t depth = o.cfg.mailbox_depth ? o.cfg.mailbox_depth : 2;
+  for (uint32_t x = 0; x < n_dcs * n_dcs; ++x)
+    if (lat[x] < 1 || lat[x] >= depth) return GSIM_ERR_INVALID;
+  for (uint32_t a = 0; a < n_dcs; ++a)
+    for (uint32_t b = 0; b < n_dcs; ++b) o.latency[a][b] = lat[a * n_dcs + b];
+  o.n_dcs = n_dcs;
   return GSIM_OK;
 }
 
@@ -1228,8 +1305,12 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
     x = mix(x, heard);
     x = mix(x, me.queued & o.active);
     bool has_acc = ap < acc.size() && acc[ap].subject == i;
-    uint32_t inb = (o.inbox[o.now & 1][i] & o.active) | (has_acc ? 0x80000000u : 0);
+    uint32_t inb = (o.inbox[o.now % Oracle::RING][i] & o.active) | (has_acc ? 0x80000000u : 0);
     x = mix(x, inb);
+    // packets still in flight on a WAN pool, nearest arrival first (what a mailbox ring of
+    // cfg.mailbox_depth slots can hold beyond the slot read next and the one just emptied)
+    for (uint32_t ahead = 1; ahead + 1 < (o.cfg.mailbox_depth ? o.cfg.mailbox_depth : 2); ++ahead)
+      x = mix(x, o.inbox[(o.now + ahead) % Oracle::RING][i] & o.active);
     for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
       if ((heard >> r) & 1) x = mix(x, (r << 8) | me.tx[r]);
     if (has_acc) {
@@ -1291,7 +1372,7 @@ int oracle_column_read(void* h, int column, void* out, size_t cap_bytes, size_t*
       case GSIM_COL_TX:
         for (int r = 0; r < GSIM_MAX_RUMORS; ++r) b[(size_t)r * cap + i] = me.tx[r];
         break;
-      case GSIM_COL_INBOX: w[i] = o.inbox[o.now & 1][i] & 0x7FFFFFFFu; break;
+      case GSIM_COL_INBOX: w[i] = o.inbox[o.now % Oracle::RING][i] & 0x7FFFFFFFu; break;
       default: return GSIM_ERR_INVALID;
     }
   }

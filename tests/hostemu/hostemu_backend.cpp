@@ -110,7 +110,7 @@ class HostEmuBackend : public GsBackend {
       }
       for (uint32_t x = 0; x < hi - lo; ++x) {
         const uint32_t i = lo + row_at(x, hi - lo);
-        const uint32_t inb = d.inbox[t & 1u][i];
+        const uint32_t inb = d.inbox[t & g.ring_mask][i];
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
         if (!(inb != 0u || due == t)) continue;
@@ -241,8 +241,7 @@ class HostEmuBackend : public GsBackend {
     for (uint32_t i = 0; i < g.n; ++i) {
       d.heard[i] &= keep;
       d.queued[i] &= keep;
-      d.inbox[0][i] &= keep;
-      d.inbox[1][i] &= keep;
+      for (uint32_t s = 0; s <= g.ring_mask; ++s) d.inbox[s][i] &= keep;
     }
     return true;
   }

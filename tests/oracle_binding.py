@@ -37,6 +37,9 @@ _SIGS = [
     ("oracle_crash_fraction", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("oracle_force_leave", _i32, [_P, _u32, _u32, _i32]),
     ("oracle_user_event", _i32, [_P, _u32, C.c_char_p, _sz, C.c_char_p, _sz, _i32, C.POINTER(_u32)]),
+    ("oracle_rumor_inject", _i32, [_P, _u32, _u32, C.POINTER(_i32)]),
+    ("oracle_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
+    ("oracle_member_watch", _i32, [_P, _u32, _i32]),
     ("oracle_step", _i32, [_P, _u32]),
     ("oracle_now", _u32, [_P]),
     ("oracle_run_until", _i32, [_P, _i32, _u32, _u32, _u32, C.POINTER(_u32)]),
@@ -129,6 +132,22 @@ class OraclePool:
         self._ck(self.lib.oracle_user_event(self.h, member, name, len(name), payload, len(payload),
                                             int(coalesce), C.byref(out)))
         return out.value
+
+    def rumor_inject(self, slot, member):
+        out = C.c_int()
+        self._ck(self.lib.oracle_rumor_inject(self.h, slot, member, C.byref(out)))
+        return bool(out.value)
+
+    def member_watch(self, member, on=True):
+        self._ck(self.lib.oracle_member_watch(self.h, member, int(on)))
+
+    def latency_set(self, lat):
+        import numpy as np
+        if lat is None:
+            self._ck(self.lib.oracle_latency_set(self.h, 0, None))
+            return
+        m = np.ascontiguousarray(lat, dtype=np.uint8)
+        self._ck(self.lib.oracle_latency_set(self.h, m.shape[0], m.ctypes.data_as(C.POINTER(C.c_uint8))))
 
     def step(self, ticks=1):
         self._ck(self.lib.oracle_step(self.h, ticks))
