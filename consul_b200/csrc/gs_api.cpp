@@ -1217,6 +1217,48 @@ static int apply_sched(gsim_pool* p) {
 // Advance `ticks` ticks.  On a sharded pool every rank runs this together: the host-side parts
 // (scheduled shutdowns, globals upload, rumor retirement) are controller calls, the tick kernels
 // run on every rank with a device barrier after each tick.
+// [U] serf.handleReap: every ReapInterval, erase members that have been Failed for longer than
+// ReconnectTimeout or Left for longer than TombstoneTimeout.  The reaper's
+// ticker fires at ticks that are multiples of ReapInterval; with Consul's production values
+// (72 h / 24 h, agent/consul/config.go:622-623) nothing can be old enough within any simulated
+// horizon and no pass is ever scheduled — only test timings (server_test.go:675-677) reach it.
+struct ReapPlan {
+  uint32_t every, reconnect, tombstone;
+};
+static uint32_t clamp_ticks(uint64_t ns, uint64_t tick) {
+  const uint64_t t = (ns + tick - 1) / tick;
+  return t > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)t;
+}
+static ReapPlan reap_plan(const gsim_pool* p) {
+  ReapPlan r;
+  r.every = p->cfg.reap_interval_ns ? clamp_ticks(p->cfg.reap_interval_ns, p->tick_ns) : 0u;
+  r.reconnect = clamp_ticks(p->cfg.reconnect_timeout_ns, p->tick_ns);
+  r.tombstone = clamp_ticks(p->cfg.tombstone_timeout_ns, p->tick_ns);
+  return r;
+}
+// first tick > now at which a reap pass can possibly find something, or GS_NEVER
+static uint32_t next_reap_tick(const gsim_pool* p, uint32_t now) {
+  const ReapPlan r = reap_plan(p);
+  if (!r.every) return GS_NEVER;
+  const uint32_t youngest = r.reconnect < r.tombstone ? r.reconnect : r.tombstone;
+  uint64_t t = (uint64_t)(now / r.every + 1u) * r.every;
+  if (t <= youngest) t = ((uint64_t)youngest / r.every + 1u) * r.every;  // nobody is that old before
+  return t >= GS_NEVER ? GS_NEVER : (uint32_t)t;
+}
+static int reap_pass(gsim_pool* p) {
+  const ReapPlan r = reap_plan(p);
+  if (!r.every || p->now == 0 || p->now % r.every != 0) return GSIM_OK;
+  if (p->now <= (r.reconnect < r.tombstone ? r.reconnect : r.tombstone)) return GSIM_OK;
+  uint32_t counts[2] = {0, 0};
+  if (!upload_globals(p)) return GSIM_ERR_CUDA;
+  if (!p->be->reap_rows(p->d, p->g_dev, p->g, p->now, r.reconnect, r.tombstone,
+                        (p->cfg.flags & GSIM_FLAG_LOG_GLOBAL_EVENTS) != 0, counts))
+    return GSIM_ERR_CUDA;
+  if (!counts[0]) return GSIM_OK;
+  p->n_established -= counts[1];
+  return refresh_after_truth_change(p);
+}
+
 static int step_locked(gsim_pool* p, uint32_t ticks) {
   if (!p->ready) return GSIM_ERR_STATE;
   p->last_ms = 0;
@@ -1227,12 +1269,16 @@ static int step_locked(gsim_pool* p, uint32_t ticks) {
     int rc = controller_call(p, nullptr, 0, [&]() -> int {
       int r = apply_sched(p);
       if (r) return r;
+      r = reap_pass(p);
+      if (r) return r;
       return upload_globals(p) ? GSIM_OK : GSIM_ERR_CUDA;
     });
     if (rc) return rc;
     uint32_t chunk = left;
     for (const Sched& s : p->sched)
       if (s.tick > p->now && s.tick - p->now < chunk) chunk = s.tick - p->now;
+    const uint32_t reap_at = next_reap_tick(p, p->now);
+    if (reap_at != GS_NEVER && reap_at - p->now < chunk) chunk = reap_at - p->now;
     if (!p->be->run_ticks(p->d, p->g_dev, p->g, p->now, chunk, use_graph, &p->last_ms,
                           &p->last_launches, p->sharded ? &p->xb : nullptr))
       return GSIM_ERR_CUDA;

@@ -50,6 +50,26 @@ GS_DEV bool gs_crash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_
   return true;
 }
 
+// [U] serf.handleReap -> reap(failedMembers, ReconnectTimeout) / reap(leftMembers, TombstoneTimeout):
+// a member that has been Failed (Left) for longer than the timeout is erased from the member
+// list (EventMemberReap).  Row a17 of SURVEY 8a; Consul shortens the timeouts in
+// agent/consul/server_test.go:675-677.  Returns bit 0 = reaped, bit 1 = it was an established
+// (non-pending) member; the caller logs the event.
+GS_DEV uint32_t gs_reap_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t now,
+                            uint32_t reconnect_ticks, uint32_t tombstone_ticks) {
+  const uint32_t k = d.key[now & 1u][i];
+  const uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
+  if (truth == GS_TRUTH_NONE || truth == GS_TRUTH_UP) return 0u;
+  uint32_t limit;
+  if (rank == GS_RANK_DEAD) limit = reconnect_ticks;
+  else if (rank == GS_RANK_LEFT) limit = tombstone_ticks;
+  else return 0u;
+  if (now - d.change_tick[i] <= limit) return 0u;
+  gs_key_store(d, g, 0u, i, d.key[0][i] & ~3u);
+  gs_key_store(d, g, 1u, i, d.key[1][i] & ~3u);
+  return 1u | (gs_key_pending(k) ? 0u : 2u);
+}
+
 // Canonical digest of one row: only fields that are semantically live are folded, so
 // that stale scratch in cold columns never matters (the oracle folds the same fields).
 GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t now) {

@@ -49,6 +49,11 @@ class GsBackend {
                        GsRecount* out) = 0;
   virtual bool state_hash(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
                           uint64_t out[4]) = 0;
+  // serf's reaper (gs_aux.h gs_reap_row) over every row; counts[0] = members erased, counts[1] =
+  // how many of them were established; logs EventMemberReap when `log_events`
+  virtual bool reap_rows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+                         uint32_t reconnect_ticks, uint32_t tombstone_ticks, bool log_events,
+                         uint32_t counts[2]) = 0;
   // clear rumor bits outside `keep` in the heard / queued / mailbox columns (slot retirement)
   virtual bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) = 0;
   virtual bool sync() = 0;

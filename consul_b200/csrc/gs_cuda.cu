@@ -326,6 +326,23 @@ __global__ void __launch_bounds__(GS_BLOCK)
 }
 
 __global__ void __launch_bounds__(GS_BLOCK)
+    gs_reap_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, uint32_t reconnect_ticks,
+                   uint32_t tombstone_ticks, uint32_t log_events, uint32_t* counts) {
+  const uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
+  uint32_t r = 0;
+  if (i < gp->n) r = gs_reap_row(d, *gp, i, now, reconnect_ticks, tombstone_ticks);
+  if (r && log_events) {
+    DevSink sink{nullptr, nullptr};
+    sink.log_event(d, *gp, now, 4u /*MEMBER_REAP*/, i, GS_EMPTY32, 0u);
+  }
+  const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (r & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (r & 2u) != 0u);
+  if ((threadIdx.x & 31u) == 0u) {
+    if (b0) atomicAdd(&counts[0], (uint32_t)__popc(b0));
+    if (b1) atomicAdd(&counts[1], (uint32_t)__popc(b1));
+  }
+}
+
+__global__ void __launch_bounds__(GS_BLOCK)
     gs_recount_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, GsRecount* out) {
   __shared__ GsRecount s;
   uint32_t* sw = reinterpret_cast<uint32_t*>(&s);
@@ -550,6 +567,19 @@ class CudaBackend : public GsBackend {
       ++launches_;
     }
     return ok(cudaGetLastError(), "crash launch") && d2h(n_crashed, cnt, 4);
+  }
+  bool reap_rows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+                 uint32_t reconnect_ticks, uint32_t tombstone_ticks, bool log_events,
+                 uint32_t counts[2]) override {
+    cudaSetDevice(dev_);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(scratch_);
+    if (!ok(cudaMemsetAsync(cnt, 0, 8, stream_), "memset")) return false;
+    if (g.n) {
+      gs_reap_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(
+          d, g_dev, now, reconnect_ticks, tombstone_ticks, log_events ? 1u : 0u, cnt);
+      ++launches_;
+    }
+    return ok(cudaGetLastError(), "reap launch") && d2h(counts, cnt, 8);
   }
   bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
                GsRecount* out) override {

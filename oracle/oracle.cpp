@@ -843,9 +843,37 @@ void apply_shutdowns(Oracle& o) {
   if (any) after_truth_change(o);
 }
 
+// [U] serf.handleReap: the reaper wakes every ReapInterval and forgets members that have been
+// Failed for longer than ReconnectTimeout, or Left for longer than TombstoneTimeout
+// (EventMemberReap).  Consul's test timings: agent/consul/server_test.go:675-677.
+void reap(Oracle& o) {
+  if (!o.cfg.reap_interval_ns) return;
+  const uint64_t every = (o.cfg.reap_interval_ns + o.tick_ns - 1) / o.tick_ns;
+  if (o.now == 0 || o.now % every != 0) return;
+  const uint64_t failed_for = (o.cfg.reconnect_timeout_ns + o.tick_ns - 1) / o.tick_ns;
+  const uint64_t left_for = (o.cfg.tombstone_timeout_ns + o.tick_ns - 1) / o.tick_ns;
+  bool any = false;
+  for (uint32_t i = 0; i < o.m.size(); ++i) {
+    Member& me = o.m[i];
+    if (me.v.truth == GSIM_TRUTH_NONE || me.v.truth == GSIM_TRUTH_UP) continue;
+    uint64_t keep_for;
+    if (me.v.rank == GSIM_RANK_DEAD) keep_for = failed_for;
+    else if (me.v.rank == GSIM_RANK_LEFT) keep_for = left_for;
+    else continue;
+    if ((uint64_t)(o.now - me.change_tick) <= keep_for) continue;
+    if (!me.v.pending) o.established--;
+    me.v.truth = GSIM_TRUTH_NONE;
+    publish(o, i);
+    if (o.cfg.flags & GSIM_FLAG_LOG_GLOBAL_EVENTS) host_event(o, GSIM_EVENT_MEMBER_REAP, i, NONE32, 0);
+    any = true;
+  }
+  if (any) after_truth_change(o);
+}
+
 void step(Oracle& o, uint32_t ticks) {
   for (uint32_t k = 0; k < ticks; ++k) {
     apply_shutdowns(o);
+    reap(o);
     if (k == 0 || o.wake.size() != o.m.size()) {  // between-tick operations may have changed anyone
       o.wake.resize(o.m.size());
       for (size_t i = 0; i < o.m.size(); ++i) o.wake[i] = wake_of(o.m[i]);

@@ -149,6 +149,20 @@ class HostEmuBackend : public GsBackend {
     *n_crashed = c;
     return true;
   }
+  bool reap_rows(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now,
+                 uint32_t reconnect_ticks, uint32_t tombstone_ticks, bool log_events,
+                 uint32_t counts[2]) override {
+    counts[0] = counts[1] = 0;
+    HostSink sink;
+    memset(&sink, 0, sizeof(sink));
+    for (uint32_t i = 0; i < g.n; ++i) {
+      const uint32_t r = gs_reap_row(d, g, i, now, reconnect_ticks, tombstone_ticks);
+      counts[0] += r & 1u;
+      counts[1] += (r >> 1) & 1u;
+      if (r && log_events) sink.log_event(d, g, now, 4u /*MEMBER_REAP*/, i, GS_EMPTY32, 0u);
+    }
+    return true;
+  }
   bool recount(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now,
                GsRecount* out) override {
     memset(out, 0, sizeof(*out));

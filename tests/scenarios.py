@@ -188,3 +188,51 @@ def event_window_scenario(make, lib, n=64, seed=31):
     compare_pools(*pools, "replay join")
     step_compare(pools, 40, 5, "after replay")
     return pools
+
+
+def lan_reap_scenario(make, lib, seed=1):
+    """TestServer_LANReap (agent/consul/server_test.go:666-733): ReconnectTimeout = TombstoneTimeout
+    = 250 ms, ReapInterval = 300 ms; three servers converge, s2 shuts down without leaving, and
+    the survivors' member lists shrink from 3 to 2 once it has been Failed and then reaped."""
+    MS = 1_000_000
+    cfg = consul_test_config(lib, capacity=8, n_initial=0, seed=seed, flags=1, phase_group=1,
+                             reconnect_timeout_ns=250 * MS, tombstone_timeout_ns=250 * MS,
+                             reap_interval_ns=300 * MS)
+    pools = make(cfg)
+    ids = [both(pools, lambda p: p.member_add(watched=True)) for _ in range(3)]
+    both(pools, lambda p: p.join(1, [0]))
+    both(pools, lambda p: p.join(2, [0]))
+    t = both(pools, lambda p: p.run_until(PRED_ALL_RUMORS_CONVERGED, 0, 400, 1))
+    assert t != NEVER
+    for p in pools:
+        for obs in ids:
+            assert len(p.members(obs)) == 3
+    for p in pools:
+        p.crash(1)                                            # s2.Shutdown(): no Leave
+    td = both(pools, lambda p: p.run_until(PRED_CRASHED_ALL_DEAD, 0, 2000, 1))
+    assert td != NEVER
+    for p in pools:
+        assert dict((m[0], m[1]) for m in p.members(0))[1] == STATUS_FAILED
+    # Failed for > 5 ticks, then the next reaper wake-up (every 6 ticks) erases it
+    seen = None
+    for k in range(20):
+        step_compare(pools, 1, 1, f"reap wait {k}")
+        if len(pools[0].members(0)) == 2:
+            seen = pools[0].now
+            break
+    assert seen is not None and seen - td > 5 and seen - td <= 5 + 6 + 1
+    for p in pools:
+        for obs in (0, 2):
+            assert sorted(m[0] for m in p.members(obs)) == [0, 2]
+        s = p.stats()
+        assert s["n_members"] == 3 and s["n_crashed"] == 0 and s["n_view_dead"] == 0
+    ev = both(pools, lambda p: [(e.type, e.subject) for e in p.poll_events()])
+    assert (2, 1) in ev and (4, 1) in ev                       # EventMemberFailed, then EventMemberReap
+    assert ev.index((2, 1)) < ev.index((4, 1))
+    # a clean leave is reaped after TombstoneTimeout as well
+    for p in pools:
+        p.leave(2)
+    step_compare(pools, 120, 4, "leave + tombstone")
+    for p in pools:
+        assert sorted(m[0] for m in p.members(0)) == [0]
+    return td, seen

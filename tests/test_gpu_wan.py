@@ -73,3 +73,10 @@ def test_c5_full_size_properties(cuda_lib):
     for x, p in enumerate(fed.pools):
         assert p.rumor_info(fed.slots[key][x])["heard_count"] == n
 
+
+
+def test_lan_reap(make, cuda_lib):
+    """SURVEY 8a row a17 on the GPU: TestServer_LANReap timings, reaper pass as a device kernel."""
+    import scenarios as sc
+    for seed in (1, 2):
+        sc.lan_reap_scenario(make, cuda_lib, seed)

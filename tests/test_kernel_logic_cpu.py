@@ -94,3 +94,9 @@ def test_oracle_threads_agree():
     mk = lambda cfg: [OraclePool(cfg, threads=1), OraclePool(cfg, threads=4)]
     sc.lossy_scenario(mk, L, n=400, ticks=200)
     sc.c3_crash(mk, L, 1500)
+
+
+def test_lan_reap(make, hostemu_lib):
+    """serf's reaper with the timings of TestServer_LANReap."""
+    for seed in (1, 2):
+        sc.lan_reap_scenario(make, hostemu_lib, seed)
