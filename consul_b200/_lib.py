@@ -20,7 +20,7 @@ GSIM_STAT_COUNT = 16
 STAT_NAMES = [
     "probes", "acks", "indirect_pings", "nacks", "probe_failures", "suspects", "confirmations",
     "deads", "refutes", "gossip_packets", "rumors_sent", "rumors_accepted", "rumors_dropped",
-    "packets_lost", "active_rows",
+    "packets_lost", "active_rows", "push_pulls",
 ]
 
 COLUMNS = {

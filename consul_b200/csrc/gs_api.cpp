@@ -249,6 +249,14 @@ static void recompute_tables(gsim_pool* p) {
   if (bits < 2) bits = 2;
   if (bits & 1u) ++bits;
   g.perm_half_bits = bits / 2;
+  // [U] memberlist/state.go schedule: the push-pull ticker runs every pushPullScale(PushPullInterval, n)
+  g.pp_interval = 0;
+  g.rot_pp = 0;
+  if ((c.flags & GSIM_FLAG_PUSH_PULL) && c.push_pull_interval_ns) {
+    g.pp_interval = ceil_ticks(gsim_push_pull_scale_ns(c.push_pull_interval_ns, n), p->tick_ns);
+    if (g.pp_interval < 2u) g.pp_interval = 2u;  // the exchange itself takes two ticks
+    g.rot_pp = (gs_phase_rot(g.seed_lo, g.seed_hi) >> 8) % g.pp_interval;
+  }
   p->g_dirty = true;
 }
 
@@ -377,6 +385,7 @@ static int init_device_state(gsim_pool* p) {
   for (uint32_t s = 0; s <= g.ring_mask; ++s) okk = okk && be->fill32(d.inbox[s], 0, cap);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
+  if (d.ppreq) okk = okk && be->fill32(d.ppreq, GS_EMPTY32, cap * 2 * GS_PPK) && be->fill32(d.pp_clk, 0, cap * 4);
   okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
   okk = okk && be->fill32(d.heard_cnt, 0, 32) && be->fill32(d.conv_tick, GS_EMPTY32, 32);
   okk = okk && be->fill32(d.view_cnt, 0, 4) && be->fill32(d.crashed_alive, 0, 1);
@@ -510,6 +519,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   okk = okk && acol(&d.event_min, 1);
   okk = okk && acol(&d.heard, 1) && acol(&d.queued, 1);
   okk = okk && acol(&d.tx, GS_MAX_RUMORS);
+  if (cfg->flags & GSIM_FLAG_PUSH_PULL)  // push-pull mailboxes: 48 B per member, only when asked for
+    okk = okk && acol(&d.ppreq, 2 * GS_PPK) && acol(&d.pp_clk, 4);
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
   if (!sharded) {
     okk = okk && alloc_col(p, &d.stats, (size_t)GSIM_STAT_COUNT);
@@ -1631,6 +1642,10 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
   add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
+  if (d.ppreq) {
+    add(d.ppreq, cap * 4 * 2 * GS_PPK);
+    add(d.pp_clk, cap * 4 * 4);
+  }
   add(d.stats, GSIM_STAT_COUNT * 8); add(d.heard_cnt, 32 * 4); add(d.conv_tick, 32 * 4);
   add(d.crashed_alive, 4); add(d.crashed_dead_tick, 4);
   return v;
@@ -1708,7 +1723,8 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   SnapHeader h;
   memcpy(&h, r, sizeof(h));
   r += sizeof(h);
-  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask)
+  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask ||
+      (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u))
     return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
   if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
   p->sched.resize(h.n_sched);

@@ -35,6 +35,10 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   d.event_min[i] = 0u;
   d.heard[i] = 0u;
   d.queued[i] = 0u;
+  if (d.ppreq != nullptr) {
+    for (uint32_t q = 0; q < 2u * GS_PPK; ++q) d.ppreq[(size_t)q * cap + i] = GS_EMPTY32;
+    for (uint32_t q = 0; q < 4u; ++q) d.pp_clk[(size_t)q * cap + i] = 0u;
+  }
 }
 
 // BASELINE config 3: crash every UP member whose Philox draw is below the threshold.
@@ -119,6 +123,13 @@ GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint
   if (inb & GS_ACC_BIT) {
     const uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;
     for (uint32_t s = 0; s < GS_K1MAX; ++s) h = gs_mix64(h, acc[(size_t)s * cap + i]);
+    if (g.pp_interval != 0u) {  // push-pull requests and partner clocks waiting in the mailbox
+      const uint32_t* req = d.ppreq + (size_t)cur * GS_PPK * cap;
+      for (uint32_t s = 0; s < GS_PPK; ++s) h = gs_mix64(h, req[(size_t)s * cap + i]);
+      const uint32_t* clk = d.pp_clk + (size_t)cur * 2u * cap;
+      h = gs_mix64(h, clk[i]);
+      h = gs_mix64(h, clk[cap + i]);
+    }
   }
   return h;
 }

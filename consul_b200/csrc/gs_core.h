@@ -31,7 +31,9 @@
 #define GS_K1MAX 5
 #define GS_RING_MAX 8            // deepest mailbox ring (WAN latency pools): latency <= GS_RING_MAX - 1
 #define GS_MAX_DCS 64u           // synthetic datacenters of a latency pool (BASELINE config 5)
-#define GS_ACC_BIT 0x80000000u   // inbox: accusation(s) pending in acc[][][]
+#define GS_ACC_BIT 0x80000000u   // inbox: auxiliary mail — accusation(s) pending in acc[][][] and/or
+                                 // push-pull requests / clocks in ppreq[][][] / pp_clk[][][]
+#define GS_PPK 4                 // push-pull requests one member serves per tick (smallest ids win)
 #define GS_WAKE_BIT 0x40000000u  // inbox: "process this row" (self-posted or by the host)
 #define GS_TILE 128u             // rows per CTA; ticker phases are uniform per tile
 #define GS_NEVER 0xFFFFFFFFu
@@ -52,7 +54,8 @@ enum {
   GS_PUR_GOSSIP = 3,
   GS_PUR_RELAY = 4,
   GS_PUR_LOSS = 5,
-  GS_PUR_CRASH = 6
+  GS_PUR_CRASH = 6,
+  GS_PUR_PUSHPULL = 7
 };
 // Loss "kind" (folded into the counter) — one draw per simulated UDP packet.
 enum {
@@ -155,6 +158,12 @@ GS_HD uint32_t gs_gossip_phase(uint32_t rot_g, uint32_t group, uint32_t P, uint3
   return ((group / P) % GI + rot_g) % GI;
 }
 
+// Push-pull ticker of a phase group ([U] memberlist/state.go schedule: pushPullTrigger with a random
+// stagger): groups are dealt round-robin over the interval like the probe phases.
+GS_HD bool gs_pp_due(uint32_t pp_interval, uint32_t rot_pp, uint32_t group, uint32_t t) {
+  return pp_interval != 0u && (t + rot_pp) % pp_interval == group % pp_interval;
+}
+
 GS_HD uint32_t gs_u4_get(const GsU4& v, uint32_t idx) {
   return idx == 0 ? v.x : idx == 1 ? v.y : idx == 2 ? v.z : v.w;
 }
@@ -239,6 +248,10 @@ struct GsGlobals {
   uint32_t ring_mask;     // mailbox ring depth - 1 (depth is a power of two, 2 by default)
   uint32_t n_dcs;         // datacenter of member i = (i / GS_TILE) % n_dcs
   uint8_t lat[GS_MAX_DCS * GS_MAX_DCS];  // EXTRA one-way latency in ticks (matrix entry - 1)
+  // Periodic push-pull anti-entropy ([U] memberlist/state.go pushPull): the members
+  // of phase group q run theirs at ticks t with (t + rot_pp) % pp_interval == q % pp_interval.
+  uint32_t pp_interval;   // pushPullScale(PushPullInterval, n) in ticks; 0 = disabled
+  uint32_t rot_pp;
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -267,6 +280,9 @@ struct GsDev {
   uint32_t* heard;
   uint32_t* queued;
   uint8_t* tx;  // [GS_MAX_RUMORS][cap]
+  // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
+  uint32_t* ppreq;   // [2][GS_PPK][cap] requester ids, kept as the GS_PPK smallest (atomicMin chain)
+  uint32_t* pp_clk;  // [2][2][cap] max of the senders' {member, event} Lamport clocks (atomicMax)
   // pool-wide device words
   unsigned long long* stats;  // [GSIM_STAT_COUNT]
   uint32_t* heard_cnt;        // [GS_MAX_RUMORS]

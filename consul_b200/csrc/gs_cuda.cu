@@ -176,7 +176,20 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
     const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
     const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
-    const bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
+    bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
+    // periodic push-pull (opt-in): the ticker of this tile's phase group (or, with per-member
+    // phases, of one of its members) fires at this tick
+    bool pp_tile = false;
+    if (g.pp_interval != 0u) {
+      if (gated) {
+        pp_tile = gs_pp_due(g.pp_interval, g.rot_pp, tile >> shift, t);
+      } else {
+#pragma unroll
+        for (uint32_t u = 0; u < 4u; ++u)
+          pp_tile |= gs_pp_due(g.pp_interval, g.rot_pp, (tile * GS_TILE + lane * 4u + u) / g.phase_group, t);
+      }
+      mine |= pp_tile;
+    }
     if (__any_sync(0xFFFFFFFFu, mine)) {
       did_work = true;
       __syncwarp();  // other lanes' copies are now visible: re-read one member per lane
@@ -187,7 +200,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       for (int u = 0; u < 4; ++u) {
         const uint32_t w = s_inb[st][wib][u * 32 + lane];
         const bool due_now = s_due[st][wib][u * 32 + lane] == t;
-        act[u] = w != 0u || due_now;
+        act[u] = w != 0u || due_now ||
+                 (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, (base + 32u * u) / g.phase_group, t));
         cand[u] = w == 0u && due_now;  // empty mailbox + ticker fired
         any_cand |= cand[u];
       }

@@ -53,6 +53,19 @@ __device__ __forceinline__ uint64_t gs_ld_sys64(const uint64_t* p) {
 }
 #define GS_LD_OTHER(p) __ldcg(p)
 #define GS_LD_OTHER64(p) gs_ld_sys64(p)
+// push-pull mailboxes: requester ids (min chain) and Lamport clocks (max), same scoping rule
+__device__ __forceinline__ uint32_t gs_atomic_min32_sys(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.global.sys.min.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t gs_atomic_max32_sys(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.global.sys.max.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+#define GS_ATOMIC_MIN32(p, v) (g.world > 1u ? gs_atomic_min32_sys((p), (v)) : atomicMin((p), (v)))
+#define GS_ATOMIC_MAX32(p, v) (g.world > 1u ? gs_atomic_max32_sys((p), (v)) : atomicMax((p), (v)))
 #else
 #define GS_DEV inline
 #define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
@@ -64,6 +77,20 @@ static inline uint64_t gs_host_atomic_min64(uint64_t* p, uint64_t v) {
   return old;
 }
 #define GS_ATOMIC_MIN64(p, v) gs_host_atomic_min64((uint64_t*)(p), (uint64_t)(v))
+static inline uint32_t gs_host_atomic_min32(uint32_t* p, uint32_t v) {
+  uint32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
+static inline uint32_t gs_host_atomic_max32(uint32_t* p, uint32_t v) {
+  uint32_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
+#define GS_ATOMIC_MIN32(p, v) gs_host_atomic_min32((p), (v))
+#define GS_ATOMIC_MAX32(p, v) gs_host_atomic_max32((p), (v))
 #define GS_LD_OTHER(p) (*(p))
 #define GS_LD_OTHER64(p) (*(p))
 #endif
@@ -84,7 +111,8 @@ enum {
   GS_ST_RUMORS_ACCEPTED,
   GS_ST_RUMORS_DROPPED,
   GS_ST_PACKETS_LOST,
-  GS_ST_ACTIVE_ROWS
+  GS_ST_ACTIVE_ROWS,
+  GS_ST_PUSH_PULLS
 };
 
 // The key column is the one column every member reads about every other member (probe targets,
@@ -267,10 +295,12 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   uint32_t queued = up ? d.queued[i] : 0u;
   if (inb != 0u) d.inbox[icur][i] = 0u;
   sink.stat(GS_ST_ACTIVE_ROWS, 1);  // scheduling diagnostic: rows that left the 4-byte scan
+  // periodic push-pull (opt-in): does this member's push-pull ticker fire now?
+  const bool pp_now = up && g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t);
 
   // ---- nothing to do this tick (a wake that only keeps the row in the active set) ----
   if ((inb & ~GS_WAKE_BIT) == 0u && gs_key_rank(k0) == GS_RANK_ALIVE && !(up && due0 == t) &&
-      !(gossip_slot && queued != 0u)) {
+      !(gossip_slot && queued != 0u) && !pp_now) {
     if (m0 & GS_META_DIRTY) {  // bring the other key buffer up to date
       gs_key_store(d, g, nxt, i, k0);
       d.meta[i] = m0 & ~GS_META_DIRTY;
@@ -285,6 +315,20 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
 
   // ---- A. consume the mailbox of this arrival tick ------------------------------
   if ((inb & ~GS_WAKE_BIT) != 0u) {
+    if ((inb & GS_ACC_BIT) && g.pp_interval != 0u) {
+      // [U] serf/delegate.go MergeRemoteState: witness the push-pull partners' clocks first
+      // (Witness(remote - 1) == max(local, remote)), then replay what they carried.
+      uint32_t* clk = d.pp_clk + (size_t)cur * 2u * cap;
+      const uint32_t cm = GS_LD_OTHER(&clk[i]), ce = GS_LD_OTHER(&clk[cap + i]);
+      if (cm | ce) {
+        clk[i] = 0u;
+        clk[cap + i] = 0u;
+        if (up) {
+          if (cm > d.ltime_member[i]) d.ltime_member[i] = cm;
+          if (ce > d.ltime_event[i]) d.ltime_event[i] = ce;
+        }
+      }
+    }
     uint32_t rbits = inb & ~(GS_ACC_BIT | GS_WAKE_BIT) & g.active_mask;
     if (rbits && up) {
       heard = d.heard[i];
@@ -361,6 +405,21 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
             }
           }
         }
+      }
+    }
+    if ((inb & GS_ACC_BIT) && g.pp_interval != 0u) {
+      // [U] memberlist/net.go handleConn(pushPullMsg) -> sendLocalState: answer every partner that
+      // opened a push-pull with what this member holds now (after merging what they pushed).
+      uint32_t* req = d.ppreq + (size_t)cur * GS_PPK * cap;
+      for (uint32_t s = 0; s < GS_PPK; ++s) {
+        const uint32_t from = GS_LD_OTHER(&req[(size_t)s * cap + i]);
+        if (from == GS_EMPTY32) break;
+        req[(size_t)s * cap + i] = GS_EMPTY32;
+        if (!up) continue;  // a dead process accepts no connection
+        uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
+        GS_ATOMIC_MAX32(&clk[from], d.ltime_member[i]);
+        GS_ATOMIC_MAX32(&clk[cap + from], d.ltime_event[i]);
+        GS_ATOMIC_OR32(&d.inbox[inxt][from], (d.heard[i] & g.active_mask) | GS_ACC_BIT);
       }
     }
   }
@@ -546,6 +605,29 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       }
       if (queued != q0) d.queued[i] = queued;
     }
+
+    // ---- F. periodic push-pull ([U] memberlist/state.go pushPull -> pushPullNode) -------------
+    // One random alive peer; the full-state exchange over TCP reduces, in this model, to the
+    // tracked-broadcast mask and the Lamport clocks (alive/suspect/dead state is one shared record
+    // per subject already).  Push now; the partner's answer arrives two ticks later.
+    if (pp_now && !(m & GS_META_ISOLATED)) {
+      uint32_t partner[1];
+      if (gs_krandom(d, g, i, t, GS_PUR_PUSHPULL, 1u, 1u, GS_EMPTY32, m, partner) != 0u) {
+        const uint32_t j = partner[0];
+        uint32_t* req = d.ppreq + (size_t)nxt * GS_PPK * cap;
+        uint32_t v = i;
+        for (uint32_t s = 0; s < GS_PPK; ++s) {
+          const uint32_t old = GS_ATOMIC_MIN32(&req[(size_t)s * cap + j], v);
+          if (old == v || old == GS_EMPTY32) break;
+          if (old > v) v = old;  // displaced a larger id: carry it to the next slot
+        }
+        uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
+        GS_ATOMIC_MAX32(&clk[j], d.ltime_member[i]);
+        GS_ATOMIC_MAX32(&clk[cap + j], d.ltime_event[i]);
+        GS_ATOMIC_OR32(&d.inbox[inxt][j], (d.heard[i] & g.active_mask) | GS_ACC_BIT);
+        sink.stat(GS_ST_PUSH_PULLS, 1);
+      }
+    }
   }
 
   // ---- E. write back ------------------------------------------------------------
@@ -605,6 +687,8 @@ GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
   if (gs_key_truth(f.kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD || rank == GS_RANK_LEFT ||
       gs_key_pending(f.kc))
     return false;  // ring entry must be skipped or needs the heard mask: generic path
+  if (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t))
+    return false;  // the push-pull ticker fires too: generic path
   uint32_t m = f.m;
   if (gs_key_truth(f.kc) == GS_TRUTH_UP && gs_extra(g, i, f.c) + gs_extra(g, f.c, i) <= g.T) {
     const uint32_t aw = gs_meta_aw(m);

@@ -20,6 +20,7 @@ NEVER = 0xFFFFFFFF
 
 FLAG_LOG_GLOBAL_EVENTS = 1
 FLAG_NO_GRAPH = 2
+FLAG_PUSH_PULL = 32
 MEMBER_WATCHED = 1
 
 

@@ -137,6 +137,12 @@ typedef struct gsim_config {
 #define GSIM_FLAG_LOG_GLOBAL_EVENTS 1u /* log Failed/Left/Join transitions of every member */
 #define GSIM_FLAG_NO_GRAPH 2u          /* launch tick kernels one by one (debug/profiling)  */
 #define GSIM_FLAG_SHARD_SYNC_SCAN 4u   /* sharded pools: scan mailboxes with ld.relaxed.sys (debug) */
+/* Periodic push-pull anti-entropy ([U] memberlist/state.go pushPull, serf/delegate.go
+ * LocalState/MergeRemoteState): every pushPullScale(push_pull_interval, n) each
+ * member exchanges its tracked-broadcast mask and Lamport clocks with one random alive peer
+ * (push at tick t, the partner's answer arrives at t+2).  Off by default: the headline configs
+ * of BASELINE.json run shorter than one push-pull interval at their sizes. */
+#define GSIM_FLAG_PUSH_PULL 32u
 
 /* Preset defaults.  LAN/WAN: [U] memberlist DefaultLANConfig/DefaultWANConfig as
  * pinned by agent/config/runtime.go:1271-1413 with Consul's overrides
@@ -285,6 +291,7 @@ enum {
   GSIM_STAT_RUMORS_DROPPED,  /* deliveries rejected (too old, min time)   */
   GSIM_STAT_PACKETS_LOST,    /* simulated UDP loss                        */
   GSIM_STAT_ACTIVE_ROWS,     /* rows that left the idle fast path         */
+  GSIM_STAT_PUSH_PULLS,      /* periodic push-pull exchanges started      */
   GSIM_STAT_COUNT = 16
 };
 typedef struct gsim_stats {

@@ -46,7 +46,8 @@ namespace {
 
 const uint32_t NONE32 = 0xFFFFFFFFu;
 enum { ST_IDLE = 0, ST_WAIT_TIMEOUT = 1, ST_WAIT_DEADLINE = 2 };
-enum { PUR_PHASE = 1, PUR_PERM = 2, PUR_GOSSIP = 3, PUR_RELAY = 4, PUR_LOSS = 5, PUR_CRASH = 6 };
+enum { PUR_PHASE = 1, PUR_PERM = 2, PUR_GOSSIP = 3, PUR_RELAY = 4, PUR_LOSS = 5, PUR_CRASH = 6, PUR_PUSHPULL = 7 };
+const uint32_t PUSHPULL_BACKLOG = 4;  // push-pull connections one member serves per tick
 enum { LK_PING = 0, LK_ACK, LK_INDREQ, LK_INDPING, LK_INDACK, LK_INDFWD, LK_NACK, LK_GOSSIP };
 const uint32_t KRANDOM_MAX_TRIES = 32;  // upstream: 3n (memberlist/util.go kRandomNodes)
 const uint32_t PROBE_SKIP_CAP = 1024;   // upstream: len(nodes)
@@ -166,6 +167,14 @@ struct Accusation {
   uint32_t subject, inc, from;
 };
 
+// One side of a periodic push-pull exchange ([U] memberlist/state.go pushPullNode, net.go
+// sendAndReceiveState): the tracked-broadcast mask travels through the inbox like any packet;
+// this record carries the sender's Lamport clocks and, for a request, who to answer.
+struct PushPull {
+  uint32_t to, from, clock_member, clock_event;
+  bool request;
+};
+
 struct Rumor {
   uint32_t kind = 0, subject = 0, inc = 0, ltime = 0, origin = 0, size = 0, qclass = 0, start = 0;
   uint32_t heard_count = 0, converged_tick = NONE32;
@@ -182,6 +191,7 @@ struct Tally {
   std::vector<Accusation> accusations;
   std::vector<gsim_event> events;
   std::vector<std::pair<uint32_t, View>> published;
+  std::vector<PushPull> pushpulls;
   int32_t crashed_dead = 0;
   Tally() { clear(); }
   void clear() {
@@ -190,6 +200,7 @@ struct Tally {
     accusations.clear();
     events.clear();
     published.clear();
+    pushpulls.clear();
     crashed_dead = 0;
   }
 };
@@ -214,6 +225,8 @@ struct Oracle {
   std::vector<uint32_t> wake;            // 0 = look every tick, else the only tick worth a look
   std::vector<Tally> tallies;            // per-thread accumulators, reused every tick
   std::vector<Accusation> arriving;      // accusations that arrive at the tick about to run
+  std::vector<PushPull> pp_arriving;     // push-pull requests / answers arriving at that tick
+  uint32_t pp_every = 0, pp_rot = 0;     // push-pull ticker period in ticks (0 = off) and rotation
   Rumor rumor[GSIM_MAX_RUMORS];
   uint32_t active = 0;
   std::vector<Scheduled> shutdowns;
@@ -246,6 +259,20 @@ void retune(Oracle& o) {
   bits = std::max(bits, 2u);
   bits += bits & 1;
   o.perm_half_bits = bits / 2;
+  // [U] state.go schedule: push-pull every pushPullScale(PushPullInterval, n)
+  o.pp_every = 0;
+  if ((o.cfg.flags & GSIM_FLAG_PUSH_PULL) && o.cfg.push_pull_interval_ns) {
+    o.pp_every = std::max(2u, to_ticks_ceil(push_pull_scale_ns(o.cfg.push_pull_interval_ns, n), o.tick_ns));
+    uint32_t rot = murmur_fmix32((uint32_t)o.cfg.seed * 0x9E3779B1u + (uint32_t)(o.cfg.seed >> 32));
+    o.pp_rot = (rot >> 8) % o.pp_every;
+  }
+}
+
+// does member i's push-pull ticker fire at tick t?  (phase groups are dealt round-robin)
+bool pushpull_due(const Oracle& o, uint32_t i, uint32_t t) {
+  if (!o.pp_every) return false;
+  const uint32_t group = i / (o.cfg.phase_group ? o.cfg.phase_group : 128);
+  return (t + o.pp_rot) % o.pp_every == group % o.pp_every;
 }
 
 // The four Feistel round keys of one (member, pass) probe ring.
@@ -422,9 +449,22 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     lo = std::lower_bound(o.arriving.begin(), o.arriving.end(), i,
                           [](const Accusation& a, uint32_t s) { return a.subject < s; });
 
+  const bool my_pushpull_tick = up && pushpull_due(o, i, t);
   if (!inbox && !accused && me.v.rank == GSIM_RANK_ALIVE && !(up && me.due == t) &&
-      !(my_gossip_tick && me.queued))
+      !(my_gossip_tick && me.queued) && !my_pushpull_tick)
     return;
+  // push-pull records addressed to me (sorted by receiver, then sender)
+  auto pp_lo = o.pp_arriving.end(), pp_hi = o.pp_arriving.end();
+  if (accused && o.pp_every) {
+    pp_lo = std::lower_bound(o.pp_arriving.begin(), o.pp_arriving.end(), i,
+                             [](const PushPull& a, uint32_t s) { return a.to < s; });
+    for (pp_hi = pp_lo; pp_hi != o.pp_arriving.end() && pp_hi->to == i;) ++pp_hi;
+  }
+  if (up)  // [U] serf/delegate.go MergeRemoteState: clocks first (Witness(remote - 1))
+    for (auto a = pp_lo; a != pp_hi; ++a) {
+      me.ltime_member = std::max(me.ltime_member, a->clock_member);
+      me.ltime_event = std::max(me.ltime_event, a->clock_event);
+    }
   // (GSIM_STAT_ACTIVE_ROWS is a scheduling diagnostic of the CUDA implementation; not modelled)
 
   // -- deliveries ------------------------------------------------------------------------
@@ -482,6 +522,17 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
           ta.c[GSIM_STAT_CONFIRMATIONS]++;
         }
       }
+    }
+  }
+
+  // -- push-pull: answer whoever connected ([U] net.go handleConn -> sendLocalState) --------------
+  if (up) {
+    uint32_t served = 0;
+    for (auto a = pp_lo; a != pp_hi && served < PUSHPULL_BACKLOG; ++a) {
+      if (!a->request) continue;
+      ++served;
+      ta.pushpulls.push_back({a->from, i, me.ltime_member, me.ltime_event, false});
+      __atomic_fetch_or(&o.inbox[(t + 1) % Oracle::RING][a->from], me.heard & o.active, __ATOMIC_RELAXED);
     }
   }
 
@@ -616,6 +667,16 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     }
   }
 
+  // -- anti-entropy ([U] memberlist.pushPull): one random alive peer, full state both ways --------
+  if (my_pushpull_tick && !me.isolated) {
+    Picks partner = k_random(o, i, me, t, PUR_PUSHPULL, 1, true, NONE32);
+    if (!partner.empty()) {
+      ta.pushpulls.push_back({partner[0], i, me.ltime_member, me.ltime_event, true});
+      __atomic_fetch_or(&o.inbox[(t + 1) % Oracle::RING][partner[0]], me.heard & o.active, __ATOMIC_RELAXED);
+      ta.c[GSIM_STAT_PUSH_PULLS]++;
+    }
+  }
+
   if (me.v.inc != before.inc || me.v.rank != before.rank) ta.published.push_back({i, me.v});
 }
 
@@ -633,6 +694,12 @@ void run_tick(Oracle& o) {
                                }),
                    o.arriving.end());
   for (const Accusation& a : o.arriving) o.inbox[t % Oracle::RING][a.subject] |= 0x80000000u;
+  // a member serves the PUSHPULL_BACKLOG smallest requester ids; sort so that they come first
+  std::sort(o.pp_arriving.begin(), o.pp_arriving.end(), [](const PushPull& a, const PushPull& b) {
+    if (a.to != b.to) return a.to < b.to;
+    return a.from < b.from;
+  });
+  for (const PushPull& a : o.pp_arriving) o.inbox[t % Oracle::RING][a.to] |= 0x80000000u;
   // Members with no mail whose only scheduled action lies at another tick cannot do anything
   // (this is exactly the idle test at the top of member_tick, evaluated from two flat arrays).
   const uint32_t* mail = o.inbox[t % Oracle::RING].data();
@@ -646,21 +713,23 @@ void run_tick(Oracle& o) {
     Tally& ta = tallies[(size_t)omp_get_thread_num()];
 #pragma omp for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
-      if (mail[i] == 0 && wake[i] != 0 && wake[i] != t) continue;
+      if (mail[i] == 0 && wake[i] != 0 && wake[i] != t && !pushpull_due(o, (uint32_t)i, t)) continue;
       member_tick(o, (uint32_t)i, t, ta);
       wake[i] = wake_of(o.m[(size_t)i]);
     }
   }
 #else
   for (uint32_t i = 0; i < n; ++i) {
-    if (mail[i] == 0 && wake[i] != 0 && wake[i] != t) continue;
+    if (mail[i] == 0 && wake[i] != 0 && wake[i] != t && !pushpull_due(o, i, t)) continue;
     member_tick(o, i, t, tallies[0]);
     wake[i] = wake_of(o.m[i]);
   }
 #endif
   // end of tick: publish, count, hand accusations to the next tick
   o.arriving.clear();
+  o.pp_arriving.clear();
   for (Tally& ta : tallies) {
+    o.pp_arriving.insert(o.pp_arriving.end(), ta.pushpulls.begin(), ta.pushpulls.end());
     for (int s = 0; s < GSIM_STAT_COUNT; ++s) o.stats[s] += ta.c[s];
     for (auto& pv : ta.published) {
       o.pub[pv.first] = pv.second;
@@ -1306,10 +1375,17 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
     if (a.inc != b.inc) return a.inc > b.inc;
     return a.from < b.from;
   });
-  size_t ap = 0;
+  // pending push-pull records per receiver
+  std::vector<PushPull> pp = o.pp_arriving;
+  std::sort(pp.begin(), pp.end(), [](const PushPull& a, const PushPull& b) {
+    if (a.to != b.to) return a.to < b.to;
+    return a.from < b.from;
+  });
+  size_t ap = 0, pq = 0;
   for (uint32_t i = 0; i < o.m.size(); ++i) {
     const Member& me = o.m[i];
     while (ap < acc.size() && acc[ap].subject < i) ++ap;
+    while (pq < pp.size() && pp[pq].to < i) ++pq;
     if (me.v.truth == GSIM_TRUTH_NONE) continue;
     const bool up = me.v.truth == GSIM_TRUTH_UP;
     const bool probing = up && me.stage != ST_IDLE;
@@ -1332,7 +1408,8 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
     uint32_t heard = me.heard & o.active;
     x = mix(x, heard);
     x = mix(x, me.queued & o.active);
-    bool has_acc = ap < acc.size() && acc[ap].subject == i;
+    const bool has_pp = pq < pp.size() && pp[pq].to == i;
+    bool has_acc = (ap < acc.size() && acc[ap].subject == i) || has_pp;  // bit 31: auxiliary mail
     uint32_t inb = (o.inbox[o.now % Oracle::RING][i] & o.active) | (has_acc ? 0x80000000u : 0);
     x = mix(x, inb);
     // packets still in flight on a WAN pool, nearest arrival first (what a mailbox ring of
@@ -1347,6 +1424,20 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
       for (; q < acc.size() && acc[q].subject == i && cnt < MAX_SUS; ++q, ++cnt)
         x = mix(x, ((uint64_t)(~acc[q].inc) << 32) | acc[q].from);
       for (; cnt < MAX_SUS; ++cnt) x = mix(x, 0xFFFFFFFFFFFFFFFFull);
+      if (o.pp_every) {  // who is waiting for an answer (smallest ids), and the partners' clocks
+        uint32_t waiting = 0, cm = 0, ce = 0;
+        for (size_t y = pq; y < pp.size() && pp[y].to == i; ++y) {
+          if (pp[y].request && waiting < PUSHPULL_BACKLOG) {
+            x = mix(x, pp[y].from);
+            ++waiting;
+          }
+          cm = std::max(cm, pp[y].clock_member);
+          ce = std::max(ce, pp[y].clock_event);
+        }
+        for (; waiting < PUSHPULL_BACKLOG; ++waiting) x = mix(x, 0xFFFFFFFFu);
+        x = mix(x, cm);
+        x = mix(x, ce);
+      }
     }
     fold(x);
   }
@@ -1404,8 +1495,10 @@ int oracle_column_read(void* h, int column, void* out, size_t cap_bytes, size_t*
       default: return GSIM_ERR_INVALID;
     }
   }
-  if (column == GSIM_COL_INBOX)
+  if (column == GSIM_COL_INBOX) {
     for (const Accusation& a : o.arriving) w[a.subject] |= 0x80000000u;
+    for (const PushPull& a : o.pp_arriving) w[a.to] |= 0x80000000u;
+  }
   return GSIM_OK;
 }
 

@@ -113,8 +113,8 @@ class HostEmuBackend : public GsBackend {
         const uint32_t inb = d.inbox[t & g.ring_mask][i];
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
-        if (!(inb != 0u || due == t)) continue;
-        if (inb == 0u && !getenv("GSIM_HOSTEMU_NO_FAST")) {  // same two tiers as the kernel
+        if (!(inb != 0u || due == t || gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t))) continue;
+        if (inb == 0u && due == t && !getenv("GSIM_HOSTEMU_NO_FAST")) {  // same two tiers as the kernel
           GsFastProbe f;
           bool acked = false;
           gs_fast_load(d, t & 1u, i, f);

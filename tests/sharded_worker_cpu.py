@@ -66,7 +66,8 @@ def wan_script(p):
 
 
 N = 3 * 4096 * world - 100          # not a multiple of the shard size: the last rank is short
-mk = lambda: lan_config(L, capacity=N + 8, n_initial=N, seed=0x5EED0009, packet_loss_ppm=30000)  # noqa: E731
+mk = lambda: lan_config(L, capacity=N + 8, n_initial=N, seed=0x5EED0009, packet_loss_ppm=30000,  # noqa: E731
+                        flags=32, push_pull_interval_ns=10**9)   # periodic push-pull on (every ~100 ticks)
 sp = ShardedPool(mk(), L)
 got = script(sp)
 if rank == 0:
