@@ -13,7 +13,9 @@
 // (agent/config/runtime.go:1271-1413, api/agent.go:299-303, agent/consul/server_test.go:221-237),
 // (3) the eventual-outcome scenarios of the reference tests (server_test.go:509-529,
 // 666-733; client_test.go:756-835) and the 100k-node design figure of
-// internal/gossip/libserf/serf.go:29-33, replayed in tests/test_oracle_scenarios.py.
+// internal/gossip/libserf/serf.go:29-33, replayed in tests/test_oracle_scenarios.py, (4) the
+// queue-order / event-window / de-dup / leave / refute predicates of SURVEY.md §8c as known-answer
+// tests in tests/test_predicate_kats.py.
 //
 // Model (documented in DESIGN.md §3): lock-step ticks of tau = gcd(ProbeInterval,
 // ProbeTimeout, GossipInterval).  Every member reads the cluster as it was published at the
