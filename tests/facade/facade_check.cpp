@@ -109,6 +109,62 @@ static void test_lan_reap_and_force_leave() {
   std::puts("PASS TestServer_LANReap / TestAgent_ForceLeave");
 }
 
+// TestServer_LANReap with its own timings (server_test.go:675-677): nobody calls RemoveFailedNode;
+// the reaper forgets s2 once it has been Failed for ReconnectTimeout.
+static void test_lan_reap_timers() {
+  gsim_config c = test_cfg();
+  c.reconnect_timeout_ns = 250ull * 1000000;
+  c.tombstone_timeout_ns = 250ull * 1000000;
+  c.reap_interval_ns = 300ull * 1000000;
+  Pool pool(c);
+  std::deque<Event> ch1;
+  Config c1, c2, c3;
+  c1.NodeName = "s1";
+  c1.EventCh = &ch1;
+  c2.NodeName = "s2";
+  c3.NodeName = "s3";
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2), s3 = Serf::Create(pool, c3);
+  s2->Join({"s1/x"}, true);
+  s3->Join({"s1/x"}, true);
+  CHECK(eventually(pool, 140, [&] { return s1->Members().size() == 3 && s2->Members().size() == 3 && s3->Members().size() == 3; }));
+  s2->Shutdown();
+  CHECK(eventually(pool, 400, [&] { return s1->Members().size() == 2 && s3->Members().size() == 2; }));
+  CHECK(count_status(*s1, StatusAlive) == 2 && count_status(*s1, StatusFailed) == 0);
+  pool.PumpEvents();
+  int failed_at = -1, reaped_at = -1, k = 0;
+  for (auto& e : ch1) {
+    if (e.Type == EventMemberFailed && e.Members[0].Name == "s2") failed_at = k;
+    if (e.Type == EventMemberReap && e.Members[0].Name == "s2") reaped_at = k;
+    ++k;
+  }
+  CHECK(failed_at >= 0 && reaped_at > failed_at);
+  std::puts("PASS TestServer_LANReap (reaper)");
+}
+
+// TestServer_JoinWAN (server_test.go:735-810): one server per datacenter, joined over the WAN
+// pool (names carry the datacenter, server_serf.go:90-93) with memberlist's WAN timing.
+static void test_join_wan() {
+  gsim_config c = Pool::DefaultWANConfig();
+  c.capacity = 16;
+  c.n_initial = 0;
+  c.seed = 43;
+  c.phase_group = 1;
+  Pool pool(c);
+  Config c1, c2;
+  c1.NodeName = "s1.dc1";
+  c1.Tags = {{"role", "consul"}, {"dc", "dc1"}};
+  c2.NodeName = "s2.dc2";
+  c2.Tags = {{"role", "consul"}, {"dc", "dc2"}};
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2);
+  CHECK(s2->Join({"s1.dc1/127.0.0.1:8302"}, true) == 1);
+  CHECK(eventually(pool, 100, [&] { return s1->Members().size() == 2 && s2->Members().size() == 2; }));
+  std::set<std::string> dcs;
+  for (auto& m : s1->Members()) dcs.insert(m.Tags.at("dc"));
+  CHECK(dcs.count("dc1") && dcs.count("dc2"));
+  CHECK(s1->Stats().at("members") == "2");
+  std::puts("PASS TestServer_JoinWAN");
+}
+
 static void test_user_event() {
   Pool pool(test_cfg());
   std::deque<Event> chs, chc;
@@ -163,6 +219,8 @@ int main() {
   try {
     test_join_lan();
     test_lan_reap_and_force_leave();
+    test_lan_reap_timers();
+    test_join_wan();
     test_user_event();
     test_leave();
   } catch (const Error& e) {

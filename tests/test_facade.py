@@ -20,7 +20,8 @@ def run(binary):
     r = subprocess.run([binary], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
-    for name in ("TestServer_JoinLAN", "TestServer_LANReap", "TestClientServer_UserEvent", "TestAgent_Leave"):
+    for name in ("TestServer_JoinLAN", "TestServer_LANReap", "TestServer_LANReap (reaper)", "TestServer_JoinWAN",
+                 "TestClientServer_UserEvent", "TestAgent_Leave"):
         assert "PASS " + name in r.stdout
 
 
