@@ -80,3 +80,13 @@ def test_lan_reap(make, cuda_lib):
     import scenarios as sc
     for seed in (1, 2):
         sc.lan_reap_scenario(make, cuda_lib, seed)
+
+
+def test_facade_extended_on_cuda():
+    """TestServer_LANReap with the reaper's own timers and TestServer_JoinWAN through the C++ serf
+    facade on libgsim.so (the round-1 facade set runs in tests/test_facade.py)."""
+    import os
+    import test_facade as tf
+    binary = tf.build(os.path.join(tf.ROOT, "consul_b200"), "gsim",
+                      os.path.join(tf.ROOT, "tests", "facade", "facade_check_cuda"))
+    tf.run(binary, extended=True)
