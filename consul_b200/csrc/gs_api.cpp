@@ -849,6 +849,8 @@ static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_ol
       if (ru.ltime >= lm_d) lm_d = ru.ltime + 1u;
     } else if (ru.kind == GSIM_RUMOR_ALIVE) {
       if (md & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_JOIN, ru.subject, dst, 0u);
+    } else if (ru.kind == GSIM_RUMOR_UPDATE) {
+      if (md & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_UPDATE, ru.subject, dst, 0u);
     }
     if (accept) {
       accepted |= 1u << r;
@@ -991,6 +993,38 @@ extern "C" int gsim_crash_fraction(gsim_pool* p, uint32_t ppm, uint32_t salt, ui
   if (n_crashed) *n_crashed = cnt;
   int rc = refresh_after_truth_change(p);
   return rc ? fail(p, rc, "recount") : GSIM_OK;
+  });
+}
+
+// (*Serf).SetTags -> [U] memberlist.UpdateNode: the member re-announces itself with new meta under
+// the next incarnation; every receiver's aliveNode takes the higher incarnation and raises
+// NotifyUpdate -> serf EventMemberUpdate.  The tags themselves stay on the host.
+extern "C" int gsim_member_update(gsim_pool* p, uint32_t id, uint32_t alive_msg_size, uint32_t* slot_out) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  uint32_t slot_local = 0;
+  if (!slot_out) slot_out = &slot_local;
+  return controller_call(p, slot_out, sizeof(uint32_t), [&]() -> int {
+  GsGlobals& g = p->g;
+  if (id >= g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t k, m;
+  if (!peek(p, p->d.key[p->now & 1u], id, &k) || !peek(p, p->d.meta, id, &m))
+    return fail(p, GSIM_ERR_CUDA, "peek");
+  if (gs_key_truth(k) != GS_TRUTH_UP || (m & GS_META_LEAVING))
+    return fail(p, GSIM_ERR_STATE, "member is not running");
+  uint32_t slot;
+  int rc = alloc_slot(p, &slot);
+  if (rc) return fail(p, rc, "no free rumor slot");
+  const uint32_t inc = gs_key_inc(k) + 1u;  // nextIncarnation
+  for (int b = 0; b < 2; ++b) {
+    uint32_t kk;
+    if (!peek(p, p->d.key[b], id, &kk)) return fail(p, GSIM_ERR_CUDA, "peek");
+    if (!poke_key(p, b, id, gs_key_with_inc(kk, inc))) return fail(p, GSIM_ERR_CUDA, "poke");
+  }
+  rc = start_rumor(p, slot, GSIM_RUMOR_UPDATE, id, inc, 0u, id, alive_msg_size ? alive_msg_size : 64u, 0u);
+  if (rc) return fail(p, rc, "start_rumor");
+  *slot_out = slot;
+  return GSIM_OK;
   });
 }
 
@@ -1151,6 +1185,8 @@ extern "C" int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* 
     if (!poke(p, p->d.ltime_member, id, lm)) return fail(p, GSIM_ERR_CUDA, "poke");
   } else if (ru.kind == GSIM_RUMOR_ALIVE) {
     if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_JOIN, ru.subject, id, 0u);
+  } else if (ru.kind == GSIM_RUMOR_UPDATE) {
+    if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_MEMBER_UPDATE, ru.subject, id, 0u);
   }
   if (!accept) return GSIM_OK;
   uint32_t c, ct;

@@ -361,6 +361,10 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         } else if (ru.kind == 1u) {
           // [U] memberlist.aliveNode for a new node -> serf.handleNodeJoin -> EventMemberJoin.
           if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, 0u /*MEMBER_JOIN*/, ru.subject, i, 0u);
+        } else if (ru.kind == 5u) {
+          // [U] memberlist.aliveNode with a higher incarnation and new meta -> NotifyUpdate ->
+          // serf.handleNodeUpdate -> EventMemberUpdate ((*Serf).SetTags at the subject).
+          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, 3u /*MEMBER_UPDATE*/, ru.subject, i, 0u);
         }
         if (accept) {
           accepted |= 1u << r;

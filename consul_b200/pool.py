@@ -146,6 +146,12 @@ class Pool:
     def member_watch(self, member: int, on: bool = True):
         self._ck(self.lib.gsim_member_watch(self.h, member, int(on)))
 
+    def member_update(self, member: int, alive_msg_size: int = 0) -> int:
+        """(*Serf).SetTags: re-announce under the next incarnation; returns the rumor slot."""
+        out = C.c_uint32()
+        self._ck(self.lib.gsim_member_update(self.h, member, alive_msg_size, C.byref(out)))
+        return out.value
+
     def latency_set(self, lat):
         """lat: square matrix (n_dcs x n_dcs) of one-way latencies in ticks (>= 1), or None."""
         if lat is None:

@@ -76,6 +76,7 @@ extern "C" {
 #define GSIM_RUMOR_JOIN_INTENT 2  /* serf messageJoin{LTime,Node}                     */
 #define GSIM_RUMOR_LEAVE_INTENT 3 /* serf messageLeave{LTime,Node}                    */
 #define GSIM_RUMOR_USER_EVENT 4   /* serf messageUserEvent{LTime,Name,Payload,CC}     */
+#define GSIM_RUMOR_UPDATE 5       /* memberlist alive{Incarnation+1, new Meta} (SetTags) */
 #define GSIM_MAX_RUMORS 30        /* inbox bits 0..29; bit 30 = wake, bit 31 = accusations */
 #define GSIM_MAX_SUSPICION_SLOTS 5 /* k+1 with k = SuspicionMult-2 <= 4               */
 
@@ -210,6 +211,12 @@ int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size_t name_len
  * pool into the other pool (the ForwardRPC of agent/consul/internal_endpoint.go:839).
  * *accepted = 1 when the member had not heard it and took it. */
 int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* accepted);
+
+/* (*Serf).SetTags(tags) — internal/gossip/libserf/serf.go:51; [U] memberlist.UpdateNode: the
+ * member re-broadcasts alive under its next incarnation; every other member raises
+ * EventMemberUpdate when it arrives.  Tags stay host-side; alive_msg_size (0 = 64) is the encoded
+ * size of the new alive message for the UDP budget. */
+int gsim_member_update(gsim_pool* p, uint32_t id, uint32_t alive_msg_size, uint32_t* slot_out);
 
 /* Event logging of one member on/off after creation (that agent's EventCh; see
  * gsim_member_desc.flags / GSIM_MEMBER_WATCHED and gsim_poll_events). */

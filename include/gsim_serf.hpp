@@ -145,6 +145,16 @@ class Serf {
     if (n_ok == 0 && !existing.empty()) throw Error(GSIM_ERR_NOT_FOUND, "Failed to join: no seeds could be contacted");
     return n_ok;
   }
+  // SetTags(tags) — internal/gossip/libserf/serf.go:51: the tags live here on the host; the
+  // re-announcement under the next incarnation (and every other member's EventMemberUpdate) is
+  // simulated.  Encoded size of the alive message grows with the tags (UDP budget).
+  void SetTags(const std::map<std::string, std::string>& tags) {
+    conf_.Tags = tags;
+    uint32_t bytes = 64;
+    for (auto& kv : tags) bytes += (uint32_t)(kv.first.size() + kv.second.size() + 2);
+    if (bytes > 512) bytes = 512;  // memberlist.MetaMaxSize
+    p_.check(gsim_member_update(p_.h_, id_, bytes, nullptr));
+  }
   void Leave() { p_.check(gsim_leave(p_.h_, id_)); }
   void Shutdown() { p_.check(gsim_crash(p_.h_, id_)); }  // without Leave(): a crash (server_test.go:725)
   void UserEvent(const std::string& name, const std::string& payload, bool coalesce) {

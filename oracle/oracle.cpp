@@ -490,6 +490,9 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
         case GSIM_RUMOR_ALIVE:  // [U] memberlist.aliveNode (new node) -> serf.handleNodeJoin
           if (me.watched) log_event(o, ta, t, GSIM_EVENT_MEMBER_JOIN, ru.subject, i, 0);
           break;
+        case GSIM_RUMOR_UPDATE:  // [U] memberlist.aliveNode (known node, newer incarnation) -> NotifyUpdate
+          if (me.watched) log_event(o, ta, t, GSIM_EVENT_MEMBER_UPDATE, ru.subject, i, 0);
+          break;
       }
       if (accept) {
         me.heard |= 1u << r;
@@ -886,6 +889,8 @@ void merge_from(Oracle& o, uint32_t dst, uint32_t src, bool ignore_old) {
       d.ltime_member = lamport_witness(d.ltime_member, ru.ltime);
     } else if (ru.kind == GSIM_RUMOR_ALIVE) {
       if (d.watched) host_event(o, GSIM_EVENT_MEMBER_JOIN, ru.subject, dst, 0);
+    } else if (ru.kind == GSIM_RUMOR_UPDATE) {
+      if (d.watched) host_event(o, GSIM_EVENT_MEMBER_UPDATE, ru.subject, dst, 0);
     }
     if (!accept) continue;
     d.heard |= 1u << r;
@@ -1200,6 +1205,8 @@ int oracle_rumor_inject(void* h, uint32_t slot, uint32_t id, int* accepted) {
     me.ltime_member = lamport_witness(me.ltime_member, ru.ltime);
   } else if (ru.kind == GSIM_RUMOR_ALIVE) {
     if (me.watched) host_event(o, GSIM_EVENT_MEMBER_JOIN, ru.subject, id, 0);
+  } else if (ru.kind == GSIM_RUMOR_UPDATE) {
+    if (me.watched) host_event(o, GSIM_EVENT_MEMBER_UPDATE, ru.subject, id, 0);
   }
   me.heard |= 1u << slot;
   me.queued |= 1u << slot;
@@ -1207,6 +1214,21 @@ int oracle_rumor_inject(void* h, uint32_t slot, uint32_t id, int* accepted) {
   ru.heard_count++;
   if (ru.heard_count == o.up_count && ru.converged_tick == NONE32) ru.converged_tick = o.now;
   if (accepted) *accepted = 1;
+  return GSIM_OK;
+}
+
+// (*Serf).SetTags -> [U] memberlist.UpdateNode: alive{nextIncarnation(), new meta} is broadcast.
+int oracle_member_update(void* h, uint32_t id, uint32_t alive_msg_size, uint32_t* slot_out) {
+  Oracle& o = *(Oracle*)h;
+  if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
+  if (o.m[id].v.truth != GSIM_TRUTH_UP || o.m[id].leaving) return GSIM_ERR_STATE;
+  int slot = free_slot(o);
+  if (slot < 0) return GSIM_ERR_CAPACITY;
+  Member& me = o.m[id];
+  me.v.inc += 1;
+  publish(o, id);
+  start_rumor(o, slot, GSIM_RUMOR_UPDATE, id, me.v.inc, 0, id, alive_msg_size ? alive_msg_size : 64, 0);
+  if (slot_out) *slot_out = (uint32_t)slot;
   return GSIM_OK;
 }
 

