@@ -27,6 +27,36 @@ CASES = [
     ("leave_300", "lan", 300, 5, [("leave", 7), ("step", 150)]),
 ]
 
+# Features added after round 1's GPU verification (WAN latency ring, push-pull, reaper, SetTags):
+# their fixtures live in scenarios_ext.json so that scenarios.json stays byte-identical.
+MS, SEC = 10**6, 10**9
+CASES_EXT = [
+    ("wan_c5_latency_event_16k", "wan", 16_384 + 77, 0x5EED0005,
+     [("cfg", dict(mailbox_depth=8)), ("latency", "c5", 64), ("event", 0, "deploy", 32), ("until", 2, 800), ("step", 120)]),
+    ("wan_slow_links_lossy_3k", "wan", 3_000, 21,
+     [("cfg", dict(mailbox_depth=8, packet_loss_ppm=200000, disable_tcp_pings=1)), ("latency", "slow", 16, 7),
+      ("add", 1), ("join", 3000, 3), ("event", 5, "e1", 7), ("crash", 10), ("crash", 300), ("crash", 1200), ("step", 700)]),
+    ("pushpull_stranded_3k", "lan", 3_000, 0x5EED00AA,
+     [("cfg", dict(flags=32, push_pull_interval_ns=1 * SEC, packet_loss_ppm=500000, retransmit_mult=1)),
+      ("event", 17, "deploy", 2), ("add", 1), ("join", 3000, 3), ("crash", 100), ("crash", 200), ("step", 900)]),
+    ("lan_reap_3", "test", 0, 1,
+     [("cfg", dict(flags=1, reconnect_timeout_ns=250 * MS, tombstone_timeout_ns=250 * MS, reap_interval_ns=300 * MS)),
+      ("add", 3), ("join", 1, 0), ("join", 2, 0), ("until", 2, 400), ("crash", 1), ("until", 3, 2000), ("step", 20),
+      ("leave", 2), ("step", 120)]),
+    ("set_tags_500", "lan", 500, 41,
+     [("cfg", dict(packet_loss_ppm=200000)), ("step", 7), ("update", 5, 120), ("until", 2, 600), ("step", 50),
+      ("update", 5, 0), ("step", 60)]),
+]
+
+
+def latency_matrix(kind, n_dcs, worst=5):
+    import numpy as np
+    a = np.arange(n_dcs)[:, None]
+    b = np.arange(n_dcs)[None, :]
+    m = 1 + ((7 * a + 13 * b) % 5 if kind == "c5" else (3 * a + 5 * b) % worst)
+    m[np.arange(n_dcs), np.arange(n_dcs)] = 1
+    return m.astype(np.uint8)
+
 
 def run_case(make_pool, cfg_fns, case):
     name, preset, n0, seed, script = case
@@ -34,6 +64,8 @@ def run_case(make_pool, cfg_fns, case):
     for op in script:
         if op[0] == "loss":
             extra["packet_loss_ppm"] = op[1]
+        if op[0] == "cfg":
+            extra.update(op[1])
     cap = n0 + 8
     kw = dict(capacity=cap, n_initial=n0, seed=seed, **extra)
     if preset == "test":
@@ -58,6 +90,10 @@ def run_case(make_pool, cfg_fns, case):
             pool.user_event(op[1], op[2].encode(), b"x" * op[3], False)
         elif op[0] == "leave":
             pool.leave(op[1])
+        elif op[0] == "latency":
+            pool.latency_set(latency_matrix(op[1], op[2], op[3] if len(op) > 3 else 5))
+        elif op[0] == "update":
+            pool.member_update(op[1], op[2])
     st = pool.stats()
     st.pop("active_rows", None)
     return {"name": name, "tick": pool.now, "results": untils, "state_hash": [f"{h:016x}" for h in pool.state_hash()],
@@ -78,4 +114,9 @@ if __name__ == "__main__":
     with open(os.path.join(HERE, "scenarios.json"), "w") as f:
         json.dump(out, f, indent=1)
     for o in out:
+        print(o["name"], o["tick"], o["results"], o["state_hash"][0])
+    ext = [run_case(lambda cfg: OraclePool(cfg, threads=1), fns, c) for c in CASES_EXT]
+    with open(os.path.join(HERE, "scenarios_ext.json"), "w") as f:
+        json.dump(ext, f, indent=1)
+    for o in ext:
         print(o["name"], o["tick"], o["results"], o["state_hash"][0])

@@ -14,6 +14,9 @@ import make_golden as mg  # noqa: E402
 
 with open(os.path.join(HERE, "golden", "scenarios.json")) as f:
     GOLDEN = {g["name"]: g for g in json.load(f)}
+with open(os.path.join(HERE, "golden", "scenarios_ext.json")) as f:
+    GOLDEN.update({g["name"]: g for g in json.load(f)})
+ALL_CASES = mg.CASES + mg.CASES_EXT
 
 
 def check(make_pool, lib, case):
@@ -26,14 +29,14 @@ def check(make_pool, lib, case):
     assert got["state_hash"] == want["state_hash"]
 
 
-@pytest.mark.parametrize("case", mg.CASES, ids=[c[0] for c in mg.CASES])
+@pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
 def test_oracle_reproduces_golden(case):
     from consul_b200 import _lib
     from oracle_binding import OraclePool
     check(lambda cfg: OraclePool(cfg, threads=2), _lib.lib(), case)
 
 
-@pytest.mark.parametrize("case", mg.CASES, ids=[c[0] for c in mg.CASES])
+@pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
 def test_kernel_body_on_host_reproduces_golden(case, hostemu_lib):
     from consul_b200.pool import Pool
     check(lambda cfg: Pool(cfg, hostemu_lib), hostemu_lib, case)

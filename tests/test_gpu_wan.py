@@ -96,3 +96,12 @@ def test_set_tags_update(make, cuda_lib):
     """(*Serf).SetTags -> EventMemberUpdate on the GPU against the oracle."""
     import scenarios as sc
     sc.set_tags_scenario(make, cuda_lib)
+
+
+@pytest.mark.parametrize("case_name", ["wan_c5_latency_event_16k", "wan_slow_links_lossy_3k", "pushpull_stranded_3k",
+                                       "lan_reap_3", "set_tags_500"])
+def test_cuda_reproduces_extended_golden(case_name, cuda_lib):
+    """tests/golden/scenarios_ext.json (oracle-generated): ticks, counters and the 256-bit digest."""
+    import test_golden as tg
+    case = [c for c in tg.mg.CASES_EXT if c[0] == case_name][0]
+    tg.check(lambda cfg: Pool(cfg, cuda_lib), cuda_lib, case)
