@@ -189,6 +189,7 @@ struct gsim_pool {
   uint32_t attached = 1;     // ranks whose memory is mapped here (including this one)
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
+  std::vector<uint32_t> graph_rp, graph_col;  // host copy of the CSR peer graph (gsim_graph_set)
   GsXbar xb;
 };
 
@@ -791,6 +792,7 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   std::lock_guard<std::mutex> lk(p->mu);
   return controller_call(p, id_out, sizeof(uint32_t), [&]() -> int {
   GsGlobals& g = p->g;
+  if (g.graph_n) return fail(p, GSIM_ERR_STATE, "the peer graph of this pool is static (gsim_graph_set)");
   if (g.n >= p->cfg.capacity) return fail(p, GSIM_ERR_CAPACITY, "member capacity exhausted");
   uint32_t slot;
   int rc = alloc_slot(p, &slot);
@@ -1203,6 +1205,45 @@ extern "C" int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* 
   });
 }
 
+// Peer graph in CSR form (north_star: "message-passing kernel over a CSR peer graph"):
+// member i's memberlist becomes col_idx[row_ptr[i] .. row_ptr[i+1]) — peer selection for gossip,
+// indirect-probe relays, push-pull and the probe ring all draw from that row instead of [0, n).
+// A graph whose every row is [0, n) reproduces the complete-graph results bit for bit.  Static
+// topology: rows for exactly the current members; gsim_member_add is refused while a graph is set.
+extern "C" int gsim_graph_set(gsim_pool* p, uint32_t n_rows, const uint32_t* row_ptr, const uint32_t* col_idx) {
+  if (!p || (n_rows && (!row_ptr || !col_idx))) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (p->sharded) return fail(p, GSIM_ERR_STATE, "peer graphs are not supported on sharded pools");
+  GsGlobals& g = p->g;
+  if (n_rows == 0) {
+    g.graph_n = 0;
+    p->d.row_ptr = p->d.col_idx = nullptr;
+    p->graph_rp.clear();
+    p->graph_col.clear();
+    p->g_dirty = true;
+    return GSIM_OK;
+  }
+  if (n_rows != g.n) return fail(p, GSIM_ERR_INVALID, "the graph must have one row per member");
+  if (row_ptr[0] != 0) return fail(p, GSIM_ERR_INVALID, "row_ptr[0] must be 0");
+  for (uint32_t i = 0; i < n_rows; ++i)
+    if (row_ptr[i + 1] < row_ptr[i]) return fail(p, GSIM_ERR_INVALID, "row_ptr must be non-decreasing");
+  const uint32_t nnz = row_ptr[n_rows];
+  for (uint32_t e = 0; e < nnz; ++e)
+    if (col_idx[e] >= g.n) return fail(p, GSIM_ERR_INVALID, "col_idx out of range");
+  uint32_t *rp_dev = nullptr, *col_dev = nullptr;
+  if (!alloc_col(p, &rp_dev, (size_t)n_rows + 1) || !alloc_col(p, &col_dev, (size_t)(nnz ? nnz : 1)))
+    return fail(p, GSIM_ERR_NOMEM, "graph allocation");
+  if (!p->be->h2d(rp_dev, row_ptr, ((size_t)n_rows + 1) * 4) || (nnz && !p->be->h2d(col_dev, col_idx, (size_t)nnz * 4)))
+    return fail(p, GSIM_ERR_CUDA, "h2d");
+  p->graph_rp.assign(row_ptr, row_ptr + n_rows + 1);
+  p->graph_col.assign(col_idx, col_idx + nnz);
+  p->d.row_ptr = rp_dev;
+  p->d.col_idx = col_dev;
+  g.graph_n = n_rows;
+  p->g_dirty = true;
+  return GSIM_OK;
+}
+
 // Turn event logging for one member on or off after creation (gsim_member_desc.flags does it at
 // creation): the EventCh of that agent, polled through gsim_poll_events.
 extern "C" int gsim_member_watch(gsim_pool* p, uint32_t id, int on) {
@@ -1416,9 +1457,17 @@ static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, siz
       !peek(p, p->d.heard, observer, &heard) || !peek(p, p->d.meta, observer, &meta))
     return GSIM_ERR_CUDA;
   size_t cnt = 0;
+  // on a CSR peer graph a member's list is itself plus its row
+  std::vector<uint8_t> in_row;
+  if (g.graph_n) {
+    in_row.assign(g.n, 0);
+    in_row[observer] = 1;
+    for (uint32_t e = p->graph_rp[observer]; e < p->graph_rp[observer + 1]; ++e) in_row[p->graph_col[e]] = 1;
+  }
   for (uint32_t c = 0; c < g.n; ++c) {
     uint32_t kc = keys[c];
     if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
+    if (g.graph_n && !in_row[c]) continue;
     if (!host_knows(g, observer, c, kc, heard, meta)) continue;
     if (out && cnt < cap) {
       gsim_member& mm = out[cnt];
@@ -1760,7 +1809,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   memcpy(&h, r, sizeof(h));
   r += sizeof(h);
   if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask ||
-      (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u))
+      (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u) || h.g.graph_n != p->g.graph_n)
     return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
   if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
   p->sched.resize(h.n_sched);

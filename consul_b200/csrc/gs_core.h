@@ -188,6 +188,13 @@ GS_HD GsU4 gs_perm_keys(uint32_t seed_lo, uint32_t seed_hi, uint32_t member, uin
   k.w = (k.y * 0x85EBCA77u) ^ k.x;
   return k;
 }
+// half the bit width of the smallest even-width power of two >= n (>= 4): the Feistel domain
+GS_HD uint32_t gs_perm_half_bits_of(uint32_t n) {
+  uint32_t bits = 2u;
+  while (bits < 32u && (1ull << bits) < (unsigned long long)n) ++bits;
+  bits += bits & 1u;
+  return bits >> 1;
+}
 GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t half_bits, const GsU4& rk) {
   const uint32_t mask = (1u << half_bits) - 1u;
   do {
@@ -252,6 +259,10 @@ struct GsGlobals {
   // of phase group q run theirs at ticks t with (t + rot_pp) % pp_interval == q % pp_interval.
   uint32_t pp_interval;   // pushPullScale(PushPullInterval, n) in ticks; 0 = disabled
   uint32_t rot_pp;
+  // Peer graph (north_star "CSR peer graph"): 0 = the complete graph, every member may
+  // pick any other; otherwise member i's memberlist is col_idx[row_ptr[i] .. row_ptr[i+1]) and
+  // graph_n == n rows are described (static topology: restricted segments, partial views).
+  uint32_t graph_n;
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -281,6 +292,8 @@ struct GsDev {
   uint32_t* queued;
   uint8_t* tx;  // [GS_MAX_RUMORS][cap]
   // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
+  const uint32_t* row_ptr;  // [graph_n + 1] CSR peer graph, null on complete-graph pools
+  const uint32_t* col_idx;  // [row_ptr[graph_n]]
   uint32_t* ppreq;   // [2][GS_PPK][cap] requester ids, kept as the GS_PPK smallest (atomicMin chain)
   uint32_t* pp_clk;  // [2][2][cap] max of the senders' {member, event} Lamport clocks (atomicMax)
   // pool-wide device words

@@ -682,6 +682,14 @@ class CudaBackend : public GsBackend {
     return cudaStreamSynchronize(stream_);
   }
   cudaGraphExec_t graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks, const GsXbar* xbar) {
+    // the column pointers are baked into the captured launches: if they changed (a peer graph was
+    // attached or removed), every cached graph is stale
+    if (have_graph_dev_ && memcmp(&graph_dev_, &d, sizeof(GsDev)) != 0) {
+      for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+      graphs_.clear();
+    }
+    graph_dev_ = d;
+    have_graph_dev_ = true;
     auto it = graphs_.find(blocks);
     if (it != graphs_.end()) return it->second;
     cudaGraph_t graph = nullptr;
@@ -724,6 +732,8 @@ class CudaBackend : public GsBackend {
   // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
   bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
+  GsDev graph_dev_;
+  bool have_graph_dev_ = false;
   uint64_t launches_ = 0;
   char err_[256];
 };

@@ -176,13 +176,25 @@ GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c,
   return false;
 }
 
+// The member list of member i as a sequence: the complete graph [0, n) by default, row i of the
+// CSR peer graph when one is set.  Same draws, same ring — only the index space changes, so a CSR
+// whose rows are all [0, n) reproduces the complete-graph results exactly.
+GS_DEV uint32_t gs_peer_count(const GsDev& d, const GsGlobals& g, uint32_t i) {
+  if (g.graph_n == 0u) return g.n;
+  return i < g.graph_n ? d.row_ptr[i + 1u] - d.row_ptr[i] : 0u;
+}
+GS_DEV uint32_t gs_peer_at(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t idx) {
+  return g.graph_n == 0u ? idx : d.col_idx[d.row_ptr[i] + idx];
+}
+
 // kRandomNodes ([U] memberlist/util.go): up to min(3n, 32) uniform draws `rand % n`,
 // rejecting excluded members and duplicates.  mode 0 = gossip targets (alive, suspect,
 // or dead for less than GossipToTheDeadTime), mode 1 = indirect-probe relays (alive only).
 GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t,
                            uint32_t purpose, uint32_t k, uint32_t mode, uint32_t exclude2,
                            uint32_t meta_i, uint32_t* out) {
-  const uint32_t n = g.n;
+  const uint32_t n = gs_peer_count(d, g, i);
+  if (n == 0u) return 0u;
   const uint32_t* keyc = d.key[t & 1u];
   uint32_t tries = 3u * n;
   if (tries > GS_KR_MAX_TRIES || n > 0x55555555u) tries = GS_KR_MAX_TRIES;
@@ -191,7 +203,7 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
   blk.x = blk.y = blk.z = blk.w = 0;
   for (uint32_t dr = 0; dr < tries && cnt < k; ++dr) {
     if ((dr & 3u) == 0u) blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, dr >> 2);
-    uint32_t c = gs_u4_get(blk, dr & 3u) % n;
+    uint32_t c = gs_peer_at(d, g, i, gs_u4_get(blk, dr & 3u) % n);
     if (c == i || c == exclude2) continue;
     uint32_t kc = GS_LD_OTHER(&keyc[c]);
     if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
@@ -533,7 +545,8 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       // [U] memberlist.probe: next eligible entry of the ring, skipping self, unknown and
       // dead/left members; a wrap re-keys the permutation (resetNodes + shuffle).
       uint32_t cursor = d.cursor[i], pass = d.pass[i];
-      const uint32_t n = g.n;
+      const uint32_t n = gs_peer_count(d, g, i);
+      const uint32_t hb = g.graph_n == 0u ? g.perm_half_bits : gs_perm_half_bits_of(n);
       GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, pass);
       uint32_t checked = 0, target = GS_EMPTY32, ktarget = 0;
       const uint32_t limit = n < GS_PROBE_SKIP_CAP ? n : GS_PROBE_SKIP_CAP;
@@ -545,7 +558,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, pass);
           continue;
         }
-        uint32_t c = gs_perm(cursor, n, g.perm_half_bits, rk);
+        uint32_t c = gs_peer_at(d, g, i, gs_perm(cursor, n, hb, rk));
         ++cursor;
         uint32_t kc = GS_LD_OTHER(&d.key[cur][c]);
         uint32_t rank = gs_key_rank(kc);
@@ -672,7 +685,7 @@ GS_DEV void gs_fast_load(const GsDev& d, uint32_t cur, uint32_t i, GsFastProbe& 
 
 GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uint32_t i,
                            GsFastProbe& f) {
-  if (g.loss_thr != 0u) return false;
+  if (g.loss_thr != 0u || g.graph_n != 0u) return false;  // CSR rows: generic path
   if (gs_key_truth(f.k) != GS_TRUTH_UP || gs_key_rank(f.k) != GS_RANK_ALIVE) return false;
   if (gs_meta_stage(f.m) != GS_STAGE_IDLE || (f.m & (GS_META_DIRTY | GS_META_ISOLATED))) return false;
   if (f.cursor >= g.n) return false;  // ring wrap: re-key in the generic path

@@ -152,6 +152,16 @@ class Pool:
         self._ck(self.lib.gsim_member_update(self.h, member, alive_msg_size, C.byref(out)))
         return out.value
 
+    def graph_set(self, row_ptr, col_idx):
+        """CSR peer graph: member i's memberlist = col_idx[row_ptr[i]:row_ptr[i+1]]; None removes it."""
+        if row_ptr is None:
+            self._ck(self.lib.gsim_graph_set(self.h, 0, None, None))
+            return
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        self._ck(self.lib.gsim_graph_set(self.h, len(rp) - 1, rp.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                         ci.ctypes.data_as(C.POINTER(C.c_uint32))))
+
     def latency_set(self, lat):
         """lat: square matrix (n_dcs x n_dcs) of one-way latencies in ticks (>= 1), or None."""
         if lat is None:

@@ -218,6 +218,18 @@ int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* accepted);
  * size of the new alive message for the UDP budget. */
 int gsim_member_update(gsim_pool* p, uint32_t id, uint32_t alive_msg_size, uint32_t* slot_out);
 
+/* Peer graph in CSR form (BASELINE north_star: "message-passing kernel over a CSR peer graph").
+ * Default: the complete graph — a converged memberlist knows every member.  With a graph, member
+ * i's memberlist is col_idx[row_ptr[i] .. row_ptr[i+1]): gossip peers, indirect-probe relays,
+ * push-pull partners and the probe ring are all drawn from that row (restricted topologies such
+ * as Consul's serf_lan_allowed_cidrs, agent/config/runtime.go:1222-1232, or network segments).
+ * n_rows must equal the current member count; rows may contain the member itself (skipped like
+ * memberlist skips the local node).  A graph whose every row is 0..n-1 gives exactly the
+ * complete-graph results.  The topology is static: gsim_member_add fails while a graph is set;
+ * n_rows = 0 removes it.  Not supported on sharded pools.  A snapshot does not carry the graph:
+ * set the same graph before gsim_restore. */
+int gsim_graph_set(gsim_pool* p, uint32_t n_rows, const uint32_t* row_ptr, const uint32_t* col_idx);
+
 /* Event logging of one member on/off after creation (that agent's EventCh; see
  * gsim_member_desc.flags / GSIM_MEMBER_WATCHED and gsim_poll_events). */
 int gsim_member_watch(gsim_pool* p, uint32_t id, int on);

@@ -229,6 +229,9 @@ struct Oracle {
   std::vector<Accusation> arriving;      // accusations that arrive at the tick about to run
   std::vector<PushPull> pp_arriving;     // push-pull requests / answers arriving at that tick
   uint32_t pp_every = 0, pp_rot = 0;     // push-pull ticker period in ticks (0 = off) and rotation
+  // restricted topology: member i only knows adjacency[i] (empty vector of vectors = everyone
+  // knows everyone, the converged memberlist)
+  std::vector<std::vector<uint32_t>> adjacency;
   Rumor rumor[GSIM_MAX_RUMORS];
   uint32_t active = 0;
   std::vector<Scheduled> shutdowns;
@@ -289,8 +292,8 @@ Rand4 ring_keys(uint64_t seed, uint32_t member, uint32_t pass) {
 }
 
 // Feistel permutation of [0,n) with cycle walking — the probe ring of one (member, pass).
-uint32_t ring_entry(const Oracle& o, uint32_t position, uint32_t n, const Rand4& keys) {
-  const uint32_t hb = o.perm_half_bits, mask = (1u << hb) - 1;
+uint32_t ring_entry(const Oracle& o, uint32_t position, uint32_t n, const Rand4& keys, uint32_t half_bits = 0) {
+  const uint32_t hb = half_bits ? half_bits : o.perm_half_bits, mask = (1u << hb) - 1;
   uint32_t x = position;
   for (;;) {
     uint32_t left = x >> hb, right = x & mask;
@@ -361,16 +364,33 @@ struct Picks {
   void push_back(uint32_t c) { v[n++] = c; }
 };
 
+// member i's memberlist as an indexable sequence
+uint32_t list_length(const Oracle& o, uint32_t i) {
+  if (o.adjacency.empty()) return (uint32_t)o.m.size();
+  return i < o.adjacency.size() ? (uint32_t)o.adjacency[i].size() : 0;
+}
+uint32_t list_entry(const Oracle& o, uint32_t i, uint32_t position) {
+  return o.adjacency.empty() ? position : o.adjacency[i][position];
+}
+uint32_t ring_half_bits(uint32_t n) {
+  uint32_t bits = 0;
+  while (bits < 32 && (1ull << bits) < n) ++bits;
+  bits = std::max(bits, 2u);
+  bits += bits & 1;
+  return bits / 2;
+}
+
 // [U] memberlist/util.go kRandomNodes
 Picks k_random(const Oracle& o, uint32_t i, const Member& me, uint32_t t, uint32_t purpose,
                                uint32_t k, bool relays, uint32_t also_exclude) {
   Picks out;
-  const uint32_t n = (uint32_t)o.m.size();
+  const uint32_t n = list_length(o, i);
+  if (!n) return out;
   uint64_t tries = std::min<uint64_t>(3ull * n, KRANDOM_MAX_TRIES);
   Rand4 block = {{0, 0, 0, 0}};
   for (uint32_t draw = 0; draw < tries && out.size() < k; ++draw) {
     if (draw % 4 == 0) block = philox4x32_10(o.cfg.seed, i, t, purpose, draw / 4);
-    uint32_t c = block.v[draw % 4] % n;  // randomOffset
+    uint32_t c = list_entry(o, i, block.v[draw % 4] % n);  // randomOffset into the member list
     if (c == i || c == also_exclude) continue;
     const View& vc = o.pub[c];
     if (vc.truth == GSIM_TRUTH_NONE) continue;
@@ -612,7 +632,8 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     }
     if (me.stage == ST_IDLE && me.due == t) {
       // [U] memberlist.probe: walk the ring to the next probe-able member
-      const uint32_t n = (uint32_t)o.m.size();
+      const uint32_t n = list_length(o, i);
+      const uint32_t half_bits = o.adjacency.empty() ? 0 : ring_half_bits(n);
       Rand4 keys = ring_keys(o.cfg.seed, i, me.pass);
       uint32_t checked = 0, target = NONE32;
       const uint32_t cap = std::min(n, PROBE_SKIP_CAP);
@@ -624,7 +645,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
           keys = ring_keys(o.cfg.seed, i, me.pass);
           continue;
         }
-        uint32_t c = ring_entry(o, me.cursor++, n, keys);
+        uint32_t c = list_entry(o, i, ring_entry(o, me.cursor++, n, keys, half_bits));
         const View& vc = o.pub[c];
         if (c == i || vc.truth == GSIM_TRUTH_NONE || vc.rank == GSIM_RANK_DEAD || vc.rank == GSIM_RANK_LEFT ||
             !knows(o, i, me, c)) {
@@ -1041,6 +1062,7 @@ int oracle_threads(void* h) { return ((Oracle*)h)->threads; }
 
 int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   Oracle& o = *(Oracle*)h;
+  if (!o.adjacency.empty()) return GSIM_ERR_STATE;  // static topology
   if (o.m.size() >= o.cfg.capacity) return GSIM_ERR_CAPACITY;
   int slot = free_slot(o);
   if (slot < 0) return GSIM_ERR_CAPACITY;
@@ -1232,6 +1254,17 @@ int oracle_member_update(void* h, uint32_t id, uint32_t alive_msg_size, uint32_t
   return GSIM_OK;
 }
 
+// CSR peer graph: adjacency[i] = col_idx[row_ptr[i] .. row_ptr[i+1])
+int oracle_graph_set(void* h, uint32_t n_rows, const uint32_t* row_ptr, const uint32_t* col_idx) {
+  Oracle& o = *(Oracle*)h;
+  o.adjacency.clear();
+  if (!n_rows) return GSIM_OK;
+  if (n_rows != o.m.size()) return GSIM_ERR_INVALID;
+  o.adjacency.resize(n_rows);
+  for (uint32_t i = 0; i < n_rows; ++i) o.adjacency[i].assign(col_idx + row_ptr[i], col_idx + row_ptr[i + 1]);
+  return GSIM_OK;
+}
+
 int oracle_member_watch(void* h, uint32_t id, int on) {
   Oracle& o = *(Oracle*)h;
   if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
@@ -1300,6 +1333,9 @@ int oracle_members(void* h, uint32_t observer, gsim_member* out, size_t cap, siz
   for (uint32_t c = 0; c < o.m.size(); ++c) {
     const View& v = o.m[c].v;
     if (v.truth == GSIM_TRUTH_NONE) continue;
+    if (!o.adjacency.empty() && c != observer &&
+        std::find(o.adjacency[observer].begin(), o.adjacency[observer].end(), c) == o.adjacency[observer].end())
+      continue;
     if (!knows(o, observer, o.m[observer], c)) continue;
     if (out && cnt < cap) {
       out[cnt].id = c;

@@ -39,6 +39,7 @@ _SIGS = [
     ("oracle_user_event", _i32, [_P, _u32, C.c_char_p, _sz, C.c_char_p, _sz, _i32, C.POINTER(_u32)]),
     ("oracle_rumor_inject", _i32, [_P, _u32, _u32, C.POINTER(_i32)]),
     ("oracle_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
+    ("oracle_graph_set", _i32, [_P, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
     ("oracle_member_watch", _i32, [_P, _u32, _i32]),
     ("oracle_member_update", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("oracle_step", _i32, [_P, _u32]),
@@ -143,6 +144,16 @@ class OraclePool:
         out = _u32()
         self._ck(self.lib.oracle_member_update(self.h, member, alive_msg_size, C.byref(out)))
         return out.value
+
+    def graph_set(self, row_ptr, col_idx):
+        import numpy as np
+        if row_ptr is None:
+            self._ck(self.lib.oracle_graph_set(self.h, 0, None, None))
+            return
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        self._ck(self.lib.oracle_graph_set(self.h, len(rp) - 1, rp.ctypes.data_as(C.POINTER(_u32)),
+                                           ci.ctypes.data_as(C.POINTER(_u32))))
 
     def member_watch(self, member, on=True):
         self._ck(self.lib.oracle_member_watch(self.h, member, int(on)))
