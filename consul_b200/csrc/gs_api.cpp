@@ -476,7 +476,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     }
     const size_t gran = be->shard_granularity();
     size_t per = ((size_t)cfg->capacity + cfg->world_size - 1) / cfg->world_size;
-    per = (per + gran - 1) / gran * gran;
+    const size_t gran_rows = gran / 2;  // the narrowest column has 2-byte elements (GS_TX)
+    per = (per + gran_rows - 1) / gran_rows * gran_rows;
     p->sharded = true;
     p->world = cfg->world_size;
     p->rank = cfg->rank;
@@ -519,7 +520,11 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   okk = okk && acol(&d.ltime_member, 1) && acol(&d.ltime_event, 1);
   okk = okk && acol(&d.event_min, 1);
   okk = okk && acol(&d.heard, 1) && acol(&d.queued, 1);
-  okk = okk && acol(&d.tx, GS_MAX_RUMORS);
+  {  // two rumors per 16-bit element (GS_TX): the narrowest sharded slice is 2 bytes per member
+    uint16_t* tx16 = nullptr;
+    okk = okk && acol(&tx16, GS_MAX_RUMORS / 2);
+    d.tx = reinterpret_cast<uint8_t*>(tx16);
+  }
   if (cfg->flags & GSIM_FLAG_PUSH_PULL)  // push-pull mailboxes: 48 B per member, only when asked for
     okk = okk && acol(&d.ppreq, 2 * GS_PPK) && acol(&d.pp_clk, 4);
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
@@ -764,7 +769,7 @@ static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subj
   h |= 1u << slot;
   q |= 1u << slot;
   if (!poke(p, p->d.heard, origin, h) || !poke(p, p->d.queued, origin, q)) return GSIM_ERR_CUDA;
-  if (!poke(p, p->d.tx, (size_t)slot * g.cap + origin, (uint8_t)0)) return GSIM_ERR_CUDA;
+  if (!poke(p, p->d.tx, GS_TX(slot, g.cap, origin), (uint8_t)0)) return GSIM_ERR_CUDA;
   if (!post_wake(p, origin)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.heard_cnt, slot, 1u)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.conv_tick, slot, g.up_count == 1u ? p->now : GS_EMPTY32)) return GSIM_ERR_CUDA;
@@ -856,7 +861,7 @@ static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_ol
     }
     if (accept) {
       accepted |= 1u << r;
-      if (!poke(p, p->d.tx, (size_t)r * g.cap + dst, (uint8_t)0)) return GSIM_ERR_CUDA;
+      if (!poke(p, p->d.tx, GS_TX(r, g.cap, dst), (uint8_t)0)) return GSIM_ERR_CUDA;
       uint32_t c;
       if (!peek(p, p->d.heard_cnt, r, &c)) return GSIM_ERR_CUDA;
       c += 1;
@@ -1193,7 +1198,7 @@ extern "C" int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* 
   if (!accept) return GSIM_OK;
   uint32_t c, ct;
   if (!poke(p, p->d.heard, id, h | (1u << slot)) || !poke(p, p->d.queued, id, q | (1u << slot)) ||
-      !poke(p, p->d.tx, (size_t)slot * g.cap + id, (uint8_t)0) || !post_wake(p, id) ||
+      !poke(p, p->d.tx, GS_TX(slot, g.cap, id), (uint8_t)0) || !post_wake(p, id) ||
       !peek(p, p->d.heard_cnt, slot, &c) || !poke(p, p->d.heard_cnt, slot, c + 1u) ||
       !peek(p, p->d.conv_tick, slot, &ct))
     return fail(p, GSIM_ERR_CUDA, "poke");
@@ -1695,6 +1700,20 @@ extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_
   (void)bytes;
   if (n_bytes) *n_bytes = out_bytes;
   if (cap_bytes < out_bytes) return fail(p, GSIM_ERR_INVALID, "buffer too small");
+  if (column == GSIM_COL_TX) {
+    // device layout: two rumors per 16-bit element (GS_TX); the caller sees [rumor][capacity] bytes
+    std::vector<uint8_t> pair(ucap * 2);
+    uint8_t* o = reinterpret_cast<uint8_t*>(out);
+    for (size_t q = 0; q < GS_MAX_RUMORS / 2; ++q) {
+      if (!p->be->d2h(pair.data(), reinterpret_cast<const uint8_t*>(src) + q * cap * 2, ucap * 2))
+        return fail(p, GSIM_ERR_CUDA, "d2h");
+      for (size_t i = 0; i < ucap; ++i) {
+        o[(2 * q) * ucap + i] = pair[2 * i];
+        o[(2 * q + 1) * ucap + i] = pair[2 * i + 1];
+      }
+    }
+    return GSIM_OK;
+  }
   for (size_t q = 0; q < planes; ++q)
     if (!p->be->d2h(reinterpret_cast<uint8_t*>(out) + q * ucap * elem,
                     reinterpret_cast<const uint8_t*>(src) + q * cap * elem, ucap * elem))

@@ -118,7 +118,7 @@ GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint
     uint32_t r = (uint32_t)__builtin_ctz(hm);
 #endif
     hm &= hm - 1;
-    h = gs_mix64(h, (r << 8) | d.tx[(size_t)r * cap + i]);
+    h = gs_mix64(h, (r << 8) | d.tx[GS_TX(r, cap, i)]);
   }
   if (inb & GS_ACC_BIT) {
     const uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;

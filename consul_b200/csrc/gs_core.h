@@ -209,6 +209,12 @@ GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t half_bits, const GsU4& r
   return x;
 }
 
+// Retransmit counter of rumor r at member i.  Two rumors share one 16-bit element so that the
+// narrowest column has 2-byte elements: a sharded pool maps every (column, rank) slice with the
+// 2 MB granularity of the virtual-memory API, which then allows 1 Mi members per GPU (1-byte
+// planes would need 2 Mi).
+#define GS_TX(r, cap, i) ((((size_t)((r) >> 1) * (size_t)(cap) + (size_t)(i)) << 1) + ((r) & 1u))
+
 // ---- tracked rumor table ------------------------------------------------------
 struct GsRumor {
   uint32_t kind;     // GSIM_RUMOR_*
@@ -290,7 +296,7 @@ struct GsDev {
   uint32_t* event_min;
   uint32_t* heard;
   uint32_t* queued;
-  uint8_t* tx;  // [GS_MAX_RUMORS][cap]
+  uint8_t* tx;  // retransmit counters, [GS_MAX_RUMORS / 2][cap][2]: see GS_TX
   // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
   const uint32_t* row_ptr;  // [graph_n + 1] CSR peer graph, null on complete-graph pools
   const uint32_t* col_idx;  // [row_ptr[graph_n]]

@@ -256,7 +256,7 @@ GS_DEV uint32_t gs_select_packet(const GsDev& d, const GsGlobals& g, uint32_t i,
         scan &= scan - 1;
         uint32_t sz = g.rumors[r].size;
         if (sz > free_b) continue;
-        uint32_t tx = d.tx[(size_t)r * g.cap + i];
+        uint32_t tx = d.tx[GS_TX(r, g.cap, i)];
         uint32_t key = (tx << 24) | ((0xFFFFu - (sz & 0xFFFFu)) << 8) | (31u - r);
         if (key < best_key) {
           best_key = key;
@@ -380,7 +380,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
         if (accept) {
           accepted |= 1u << r;
-          d.tx[(size_t)r * cap + i] = 0;  // queued with transmits = 0
+          d.tx[GS_TX(r, cap, i)] = 0;  // queued with transmits = 0
           sink.heard(r);
           sink.stat(GS_ST_RUMORS_ACCEPTED, 1);
         } else {
@@ -611,8 +611,8 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           uint32_t r = (uint32_t)__builtin_ctz(pm);
 #endif
           pm &= pm - 1;
-          uint32_t tx = (uint32_t)d.tx[(size_t)r * cap + i] + 1u;
-          d.tx[(size_t)r * cap + i] = (uint8_t)tx;
+          uint32_t tx = (uint32_t)d.tx[GS_TX(r, cap, i)] + 1u;
+          d.tx[GS_TX(r, cap, i)] = (uint8_t)tx;
           if (tx >= g.retransmit_limit) queued &= ~(1u << r);  // broadcast finished
           sink.stat(GS_ST_RUMORS_SENT, 1);
         }

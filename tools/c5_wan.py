@@ -5,9 +5,9 @@ delivered it.  Prints one JSON line (ticks to convergence, bridge re-fires, kern
   1 GPU :  python tools/c5_wan.py --members 8388608
   N GPUs:  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/c5_wan.py --members M
 
-Both pools are sharded over all N ranks (co-sharded).  A sharded pool needs a multiple of 2 Mi
-members per rank (2 MB mapping granularity of the 1-byte retransmit-counter planes), so at 8 GPUs
-the smallest co-sharded pool is 16 Mi members; 8 Mi pools fit 1, 2 or 4 GPUs.
+Both pools are sharded over all N ranks (co-sharded).  A sharded pool holds a multiple of 1 Mi
+members per rank (2 MB mapping granularity over the narrowest, 2-byte column), so the 8 Mi pools
+of config 5 shard evenly over 1, 2, 4 or 8 GPUs.
 """
 import argparse
 import json
