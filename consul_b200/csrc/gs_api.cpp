@@ -220,6 +220,13 @@ static bool poke(gsim_pool* p, T* col, size_t i, T v) {
 
 // Host-side write of a member's key word: every replica on a sharded pool.
 static bool poke_key(gsim_pool* p, uint32_t buf, uint32_t i, uint32_t k) {
+  if (p->d.kst) {  // GS_KSTAT builds: keep the member's status byte in step (see gs_kst_code)
+    uint8_t b;
+    if (!peek(p, p->d.kst, i, &b)) return false;
+    const uint32_t code = gs_kst_code(k);
+    b = (uint8_t)(buf ? ((b & 0x0Fu) | (code << 4)) : ((b & 0xF0u) | code));
+    if (!poke(p, p->d.kst, i, b)) return false;
+  }
   if (!p->sharded) return poke(p, p->d.key[buf], i, k);
   for (uint32_t r = 0; r < p->world; ++r)
     if (!poke(p, p->d.key_rep[buf], (size_t)r * p->g.key_stride + i, k)) return false;
@@ -384,6 +391,7 @@ static int init_device_state(gsim_pool* p) {
   const size_t key_words = p->sharded ? (size_t)g.key_stride * p->world : cap;
   okk = okk && be->fill32(d.key_rep[0], 0, key_words) && be->fill32(d.key_rep[1], 0, key_words);
   for (uint32_t s = 0; s <= g.ring_mask; ++s) okk = okk && be->fill32(d.inbox[s], 0, cap);
+  if (d.kst) okk = okk && be->fill8(d.kst, 0, cap);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   if (d.ppreq) okk = okk && be->fill32(d.ppreq, GS_EMPTY32, cap * 2 * GS_PPK) && be->fill32(d.pp_clk, 0, cap * 4);
@@ -509,6 +517,9 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       d.key[b] = okk ? d.key_rep[b] + (size_t)cfg->rank * g.key_stride : nullptr;
     }
   }
+#ifdef GS_KSTAT
+  if (!sharded) okk = okk && alloc_col(p, &d.kst, cap);  // performance variant: status replica
+#endif
   g.ring_mask = ring_depth - 1u;
   for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && acol(&d.inbox[s], 1);
   okk = okk && acol(&d.due, 1) && acol(&d.meta, 1);
@@ -1746,6 +1757,7 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
   add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
+  if (d.kst) add(d.kst, cap);
   if (d.ppreq) {
     add(d.ppreq, cap * 4 * 2 * GS_PPK);
     add(d.pp_clk, cap * 4 * 4);

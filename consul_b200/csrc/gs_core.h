@@ -79,6 +79,18 @@ GS_HD uint32_t gs_key_pending(uint32_t k) { return (k >> 4) & 1u; }
 GS_HD uint32_t gs_key_inc(uint32_t k) { return k >> 5; }
 GS_HD uint32_t gs_key_with_rank(uint32_t k, uint32_t rank) { return (k & ~(3u << 2)) | (rank << 2); }
 GS_HD uint32_t gs_key_with_inc(uint32_t k, uint32_t inc) { return (k & 31u) | (inc << 5); }
+// Status replica (GS_KSTAT builds): what a prober or gossiper needs to know about a peer is its
+// truth and rank — 4 bits — not its 27-bit incarnation.  At 64 Mi members the key column is 256 MB
+// per buffer and every random 4-byte gather costs a DRAM sector; one status byte per member holds
+// both buffers' views in 64 MB, small enough to stay in the 126 MB L2.  Code = rank<<2 | truth,
+// 0 = no such member, GS_KST_PENDING (rank 1, truth 0: otherwise meaningless) = "pending joiner,
+// read the full key".
+#define GS_KST_PENDING 4u
+GS_HD uint32_t gs_kst_code(uint32_t k) {
+  if ((k & 3u) == 0u) return 0u;
+  if ((k >> 4) & 1u) return GS_KST_PENDING;
+  return k & 15u;
+}
 
 // ---- meta word ------------------------------------------------------------
 #define GS_META_AW_MASK 0x7u
@@ -298,6 +310,9 @@ struct GsDev {
   uint32_t* queued;
   uint8_t* tx;  // retransmit counters, [GS_MAX_RUMORS / 2][cap][2]: see GS_TX
   // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
+  // GS_KSTAT builds (performance variant, see gs_kst_code): one byte per member with the 4-bit view
+  // of key[0] (low nibble) and key[1] (high nibble) that peer selection needs; null otherwise
+  uint8_t* kst;
   const uint32_t* row_ptr;  // [graph_n + 1] CSR peer graph, null on complete-graph pools
   const uint32_t* col_idx;  // [row_ptr[graph_n]]
   uint32_t* ppreq;   // [2][GS_PPK][cap] requester ids, kept as the GS_PPK smallest (atomicMin chain)

@@ -527,6 +527,30 @@ class CudaBackend : public GsBackend {
       return true;
     }
     cudaSetDevice(dev_);
+#ifdef GS_KSTAT
+    // performance variant: keep the status replica (1 byte per member, gathered at random by every
+    // prober) resident in L2 — persisting hits for the window, streaming for everything else.
+    // Set on the stream before any capture, so graph kernel nodes inherit it.
+    if (d.kst != nullptr && !l2_window_set_ && getenv("GSIM_NO_L2_WINDOW") == nullptr) {
+      l2_window_set_ = true;
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev_) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        size_t bytes = g.cap;
+        if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+        size_t carve = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.base_ptr = d.kst;
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)carve / (float)bytes;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError();  // best effort: an unsupported attribute must not fail the step
+      }
+    }
+#endif
     // persistent launch: one warp per 128-member tile up to a full machine (SMs x resident CTAs)
     uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
     if (g.world > 1 && tiles > g.rows_per_rank / GS_TILE) tiles = g.rows_per_rank / GS_TILE;
@@ -734,6 +758,7 @@ class CudaBackend : public GsBackend {
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   GsDev graph_dev_;
   bool have_graph_dev_ = false;
+  bool l2_window_set_ = false;
   uint64_t launches_ = 0;
   char err_[256];
 };

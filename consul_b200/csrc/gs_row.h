@@ -120,12 +120,45 @@ enum {
 // in local HBM; a key changes rarely (suspect, dead, refute, join), and whoever changes it
 // writes all replicas (remote stores over NVLink, ordered by the closing fence.sys).
 GS_DEV void gs_key_store(const GsDev& d, const GsGlobals& g, uint32_t buf, uint32_t i, uint32_t k) {
+#ifdef GS_KSTAT
+  if (d.kst != nullptr) {  // the member's status byte: only its owner (or the host) ever writes it
+    const uint32_t b = d.kst[i], code = gs_kst_code(k);
+    d.kst[i] = (uint8_t)(buf ? ((b & 0x0Fu) | (code << 4)) : ((b & 0xF0u) | code));
+  }
+#endif
   if (g.world <= 1u) {
     d.key[buf][i] = k;
     return;
   }
   for (uint32_t r = 0; r < g.world; ++r) d.key_rep[buf][(size_t)r * g.key_stride + i] = k;
 }
+
+// What member c looks like to its peers in buffer `cur`: the key word.  GS_KSTAT builds answer
+// from the status byte (inc reads as 0, pending as 0) unless the member is a pending joiner; a
+// caller that needs the incarnation asks for the full key.
+GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_inc) {
+#ifdef GS_KSTAT
+  if (d.kst != nullptr && !need_inc) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = __ldcg(reinterpret_cast<const unsigned char*>(d.kst) + c);
+#else
+    const uint32_t b = d.kst[c];
+#endif
+    const uint32_t code = (b >> (cur * 4u)) & 15u;
+    if (code != GS_KST_PENDING) return code;
+  }
+#else
+  (void)need_inc;
+#endif
+  return GS_LD_OTHER(&d.key[cur][c]);
+}
+
+// incarnation of peer c whose key-like word k came from gs_peer_key(..., false)
+#ifdef GS_KSTAT
+#define GS_PEER_INC(d, cur, c, k) gs_key_inc(gs_peer_key((d), (cur), (c), true))
+#else
+#define GS_PEER_INC(d, cur, c, k) gs_key_inc(k)
+#endif
 
 // WAN latency pools (BASELINE config 5): EXTRA one-way latency in ticks from src to dst on top
 // of the one tick every packet takes; 0 everywhere on a pool without datacenters.  An all-zero
@@ -195,7 +228,6 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
                            uint32_t meta_i, uint32_t* out) {
   const uint32_t n = gs_peer_count(d, g, i);
   if (n == 0u) return 0u;
-  const uint32_t* keyc = d.key[t & 1u];
   uint32_t tries = 3u * n;
   if (tries > GS_KR_MAX_TRIES || n > 0x55555555u) tries = GS_KR_MAX_TRIES;
   uint32_t cnt = 0;
@@ -205,7 +237,7 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
     if ((dr & 3u) == 0u) blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, dr >> 2);
     uint32_t c = gs_peer_at(d, g, i, gs_u4_get(blk, dr & 3u) % n);
     if (c == i || c == exclude2) continue;
-    uint32_t kc = GS_LD_OTHER(&keyc[c]);
+    uint32_t kc = gs_peer_key(d, t & 1u, c, false);
     if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
     uint32_t rank = gs_key_rank(kc);
     if (mode == 1u) {
@@ -476,7 +508,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
     if (stage == GS_STAGE_WAIT_T && due == t) {
       // ProbeTimeout elapsed without a direct ack: k indirect probes + TCP fallback.
       const uint32_t j = d.probe_tgt[i];
-      const uint32_t kj = GS_LD_OTHER(&d.key[cur][j]);
+      const uint32_t kj = gs_peer_key(d, cur, j, false);
       const bool j_up = gs_key_truth(kj) == GS_TRUTH_UP;
       uint32_t relays[8];
       uint32_t kk = g.indirect_checks > 8u ? 8u : g.indirect_checks;
@@ -488,7 +520,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       const uint32_t budget = g.P * (gs_meta_aw(m) + 1u) - g.T;
       for (uint32_t q = 0; q < nr; ++q) {
         const uint32_t r = relays[q];
-        const bool r_up = gs_key_truth(GS_LD_OTHER(&d.key[cur][r])) == GS_TRUTH_UP;
+        const bool r_up = gs_key_truth(gs_peer_key(d, cur, r, false)) == GS_TRUTH_UP;
         sink.stat(GS_ST_INDIRECT_PINGS, 1);
         if (!(r_up && !gs_lost(g, sink, i, r, t, GS_LK_INDREQ, q))) continue;  // no nack either
         const uint32_t via = gs_extra(g, i, r) + gs_extra(g, r, i);
@@ -560,7 +592,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
         uint32_t c = gs_peer_at(d, g, i, gs_perm(cursor, n, hb, rk));
         ++cursor;
-        uint32_t kc = GS_LD_OTHER(&d.key[cur][c]);
+        uint32_t kc = gs_peer_key(d, cur, c, false);
         uint32_t rank = gs_key_rank(kc);
         if (c == i || gs_key_truth(kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD ||
             rank == GS_RANK_LEFT || !gs_knows(d, g, i, c, kc, m)) {
@@ -586,7 +618,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         } else {
           m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
           d.probe_tgt[i] = target;
-          d.probe_inc[i] = gs_key_inc(ktarget);
+          d.probe_inc[i] = GS_PEER_INC(d, cur, target, ktarget);  // the incarnation it will accuse
           due = t + g.T;
         }
       } else {
@@ -692,7 +724,7 @@ GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uin
   GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, f.pass);
   f.c = gs_perm(f.cursor, g.n, g.perm_half_bits, rk);
   if (f.c == i) return false;
-  f.kc = GS_LD_OTHER(&d.key[cur][f.c]);
+  f.kc = gs_peer_key(d, cur, f.c, false);
   return true;
 }
 
@@ -715,7 +747,7 @@ GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
   } else {
     m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
     d.probe_tgt[i] = f.c;
-    d.probe_inc[i] = gs_key_inc(f.kc);
+    d.probe_inc[i] = GS_PEER_INC(d, t & 1u, f.c, f.kc);
     d.due[i] = t + g.T;
     *acked = false;
   }
