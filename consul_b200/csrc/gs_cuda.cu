@@ -461,6 +461,12 @@ class CudaBackend : public GsBackend {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel, GS_BLOCK, 0) != cudaSuccess || occ < 1)
       occ = 4;
+    // measurement knob: fewer resident CTAs per SM leave room for the NEXT tick's CTAs to become
+    // resident early under programmatic dependent launch (a full machine cannot overlap)
+    if (const char* e = getenv("GSIM_CTAS_PER_SM")) {
+      const int want = atoi(e);
+      if (want >= 1 && want < occ) occ = want;
+    }
     full_grid_ = (uint32_t)(sms * occ);
     scratch_ = nullptr;
     cudaMalloc(&scratch_, 4096);
