@@ -140,6 +140,22 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   const uint32_t shift = g.phase_shift;
   DevSink sink{s_stat, s_heard};
 
+#ifdef GS_EARLY_A
+  // Performance variant: which tiles of this chunk start a probe at this tick is known
+  // arithmetically, so their own columns (key, meta, cursor, pass: 16 lines of 128 B per tile) are
+  // pulled towards this SM now, while the mailbox scan of the chunk is still in flight — one
+  // dependent L2 round trip less on the critical path of a latency-bound tick (1 M members).
+  if (gated) {
+    for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+      if (gs_probe_phase(g.rot_p, tile >> shift, P) != pslot) continue;
+      if (lane < 16u) {
+        const uint32_t c4 = lane >> 2;
+        const uint32_t* col = c4 == 0u ? d.key[cur] : c4 == 1u ? d.meta : c4 == 2u ? d.cursor : d.pass;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (size_t)tile * GS_TILE + (lane & 3u) * 32u));
+      }
+    }
+  }
+#endif
   uint32_t tq = t_begin;  // next tile to issue
   bool did_work = false;  // this thread touched global state (needs the closing fence when sharded)
   auto issue = [&](uint32_t st) {
