@@ -31,3 +31,18 @@ def test_join_that_reaches_nobody_and_repeated_operations(make, cuda_lib):
 
 def test_zero_length_horizons(make, cuda_lib):
     ec.test_zero_length_horizons(make, cuda_lib)
+
+
+def test_torch_free_quickcheck_binary():
+    """tests/facade/gpu_quickcheck.cpp: libgsim.so against liboracle.so, no Python in the loop."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "tests", "facade", "gpu_quickcheck_cuda")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "facade", "gpu_quickcheck.cpp"),
+                    "-L" + os.path.join(root, "consul_b200"), "-lgsim", "-L" + os.path.join(root, "oracle"), "-loracle",
+                    "-Wl,-rpath," + os.path.join(root, "consul_b200"), "-Wl,-rpath," + os.path.join(root, "oracle"),
+                    "-o", out], check=True)
+    r = subprocess.run([out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr

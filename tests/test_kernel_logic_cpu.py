@@ -105,3 +105,17 @@ def test_lan_reap(make, hostemu_lib):
 def test_set_tags_update(make, hostemu_lib):
     """serf.SetTags / memberlist.UpdateNode / EventMemberUpdate."""
     sc.set_tags_scenario(make, hostemu_lib)
+
+
+def test_quickcheck_harness_on_host_emulation(hostemu_lib, tmp_path):
+    """The torch-free C++ parity harness (tests/facade/gpu_quickcheck.cpp) itself, linked against the
+    host emulation: all seven scenarios agree with the oracle."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "quickcheck_cpu")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "facade", "gpu_quickcheck.cpp"),
+                    "-L" + os.path.join(root, "tests", "hostemu"), "-lgsim_hostemu", "-L" + os.path.join(root, "oracle"),
+                    "-loracle", "-Wl,-rpath," + os.path.join(root, "tests", "hostemu"),
+                    "-Wl,-rpath," + os.path.join(root, "oracle"), "-o", out], check=True)
+    r = subprocess.run([out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("PASS ") == 7 and "ALL PASS" in r.stdout, r.stdout + r.stderr
