@@ -392,6 +392,8 @@ static int init_device_state(gsim_pool* p) {
   okk = okk && be->fill32(d.key_rep[0], 0, key_words) && be->fill32(d.key_rep[1], 0, key_words);
   for (uint32_t s = 0; s <= g.ring_mask; ++s) okk = okk && be->fill32(d.inbox[s], 0, cap);
   if (d.kst) okk = okk && be->fill8(d.kst, 0, cap);
+  for (uint32_t s = 0; s <= g.ring_mask; ++s)
+    if (d.mailmap[s]) okk = okk && be->fill32(d.mailmap[s], 0, cap / 32);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   if (d.ppreq) okk = okk && be->fill32(d.ppreq, GS_EMPTY32, cap * 2 * GS_PPK) && be->fill32(d.pp_clk, 0, cap * 4);
@@ -519,6 +521,10 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   }
 #ifdef GS_KSTAT
   if (!sharded) okk = okk && alloc_col(p, &d.kst, cap);  // performance variant: status replica
+#endif
+#ifdef GS_MAILMAP
+  if (!sharded)  // performance variant: 1 bit per member and arrival slot
+    for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && alloc_col(p, &d.mailmap[s], cap / 32);
 #endif
   g.ring_mask = ring_depth - 1u;
   for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && acol(&d.inbox[s], 1);
@@ -755,6 +761,10 @@ static int alloc_slot(gsim_pool* p, uint32_t* slot_out) {
 // next tick: set the wake bit in the mailbox that tick will read.
 static bool post_wake(gsim_pool* p, uint32_t row) {
   uint32_t* col = p->d.inbox[p->now & p->g.ring_mask];
+  if (uint32_t* map = p->d.mailmap[p->now & p->g.ring_mask]) {  // GS_MAILMAP builds: raise the member's bit
+    uint32_t mw;
+    if (!peek(p, map, row >> 5, &mw) || !poke(p, map, row >> 5, mw | (1u << (row & 31u)))) return false;
+  }
   uint32_t w;
   if (!peek(p, col, row, &w)) return false;
   return poke(p, col, row, w | GS_WAKE_BIT);
@@ -1758,6 +1768,8 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
   add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
   if (d.kst) add(d.kst, cap);
+  for (uint32_t s = 0; s <= p->g.ring_mask; ++s)
+    if (d.mailmap[s]) add(d.mailmap[s], cap / 32 * 4);
   if (d.ppreq) {
     add(d.ppreq, cap * 4 * 2 * GS_PPK);
     add(d.pp_clk, cap * 4 * 4);

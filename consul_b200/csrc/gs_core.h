@@ -293,6 +293,9 @@ struct GsDev {
   uint32_t* key[2];      // the key column this rank READS (its own replica when sharded)
   uint32_t* key_rep[2];  // replica 0; replica r at + r*key_stride.  Writers update every replica.
   uint32_t* inbox[GS_RING_MAX];  // arrival-tick ring; slots >= ring depth are null
+  // GS_MAILMAP builds (performance variant): one bit per member and arrival slot, set whenever the
+  // mailbox word becomes non-zero — the scan reads 1 bit instead of 4 bytes per member; null otherwise
+  uint32_t* mailmap[GS_RING_MAX];
   uint32_t* due;
   uint32_t* meta;
   uint32_t* cursor;

@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   __shared__ uint32_t s_heard[32];
   __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
+#ifdef GS_MAILMAP
+  __shared__ __align__(16) uint32_t s_flag[GS_STAGES][GS_WARPS][4];  // the tile's 128 mailbox bits
+#endif
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
@@ -136,6 +139,13 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
   const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
   const uint32_t* __restrict__ inbox_cur = d.inbox[t & g.ring_mask];  // this tick's arrival slot
+#ifdef GS_MAILMAP
+  // Performance variant: the scan reads one BIT per member (16 bytes per tile) and touches the
+  // 4-byte mailbox word only of members whose bit is raised; the warp lowers a tile's bits once
+  // the tile has been processed (nobody posts into the slot being consumed).
+  uint32_t* const mailmap_cur = d.mailmap[t & g.ring_mask];
+  const bool use_map = mailmap_cur != nullptr;
+#endif
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
   DevSink sink{s_stat, s_heard};
@@ -168,6 +178,11 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
                      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(inbox_cur + off) : "memory");
         *reinterpret_cast<uint4*>(&s_inb[st][wib][lane * 4u]) = v;
       } else {
+#ifdef GS_MAILMAP
+        if (use_map) {
+          if (lane == 0u) gs_cp_async16(&s_flag[st][wib][0], mailmap_cur + (size_t)tq * 4u);
+        } else
+#endif
         gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
       }
       bool gate = true;
@@ -190,7 +205,17 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   for (uint32_t tile = t_begin; tile < t_end; ++tile) {
     issue((st + GS_STAGES - 1u) % GS_STAGES);
     gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
+#ifdef GS_MAILMAP
+    uint4 i4;
+    if (use_map) {
+      __syncwarp();  // lane 0's copy of the tile's bits is visible to the whole warp
+      i4 = *reinterpret_cast<const uint4*>(&s_flag[st][wib][0]);
+    } else {
+      i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
+    }
+#else
     const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
+#endif
     const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
     bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
     // periodic push-pull (opt-in): the ticker of this tile's phase group (or, with per-member
@@ -214,7 +239,18 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       bool any_cand = false;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+#ifdef GS_MAILMAP
+        uint32_t w;
+        if (use_map) {  // member base + 32u is bit `lane` of the tile's word u
+          const uint32_t fw = u == 0 ? i4.x : u == 1 ? i4.y : u == 2 ? i4.z : i4.w;
+          w = ((fw >> lane) & 1u) ? inbox_cur[base + 32u * u] : 0u;
+          s_inb[st][wib][u * 32 + lane] = w;  // gs_row_step below takes it from here
+        } else {
+          w = s_inb[st][wib][u * 32 + lane];
+        }
+#else
         const uint32_t w = s_inb[st][wib][u * 32 + lane];
+#endif
         const bool due_now = s_due[st][wib][u * 32 + lane] == t;
         act[u] = w != 0u || due_now ||
                  (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, (base + 32u * u) / g.phase_group, t));
@@ -251,6 +287,10 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
           if (a) gs_row_step(d, g, base + 32u * u, t, gslot, s_inb[st][wib][u * 32 + lane], sink);
         }
       }
+#ifdef GS_MAILMAP
+      if (use_map && lane == 0u && (i4.x | i4.y | i4.z | i4.w) != 0u)  // this tile's mail is consumed
+        *reinterpret_cast<uint4*>(mailmap_cur + (size_t)tile * 4u) = make_uint4(0u, 0u, 0u, 0u);
+#endif
       __syncwarp();  // everyone is done with this stage before it is refilled
     }
     st = (st + 1u) % GS_STAGES;

@@ -153,6 +153,19 @@ GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_
   return GS_LD_OTHER(&d.key[cur][c]);
 }
 
+// Deliver `bits` into member j's mailbox word of arrival slot `slot` (commutative).  GS_MAILMAP
+// builds also raise the member's bit in the slot's bitmap when the word was empty: the word only
+// ever becomes non-zero through this function (or the host's post_wake), and nobody posts into
+// the slot that is being consumed, so "word != 0 implies bit set" holds at every scan.
+GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, uint32_t slot, uint32_t j, uint32_t bits) {
+  const uint32_t old = GS_ATOMIC_OR32(&d.inbox[slot][j], bits);
+#ifdef GS_MAILMAP
+  if (old == 0u && d.mailmap[slot] != nullptr) GS_ATOMIC_OR32(&d.mailmap[slot][j >> 5], 1u << (j & 31u));
+#else
+  (void)old;
+#endif
+}
+
 // incarnation of peer c whose key-like word k came from gs_peer_key(..., false)
 #ifdef GS_KSTAT
 #define GS_PEER_INC(d, cur, c, k) gs_key_inc(gs_peer_key((d), (cur), (c), true))
@@ -349,7 +362,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       gs_key_store(d, g, nxt, i, k0);
       d.meta[i] = m0 & ~GS_META_DIRTY;
     }
-    if (queued != 0u) GS_ATOMIC_OR32(&d.inbox[inxt][i], GS_WAKE_BIT);
+    if (queued != 0u) gs_post(d, g, inxt, i, GS_WAKE_BIT);
     return;
   }
 
@@ -467,7 +480,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
         GS_ATOMIC_MAX32(&clk[from], d.ltime_member[i]);
         GS_ATOMIC_MAX32(&clk[cap + from], d.ltime_event[i]);
-        GS_ATOMIC_OR32(&d.inbox[inxt][from], (d.heard[i] & g.active_mask) | GS_ACC_BIT);
+        gs_post(d, g, inxt, from, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
       }
     }
   }
@@ -569,7 +582,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         if (old == v || old == GS_EMPTY64) break;
         if (old > v) v = old;  // displaced a larger entry: carry it to the next slot
       }
-      GS_ATOMIC_OR32(&d.inbox[inxt][j], GS_ACC_BIT);
+      gs_post(d, g, inxt, j, GS_ACC_BIT);
       sink.stat(GS_ST_PROBE_FAILURES, 1);
       stage = GS_STAGE_IDLE;  // due == t: the buffered ticker fires immediately
     }
@@ -650,7 +663,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
         sink.stat(GS_ST_GOSSIP_PACKETS, 1);
         if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q))
-          GS_ATOMIC_OR32(&d.inbox[(t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask][peers[q]], pkt);
+          gs_post(d, g, (t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask, peers[q], pkt);
       }
       if (queued != q0) d.queued[i] = queued;
     }
@@ -673,7 +686,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
         GS_ATOMIC_MAX32(&clk[j], d.ltime_member[i]);
         GS_ATOMIC_MAX32(&clk[cap + j], d.ltime_event[i]);
-        GS_ATOMIC_OR32(&d.inbox[inxt][j], (d.heard[i] & g.active_mask) | GS_ACC_BIT);
+        gs_post(d, g, inxt, j, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
         sink.stat(GS_ST_PUSH_PULLS, 1);
       }
     }
@@ -692,7 +705,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   // stay in the active set while something time-driven is pending: a running suspicion
   // timer, a stale key buffer, or a non-empty broadcast queue
   if (gs_key_rank(k) == GS_RANK_SUSPECT || (m & GS_META_DIRTY) || queued != 0u)
-    GS_ATOMIC_OR32(&d.inbox[inxt][i], GS_WAKE_BIT);
+    gs_post(d, g, inxt, i, GS_WAKE_BIT);
 }
 
 // ---------------------------------------------------------------------------------------

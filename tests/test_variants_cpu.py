@@ -1,7 +1,9 @@
-"""The GS_KSTAT performance variant (status replica for peer gathers, DESIGN §8 round-2 plan) must
-be semantics-neutral: the kernel body compiled with -DGS_KSTAT=1 reproduces the golden fixtures
-and matches the oracle on the scenarios that change keys (crash, refute, leave, join, reap,
-SetTags, snapshot/restore).  The default build does not define GS_KSTAT."""
+"""The compile-time performance variants (DESIGN §8 round-2 plan) must be semantics-neutral:
+  GS_KSTAT    4-bit status replica for peer gathers
+  GS_MAILMAP  one mailbox BIT per member for the scan, the 4-byte word only when the bit is raised
+The row logic compiled with each of them (and both) reproduces the golden fixtures and matches the
+oracle on the scenarios that change keys and mailboxes (crash, refute, leave, join, reap, SetTags,
+push-pull, WAN latency, snapshot/restore).  The default build defines neither."""
 import os
 import subprocess
 
@@ -16,16 +18,19 @@ from oracle_binding import OraclePool
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def kstat_lib():
-    out = os.path.join(ROOT, "tests", "hostemu", "libgsim_hostemu_kstat.so")
+VARIANTS = {"kstat": ["-DGS_KSTAT=1"], "mailmap": ["-DGS_MAILMAP=1"], "both": ["-DGS_KSTAT=1", "-DGS_MAILMAP=1"]}
+
+
+@pytest.fixture(scope="module", params=list(VARIANTS))
+def kstat_lib(request):
+    out = os.path.join(ROOT, "tests", "hostemu", "libgsim_hostemu_%s.so" % request.param)
     srcs = [os.path.join(ROOT, "consul_b200", "csrc", "gs_api.cpp"),
             os.path.join(ROOT, "tests", "hostemu", "hostemu_backend.cpp")]
     newest = max(os.path.getmtime(os.path.join(ROOT, "consul_b200", "csrc", f))
                  for f in os.listdir(os.path.join(ROOT, "consul_b200", "csrc")))
     if not os.path.exists(out) or os.path.getmtime(out) < max(newest, os.path.getmtime(srcs[1])):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DGS_KSTAT=1",
-                        "-DGS_MAKE_BACKEND=gs_make_hostemu_backend", "-o", out] + srcs, check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + VARIANTS[request.param] +
+                       ["-DGS_MAKE_BACKEND=gs_make_hostemu_backend", "-o", out] + srcs, check=True)
     return _lib.load(out)
 
 
@@ -70,3 +75,13 @@ def test_variant_scenarios_against_oracle(make, kstat_lib):
     sc.leave_scenario(make, kstat_lib)
     sc.lan_reap_scenario(make, kstat_lib, 1)
     sc.set_tags_scenario(make, kstat_lib)
+    sc.event_window_scenario(make, kstat_lib)
+    sc.budget_scenario(make, kstat_lib)
+    import test_latency_cpu as wl
+    import test_pushpull_cpu as pp
+    from consul_b200.pool import FLAG_PUSH_PULL, wan_config
+    wl.test_event_dissemination_parity(make, kstat_lib, wan_config, 64)
+    wl.test_lossy_crash_parity_with_latency(make, kstat_lib)
+    wl.test_snapshot_restore_with_packets_in_flight(kstat_lib)
+    pp.stranded_event(make, kstat_lib, FLAG_PUSH_PULL, n=1500, ticks=500)
+    pp.test_snapshot_restore_mid_exchange(kstat_lib)
