@@ -313,13 +313,19 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     h.out_bytes = (uint32_t)(out ? out_bytes : 0);
     h.node_ticks = p->node_ticks;
     uint8_t* w = blob.data();
+    if (sizeof(h) + sizeof(GsGlobals) + (size_t)h.n_sched * sizeof(Sched) + h.out_bytes > GS_BLOB_BYTES) {
+      // every rank must still leave the barrier: publish the error instead of the state
+      fail(p, GSIM_ERR_INVALID, "state blob overflow (too many scheduled shutdowns for a sharded pool)");
+      h.rc = GSIM_ERR_INVALID;
+      h.n_sched = 0;
+      h.out_bytes = 0;
+    }
     memcpy(w, &h, sizeof(h)); w += sizeof(h);
     memcpy(w, &p->g, sizeof(GsGlobals)); w += sizeof(GsGlobals);
     if (h.n_sched) memcpy(w, p->sched.data(), h.n_sched * sizeof(Sched));
     w += h.n_sched * sizeof(Sched);
-    if (h.out_bytes) memcpy(w, out, h.out_bytes);
+    if (out && h.out_bytes) memcpy(w, out, h.out_bytes);
     w += h.out_bytes;
-    if ((size_t)(w - blob.data()) > GS_BLOB_BYTES) return fail(p, GSIM_ERR_INVALID, "state blob overflow");
     if (!p->be->h2d(blob_dev, blob.data(), (size_t)(w - blob.data()))) return fail(p, GSIM_ERR_CUDA, "blob h2d");
     if (!p->be->xbar_host(p->xb)) return fail(p, GSIM_ERR_CUDA, "barrier");
     return h.rc;
