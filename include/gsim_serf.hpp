@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -60,6 +61,11 @@ struct Config {
   std::string NodeName;
   std::map<std::string, std::string> Tags;
   std::deque<Event>* EventCh = nullptr;  // serf.Config.EventCh (server.go:504-505)
+  // serf.Config.Merge (agent/consul/server_serf.go:234-239 installs lanMergeDelegate /
+  // wanMergeDelegate, agent/consul/merge.go:34,111): called on BOTH sides of a join's push-pull
+  // with the other side's member list; a non-empty return value is the error that cancels the
+  // merge with that peer.  The delegate itself is Consul code and stays on the host.
+  std::function<std::string(const std::vector<Member>&)> Merge;
 };
 
 class Error : public std::runtime_error {
@@ -135,11 +141,25 @@ class Serf {
   // Join(existing, ignoreOld) -> number of nodes contacted; throws if none could be.
   int Join(const std::vector<std::string>& existing, bool ignoreOld) {
     std::vector<uint32_t> seeds;
+    std::string merge_err;
     for (const std::string& a : existing) {
       std::string node = a.substr(0, a.find('/'));  // "node/ip:port", "node.dc/ip:port"
       auto it = p_.by_name_.find(node);
-      if (it != p_.by_name_.end()) seeds.push_back(it->second);
+      if (it == p_.by_name_.end()) continue;
+      // [U] memberlist pushPullNode -> MergeDelegate.NotifyMerge on both ends before any state is merged
+      Serf* peer = it->second < p_.by_id_.size() ? p_.by_id_[it->second] : nullptr;
+      if (peer && peer != this) {
+        std::string err;
+        if (conf_.Merge) err = conf_.Merge(peer->Members());
+        if (err.empty() && peer->conf_.Merge) err = peer->conf_.Merge(Members());
+        if (!err.empty()) {  // this peer refused (or was refused): not contacted
+          merge_err = err;
+          continue;
+        }
+      }
+      seeds.push_back(it->second);
     }
+    if (seeds.empty() && !merge_err.empty()) throw Error(GSIM_ERR_STATE, "Failed to join: " + merge_err);
     int n_ok = 0;
     p_.check(gsim_join(p_.h_, id_, seeds.data(), seeds.size(), ignoreOld ? 1 : 0, &n_ok));
     if (n_ok == 0 && !existing.empty()) throw Error(GSIM_ERR_NOT_FOUND, "Failed to join: no seeds could be contacted");

@@ -196,6 +196,51 @@ static void test_set_tags() {
   std::puts("PASS Serf.SetTags / EventMemberUpdate");
 }
 
+// serf.Config.Merge: Consul's lanMergeDelegate refuses members of another datacenter
+// (agent/consul/merge.go:34-88; table in merge_test.go TestMerge_LAN "client/server in the wrong
+// datacenter").  The delegate is host code; what the gossip layer owes it is the call on both
+// sides of the join and the cancelled merge.
+static void test_merge_delegate() {
+  Pool pool(test_cfg());
+  auto lan_merge = [](const std::string& dc) {
+    return [dc](const std::vector<Member>& members) -> std::string {
+      for (auto& m : members) {
+        auto it = m.Tags.find("dc");
+        if (it != m.Tags.end() && it->second != dc) return "Member '" + m.Name + "' part of wrong datacenter '" + it->second + "'";
+      }
+      return "";
+    };
+  };
+  Config c1, c2, c3;
+  c1.NodeName = "node0";
+  c1.Tags = {{"role", "consul"}, {"dc", "dc1"}};
+  c1.Merge = lan_merge("dc1");
+  c2.NodeName = "node1";
+  c2.Tags = {{"role", "node"}, {"dc", "dc2"}};  // a client of the wrong datacenter, no delegate of its own
+  c3.NodeName = "node2";
+  c3.Tags = {{"role", "node"}, {"dc", "dc1"}};
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2), s3 = Serf::Create(pool, c3);
+  bool refused = false;
+  try {
+    s2->Join({"node0/127.0.0.1:8301"}, true);
+  } catch (const Error& e) {
+    refused = std::string(e.what()).find("wrong datacenter") != std::string::npos;
+  }
+  CHECK(refused);
+  CHECK(s3->Join({"node0/127.0.0.1:8301"}, true) == 1);  // the good cluster merges
+  pool.Step(60);
+  CHECK(s1->Members().size() == 2 && s3->Members().size() == 2 && s2->Members().size() == 1);
+  // a mixed seed list: the refusing peer is skipped, the acceptable one is contacted
+  Config c4;
+  c4.NodeName = "node3";
+  c4.Tags = {{"role", "node"}, {"dc", "dc2"}};
+  auto s4 = Serf::Create(pool, c4);
+  CHECK(s4->Join({"node0/x", "node1/x"}, true) == 1);  // node0 refuses dc2, node1 (dc2, no delegate) accepts
+  pool.Step(60);
+  CHECK(s4->Members().size() == 2 && s2->Members().size() == 2 && s1->Members().size() == 2);
+  std::puts("PASS TestMerge_LAN (delegate called on both sides, merge cancelled)");
+}
+
 static void test_user_event() {
   Pool pool(test_cfg());
   std::deque<Event> chs, chc;
@@ -255,6 +300,7 @@ int main(int argc, char** argv) {
       test_lan_reap_timers();
       test_join_wan();
       test_set_tags();
+      test_merge_delegate();
       std::puts("ALL PASS");
       return 0;
     }
