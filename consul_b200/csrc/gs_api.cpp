@@ -202,6 +202,7 @@ static uint64_t gcd64(uint64_t a, uint64_t b) {
   return a;
 }
 static uint32_t ceil_ticks(uint64_t ns, uint64_t tick) { return (uint32_t)((ns + tick - 1) / tick); }
+static uint32_t clamp_ticks(uint64_t ns, uint64_t tick);
 
 static int fail(gsim_pool* p, int code, const char* msg) {
   p->err = msg ? msg : "";
@@ -401,6 +402,7 @@ static int init_device_state(gsim_pool* p) {
   for (uint32_t s = 0; s <= g.ring_mask; ++s)
     if (d.mailmap[s]) okk = okk && be->fill32(d.mailmap[s], 0, cap / 32);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
+  okk = okk && be->fill32(d.reap_after, 0, cap);
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   if (d.ppreq) okk = okk && be->fill32(d.ppreq, GS_EMPTY32, cap * 2 * GS_PPK) && be->fill32(d.pp_clk, 0, cap * 4);
   okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
@@ -539,7 +541,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
   okk = okk && acol(&d.probe_tgt, 1) && acol(&d.probe_inc, 1);
   okk = okk && acol(&d.sus_start, 1) && acol(&d.sus_from, GS_K1MAX);
   okk = okk && acol(&d.acc, GS_K1MAX * 2);
-  okk = okk && acol(&d.change_tick, 1);
+  okk = okk && acol(&d.change_tick, 1) && acol(&d.reap_after, 1);
   okk = okk && acol(&d.ltime_member, 1) && acol(&d.ltime_event, 1);
   okk = okk && acol(&d.event_min, 1);
   okk = okk && acol(&d.heard, 1) && acol(&d.queued, 1);
@@ -1276,6 +1278,26 @@ extern "C" int gsim_graph_set(gsim_pool* p, uint32_t n_rows, const uint32_t* row
   return GSIM_OK;
 }
 
+// serf.Config.ReconnectTimeoutOverride (internal/gossip/libserf/serf.go:68-85: a member may
+// advertise its own reconnect timeout in a tag; agent/consul/client_test.go:862-894).  The callback
+// is host code; its result for one member is stored here and used by the reaper instead of the
+// pool's ReconnectTimeout.  0 restores the default.
+extern "C" int gsim_member_reconnect_timeout_set(gsim_pool* p, uint32_t id, uint64_t timeout_ns) {
+  if (!p) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  return controller_call(p, nullptr, 0, [&]() -> int {
+  if (id >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  uint32_t ticks = timeout_ns ? clamp_ticks(timeout_ns, p->tick_ns) : 0u;
+  if (timeout_ns && ticks == 0u) ticks = 1u;
+  if (!poke(p, p->d.reap_after, id, ticks)) return fail(p, GSIM_ERR_CUDA, "poke");
+  if (ticks && (p->g.reap_min_override == 0u || ticks < p->g.reap_min_override)) {
+    p->g.reap_min_override = ticks;
+    p->g_dirty = true;
+  }
+  return GSIM_OK;
+  });
+}
+
 // Turn event logging for one member on or off after creation (gsim_member_desc.flags does it at
 // creation): the EventCh of that agent, polled through gsim_poll_events.
 extern "C" int gsim_member_watch(gsim_pool* p, uint32_t id, int on) {
@@ -1360,7 +1382,8 @@ static ReapPlan reap_plan(const gsim_pool* p) {
 static uint32_t next_reap_tick(const gsim_pool* p, uint32_t now) {
   const ReapPlan r = reap_plan(p);
   if (!r.every) return GS_NEVER;
-  const uint32_t youngest = r.reconnect < r.tombstone ? r.reconnect : r.tombstone;
+  uint32_t youngest = r.reconnect < r.tombstone ? r.reconnect : r.tombstone;
+  if (p->g.reap_min_override && p->g.reap_min_override < youngest) youngest = p->g.reap_min_override;
   uint64_t t = (uint64_t)(now / r.every + 1u) * r.every;
   if (t <= youngest) t = ((uint64_t)youngest / r.every + 1u) * r.every;  // nobody is that old before
   return t >= GS_NEVER ? GS_NEVER : (uint32_t)t;
@@ -1368,7 +1391,9 @@ static uint32_t next_reap_tick(const gsim_pool* p, uint32_t now) {
 static int reap_pass(gsim_pool* p) {
   const ReapPlan r = reap_plan(p);
   if (!r.every || p->now == 0 || p->now % r.every != 0) return GSIM_OK;
-  if (p->now <= (r.reconnect < r.tombstone ? r.reconnect : r.tombstone)) return GSIM_OK;
+  uint32_t youngest = r.reconnect < r.tombstone ? r.reconnect : r.tombstone;
+  if (p->g.reap_min_override && p->g.reap_min_override < youngest) youngest = p->g.reap_min_override;
+  if (p->now <= youngest) return GSIM_OK;
   uint32_t counts[2] = {0, 0};
   if (!upload_globals(p)) return GSIM_ERR_CUDA;
   if (!p->be->reap_rows(p->d, p->g_dev, p->g, p->now, r.reconnect, r.tombstone,
@@ -1771,6 +1796,7 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   add(d.due, cap * 4); add(d.meta, cap * 4); add(d.cursor, cap * 4); add(d.pass, cap * 4);
   add(d.probe_tgt, cap * 4); add(d.probe_inc, cap * 4); add(d.sus_start, cap * 4);
   add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
+  add(d.reap_after, cap * 4);
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
   add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
   if (d.kst) add(d.kst, cap);

@@ -30,6 +30,7 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
     d.acc[((size_t)GS_K1MAX + q) * cap + i] = GS_EMPTY64;
   }
   d.change_tick[i] = 0u;
+  d.reap_after[i] = 0u;
   d.ltime_member[i] = 1u;
   d.ltime_event[i] = 1u;
   d.event_min[i] = 0u;
@@ -65,7 +66,7 @@ GS_DEV uint32_t gs_reap_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint
   const uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
   if (truth == GS_TRUTH_NONE || truth == GS_TRUTH_UP) return 0u;
   uint32_t limit;
-  if (rank == GS_RANK_DEAD) limit = reconnect_ticks;
+  if (rank == GS_RANK_DEAD) limit = d.reap_after[i] != 0u ? d.reap_after[i] : reconnect_ticks;  // ReconnectTimeoutOverride
   else if (rank == GS_RANK_LEFT) limit = tombstone_ticks;
   else return 0u;
   if (now - d.change_tick[i] <= limit) return 0u;

@@ -281,6 +281,7 @@ struct GsGlobals {
   // pick any other; otherwise member i's memberlist is col_idx[row_ptr[i] .. row_ptr[i+1]) and
   // graph_n == n rows are described (static topology: restricted segments, partial views).
   uint32_t graph_n;
+  uint32_t reap_min_override;  // smallest per-member ReconnectTimeout override so far (ticks), 0 = none
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -306,6 +307,7 @@ struct GsDev {
   uint32_t* sus_from;  // [GS_K1MAX][cap]
   uint64_t* acc;       // [2][GS_K1MAX][cap]
   uint32_t* change_tick;
+  uint32_t* reap_after;  // per-member ReconnectTimeout override in ticks, 0 = the pool's (cold: reaper only)
   uint32_t* ltime_member;
   uint32_t* ltime_event;
   uint32_t* event_min;

@@ -162,6 +162,10 @@ class Pool:
         self._ck(self.lib.gsim_graph_set(self.h, len(rp) - 1, rp.ctypes.data_as(C.POINTER(C.c_uint32)),
                                          ci.ctypes.data_as(C.POINTER(C.c_uint32))))
 
+    def member_reconnect_timeout_set(self, member: int, timeout_ns: int):
+        """serf.Config.ReconnectTimeoutOverride result for one member (0 = the pool's value)."""
+        self._ck(self.lib.gsim_member_reconnect_timeout_set(self.h, member, timeout_ns))
+
     def latency_set(self, lat):
         """lat: square matrix (n_dcs x n_dcs) of one-way latencies in ticks (>= 1), or None."""
         if lat is None:

@@ -230,6 +230,12 @@ int gsim_member_update(gsim_pool* p, uint32_t id, uint32_t alive_msg_size, uint3
  * set the same graph before gsim_restore. */
 int gsim_graph_set(gsim_pool* p, uint32_t n_rows, const uint32_t* row_ptr, const uint32_t* col_idx);
 
+/* serf.Config.ReconnectTimeoutOverride — internal/gossip/libserf/serf.go:68-85 (a member
+ * advertises its own reconnect timeout in the "rc_tm" tag; agent/consul/client_test.go:862-894).
+ * The override callback is host code; its result for member `id` is stored with the member and
+ * used by the reaper instead of the pool's reconnect_timeout_ns.  0 = the pool's value. */
+int gsim_member_reconnect_timeout_set(gsim_pool* p, uint32_t id, uint64_t timeout_ns);
+
 /* Event logging of one member on/off after creation (that agent's EventCh; see
  * gsim_member_desc.flags / GSIM_MEMBER_WATCHED and gsim_poll_events). */
 int gsim_member_watch(gsim_pool* p, uint32_t id, int on);

@@ -66,6 +66,10 @@ struct Config {
   // with the other side's member list; a non-empty return value is the error that cancels the
   // merge with that peer.  The delegate itself is Consul code and stays on the host.
   std::function<std::string(const std::vector<Member>&)> Merge;
+  // serf.Config.ReconnectTimeoutOverride (libserf/serf.go:68-85 reads the member's "rc_tm" tag):
+  // given a member and the pool's ReconnectTimeout in ns, returns the timeout to use for it.
+  // Evaluated for this agent's own member record at Create and after SetTags.
+  std::function<uint64_t(const Member&, uint64_t)> ReconnectTimeoutOverride;
 };
 
 class Error : public std::runtime_error {
@@ -78,7 +82,7 @@ class Serf;
 
 class Pool {
  public:
-  explicit Pool(const gsim_config& cfg) {
+  explicit Pool(const gsim_config& cfg) : default_reconnect_ns_(cfg.reconnect_timeout_ns) {
     int rc = gsim_pool_create(&cfg, &h_);
     if (rc != 0) throw Error(rc, gsim_strerror(rc));
   }
@@ -116,6 +120,7 @@ class Pool {
  private:
   friend class Serf;
   gsim_pool* h_ = nullptr;
+  uint64_t default_reconnect_ns_ = 0;
   std::map<std::string, uint32_t> by_name_;
   std::vector<Serf*> by_id_;
 };
@@ -135,6 +140,7 @@ class Serf {
     pool.by_name_[conf.NodeName] = id;
     if (pool.by_id_.size() <= id) pool.by_id_.resize(id + 1, nullptr);
     pool.by_id_[id] = s.get();
+    s->apply_reconnect_override();
     return s;
   }
 
@@ -174,6 +180,7 @@ class Serf {
     for (auto& kv : tags) bytes += (uint32_t)(kv.first.size() + kv.second.size() + 2);
     if (bytes > 512) bytes = 512;  // memberlist.MetaMaxSize
     p_.check(gsim_member_update(p_.h_, id_, bytes, nullptr));
+    apply_reconnect_override();
   }
   void Leave() { p_.check(gsim_leave(p_.h_, id_)); }
   void Shutdown() { p_.check(gsim_crash(p_.h_, id_)); }  // without Leave(): a crash (server_test.go:725)
@@ -214,6 +221,12 @@ class Serf {
  private:
   friend class Pool;
   Serf(Pool& p, uint32_t id, const Config& c) : p_(p), id_(id), conf_(c) {}
+  void apply_reconnect_override() {
+    if (!conf_.ReconnectTimeoutOverride) return;
+    const uint64_t dflt = p_.default_reconnect_ns_;
+    const uint64_t t = conf_.ReconnectTimeoutOverride(p_.describe(id_, StatusAlive, 0), dflt);
+    p_.check(gsim_member_reconnect_timeout_set(p_.h_, id_, t == dflt ? 0 : t));
+  }
   void force_leave(const std::string& node, int prune) {
     auto it = p_.by_name_.find(node);
     if (it == p_.by_name_.end()) return;

@@ -156,6 +156,7 @@ struct Member {
   uint32_t sus_from[MAX_SUS];
   uint32_t n_sus_from = 0;
   uint32_t change_tick = 0;
+  uint64_t own_reconnect_timeout_ns = 0;  // ReconnectTimeoutOverride result for this member (0: pool default)
   uint32_t ltime_member = 1, ltime_event = 1, event_min = 0;
   uint32_t heard = 0, queued = 0;
   uint8_t tx[GSIM_MAX_RUMORS];
@@ -954,7 +955,9 @@ void reap(Oracle& o) {
     Member& me = o.m[i];
     if (me.v.truth == GSIM_TRUTH_NONE || me.v.truth == GSIM_TRUTH_UP) continue;
     uint64_t keep_for;
-    if (me.v.rank == GSIM_RANK_DEAD) keep_for = failed_for;
+    if (me.v.rank == GSIM_RANK_DEAD)
+      keep_for = me.own_reconnect_timeout_ns ? std::max<uint64_t>(1, (me.own_reconnect_timeout_ns + o.tick_ns - 1) / o.tick_ns)
+                                             : failed_for;
     else if (me.v.rank == GSIM_RANK_LEFT) keep_for = left_for;
     else continue;
     if ((uint64_t)(o.now - me.change_tick) <= keep_for) continue;
@@ -1262,6 +1265,13 @@ int oracle_graph_set(void* h, uint32_t n_rows, const uint32_t* row_ptr, const ui
   if (n_rows != o.m.size()) return GSIM_ERR_INVALID;
   o.adjacency.resize(n_rows);
   for (uint32_t i = 0; i < n_rows; ++i) o.adjacency[i].assign(col_idx + row_ptr[i], col_idx + row_ptr[i + 1]);
+  return GSIM_OK;
+}
+
+int oracle_member_reconnect_timeout_set(void* h, uint32_t id, uint64_t timeout_ns) {
+  Oracle& o = *(Oracle*)h;
+  if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
+  o.m[id].own_reconnect_timeout_ns = timeout_ns;
   return GSIM_OK;
 }
 

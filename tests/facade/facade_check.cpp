@@ -241,6 +241,40 @@ static void test_merge_delegate() {
   std::puts("PASS TestMerge_LAN (delegate called on both sides, merge cancelled)");
 }
 
+// TestClient_ShortReconnectTimeout (agent/consul/client_test.go:862-894): clients advertise
+// rc_tm=100ms; libserf's ReconnectOverride (internal/gossip/libserf/serf.go:68-85) turns the tag
+// into the member's reconnect timeout; ReapInterval 50 ms.
+static void test_short_reconnect_timeout() {
+  gsim_config c = test_cfg();
+  c.reap_interval_ns = 50ull * 1000000;
+  Pool pool(c);
+  auto reconnect_override = [](const Member& m, uint64_t dflt) -> uint64_t {
+    auto it = m.Tags.find("rc_tm");
+    if (it == m.Tags.end()) return dflt;
+    const uint64_t ms = std::strtoull(it->second.c_str(), nullptr, 10);  // "100ms"
+    return ms ? ms * 1000000ull : dflt;
+  };
+  Config cs, c0, c1;
+  cs.NodeName = "server";
+  cs.Tags = {{"role", "consul"}};
+  cs.ReconnectTimeoutOverride = reconnect_override;
+  c0.NodeName = "client0";
+  c0.Tags = {{"role", "node"}, {"rc_tm", "100ms"}};
+  c0.ReconnectTimeoutOverride = reconnect_override;
+  c1.NodeName = "client1";
+  c1.Tags = {{"role", "node"}, {"rc_tm", "100ms"}};
+  c1.ReconnectTimeoutOverride = reconnect_override;
+  auto srv = Serf::Create(pool, cs), cl0 = Serf::Create(pool, c0), cl1 = Serf::Create(pool, c1);
+  cl0->Join({"server/x"}, true);
+  cl1->Join({"server/x"}, true);
+  CHECK(eventually(pool, 140, [&] { return srv->Members().size() == 3 && cl0->Members().size() == 3; }));
+  cl1->Shutdown();
+  // 1 s of simulated time (20 ticks of 50 ms) after the failure is detected is the test's allowance
+  CHECK(eventually(pool, 400, [&] { return count_status(*srv, StatusFailed) == 1 || srv->Members().size() == 2; }));
+  CHECK(eventually(pool, 20, [&] { return srv->Members().size() == 2 && cl0->Members().size() == 2; }));
+  std::puts("PASS TestClient_ShortReconnectTimeout");
+}
+
 static void test_user_event() {
   Pool pool(test_cfg());
   std::deque<Event> chs, chc;
@@ -301,6 +335,7 @@ int main(int argc, char** argv) {
       test_join_wan();
       test_set_tags();
       test_merge_delegate();
+      test_short_reconnect_timeout();
       std::puts("ALL PASS");
       return 0;
     }

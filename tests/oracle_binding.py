@@ -40,6 +40,7 @@ _SIGS = [
     ("oracle_rumor_inject", _i32, [_P, _u32, _u32, C.POINTER(_i32)]),
     ("oracle_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
     ("oracle_graph_set", _i32, [_P, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
+    ("oracle_member_reconnect_timeout_set", _i32, [_P, _u32, C.c_uint64]),
     ("oracle_member_watch", _i32, [_P, _u32, _i32]),
     ("oracle_member_update", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("oracle_step", _i32, [_P, _u32]),
@@ -154,6 +155,9 @@ class OraclePool:
         ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
         self._ck(self.lib.oracle_graph_set(self.h, len(rp) - 1, rp.ctypes.data_as(C.POINTER(_u32)),
                                            ci.ctypes.data_as(C.POINTER(_u32))))
+
+    def member_reconnect_timeout_set(self, member, timeout_ns):
+        self._ck(self.lib.oracle_member_reconnect_timeout_set(self.h, member, timeout_ns))
 
     def member_watch(self, member, on=True):
         self._ck(self.lib.oracle_member_watch(self.h, member, int(on)))

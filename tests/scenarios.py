@@ -274,3 +274,42 @@ def set_tags_scenario(make, lib, n=500, seed=41):
         except Exception:
             pass
     step_compare(pools, 60, 10, "after second update")
+
+
+def short_reconnect_timeout_scenario(make, lib, seed=1):
+    """TestClient_ShortReconnectTimeout (agent/consul/client_test.go:862-894): ReapInterval 50 ms
+    everywhere, the clients advertise a reconnect timeout of 100 ms (libserf/serf.go:68-85 turns
+    the tag into serf's ReconnectTimeoutOverride); the pool default stays at 72 h.  A client that
+    shuts down is forgotten by the others shortly after it is declared Failed; a failed SERVER
+    (no override) stays Failed."""
+    MS = 1_000_000
+    cfg = consul_test_config(lib, capacity=8, n_initial=0, seed=seed, flags=1, phase_group=1, reap_interval_ns=50 * MS)
+    pools = make(cfg)
+    server, server2, c0, c1 = [both(pools, lambda p: p.member_add(watched=True)) for _ in range(4)]
+    for p in pools:
+        p.member_reconnect_timeout_set(c0, 100 * MS)
+        p.member_reconnect_timeout_set(c1, 100 * MS)
+    for m in (server2, c0, c1):
+        both(pools, lambda p: p.join(m, [server]))
+    assert both(pools, lambda p: p.run_until(PRED_ALL_RUMORS_CONVERGED, 0, 400, 1)) != NEVER
+    for p in pools:
+        assert len(p.members(server)) == 4
+        p.crash(c1)
+    td = both(pools, lambda p: p.run_until(PRED_CRASHED_ALL_DEAD, 0, 2000, 1))
+    assert td != NEVER
+    step_compare(pools, 4, 1, "reap the client")
+    for p in pools:
+        assert sorted(m[0] for m in p.members(server)) == [server, server2, c0]
+        assert sorted(m[0] for m in p.members(c0)) == [server, server2, c0]
+        p.crash(server2)
+    td2 = both(pools, lambda p: p.run_until(PRED_CRASHED_ALL_DEAD, 0, 2000, 1))
+    assert td2 != NEVER
+    step_compare(pools, 200, 20, "a server without override stays Failed")
+    for p in pools:
+        assert dict((m[0], m[1]) for m in p.members(server))[server2] == STATUS_FAILED
+        p.member_reconnect_timeout_set(server2, 100 * MS)        # tags changed: now it may be forgotten
+    step_compare(pools, 3, 1, "override set later")
+    for p in pools:
+        assert sorted(m[0] for m in p.members(server)) == [server, c0]
+    ev = both(pools, lambda p: [(e.type, e.subject) for e in p.poll_events()])
+    assert (4, c1) in ev and (4, server2) in ev                   # EventMemberReap for both

@@ -105,3 +105,9 @@ def test_cuda_reproduces_extended_golden(case_name, cuda_lib):
     import test_golden as tg
     case = [c for c in tg.mg.CASES_EXT if c[0] == case_name][0]
     tg.check(lambda cfg: Pool(cfg, cuda_lib), cuda_lib, case)
+
+
+def test_short_reconnect_timeout(make, cuda_lib):
+    """serf.Config.ReconnectTimeoutOverride (TestClient_ShortReconnectTimeout timings) on the GPU."""
+    import scenarios as sc
+    sc.short_reconnect_timeout_scenario(make, cuda_lib, 1)

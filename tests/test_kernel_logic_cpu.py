@@ -119,3 +119,9 @@ def test_quickcheck_harness_on_host_emulation(hostemu_lib, tmp_path):
                     "-Wl,-rpath," + os.path.join(root, "oracle"), "-o", out], check=True)
     r = subprocess.run([out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.count("PASS ") == 7 and "ALL PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_short_reconnect_timeout(make, hostemu_lib):
+    """serf.Config.ReconnectTimeoutOverride with the timings of TestClient_ShortReconnectTimeout."""
+    for seed in (1, 2):
+        sc.short_reconnect_timeout_scenario(make, hostemu_lib, seed)
