@@ -1116,20 +1116,22 @@ extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int
   std::lock_guard<std::mutex> lk(p->mu);
   return controller_call(p, nullptr, 0, [&]() -> int {
   if (via >= p->g.n || target >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
-  // [U] serf.RemoveFailedNode: a forged leave intent turns Failed into Left
-  uint32_t any_truth = 0;
-  for (int b = 0; b < 2; ++b) {
-    uint32_t k;
-    if (!peek(p, p->d.key[b], target, &k)) return fail(p, GSIM_ERR_CUDA, "peek");
-    if (gs_key_rank(k) == GS_RANK_DEAD) k = gs_key_with_rank(k, GS_RANK_LEFT);
-    if (prune && gs_key_rank(k) == GS_RANK_LEFT && gs_key_truth(k) != GS_TRUTH_UP && gs_key_truth(k) != GS_TRUTH_NONE) {
-      if (b == 0 && !gs_key_pending(k)) p->n_established -= 1;
-      k &= ~3u;
-    }
-    any_truth = gs_key_truth(k);
-    if (!poke_key(p, b, target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
+  // [U] serf.RemoveFailedNode: a forged leave intent turns Failed into Left.  The decision is
+  // taken on the member's CURRENT record (the buffer the next tick reads); the other buffer may
+  // still hold the previous state (DIRTY), so the result is written to both and DIRTY is dropped.
+  uint32_t k, m;
+  if (!peek(p, p->d.key[p->now & 1u], target, &k) || !peek(p, p->d.meta, target, &m))
+    return fail(p, GSIM_ERR_CUDA, "peek");
+  const uint32_t k_before = k;
+  if (gs_key_rank(k) == GS_RANK_DEAD) k = gs_key_with_rank(k, GS_RANK_LEFT);
+  if (prune && gs_key_rank(k) == GS_RANK_LEFT && gs_key_truth(k) != GS_TRUTH_UP && gs_key_truth(k) != GS_TRUTH_NONE) {
+    if (!gs_key_pending(k)) p->n_established -= 1;
+    k &= ~3u;
   }
-  (void)any_truth;
+  if (k != k_before) {
+    if (!poke_key(p, 0, target, k) || !poke_key(p, 1, target, k)) return fail(p, GSIM_ERR_CUDA, "poke");
+    if ((m & GS_META_DIRTY) && !poke(p, p->d.meta, target, m & ~GS_META_DIRTY)) return fail(p, GSIM_ERR_CUDA, "poke");
+  }
   int rc = refresh_after_truth_change(p);
   return rc ? fail(p, rc, "recount") : GSIM_OK;
   });
