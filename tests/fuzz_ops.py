@@ -47,6 +47,18 @@ def random_config(rng: random.Random, lib):
     return fn(lib, **kw), latency
 
 
+def random_graph(rng: random.Random, n: int):
+    """A sparse static topology: every member knows itself, a window of neighbours and a few
+    random others (directed; some members may end up knowing nobody else)."""
+    rows = []
+    for i in range(n):
+        row = {i} | {(i + d) % n for d in range(1, rng.choice([1, 2, 9]))} | {rng.randrange(n) for _ in range(rng.choice([0, 2, 6]))}
+        rows.append(sorted(row))
+    rp = np.zeros(n + 1, dtype=np.uint32)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    return rp, np.concatenate([np.array(r, dtype=np.uint32) for r in rows])
+
+
 def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
     rng = random.Random(seed)
     cfg, latency = random_config(rng, lib)
@@ -54,6 +66,10 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
     if latency is not None:
         for p in pools:
             p.latency_set(latency)
+    if cfg.n_initial >= 5 and rng.random() < 0.2:              # static CSR topology (member_add then fails alike)
+        rp, ci = random_graph(rng, cfg.n_initial)
+        for p in pools:
+            p.graph_set(rp, ci)
     log = []
 
     def both(fn, what):
@@ -106,6 +122,13 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
         elif r < 0.63:
             slot = rng.randrange(30)
             both(lambda p: p.rumor_retire(slot), f"retire {slot}")
+        elif r < 0.645 and hasattr(pools[0], "snapshot"):
+            ev = [sorted((e.tick, e.type, e.subject, e.observer, e.ltime) for e in p.poll_events()) for p in pools]
+            assert ev[0] == ev[1], (seed, "event logs differ")     # (a restore starts with an empty event log)
+            blob = pools[0].snapshot()                     # checkpoint / resume must be invisible
+            pools[0].step(3)
+            pools[0].restore(blob)
+            log.append(("snapshot+3 ticks+restore", None))
         elif r < 0.66 and n > 10 and cfg.capacity > n:
             ppm = rng.choice([50000, 300000])
             both(lambda p: p.crash_fraction(ppm, step), f"crash_fraction {ppm}")
