@@ -98,9 +98,21 @@ def federation_script(make_pool):
     return out
 
 
+# randomised operation sequences through the controller protocol (every rank issues every call and
+# keeps its own oracle; digest and counters are compared after every operation)
+import fuzz_ops  # noqa: E402
+from oracle_binding import OraclePool as _Oracle  # noqa: E402
+fuzz_ok = True
+for fseed in (3, 17, 251, 404):
+    try:
+        fuzz_ops.run_sequence(lambda cfg: [ShardedPool(cfg, L), _Oracle(cfg)], L, fseed, n_ops=40, columns=False)
+    except AssertionError as e:
+        fuzz_ok = False
+        print("FUZZ MISMATCH rank", rank, "seed", fseed, str(e)[:800], flush=True)
+
 mkf = lambda seed: wan_config(L, capacity=N, n_initial=N, seed=seed, mailbox_depth=8)  # noqa: E731
 gotf = federation_script(lambda seed: ShardedPool(mkf(seed), L))
-ok = True
+ok = fuzz_ok
 if rank == 0:
     from oracle_binding import OraclePool
     for name, ref in (("unsharded", Pool(mk(), L)), ("oracle", OraclePool(mk()))):
