@@ -85,3 +85,9 @@ def test_variant_scenarios_against_oracle(make, kstat_lib):
     wl.test_snapshot_restore_with_packets_in_flight(kstat_lib)
     pp.stranded_event(make, kstat_lib, FLAG_PUSH_PULL, n=1500, ticks=500)
     pp.test_snapshot_restore_mid_exchange(kstat_lib)
+
+
+def test_variant_random_sequences(make, kstat_lib):
+    import fuzz_ops
+    for seed in list(range(1000, 1030)) + [251]:
+        fuzz_ops.run_sequence(make, kstat_lib, seed)
