@@ -14,7 +14,11 @@ ap.add_argument("--event", action="store_true")
 ap.add_argument("--crash-ppm", type=int, default=0)
 ap.add_argument("--nograph", action="store_true")
 a = ap.parse_args()
-p = Pool(lan_config(capacity=a.members + 1, n_initial=a.members, seed=0x5EED0001, flags=2 if a.nograph else 0))
+lib = None
+if os.environ.get("GSIM_LIB"):                      # a kernel variant built by tools/build_variants.sh
+    from consul_b200 import _lib
+    lib = _lib.load(os.environ["GSIM_LIB"])
+p = Pool(lan_config(lib, capacity=a.members + 1, n_initial=a.members, seed=0x5EED0001, flags=2 if a.nograph else 0), lib)
 if a.join:
     x = p.member_add()
     p.join(x, [0])
