@@ -15,7 +15,9 @@
 // 666-733; client_test.go:756-835) and the 100k-node design figure of
 // internal/gossip/libserf/serf.go:29-33, replayed in tests/test_oracle_scenarios.py, (4) the
 // queue-order / event-window / de-dup / leave / refute predicates of SURVEY.md §8c as known-answer
-// tests in tests/test_predicate_kats.py.
+// tests in tests/test_predicate_kats.py, (5) oracle/m0_memberlist.py — a full-fidelity per-observer
+// restatement ("M0") whose outcomes, exact counts and detection / dissemination times this
+// projected model ("M1") must reproduce (tests/test_m0_crosscheck.py).
 //
 // Model (documented in DESIGN.md §3): lock-step ticks of tau = gcd(ProbeInterval,
 // ProbeTimeout, GossipInterval).  Every member reads the cluster as it was published at the
