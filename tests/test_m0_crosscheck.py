@@ -146,3 +146,45 @@ def test_m0_refutes_under_loss_like_m1(hostemu_lib):
     assert s["refutes"] > 0 and int((p.column("key")[:n] >> 5).max()) > 1
     # same order of magnitude of false suspicion (per-observer suspicion in M0 vs one shared record in M1)
     assert 0.2 <= (s["refutes"] + 1) / (refutes0 + 1) <= 5.0, (s["refutes"], refutes0)
+
+
+def test_join_cascade_matches_full_fidelity_model(hostemu_lib):
+    """BASELINE config 2 in small: one joiner into a converged cluster of 300; ticks until everybody
+    lists it.  M0: every agent's own memberlist has to learn the alive message; M1: the tracked
+    alive rumor's heard-bits."""
+    n, seeds = 300, 10
+    t0, t1 = [], []
+    for seed in range(seeds):
+        net = m0.Network(m0.Config(), seed=seed)
+        net.converged_cluster(n)
+        x = net.create()
+        assert net.join(x, 0) == 1
+        t = net.first_tick(lambda: all(x in a.views for a in net.agents) and len(net.agents[x].views) == n + 1, 400)
+        assert t is not None
+        t0.append(t)
+        p = OraclePool(lan_config(hostemu_lib, capacity=n + 1, n_initial=n, seed=3000 + seed, phase_group=1))
+        y = p.member_add()
+        assert p.join(y, [0]) == 1
+        t = p.run_until(PRED_ALL_RUMORS_CONVERGED, 0, 400, 1)
+        assert t != NEVER and len(p.members(y)) == n + 1
+        t1.append(t)
+    assert abs(st.mean(t0) - st.mean(t1)) <= 2.0, (t0, t1)
+
+
+def test_stranded_broadcast_coverage_matches_full_fidelity_model(hostemu_lib):
+    """50 % loss and RetransmitMult 1: gossip alone reaches only part of 400 agents — the same part,
+    on average, in both models (the epidemic's final size is a property of the protocol)."""
+    n, seeds = 400, 10
+    c0, c1 = [], []
+    for seed in range(seeds):
+        net = m0.Network(m0.Config(loss=0.5, retransmit_mult=1), seed=seed)
+        net.converged_cluster(n)
+        key = net.user_event(7, b"e", b"p")
+        net.step(120)
+        c0.append(sum(1 for a in net.agents if any(k == key for _, k in a.delivered)) / n)
+        p = OraclePool(lan_config(hostemu_lib, capacity=n, n_initial=n, seed=4000 + seed, phase_group=1,
+                                  packet_loss_ppm=500000, retransmit_mult=1))
+        slot = p.user_event(7, b"e", b"p", False)
+        p.step(120)
+        c1.append(p.rumor_info(slot)["heard_count"] / n)
+    assert 0.3 < st.mean(c0) < 1.0 and abs(st.mean(c0) - st.mean(c1)) <= 0.08, (c0, c1)
