@@ -46,6 +46,9 @@
 enum { GS_TRUTH_NONE = 0, GS_TRUTH_UP = 1, GS_TRUTH_CRASHED = 2, GS_TRUTH_GONE = 3 };
 enum { GS_RANK_ALIVE = 0, GS_RANK_SUSPECT = 1, GS_RANK_DEAD = 2, GS_RANK_LEFT = 3 };
 enum { GS_STAGE_IDLE = 0, GS_STAGE_WAIT_T = 1, GS_STAGE_WAIT_P = 2 };
+// tracked-broadcast kinds and event types: the public GSIM_RUMOR_* / GSIM_EVENT_* values
+enum { GS_RUMOR_ALIVE = 1, GS_RUMOR_JOIN_INTENT = 2, GS_RUMOR_LEAVE_INTENT = 3, GS_RUMOR_USER_EVENT = 4, GS_RUMOR_UPDATE = 5 };
+enum { GS_EV_MEMBER_JOIN = 0, GS_EV_MEMBER_FAILED = 2, GS_EV_MEMBER_UPDATE = 3, GS_EV_MEMBER_REAP = 4, GS_EV_USER = 5 };
 
 // Philox counter "purpose" words.
 enum {

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     // Sharded pool, acquire side of the inter-tick barrier: tick t may start once every rank has
     // published "all ticks < t done" in this rank's progress array (written by the peers over
     // NVLink with st.release.sys at the end of their previous tick, see the end of this kernel).
-    if (tid < g.world && !(g.flags & 16u)) {  // flag 16: timing experiment only (no wait)
+    if (tid < g.world) {
       uint32_t v;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(d.tick_flags[g.rank] + tid) : "memory");
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // Sharded pools: mailbox deliveries to other GPUs are fire-and-forget reductions over NVLink;
   // a system-scope fence by the issuing thread is what guarantees they have been performed at
   // the owner before this rank can signal the inter-tick barrier.
-  if (g.world > 1u && did_work && !(g.flags & 8u)) __threadfence_system();  // flag 8: timing experiment only
+  if (g.world > 1u && did_work) __threadfence_system();
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(GS_BLOCK)
   if (i < gp->n) r = gs_reap_row(d, *gp, i, now, reconnect_ticks, tombstone_ticks);
   if (r && log_events) {
     DevSink sink{nullptr, nullptr};
-    sink.log_event(d, *gp, now, 4u /*MEMBER_REAP*/, i, GS_EMPTY32, 0u);
+    sink.log_event(d, *gp, now, GS_EV_MEMBER_REAP, i, GS_EMPTY32, 0u);
   }
   const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (r & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (r & 2u) != 0u);
   if ((threadIdx.x & 31u) == 0u) {

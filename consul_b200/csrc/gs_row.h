@@ -217,7 +217,7 @@ GS_DEV bool gs_knows(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t c,
     uint32_t r = (uint32_t)__builtin_ctz(am);
 #endif
     am &= am - 1;
-    if (g.rumors[r].kind == 1u /*ALIVE*/ && g.rumors[r].subject == c) return (heard_i >> r) & 1u;
+    if (g.rumors[r].kind == GS_RUMOR_ALIVE && g.rumors[r].subject == c) return (heard_i >> r) & 1u;
   }
   return false;
 }
@@ -400,7 +400,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         fresh &= fresh - 1;
         const GsRumor& ru = g.rumors[r];
         bool accept = true;
-        if (ru.kind == 4u /*USER_EVENT*/) {
+        if (ru.kind == GS_RUMOR_USER_EVENT) {
           // [U] serf.handleUserEvent: Witness, then eventMinTime and buffer-window checks.
           uint32_t c = d.ltime_event[i];
           if (ru.ltime >= c) {
@@ -410,18 +410,18 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           if (ru.ltime < d.event_min[i]) accept = false;
           else if (c > g.event_buffer && ru.ltime < c - g.event_buffer) accept = false;
           if (accept && (m & GS_META_WATCHED))
-            gs_log_event(d, g, sink, t, 5u /*EVENT_USER*/, r, i, ru.ltime);
-        } else if (ru.kind == 2u || ru.kind == 3u) {
+            gs_log_event(d, g, sink, t, GS_EV_USER, r, i, ru.ltime);
+        } else if (ru.kind == GS_RUMOR_JOIN_INTENT || ru.kind == GS_RUMOR_LEAVE_INTENT) {
           // [U] serf.handleNodeJoinIntent / handleNodeLeaveIntent: clock.Witness(LTime).
           uint32_t c = d.ltime_member[i];
           if (ru.ltime >= c) d.ltime_member[i] = ru.ltime + 1u;
-        } else if (ru.kind == 1u) {
+        } else if (ru.kind == GS_RUMOR_ALIVE) {
           // [U] memberlist.aliveNode for a new node -> serf.handleNodeJoin -> EventMemberJoin.
-          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, 0u /*MEMBER_JOIN*/, ru.subject, i, 0u);
-        } else if (ru.kind == 5u) {
+          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, GS_EV_MEMBER_JOIN, ru.subject, i, 0u);
+        } else if (ru.kind == GS_RUMOR_UPDATE) {
           // [U] memberlist.aliveNode with a higher incarnation and new meta -> NotifyUpdate ->
           // serf.handleNodeUpdate -> EventMemberUpdate ((*Serf).SetTags at the subject).
-          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, 3u /*MEMBER_UPDATE*/, ru.subject, i, 0u);
+          if (m & GS_META_WATCHED) gs_log_event(d, g, sink, t, GS_EV_MEMBER_UPDATE, ru.subject, i, 0u);
         }
         if (accept) {
           accepted |= 1u << r;
@@ -510,7 +510,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         d.change_tick[i] = t;
         sink.stat(GS_ST_DEADS, 1);
         if (truth == GS_TRUTH_CRASHED) sink.crashed_dead(d, t);
-        if (g.flags & 1u) gs_log_event(d, g, sink, t, 2u /*MEMBER_FAILED*/, i, GS_EMPTY32, 0u);
+        if (g.flags & 1u) gs_log_event(d, g, sink, t, GS_EV_MEMBER_FAILED, i, GS_EMPTY32, 0u);
       }
     }
   }

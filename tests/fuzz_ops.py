@@ -95,7 +95,7 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
             both(lambda p: p.member_add(watched=rng_bool(seed, step)), "add")
         elif r < 0.22 and n:
             a, b = pick(), pick()
-            both(lambda p: p.join(a, [b, pick.__call__() if False else b], rng_bool(seed, step + 1)), f"join {a}->{b}")
+            both(lambda p: p.join(a, [b, b], rng_bool(seed, step + 1)), f"join {a}->{b}")
         elif r < 0.30 and n:
             m = pick()
             both(lambda p: p.user_event(m, b"e%d" % step, b"x" * (step % 40), False), f"event {m}")

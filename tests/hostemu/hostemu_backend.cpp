@@ -49,6 +49,7 @@ class HostEmuBackend : public GsBackend {
   HostEmuBackend() {
     const char* o = getenv("GSIM_HOSTEMU_ORDER");
     order_ = o ? atoi(o) : 0;
+    no_fast_ = getenv("GSIM_HOSTEMU_NO_FAST") != nullptr;  // generic path only (debugging aid)
     err_[0] = 0;
   }
   const char* name() const override { return "hostemu (tests only)"; }
@@ -116,7 +117,7 @@ class HostEmuBackend : public GsBackend {
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
         if (!(inb != 0u || due == t || gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t))) continue;
-        if (inb == 0u && due == t && !getenv("GSIM_HOSTEMU_NO_FAST")) {  // same two tiers as the kernel
+        if (inb == 0u && due == t && !no_fast_) {  // same two tiers as the kernel
           GsFastProbe f;
           bool acked = false;
           gs_fast_load(d, t & 1u, i, f);
@@ -163,7 +164,7 @@ class HostEmuBackend : public GsBackend {
       const uint32_t r = gs_reap_row(d, g, i, now, reconnect_ticks, tombstone_ticks);
       counts[0] += r & 1u;
       counts[1] += (r >> 1) & 1u;
-      if (r && log_events) sink.log_event(d, g, now, 4u /*MEMBER_REAP*/, i, GS_EMPTY32, 0u);
+      if (r && log_events) sink.log_event(d, g, now, GS_EV_MEMBER_REAP, i, GS_EMPTY32, 0u);
     }
     return true;
   }
@@ -269,6 +270,7 @@ class HostEmuBackend : public GsBackend {
 
  private:
   int order_;
+  bool no_fast_ = false;
   uint64_t launches_ = 0;
   bool sharded_ = false;
   uint32_t world_ = 1, rank_ = 0;
