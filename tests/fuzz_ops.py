@@ -7,7 +7,7 @@ import random
 import numpy as np
 
 from consul_b200.pool import FLAG_PUSH_PULL, consul_test_config, lan_config, wan_config
-from parity import compare_pools
+from parity import check_invariants, compare_pools
 
 MS = 1_000_000
 
@@ -72,6 +72,7 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
         for p in pools:
             p.graph_set(rp, ci)
     log = []
+    inv = None
 
     def both(fn, what):
         out = []
@@ -140,6 +141,8 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
             log.append((f"step {k}", None))
         try:
             compare_pools(pools[0], pools[1], f"seed {seed} after op {step}: {log[-1][0]}", columns=columns)
+            if columns and step % 4 == 0:
+                inv = check_invariants(pools[0], inv, f"seed {seed} after op {step}")
         except AssertionError as e:
             raise AssertionError(f"{e}\nlast ops: {log[-8:]}") from None
     if getattr(pools[0], "rank", 0) == 0:                      # a sharded pool's log is served by rank 0

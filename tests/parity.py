@@ -82,3 +82,58 @@ def compare_pools(a, b, where="", columns=True):
         compare_columns(a, b, where)
     ha, hb = a.state_hash(), b.state_hash()
     assert ha == hb, f"state hash differs {where}: {ha} vs {hb}"
+
+
+def check_invariants(p, prev=None, where=""):
+    """Size-independent invariants of the pool state (no oracle needed: usable at BASELINE's full
+    sizes).  `prev` = the dict returned by an earlier call on the same pool: monotone quantities
+    (incarnations, Lamport clocks) must not have gone backwards.  Returns the new snapshot."""
+    s = p.stats()
+    n, now = s["n_members"], p.now
+    if n == 0:
+        return {"n": 0}
+    act = active_mask(p)
+    col = {name: p.column(name) for name in ("key", "meta", "due", "cursor", "probe_tgt", "ltime_member",
+                                             "ltime_event", "heard", "queued", "tx", "sus_from")}
+    key, meta = col["key"][:n], col["meta"][:n]
+    truth, rank, inc = key & 3, (key >> 2) & 3, key >> 5
+    exists, up = truth != 0, truth == 1
+    stage, aw = (meta >> 3) & 3, meta & 7
+    heard, queued = col["heard"][:n] & act, col["queued"][:n] & act
+    limit = s["retransmit_limit"]
+
+    def ok(cond, msg):
+        assert bool(np.all(cond)), f"invariant violated {where}: {msg} (rows {np.nonzero(~np.asarray(cond))[0][:5].tolist()})"
+
+    ok(inc[exists] >= 1, "an existing member has incarnation >= 1")
+    ok(stage <= 2, "probe stage is IDLE / WAIT_T / WAIT_P")
+    ok(aw[exists] < 8, "awareness below AwarenessMaxMultiplier")
+    ok((queued[up] & ~heard[up]) == 0, "a member only re-broadcasts what it has heard")
+    ok(col["due"][:n][up] >= now, "no running member has a probe action in the past")
+    probing = up & (stage != 0)
+    ok(col["probe_tgt"][:n][probing] < n, "an in-flight probe has a real target")
+    ok(col["ltime_member"][:n][exists] >= 1, "member clock starts at 1")
+    ok(col["ltime_event"][:n][exists] >= 1, "event clock starts at 1")
+    for r in range(GSIM_MAX_RUMORS):
+        if not (act >> r) & 1:
+            continue
+        tx = col["tx"][r][:n].astype(np.int64)
+        has = ((heard >> r) & 1).astype(bool) & up
+        q = ((queued >> r) & 1).astype(bool) & up
+        ok(tx[has] <= limit, f"rumor {r}: transmits never exceed the retransmit limit")
+        ok(tx[q] < limit, f"rumor {r}: a queued broadcast still has budget")
+        info = p.rumor_info(r)
+        assert info["heard_count"] == int(has.sum()), f"{where}: rumor {r} heard_count {info['heard_count']} != {int(has.sum())}"
+        assert info["queued_count"] == int(q.sum()), f"{where}: rumor {r} queued_count"
+    suspects = exists & (rank == 1)
+    ok(col["sus_from"][0][:n][suspects] != 0xFFFFFFFF, "a suspect has a first accuser")
+    assert s["n_up"] == int(up.sum()) and s["n_view_dead"] == int((exists & (rank == 2)).sum()), f"{where}: recount"
+    snap = {"n": n, "inc": inc.copy(), "lm": col["ltime_member"][:n].copy(), "le": col["ltime_event"][:n].copy(),
+            "exists": exists.copy()}
+    if prev and prev.get("n"):
+        m = prev["n"]
+        both = prev["exists"] & exists[:m]
+        ok(inc[:m][both] >= prev["inc"][both], "incarnations never decrease")
+        ok(col["ltime_member"][:m][both] >= prev["lm"][both], "member clocks never decrease")
+        ok(col["ltime_event"][:m][both] >= prev["le"][both], "event clocks never decrease")
+    return snap

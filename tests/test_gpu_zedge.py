@@ -46,3 +46,26 @@ def test_torch_free_quickcheck_binary():
                     "-o", out], check=True)
     r = subprocess.run([out], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_invariants_at_scale(cuda_lib):
+    """4 Mi members — beyond what the oracle is asked to follow tick by tick: a join, two events and
+    a 5 % crash wave with 10 % packet loss; the state invariants (tests/parity.py check_invariants:
+    queued within heard, transmits within the limit, counters equal to recounts, no probe action in
+    the past, incarnations and Lamport clocks monotone) hold at every checkpoint."""
+    from consul_b200.pool import lan_config
+    from parity import check_invariants
+    n = 4 * 1024 * 1024
+    p = Pool(lan_config(cuda_lib, capacity=n + 2, n_initial=n, seed=0x5EED0077, packet_loss_ppm=100000), cuda_lib)
+    x = p.member_add()
+    p.join(x, [0])
+    p.user_event(5, b"deploy", b"x" * 32, False)
+    snap = check_invariants(p, None, "t=0")
+    for k, ticks in enumerate((7, 64, 129, 300)):
+        if k == 1:
+            assert p.crash_fraction(50000, 1) > 0
+            p.user_event(9, b"second", b"", False)
+        p.step(ticks)
+        snap = check_invariants(p, snap, f"checkpoint {k}")
+    s = p.stats()
+    assert s["suspects"] > 0 and s["deads"] > 0 and s["rumors_accepted"] > 2 * n
