@@ -27,6 +27,10 @@ for k in 1 2; do
   echo "== GSIM_CTAS_PER_SM=$k" >> $OUT/knobs.log
   GSIM_CTAS_PER_SM=$k python tools/variant_bench.py consul_b200/libgsim.so consul_b200/libgsim_both.so >> $OUT/knobs.log 2>&1
 done
+for k in 1 2 3; do   # several ticks per cooperative launch: the grid barrier is cheaper with fewer CTAs
+  echo "== GSIM_MULTI_TICK=1 GSIM_CTAS_PER_SM=$k" >> $OUT/knobs.log
+  GSIM_MULTI_TICK=1 GSIM_CTAS_PER_SM=$k python tools/variant_bench.py consul_b200/libgsim.so >> $OUT/knobs.log 2>&1
+done
 echo "== GSIM_NO_PDL=1" >> $OUT/knobs.log
 GSIM_NO_PDL=1 python tools/variant_bench.py consul_b200/libgsim.so >> $OUT/knobs.log 2>&1
 echo "== GSIM_NO_L2_WINDOW=1 (kstat without the persistence window)" >> $OUT/knobs.log
