@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
         uint32_t w;
         if (use_map) {  // member base + 32u is bit `lane` of the tile's word u
           const uint32_t fw = u == 0 ? i4.x : u == 1 ? i4.y : u == 2 ? i4.z : i4.w;
-          w = ((fw >> lane) & 1u) ? inbox_cur[base + 32u * u] : 0u;
+          w = ((fw >> lane) & 1u) ? __ldcg(inbox_cur + base + 32u * u) : 0u;  // L2: written by other SMs
           s_inb[st][wib][u * 32 + lane] = w;  // gs_row_step below takes it from here
         } else {
           w = s_inb[st][wib][u * 32 + lane];
