@@ -403,6 +403,14 @@ static int init_device_state(gsim_pool* p) {
     if (d.mailmap[s]) okk = okk && be->fill32(d.mailmap[s], 0, cap / 32);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill32(d.reap_after, 0, cap);
+  // rows that were never created hold the same defaults gs_init_row writes, so that a column
+  // nobody has touched is one repeated word (gsim_snapshot stores such planes as a fill)
+  okk = okk && be->fill32(d.cursor, 0, cap) && be->fill32(d.pass, 0, cap) && be->fill32(d.probe_tgt, 0, cap) &&
+        be->fill32(d.probe_inc, 0, cap) && be->fill32(d.sus_start, 0, cap) && be->fill32(d.change_tick, 0, cap) &&
+        be->fill32(d.event_min, 0, cap) && be->fill32(d.heard, 0, cap) && be->fill32(d.queued, 0, cap) &&
+        be->fill32(d.ltime_member, 1, cap) && be->fill32(d.ltime_event, 1, cap) && be->fill32(d.meta, 0, cap) &&
+        be->fill32(d.sus_from, GS_EMPTY32, cap * GS_K1MAX) &&
+        be->fill32(reinterpret_cast<uint32_t*>(d.acc), GS_EMPTY32, cap * GS_K1MAX * 2 * 2);
   okk = okk && be->fill8(d.tx, 0, cap * GS_MAX_RUMORS);
   if (d.ppreq) okk = okk && be->fill32(d.ppreq, GS_EMPTY32, cap * 2 * GS_PPK) && be->fill32(d.pp_clk, 0, cap * 4);
   okk = okk && be->fill32(reinterpret_cast<uint32_t*>(d.stats), 0, GSIM_STAT_COUNT * 2);
@@ -1784,32 +1792,38 @@ extern "C" int gsim_column_read(gsim_pool* p, int column, void* out, size_t cap_
 }
 
 // ---- checkpoint / resume ------------------------------------------------------------
+// A snapshot is a header followed by the columns, plane by plane.  Most planes of the cold columns
+// hold one repeated 32-bit word (empty accusation slots, untouched retransmit counters, zero
+// change ticks ...): such a plane is stored as (tag 1, word) and restored with a device fill
+// instead of a host->device copy; everything else is (tag 0, raw bytes).
 struct SnapCol {
   void* ptr;
-  size_t bytes;
+  size_t bytes;      // all planes together
+  uint32_t planes;   // equally sized, each a multiple of 4 bytes
+  bool may_fill;     // planes may be stored as a repeated word
 };
 static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   const GsDev& d = p->d;
   const size_t cap = p->g.cap;
   std::vector<SnapCol> v;
-  auto add = [&](void* q, size_t b) { v.push_back(SnapCol{q, b}); };
-  add(d.key[0], cap * 4); add(d.key[1], cap * 4);
+  auto add = [&](void* q, size_t b, uint32_t planes = 1, bool may_fill = true) { v.push_back(SnapCol{q, b, planes, may_fill}); };
+  add(d.key[0], cap * 4, 1, false); add(d.key[1], cap * 4, 1, false);  // (replicated per rank when sharded)
   for (uint32_t s = 0; s <= p->g.ring_mask; ++s) add(d.inbox[s], cap * 4);
   add(d.due, cap * 4); add(d.meta, cap * 4); add(d.cursor, cap * 4); add(d.pass, cap * 4);
   add(d.probe_tgt, cap * 4); add(d.probe_inc, cap * 4); add(d.sus_start, cap * 4);
-  add(d.sus_from, cap * 4 * GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2); add(d.change_tick, cap * 4);
+  add(d.sus_from, cap * 4 * GS_K1MAX, GS_K1MAX); add(d.acc, cap * 8 * GS_K1MAX * 2, GS_K1MAX * 2); add(d.change_tick, cap * 4);
   add(d.reap_after, cap * 4);
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
-  add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS);
+  add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS, GS_MAX_RUMORS / 2);
   if (d.kst) add(d.kst, cap);
   for (uint32_t s = 0; s <= p->g.ring_mask; ++s)
     if (d.mailmap[s]) add(d.mailmap[s], cap / 32 * 4);
   if (d.ppreq) {
-    add(d.ppreq, cap * 4 * 2 * GS_PPK);
-    add(d.pp_clk, cap * 4 * 4);
+    add(d.ppreq, cap * 4 * 2 * GS_PPK, 2 * GS_PPK);
+    add(d.pp_clk, cap * 4 * 4, 4);
   }
-  add(d.stats, GSIM_STAT_COUNT * 8); add(d.heard_cnt, 32 * 4); add(d.conv_tick, 32 * 4);
-  add(d.crashed_alive, 4); add(d.crashed_dead_tick, 4);
+  add(d.stats, GSIM_STAT_COUNT * 8, 1, false); add(d.heard_cnt, 32 * 4, 1, false); add(d.conv_tick, 32 * 4, 1, false);
+  add(d.crashed_alive, 4, 1, false); add(d.crashed_dead_tick, 4, 1, false);
   return v;
 }
 struct SnapHeader {
@@ -1825,7 +1839,7 @@ static const uint64_t SNAP_MAGIC = 0x4753494D534E4150ull;  // "GSIMSNAP"
 static size_t snap_size(gsim_pool* p) {
   size_t s = sizeof(SnapHeader) + p->sched.size() * sizeof(Sched);
   for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) s += 12 + p->rh[r].name.size() + p->rh[r].payload.size();
-  for (const SnapCol& c : snap_cols(p)) s += c.bytes;
+  for (const SnapCol& c : snap_cols(p)) s += c.bytes + 4u * c.planes;  // upper bound: every plane raw
   return s;
 }
 
@@ -1845,10 +1859,11 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
   if (n_bytes) *n_bytes = need;
   if (cap_bytes < need) return fail(p, GSIM_ERR_INVALID, "buffer too small");
   uint8_t* w = reinterpret_cast<uint8_t*>(out);
+  uint8_t* const w0 = w;
   SnapHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = SNAP_MAGIC;
-  h.version = 1;
+  h.version = 2;
   h.cap = p->g.cap;
   h.now = p->now;
   h.n_sched = (uint32_t)p->sched.size();
@@ -1870,9 +1885,18 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
     w += hdr[1];
   }
   for (const SnapCol& c : snap_cols(p)) {
-    if (!p->be->d2h(w, c.ptr, c.bytes)) return fail(p, GSIM_ERR_CUDA, "d2h");
-    w += c.bytes;
+    const size_t pb = c.bytes / c.planes;
+    for (uint32_t q = 0; q < c.planes; ++q) {
+      uint8_t* raw = w + 4;
+      if (!p->be->d2h(raw, reinterpret_cast<uint8_t*>(c.ptr) + (size_t)q * pb, pb)) return fail(p, GSIM_ERR_CUDA, "d2h");
+      // one repeated word?  (buf[0..n-4) == buf[4..n) iff all 32-bit words are equal)
+      const bool uniform = c.may_fill && pb >= 8 && memcmp(raw, raw + 4, pb - 4) == 0;
+      const uint32_t tag = uniform ? 1u : 0u;
+      memcpy(w, &tag, 4);
+      w += 4 + (uniform ? 4 : pb);
+    }
   }
+  if (n_bytes) *n_bytes = (size_t)(w - w0);  // what was actually written (<= gsim_snapshot_size)
   return GSIM_OK;
 }
 
@@ -1885,7 +1909,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   SnapHeader h;
   memcpy(&h, r, sizeof(h));
   r += sizeof(h);
-  if (h.magic != SNAP_MAGIC || h.version != 1 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask ||
+  if (h.magic != SNAP_MAGIC || h.version != 2 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask ||
       (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u) || h.g.graph_n != p->g.graph_n)
     return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
   if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
@@ -1905,7 +1929,29 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
     p->rh[x].coalesce = (int)hdr[2];
   }
   for (const SnapCol& c : snap_cols(p)) {
-    if ((size_t)(end - r) < c.bytes) return fail(p, GSIM_ERR_INVALID, "truncated");
+    if (c.may_fill) {  // plane by plane: a device fill or a copy
+      const size_t pb = c.bytes / c.planes;
+      for (uint32_t q = 0; q < c.planes; ++q) {
+        if (end - r < 8) return fail(p, GSIM_ERR_INVALID, "truncated");
+        uint32_t tag, word;
+        memcpy(&tag, r, 4);
+        memcpy(&word, r + 4, 4);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.ptr) + (size_t)q * pb;
+        if (tag == 1u) {
+          if (!p->be->fill32(reinterpret_cast<uint32_t*>(dst), word, pb / 4)) return fail(p, GSIM_ERR_CUDA, "fill");
+          r += 8;
+        } else if (tag == 0u) {
+          if ((size_t)(end - r) < 4 + pb) return fail(p, GSIM_ERR_INVALID, "truncated");
+          if (!p->be->h2d(dst, r + 4, pb)) return fail(p, GSIM_ERR_CUDA, "h2d");
+          r += 4 + pb;
+        } else {
+          return fail(p, GSIM_ERR_INVALID, "corrupt snapshot");
+        }
+      }
+      continue;
+    }
+    if ((size_t)(end - r) < 4 + c.bytes) return fail(p, GSIM_ERR_INVALID, "truncated");
+    r += 4;  // tag 0 (these columns are always stored raw)
     if (!p->be->h2d(c.ptr, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
     if (p->sharded && (c.ptr == p->d.key[0] || c.ptr == p->d.key[1])) {
       // the key column is replicated per rank: restore every replica
