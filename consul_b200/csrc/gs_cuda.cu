@@ -492,6 +492,11 @@ static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const G
   return cudaLaunchCooperativeKernel((const void*)gs_tick_kernel, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
 }
 
+__global__ void __launch_bounds__(GS_BLOCK) gs_fill32_kernel(uint32_t* dst, uint32_t value, size_t count) {
+  for (size_t x = (size_t)blockIdx.x * GS_BLOCK + threadIdx.x; x < count; x += (size_t)gridDim.x * GS_BLOCK)
+    dst[x] = value;
+}
+
 __global__ void __launch_bounds__(GS_BLOCK) gs_and_kernel(GsDev d, uint32_t n, uint32_t keep) {
   const uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
   if (i >= n) return;
@@ -756,16 +761,13 @@ class CudaBackend : public GsBackend {
 
  private:
   cudaError_t cudaMemsetD32Async_(uint32_t* dst, uint32_t value, size_t count) {
-    // no runtime-API 32-bit memset: stage a small pattern buffer through the host
-    const size_t chunk = 1u << 16;
-    static thread_local uint32_t pat[1u << 16];
-    for (size_t x = 0; x < chunk; ++x) pat[x] = value;
-    for (size_t off = 0; off < count; off += chunk) {
-      size_t c = count - off < chunk ? count - off : chunk;
-      cudaError_t e = cudaMemcpyAsync(dst + off, pat, c * 4, cudaMemcpyHostToDevice, stream_);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaStreamSynchronize(stream_);
+    // the runtime API has no 32-bit memset: a grid-stride fill kernel on the pool's stream
+    if (!count) return cudaSuccess;
+    size_t blocks = (count + GS_BLOCK - 1) / GS_BLOCK;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    gs_fill32_kernel<<<(unsigned)blocks, GS_BLOCK, 0, stream_>>>(dst, value, count);
+    ++launches_;
+    return cudaGetLastError();
   }
   cudaGraphExec_t graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks, const GsXbar* xbar) {
     // the column pointers are baked into the captured launches: if they changed (a peer graph was
