@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // Sharded pools: mailbox deliveries to other GPUs are fire-and-forget reductions over NVLink;
   // a system-scope fence by the issuing thread is what guarantees they have been performed at
   // the owner before this rank can signal the inter-tick barrier.
-  if (g.world > 1u && did_work) __threadfence_system();
+  if (g.world > 1u && did_work && !(g.flags & 8u)) __threadfence_system();  // 8: GSIM_FLAG_SHARD_LEAN_FENCE
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {

@@ -138,6 +138,10 @@ typedef struct gsim_config {
 #define GSIM_FLAG_LOG_GLOBAL_EVENTS 1u /* log Failed/Left/Join transitions of every member */
 #define GSIM_FLAG_NO_GRAPH 2u          /* launch tick kernels one by one (debug/profiling)  */
 #define GSIM_FLAG_SHARD_SYNC_SCAN 4u   /* sharded pools: scan mailboxes with ld.relaxed.sys (debug) */
+/* Sharded pools, measurement only: drop the per-thread fence.sys at the end of a tick and rely on
+ * the cumulativity of the one fence the releasing thread executes after the CTA barrier.  Not a
+ * supported mode until the 2/4/8-GPU digest tests have passed with it. */
+#define GSIM_FLAG_SHARD_LEAN_FENCE 8u
 /* Periodic push-pull anti-entropy ([U] memberlist/state.go pushPull, serf/delegate.go
  * LocalState/MergeRemoteState): every pushPullScale(push_pull_interval, n) each
  * member exchanges its tracked-broadcast mask and Lamport clocks with one random alive peer
