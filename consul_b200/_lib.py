@@ -116,6 +116,7 @@ SIGNATURES = [
     ("gsim_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
     ("gsim_graph_set", _i32, [_P, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
     ("gsim_member_reconnect_timeout_set", _i32, [_P, _u32, _u64]),
+    ("gsim_coordinate_get", _i32, [_P, _u32, C.POINTER(C.c_double)]),
     ("gsim_member_watch", _i32, [_P, _u32, _i32]),
     ("gsim_member_update", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("gsim_step", _i32, [_P, _u32]),

@@ -18,6 +18,7 @@
 
 #include "../../include/gsim.h"
 #include "gs_backend.h"
+#include "gs_coord.h"
 
 #ifndef GS_MAKE_BACKEND
 #define GS_MAKE_BACKEND gs_make_cuda_backend
@@ -558,6 +559,16 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     okk = okk && acol(&tx16, GS_MAX_RUMORS / 2);
     d.tx = reinterpret_cast<uint8_t*>(tx16);
   }
+  if (cfg->flags & GSIM_FLAG_COORDINATES) {  // Vivaldi state: 348 B per member, only when asked for
+    if (sharded) {
+      g_create_err = "network coordinates are not supported on sharded pools yet";
+      fprintf(stderr, "libgsim: %s\n", g_create_err.c_str());
+      gsim_pool_destroy(p);
+      return GSIM_ERR_INVALID;
+    }
+    okk = okk && alloc_col(p, &d.coord, cap * 2 * GS_COORD_WORDS) && alloc_col(p, &d.ctag, cap * 2) &&
+          alloc_col(p, &d.adj, cap * GS_ADJ_WINDOW) && alloc_col(p, &d.adj_idx, cap);
+  }
   if (cfg->flags & GSIM_FLAG_PUSH_PULL)  // push-pull mailboxes: 48 B per member, only when asked for
     okk = okk && acol(&d.ppreq, 2 * GS_PPK) && acol(&d.pp_clk, 4);
   uint32_t evcap = cfg->event_log_capacity ? cfg->event_log_capacity : 65536u;
@@ -641,6 +652,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     g.rot_g = (rot >> 16) % g.GI;
   }
   g.rows_per_rank = (uint32_t)p->rows_per_rank;
+  g.tick_seconds = (double)tick / 1.0e9;
+  g.coord_base_rtt_s = 0.0005;  // a direct ack inside one tick: half a millisecond on top of the matrix
   recompute_tables(p);
   if (!sharded && init_device_state(p) != GSIM_OK) {  // sharded pools: gsim_shard_ready
     g_create_err = be->last_error();
@@ -1308,6 +1321,23 @@ extern "C" int gsim_member_reconnect_timeout_set(gsim_pool* p, uint32_t id, uint
   });
 }
 
+// (*Serf).GetCoordinate / GetCachedCoordinate(name) — agent/router/router.go:62-67: the member's
+// current network coordinate (vec[8], error, adjustment, height; seconds).
+extern "C" int gsim_coordinate_get(gsim_pool* p, uint32_t id, double out[11]) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  GS_CONTROLLER_ONLY(p);
+  if (!p->d.coord) return fail(p, GSIM_ERR_STATE, "the pool was created without GSIM_FLAG_COORDINATES");
+  if (id >= p->g.n) return fail(p, GSIM_ERR_NOT_FOUND, "unknown member");
+  const size_t cap = p->g.cap;
+  uint32_t ta, tb;
+  if (!peek(p, p->d.ctag, id, &ta) || !peek(p, p->d.ctag, cap + id, &tb)) return fail(p, GSIM_ERR_CUDA, "peek");
+  const size_t slot = tb > ta ? 1 : 0;
+  for (size_t x = 0; x < GS_COORD_WORDS; ++x)
+    if (!peek(p, p->d.coord, (slot * GS_COORD_WORDS + x) * cap + id, &out[x])) return fail(p, GSIM_ERR_CUDA, "peek");
+  return GSIM_OK;
+}
+
 // Turn event logging for one member on or off after creation (gsim_member_desc.flags does it at
 // creation): the EventCh of that agent, polled through gsim_poll_events.
 extern "C" int gsim_member_watch(gsim_pool* p, uint32_t id, int on) {
@@ -1818,6 +1848,12 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   if (d.kst) add(d.kst, cap);
   for (uint32_t s = 0; s <= p->g.ring_mask; ++s)
     if (d.mailmap[s]) add(d.mailmap[s], cap / 32 * 4);
+  if (d.coord) {
+    add(d.coord, cap * 8 * 2 * GS_COORD_WORDS, 2 * GS_COORD_WORDS);
+    add(d.ctag, cap * 4 * 2, 2);
+    add(d.adj, cap * 8 * GS_ADJ_WINDOW, GS_ADJ_WINDOW);
+    add(d.adj_idx, cap * 4);
+  }
   if (d.ppreq) {
     add(d.ppreq, cap * 4 * 2 * GS_PPK, 2 * GS_PPK);
     add(d.pp_clk, cap * 4 * 4, 4);

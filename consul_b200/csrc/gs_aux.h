@@ -36,6 +36,20 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   d.event_min[i] = 0u;
   d.heard[i] = 0u;
   d.queued[i] = 0u;
+  if (d.coord != nullptr) {  // [U] coordinate.NewCoordinate: the origin, maximal error, minimal height
+    GsCoord o;
+    gs_coord_origin(o);
+    for (uint32_t slot = 0; slot < 2u; ++slot) {
+      double* out = d.coord + ((size_t)slot * GS_COORD_WORDS) * cap + i;
+      for (uint32_t x = 0; x < GS_COORD_DIM; ++x) out[(size_t)x * cap] = o.vec[x];
+      out[(size_t)8 * cap] = o.error;
+      out[(size_t)9 * cap] = o.adjustment;
+      out[(size_t)10 * cap] = o.height;
+      d.ctag[(size_t)slot * cap + i] = 0u;
+    }
+    for (uint32_t s = 0; s < GS_ADJ_WINDOW; ++s) d.adj[(size_t)s * cap + i] = 0.0;
+    d.adj_idx[i] = 0u;
+  }
   if (d.ppreq != nullptr) {
     for (uint32_t q = 0; q < 2u * GS_PPK; ++q) d.ppreq[(size_t)q * cap + i] = GS_EMPTY32;
     for (uint32_t q = 0; q < 4u; ++q) d.pp_clk[(size_t)q * cap + i] = 0u;
@@ -120,6 +134,16 @@ GS_DEV uint64_t gs_hash_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint
 #endif
     hm &= hm - 1;
     h = gs_mix64(h, (r << 8) | d.tx[GS_TX(r, cap, i)]);
+  }
+  if (d.coord != nullptr) {  // the member's current coordinate, bit for bit, and its adjustment window
+    const uint32_t slot = d.ctag[cap + i] > d.ctag[i] ? 1u : 0u;
+    const double* c = d.coord + ((size_t)slot * GS_COORD_WORDS) * cap + i;
+    for (uint32_t x = 0; x < GS_COORD_WORDS; ++x) {
+      uint64_t bits;
+      memcpy(&bits, &c[(size_t)x * cap], 8);
+      h = gs_mix64(h, bits);
+    }
+    h = gs_mix64(h, d.adj_idx[i]);
   }
   if (inb & GS_ACC_BIT) {
     const uint64_t* acc = d.acc + (size_t)cur * GS_K1MAX * cap;

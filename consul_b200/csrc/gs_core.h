@@ -285,6 +285,10 @@ struct GsGlobals {
   // graph_n == n rows are described (static topology: restricted segments, partial views).
   uint32_t graph_n;
   uint32_t reap_min_override;  // smallest per-member ReconnectTimeout override so far (ticks), 0 = none
+  uint32_t coord_pad;
+  // network coordinates (gs_coord.h, GSIM_FLAG_COORDINATES): round trip fed to Vivaldi on a direct
+  // ack = coord_base_rtt_s + (extra latency there and back) * tick_seconds
+  double coord_base_rtt_s, tick_seconds;
   GsRumor rumors[GS_MAX_RUMORS];
 };
 
@@ -317,6 +321,11 @@ struct GsDev {
   uint32_t* heard;
   uint32_t* queued;
   uint8_t* tx;  // retransmit counters, [GS_MAX_RUMORS / 2][cap][2]: see GS_TX
+  // network coordinates (gs_coord.h; null unless GSIM_FLAG_COORDINATES)
+  double* coord;        // [2 slots][GS_COORD_WORDS][cap]
+  uint32_t* ctag;       // [2 slots][cap]  tick the slot was written + 1 (0 = initial origin)
+  double* adj;          // [GS_ADJ_WINDOW][cap] adjustment samples
+  uint32_t* adj_idx;    // [cap]
   // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
   // GS_KSTAT builds (performance variant, see gs_kst_code): one byte per member with the 4-bit view
   // of key[0] (low nibble) and key[1] (high nibble) that peer selection needs; null otherwise

@@ -17,7 +17,10 @@
 // atomics (atomicOr on inbox[(t+1)&1], atomicMin chain on acc[(t+1)&1]) and consumed by
 // the receiving row in tick t+1.  Results do not depend on block scheduling.
 #pragma once
+#include <string.h>
+
 #include "gs_core.h"
+#include "gs_coord.h"
 
 #if defined(__CUDA_ARCH__)
 #define GS_DEV __device__ __forceinline__
@@ -231,6 +234,45 @@ GS_DEV uint32_t gs_peer_count(const GsDev& d, const GsGlobals& g, uint32_t i) {
 }
 GS_DEV uint32_t gs_peer_at(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t idx) {
   return g.graph_n == 0u ? idx : d.col_idx[d.row_ptr[i] + idx];
+}
+
+// ---- network coordinates: slot selection and the update on a direct ack (gs_coord.h) ---------
+GS_DEV uint32_t gs_coord_slot_for_reader(const GsDev& d, size_t cap, uint32_t j, uint32_t t) {
+  const uint32_t a = GS_LD_OTHER(&d.ctag[j]), b = GS_LD_OTHER(&d.ctag[cap + j]);
+  // a slot is readable at tick t if it was written before t (tag = tick + 1 <= t); newer wins
+  return (b <= t && (a > t || b > a)) ? 1u : 0u;
+}
+GS_DEV void gs_coord_load(const GsDev& d, size_t cap, uint32_t slot, uint32_t j, GsCoord& c) {
+  const double* base = d.coord + ((size_t)slot * GS_COORD_WORDS) * cap + j;
+  double w[GS_COORD_WORDS];
+  for (uint32_t x = 0; x < GS_COORD_WORDS; ++x) {
+    const uint64_t bits = GS_LD_OTHER64(reinterpret_cast<const uint64_t*>(base + (size_t)x * cap));
+    memcpy(&w[x], &bits, 8);
+  }
+  for (uint32_t x = 0; x < GS_COORD_DIM; ++x) c.vec[x] = w[x];
+  c.error = w[8];
+  c.adjustment = w[9];
+  c.height = w[10];
+}
+// [U] serf/ping_delegate.go NotifyPingComplete -> coordinate.Client.Update: member i got a direct
+// ack from j at tick t.
+GS_DEV void gs_coord_on_ack(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t j, uint32_t t) {
+  const size_t cap = g.cap;
+  const uint32_t ta = d.ctag[i], tb = d.ctag[cap + i];
+  const uint32_t mine = tb > ta ? 1u : 0u, spare = mine ^ 1u;  // the owner overwrites its OLDER slot
+  GsCoord c, other;
+  gs_coord_load(d, cap, mine, i, c);
+  gs_coord_load(d, cap, gs_coord_slot_for_reader(d, cap, j, t), j, other);
+  const double rtt = g.coord_base_rtt_s + (double)(gs_extra(g, i, j) + gs_extra(g, j, i)) * g.tick_seconds;
+  uint32_t idx = d.adj_idx[i];
+  gs_coord_client_update(c, other, rtt, d.adj + i, cap, &idx, g.seed_lo, g.seed_hi, i, t);
+  d.adj_idx[i] = idx;
+  double* out = d.coord + ((size_t)spare * GS_COORD_WORDS) * cap + i;
+  for (uint32_t x = 0; x < GS_COORD_DIM; ++x) out[(size_t)x * cap] = c.vec[x];
+  out[(size_t)8 * cap] = c.error;
+  out[(size_t)9 * cap] = c.adjustment;
+  out[(size_t)10 * cap] = c.height;
+  d.ctag[(size_t)spare * cap + i] = t + 1u;
 }
 
 // kRandomNodes ([U] memberlist/util.go): up to min(3n, 32) uniform draws `rand % n`,
@@ -628,6 +670,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
           due = t + g.P;
           sink.stat(GS_ST_ACKS, 1);
+          if (d.coord != nullptr) gs_coord_on_ack(d, g, i, target, t);  // the ack carries the peer's coordinate
         } else {
           m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
           d.probe_tgt[i] = target;
@@ -730,7 +773,7 @@ GS_DEV void gs_fast_load(const GsDev& d, uint32_t cur, uint32_t i, GsFastProbe& 
 
 GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uint32_t i,
                            GsFastProbe& f) {
-  if (g.loss_thr != 0u || g.graph_n != 0u) return false;  // CSR rows: generic path
+  if (g.loss_thr != 0u || g.graph_n != 0u || d.coord != nullptr) return false;  // CSR rows, coordinates: generic path
   if (gs_key_truth(f.k) != GS_TRUTH_UP || gs_key_rank(f.k) != GS_RANK_ALIVE) return false;
   if (gs_meta_stage(f.m) != GS_STAGE_IDLE || (f.m & (GS_META_DIRTY | GS_META_ISOLATED))) return false;
   if (f.cursor >= g.n) return false;  // ring wrap: re-key in the generic path

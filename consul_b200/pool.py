@@ -21,6 +21,7 @@ NEVER = 0xFFFFFFFF
 FLAG_LOG_GLOBAL_EVENTS = 1
 FLAG_NO_GRAPH = 2
 FLAG_PUSH_PULL = 32
+FLAG_COORDINATES = 64
 MEMBER_WATCHED = 1
 
 
@@ -165,6 +166,13 @@ class Pool:
     def member_reconnect_timeout_set(self, member: int, timeout_ns: int):
         """serf.Config.ReconnectTimeoutOverride result for one member (0 = the pool's value)."""
         self._ck(self.lib.gsim_member_reconnect_timeout_set(self.h, member, timeout_ns))
+
+    def coordinate(self, member: int):
+        """(*Serf).GetCoordinate: (vec[8], error, adjustment, height) in seconds."""
+        out = (C.c_double * 11)()
+        self._ck(self.lib.gsim_coordinate_get(self.h, member, out))
+        v = [float(x) for x in out]
+        return v[:8], v[8], v[9], v[10]
 
     def latency_set(self, lat):
         """lat: square matrix (n_dcs x n_dcs) of one-way latencies in ticks (>= 1), or None."""

@@ -148,6 +148,11 @@ typedef struct gsim_config {
  * (push at tick t, the partner's answer arrives at t+2).  Off by default: the headline configs
  * of BASELINE.json run shorter than one push-pull interval at their sizes. */
 #define GSIM_FLAG_PUSH_PULL 32u
+/* Network coordinates ([U] serf/coordinate: Vivaldi with height, adjustment window and gravity;
+ * SURVEY 8f N3).  Every direct probe ack updates the prober's coordinate with the measured round
+ * trip (0.5 ms + the latency matrix there and back) and the target's coordinate.  348 B per
+ * member; single-GPU pools.  IEEE double arithmetic, bit-identical to the oracle. */
+#define GSIM_FLAG_COORDINATES 64u
 
 /* Preset defaults.  LAN/WAN: [U] memberlist DefaultLANConfig/DefaultWANConfig as
  * pinned by agent/config/runtime.go:1271-1413 with Consul's overrides
@@ -239,6 +244,10 @@ int gsim_graph_set(gsim_pool* p, uint32_t n_rows, const uint32_t* row_ptr, const
  * The override callback is host code; its result for member `id` is stored with the member and
  * used by the reaper instead of the pool's reconnect_timeout_ns.  0 = the pool's value. */
 int gsim_member_reconnect_timeout_set(gsim_pool* p, uint32_t id, uint64_t timeout_ns);
+
+/* (*Serf).GetCoordinate() / GetCachedCoordinate(name) — agent/router/router.go:62-67.
+ * out = {Vec[0..7], Error, Adjustment, Height} in seconds, as coordinate.Coordinate. */
+int gsim_coordinate_get(gsim_pool* p, uint32_t id, double out[11]);
 
 /* Event logging of one member on/off after creation (that agent's EventCh; see
  * gsim_member_desc.flags / GSIM_MEMBER_WATCHED and gsim_poll_events). */

@@ -9,7 +9,7 @@
 set -e
 cd "$(dirname "$0")/.."
 SRC="consul_b200/csrc/gs_cuda.cu consul_b200/csrc/gs_vmm.cu consul_b200/csrc/gs_api.cpp"
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -ffp-contract=off -shared"
 nvcc $FLAGS -DGS_KSTAT=1 -o consul_b200/libgsim_kstat.so $SRC
 nvcc $FLAGS -DGS_MAILMAP=1 -o consul_b200/libgsim_mailmap.so $SRC
 nvcc $FLAGS -DGS_KSTAT=1 -DGS_MAILMAP=1 -o consul_b200/libgsim_both.so $SRC
