@@ -14,6 +14,7 @@
 // One serf::Pool = one gossip pool (LAN or WAN) = one gsim_pool on the device; every
 // serf::Create on it adds a virtual agent.  Time is explicit: Pool::Step(ticks).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -55,6 +56,19 @@ struct Event {
   uint32_t LTime = 0;           // user events
   std::string Name, Payload;
   uint32_t Tick = 0;
+};
+
+// coordinate.Coordinate ([U] serf/coordinate/coordinate.go), seconds
+struct Coordinate {
+  double Vec[8];
+  double Error, Adjustment, Height;
+  // Coordinate.DistanceTo(other) in seconds
+  double DistanceTo(const Coordinate& o) const {
+    double sum = 0.0;
+    for (int k = 0; k < 8; ++k) sum += (Vec[k] - o.Vec[k]) * (Vec[k] - o.Vec[k]);
+    const double raw = std::sqrt(sum) + Height + o.Height, adjusted = raw + Adjustment + o.Adjustment;
+    return adjusted > 0.0 ? adjusted : raw;
+  }
 };
 
 struct Config {
@@ -112,6 +126,16 @@ class Pool {
   // Deliver pending serf events to the EventCh of every agent created on this pool.
   void PumpEvents();
   Member describe(uint32_t id, int status, uint32_t inc);
+  Coordinate coordinate_of(uint32_t id) {
+    double w[11];
+    check(gsim_coordinate_get(h_, id, w));
+    Coordinate c;
+    for (int k = 0; k < 8; ++k) c.Vec[k] = w[k];
+    c.Error = w[8];
+    c.Adjustment = w[9];
+    c.Height = w[10];
+    return c;
+  }
   gsim_pool* handle() { return h_; }
   void check(int rc) {
     if (rc != 0) throw Error(rc, std::string(gsim_last_error(h_)).empty() ? gsim_strerror(rc) : gsim_last_error(h_));
@@ -181,6 +205,15 @@ class Serf {
     if (bytes > 512) bytes = 512;  // memberlist.MetaMaxSize
     p_.check(gsim_member_update(p_.h_, id_, bytes, nullptr));
     apply_reconnect_override();
+  }
+  // GetCoordinate() / GetCachedCoordinate(name) — agent/router/router.go:62-67: Vivaldi network
+  // coordinates (pools created with GSIM_FLAG_COORDINATES).
+  Coordinate GetCoordinate() { return p_.coordinate_of(id_); }
+  bool GetCachedCoordinate(const std::string& name, Coordinate* out) {
+    auto it = p_.by_name_.find(name);
+    if (it == p_.by_name_.end()) return false;
+    *out = p_.coordinate_of(it->second);
+    return true;
   }
   void Leave() { p_.check(gsim_leave(p_.h_, id_)); }
   void Shutdown() { p_.check(gsim_crash(p_.h_, id_)); }  // without Leave(): a crash (server_test.go:725)

@@ -50,7 +50,7 @@ namespace {
 
 const uint32_t NONE32 = 0xFFFFFFFFu;
 enum { ST_IDLE = 0, ST_WAIT_TIMEOUT = 1, ST_WAIT_DEADLINE = 2 };
-enum { PUR_PHASE = 1, PUR_PERM = 2, PUR_GOSSIP = 3, PUR_RELAY = 4, PUR_LOSS = 5, PUR_CRASH = 6, PUR_PUSHPULL = 7 };
+enum { PUR_PHASE = 1, PUR_PERM = 2, PUR_GOSSIP = 3, PUR_RELAY = 4, PUR_LOSS = 5, PUR_CRASH = 6, PUR_PUSHPULL = 7, PUR_COORD = 8 };
 const uint32_t PUSHPULL_BACKLOG = 4;  // push-pull connections one member serves per tick
 enum { LK_PING = 0, LK_ACK, LK_INDREQ, LK_INDPING, LK_INDACK, LK_INDFWD, LK_NACK, LK_GOSSIP };
 const uint32_t KRANDOM_MAX_TRIES = 32;  // upstream: 3n (memberlist/util.go kRandomNodes)
@@ -141,6 +141,78 @@ uint32_t refute_incarnation(uint32_t cur, uint32_t accused) {
   return inc;
 }
 
+// ---- network coordinates ([U] serf/coordinate: Vivaldi + height + adjustment + gravity) ------------
+// Restated from the published algorithm (client.go Update = updateVivaldi, updateAdjustment,
+// updateGravity; coordinate.go DistanceTo, ApplyForce, unitVectorAt), minus the per-peer latency
+// filter.  Plain doubles in the textual order of the formulas; built with -ffp-contract=off.
+struct Coordinate {
+  double v[8];
+  double err, adj, h;
+};
+const int ADJ_WINDOW = 20;
+const double V_ERR_MAX = 1.5, V_CE = 0.25, V_CC = 0.25, V_HEIGHT_MIN = 10.0e-6, V_RHO = 150.0, V_ZERO = 1.0e-6;
+
+Coordinate origin_coordinate() {
+  Coordinate c;
+  for (double& x : c.v) x = 0.0;
+  c.err = V_ERR_MAX;
+  c.adj = 0.0;
+  c.h = V_HEIGHT_MIN;
+  return c;
+}
+double norm8(const double* v) {
+  double acc = 0.0;
+  for (int k = 0; k < 8; ++k) acc += v[k] * v[k];
+  return sqrt(acc);
+}
+double raw_distance(const Coordinate& a, const Coordinate& b) {
+  double d[8];
+  for (int k = 0; k < 8; ++k) d[k] = a.v[k] - b.v[k];
+  return norm8(d) + a.h + b.h;
+}
+double distance_seconds(const Coordinate& a, const Coordinate& b) {  // DistanceTo(...).Seconds()
+  double dist = raw_distance(a, b);
+  double with_adjustments = dist + a.adj + b.adj;
+  if (with_adjustments > 0.0) dist = with_adjustments;
+  int64_t nanos = (int64_t)(dist * 1.0e9);  // time.Duration truncates
+  return (double)(nanos / 1000000000) + (double)(nanos % 1000000000) / 1.0e9;
+}
+void apply_force(Coordinate& c, double force, const Coordinate& other, uint64_t seed, uint32_t member, uint32_t tick,
+                 uint32_t which) {
+  double u[8];
+  for (int k = 0; k < 8; ++k) u[k] = c.v[k] - other.v[k];
+  double mag = norm8(u);
+  if (mag > V_ZERO) {
+    double inv = 1.0 / mag;
+    for (int k = 0; k < 8; ++k) u[k] = u[k] * inv;
+  } else {  // coincident points: a pseudo-random direction
+    Rand4 a = philox4x32_10(seed, member, tick, PUR_COORD, which * 2), b = philox4x32_10(seed, member, tick, PUR_COORD, which * 2 + 1);
+    for (int k = 0; k < 4; ++k) {
+      u[k] = (double)a.v[k] / 4294967296.0 - 0.5;
+      u[4 + k] = (double)b.v[k] / 4294967296.0 - 0.5;
+    }
+    double m2 = norm8(u);
+    if (m2 > V_ZERO) {
+      double inv = 1.0 / m2;
+      for (int k = 0; k < 8; ++k) u[k] = u[k] * inv;
+    } else {
+      for (int k = 0; k < 8; ++k) u[k] = 0.0;
+      u[0] = 1.0;
+    }
+    mag = 0.0;
+  }
+  for (int k = 0; k < 8; ++k) c.v[k] = c.v[k] + u[k] * force;
+  if (mag > V_ZERO) {
+    c.h = (c.h + other.h) * force / mag + c.h;
+    if (!(c.h > V_HEIGHT_MIN)) c.h = V_HEIGHT_MIN;
+  }
+}
+bool coordinate_is_valid(const Coordinate& c) {
+  bool ok = std::isfinite(c.err) && std::isfinite(c.adj) && std::isfinite(c.h);
+  for (double x : c.v) ok = ok && std::isfinite(x);
+  return ok;
+}
+
 // ---- data ---------------------------------------------------------------------------------
 struct View {  // what everybody else can read about a member during a tick
   uint8_t truth = 0, rank = 0, pending = 0;
@@ -159,10 +231,14 @@ struct Member {
   uint32_t n_sus_from = 0;
   uint32_t change_tick = 0;
   uint64_t own_reconnect_timeout_ns = 0;  // ReconnectTimeoutOverride result for this member (0: pool default)
+  Coordinate coord = origin_coordinate();  // serf's coordinate client of this member
+  double adj_samples[ADJ_WINDOW];
+  uint32_t adj_index = 0;
   uint32_t ltime_member = 1, ltime_event = 1, event_min = 0;
   uint32_t heard = 0, queued = 0;
   uint8_t tx[GSIM_MAX_RUMORS];
   Member() {
+    for (double& x : adj_samples) x = 0.0;
     memset(tx, 0, sizeof(tx));
     for (int i = 0; i < MAX_SUS; ++i) sus_from[i] = NONE32;
   }
@@ -196,6 +272,7 @@ struct Tally {
   std::vector<Accusation> accusations;
   std::vector<gsim_event> events;
   std::vector<std::pair<uint32_t, View>> published;
+  std::vector<uint32_t> moved;  // members whose coordinate changed in this tick
   std::vector<PushPull> pushpulls;
   int32_t crashed_dead = 0;
   Tally() { clear(); }
@@ -205,6 +282,7 @@ struct Tally {
     accusations.clear();
     events.clear();
     published.clear();
+    moved.clear();
     pushpulls.clear();
     crashed_dead = 0;
   }
@@ -221,6 +299,7 @@ struct Oracle {
   std::vector<Member> m;
   std::vector<View> pub;                 // published views (state at the start of the tick)
   std::vector<uint32_t> pub_change_tick; // published change ticks
+  std::vector<Coordinate> pub_coord;     // published coordinates (GSIM_FLAG_COORDINATES), as of the tick start
   static const uint32_t RING = 8;        // arrival slots kept per member (one-way latency <= 7 ticks)
   std::vector<uint32_t> inbox[RING];     // rumor bits by arrival tick mod RING (bit 31: accused)
   // WAN pools (BASELINE config 5): one-way latency in ticks between synthetic datacenters;
@@ -668,6 +747,32 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
           if (me.awareness) me.awareness--;
           me.due = t + o.P;
           ta.c[GSIM_STAT_ACKS]++;
+          if (o.cfg.flags & GSIM_FLAG_COORDINATES) {
+            // [U] serf/ping_delegate.go NotifyPingComplete -> coordinate.Client.Update(other, rtt)
+            const Coordinate& other = o.pub_coord[target];
+            double rtt = 0.0005 + (double)round_trip(o, i, target) * ((double)o.tick_ns / 1.0e9);
+            Coordinate& c = me.coord;
+            double dist = distance_seconds(c, other);                       // updateVivaldi
+            if (rtt < V_ZERO) rtt = V_ZERO;
+            double wrongness = fabs(dist - rtt) / rtt;
+            double total_error = c.err + other.err;
+            if (total_error < V_ZERO) total_error = V_ZERO;
+            double weight = c.err / total_error;
+            c.err = V_CE * weight * wrongness + c.err * (1.0 - V_CE * weight);
+            if (c.err > V_ERR_MAX) c.err = V_ERR_MAX;
+            double force = V_CC * weight * (rtt - dist);
+            apply_force(c, force, other, o.cfg.seed, i, t, 0);
+            me.adj_samples[me.adj_index] = rtt - raw_distance(c, other);    // updateAdjustment
+            me.adj_index = (me.adj_index + 1) % ADJ_WINDOW;
+            double sum = 0.0;
+            for (double x : me.adj_samples) sum += x;
+            c.adj = sum / (2.0 * (double)ADJ_WINDOW);
+            Coordinate org = origin_coordinate();                            // updateGravity
+            double q = distance_seconds(org, c) / V_RHO;
+            apply_force(c, -1.0 * (q * q), org, o.cfg.seed, i, t, 1);
+            if (!coordinate_is_valid(c)) c = origin_coordinate();
+            ta.moved.push_back(i);
+          }
         } else {
           me.stage = ST_WAIT_TIMEOUT;
           me.probe_target = target;
@@ -764,6 +869,7 @@ void run_tick(Oracle& o) {
       o.pub[pv.first] = pv.second;
       o.pub_change_tick[pv.first] = o.m[pv.first].change_tick;
     }
+    for (uint32_t who : ta.moved) o.pub_coord[who] = o.m[who].coord;
     o.arriving.insert(o.arriving.end(), ta.accusations.begin(), ta.accusations.end());
     for (const gsim_event& e : ta.events) {
       if (o.events.size() < o.evcap) o.events.push_back(e);
@@ -1043,6 +1149,7 @@ void* oracle_create(const gsim_config* cfg, int threads) {
   o->m.resize(cfg->n_initial);
   o->pub.resize(cfg->n_initial);
   o->pub_change_tick.assign(cfg->n_initial, 0);
+  o->pub_coord.assign(cfg->n_initial, origin_coordinate());
   for (uint32_t b = 0; b < Oracle::RING; ++b) o->inbox[b].assign(cfg->n_initial, 0);
   memset(o->latency, 1, sizeof(o->latency));
   o->up_count = cfg->n_initial;
@@ -1075,6 +1182,7 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   o.m.emplace_back();
   o.pub.emplace_back();
   o.pub_change_tick.push_back(0);
+  o.pub_coord.push_back(origin_coordinate());
   for (uint32_t b = 0; b < Oracle::RING; ++b) o.inbox[b].push_back(0);
   Member& me = o.m.back();
   me.v.truth = GSIM_TRUTH_UP;
@@ -1274,6 +1382,18 @@ int oracle_member_reconnect_timeout_set(void* h, uint32_t id, uint64_t timeout_n
   Oracle& o = *(Oracle*)h;
   if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
   o.m[id].own_reconnect_timeout_ns = timeout_ns;
+  return GSIM_OK;
+}
+
+int oracle_coordinate_get(void* h, uint32_t id, double out[11]) {
+  Oracle& o = *(Oracle*)h;
+  if (!(o.cfg.flags & GSIM_FLAG_COORDINATES)) return GSIM_ERR_STATE;
+  if (id >= o.m.size()) return GSIM_ERR_NOT_FOUND;
+  const Coordinate& c = o.m[id].coord;
+  for (int k = 0; k < 8; ++k) out[k] = c.v[k];
+  out[8] = c.err;
+  out[9] = c.adj;
+  out[10] = c.h;
   return GSIM_OK;
 }
 
@@ -1490,6 +1610,16 @@ int oracle_state_hash(void* h, uint64_t out[4]) {
       x = mix(x, o.inbox[(o.now + ahead) % Oracle::RING][i] & o.active);
     for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
       if ((heard >> r) & 1) x = mix(x, (r << 8) | me.tx[r]);
+    if (o.cfg.flags & GSIM_FLAG_COORDINATES) {
+      const Coordinate& c = me.coord;
+      const double words[11] = {c.v[0], c.v[1], c.v[2], c.v[3], c.v[4], c.v[5], c.v[6], c.v[7], c.err, c.adj, c.h};
+      for (double w : words) {
+        uint64_t bits;
+        memcpy(&bits, &w, 8);
+        x = mix(x, bits);
+      }
+      x = mix(x, me.adj_index);
+    }
     if (has_acc) {
       int cnt = 0;
       size_t q = ap;

@@ -275,6 +275,40 @@ static void test_short_reconnect_timeout() {
   std::puts("PASS TestClient_ShortReconnectTimeout");
 }
 
+// GetCoordinate / GetCachedCoordinate (agent/router/router.go:62-67 sorts servers by the distance
+// between these): two datacenters 1 s apart end up about 1 s apart in coordinate space.
+static void test_coordinates() {
+  gsim_config c = Pool::DefaultWANConfig();
+  c.capacity = 256;
+  c.n_initial = 254;  // two tiles of anonymous members = two datacenters, plus two named agents
+  c.seed = 9;
+  c.flags = GSIM_FLAG_COORDINATES;
+  c.mailbox_depth = 8;
+  Pool pool(c);
+  const uint8_t lat[4] = {1, 2, 2, 1};  // one tick of extra latency each way between the datacenters
+  CHECK(gsim_latency_set(pool.handle(), 2, lat) == 0);
+  Config ca, cb;
+  ca.NodeName = "a.dc2";
+  cb.NodeName = "b.dc2";
+  auto a = Serf::Create(pool, ca), b = Serf::Create(pool, cb);  // ids 254, 255: second tile = datacenter 1
+  uint32_t seed = 0;
+  int n_ok = 0;
+  CHECK(gsim_join(pool.handle(), a->id(), &seed, 1, 1, &n_ok) == 0 && n_ok == 1);
+  CHECK(gsim_join(pool.handle(), b->id(), &seed, 1, 1, &n_ok) == 0 && n_ok == 1);
+  pool.Step(3000);
+  Coordinate here = a->GetCoordinate(), near, far;
+  CHECK(a->GetCachedCoordinate("b.dc2", &near) && !a->GetCachedCoordinate("nosuch", &near));
+  double w[11];
+  CHECK(gsim_coordinate_get(pool.handle(), 3, w) == 0);  // member 3 lives in the other datacenter
+  for (int k = 0; k < 8; ++k) far.Vec[k] = w[k];
+  far.Error = w[8];
+  far.Adjustment = w[9];
+  far.Height = w[10];
+  CHECK(here.DistanceTo(near) < 0.2);                                  // same datacenter: sub-tick
+  CHECK(here.DistanceTo(far) > 0.6 && here.DistanceTo(far) < 1.4);     // 2 x 0.5 s of extra latency
+  std::puts("PASS GetCoordinate / GetCachedCoordinate");
+}
+
 static void test_user_event() {
   Pool pool(test_cfg());
   std::deque<Event> chs, chc;
@@ -336,6 +370,7 @@ int main(int argc, char** argv) {
       test_set_tags();
       test_merge_delegate();
       test_short_reconnect_timeout();
+      test_coordinates();
       std::puts("ALL PASS");
       return 0;
     }

@@ -6,7 +6,7 @@ import random
 
 import numpy as np
 
-from consul_b200.pool import FLAG_PUSH_PULL, consul_test_config, lan_config, wan_config
+from consul_b200.pool import FLAG_COORDINATES, FLAG_PUSH_PULL, consul_test_config, lan_config, wan_config
 from parity import check_invariants, compare_pools
 
 MS = 1_000_000
@@ -29,6 +29,8 @@ def random_config(rng: random.Random, lib):
     if rng.random() < 0.3:
         kw["flags"] |= FLAG_PUSH_PULL
         kw["push_pull_interval_ns"] = rng.choice([300, 1000, 4000]) * MS
+    if rng.random() < 0.2:
+        kw["flags"] |= FLAG_COORDINATES                      # the digest folds every coordinate bit for bit
     if rng.random() < 0.3:
         kw.update(reap_interval_ns=rng.choice([100, 500]) * MS, reconnect_timeout_ns=rng.choice([200, 2000]) * MS,
                   tombstone_timeout_ns=rng.choice([200, 2000]) * MS)
@@ -59,9 +61,11 @@ def random_graph(rng: random.Random, n: int):
     return rp, np.concatenate([np.array(r, dtype=np.uint32) for r in rows])
 
 
-def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True):
+def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True, single_gpu_features: bool = True):
     rng = random.Random(seed)
     cfg, latency = random_config(rng, lib)
+    if not single_gpu_features:                                # sharded pools: no network coordinates yet
+        cfg.flags &= ~FLAG_COORDINATES
     pools = make(cfg)
     if latency is not None:
         for p in pools:

@@ -41,6 +41,7 @@ _SIGS = [
     ("oracle_latency_set", _i32, [_P, _u32, C.POINTER(C.c_uint8)]),
     ("oracle_graph_set", _i32, [_P, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
     ("oracle_member_reconnect_timeout_set", _i32, [_P, _u32, C.c_uint64]),
+    ("oracle_coordinate_get", _i32, [_P, _u32, C.POINTER(C.c_double)]),
     ("oracle_member_watch", _i32, [_P, _u32, _i32]),
     ("oracle_member_update", _i32, [_P, _u32, _u32, C.POINTER(_u32)]),
     ("oracle_step", _i32, [_P, _u32]),
@@ -158,6 +159,12 @@ class OraclePool:
 
     def member_reconnect_timeout_set(self, member, timeout_ns):
         self._ck(self.lib.oracle_member_reconnect_timeout_set(self.h, member, timeout_ns))
+
+    def coordinate(self, member):
+        out = (C.c_double * 11)()
+        self._ck(self.lib.oracle_coordinate_get(self.h, member, out))
+        v = [float(x) for x in out]
+        return v[:8], v[8], v[9], v[10]
 
     def member_watch(self, member, on=True):
         self._ck(self.lib.oracle_member_watch(self.h, member, int(on)))

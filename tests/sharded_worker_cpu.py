@@ -105,7 +105,8 @@ from oracle_binding import OraclePool as _Oracle  # noqa: E402
 fuzz_ok = True
 for fseed in (3, 17, 251, 404):
     try:
-        fuzz_ops.run_sequence(lambda cfg: [ShardedPool(cfg, L), _Oracle(cfg)], L, fseed, n_ops=40, columns=False)
+        fuzz_ops.run_sequence(lambda cfg: [ShardedPool(cfg, L), _Oracle(cfg)], L, fseed, n_ops=40, columns=False,
+                              single_gpu_features=False)
     except AssertionError as e:
         fuzz_ok = False
         print("FUZZ MISMATCH rank", rank, "seed", fseed, str(e)[:800], flush=True)

@@ -21,7 +21,7 @@ def run(binary, extended=False):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
     names = ("TestServer_LANReap (reaper)", "TestServer_JoinWAN", "Serf.SetTags", "TestMerge_LAN",
-             "TestClient_ShortReconnectTimeout") if extended else \
+             "TestClient_ShortReconnectTimeout", "GetCoordinate") if extended else \
         ("TestServer_JoinLAN", "TestServer_LANReap", "TestClientServer_UserEvent", "TestAgent_Leave")
     for name in names:
         assert "PASS " + name in r.stdout
