@@ -28,7 +28,13 @@
 
 namespace {
 
-struct DevSink {
+// COORDS selects the tick-kernel instantiation that carries the network-coordinate update
+// (gs_coord.h, ~150 double-precision operations per direct ack).  The default instantiation
+// contains none of that code, so pools without GSIM_FLAG_COORDINATES run exactly the kernel the
+// round-1 profiles describe.
+template <bool COORDS>
+struct DevSinkT {
+  static constexpr bool kCoords = COORDS;
   uint32_t* s_stat;
   uint32_t* s_heard;
   __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx], v); }
@@ -55,6 +61,7 @@ struct DevSink {
     }
   }
 };
+typedef DevSinkT<false> DevSink;
 
 #ifndef GS_MIN_BLOCKS
 #define GS_MIN_BLOCKS 3
@@ -86,6 +93,7 @@ __device__ __forceinline__ void gs_cp_async_wait() {
 // path together — own columns, target gathers and commits are each issued for all four
 // before the first is consumed — so the tile pays two dependent memory latencies, not eight.
 // Whatever the fast path declines goes to the generic gs_row_step.
+template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
   __shared__ uint32_t s_stat[GS_NSTAT];
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 #endif
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
-  DevSink sink{s_stat, s_heard};
+  DevSinkT<COORDS> sink{s_stat, s_heard};
 
 #ifdef GS_EARLY_A
   // Performance variant: which tiles of this chunk start a probe at this tick is known
@@ -480,7 +488,8 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gs_tick_kernel, d, g_dev, k, 1u);
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_tick_kernel<true>, d, g_dev, k, 1u)
+                 : cudaLaunchKernelEx(&cfg, gs_tick_kernel<false>, d, g_dev, k, 1u);
 }
 
 // Several ticks in one cooperative launch (single-GPU pools).
@@ -489,7 +498,8 @@ static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const G
   GsDev dd = d;
   uint32_t k0 = 0;
   void* args[] = {(void*)&dd, (void*)&g_dev, (void*)&k0, (void*)&n_ticks};
-  return cudaLaunchCooperativeKernel((const void*)gs_tick_kernel, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
+  const void* fn = d.coord ? (const void*)gs_tick_kernel<true> : (const void*)gs_tick_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
 }
 
 __global__ void __launch_bounds__(GS_BLOCK) gs_fill32_kernel(uint32_t* dst, uint32_t value, size_t count) {
@@ -520,7 +530,7 @@ class CudaBackend : public GsBackend {
     cudaEventCreate(&ev1_);
     int sms = 148, occ = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel, GS_BLOCK, 0) != cudaSuccess || occ < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel<false>, GS_BLOCK, 0) != cudaSuccess || occ < 1)
       occ = 4;
     // measurement knob: fewer resident CTAs per SM leave room for the NEXT tick's CTAs to become
     // resident early under programmatic dependent launch (a full machine cannot overlap)

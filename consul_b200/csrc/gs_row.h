@@ -237,13 +237,13 @@ GS_DEV uint32_t gs_peer_at(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
 }
 
 // ---- network coordinates: slot selection and the update on a direct ack (gs_coord.h) ---------
-GS_DEV uint32_t gs_coord_slot_for_reader(const GsDev& d, size_t cap, uint32_t j, uint32_t t) {
-  const uint32_t a = GS_LD_OTHER(&d.ctag[j]), b = GS_LD_OTHER(&d.ctag[cap + j]);
+GS_DEV uint32_t gs_coord_slot_for_reader(const uint32_t* ctag, size_t cap, uint32_t j, uint32_t t) {
+  const uint32_t a = GS_LD_OTHER(&ctag[j]), b = GS_LD_OTHER(&ctag[cap + j]);
   // a slot is readable at tick t if it was written before t (tag = tick + 1 <= t); newer wins
   return (b <= t && (a > t || b > a)) ? 1u : 0u;
 }
-GS_DEV void gs_coord_load(const GsDev& d, size_t cap, uint32_t slot, uint32_t j, GsCoord& c) {
-  const double* base = d.coord + ((size_t)slot * GS_COORD_WORDS) * cap + j;
+GS_DEV void gs_coord_load(const double* coord, size_t cap, uint32_t slot, uint32_t j, GsCoord& c) {
+  const double* base = coord + ((size_t)slot * GS_COORD_WORDS) * cap + j;
   double w[GS_COORD_WORDS];
   for (uint32_t x = 0; x < GS_COORD_WORDS; ++x) {
     const uint64_t bits = GS_LD_OTHER64(reinterpret_cast<const uint64_t*>(base + (size_t)x * cap));
@@ -256,23 +256,32 @@ GS_DEV void gs_coord_load(const GsDev& d, size_t cap, uint32_t slot, uint32_t j,
 }
 // [U] serf/ping_delegate.go NotifyPingComplete -> coordinate.Client.Update: member i got a direct
 // ack from j at tick t.
-GS_DEV void gs_coord_on_ack(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t j, uint32_t t) {
+// (out of line on the device: ~150 double-precision operations must not cost the tick kernel's hot
+// path a single register)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void gs_coord_on_ack(double* coord, uint32_t* ctag, double* adj, uint32_t* adj_idx, const GsGlobals& g, uint32_t i,
+                     uint32_t j, uint32_t t) {  // (column pointers by value: taking the address of the
+                                                 // kernel's GsDev parameter would copy it to the stack)
   const size_t cap = g.cap;
-  const uint32_t ta = d.ctag[i], tb = d.ctag[cap + i];
+  const uint32_t ta = ctag[i], tb = ctag[cap + i];
   const uint32_t mine = tb > ta ? 1u : 0u, spare = mine ^ 1u;  // the owner overwrites its OLDER slot
   GsCoord c, other;
-  gs_coord_load(d, cap, mine, i, c);
-  gs_coord_load(d, cap, gs_coord_slot_for_reader(d, cap, j, t), j, other);
+  gs_coord_load(coord, cap, mine, i, c);
+  gs_coord_load(coord, cap, gs_coord_slot_for_reader(ctag, cap, j, t), j, other);
   const double rtt = g.coord_base_rtt_s + (double)(gs_extra(g, i, j) + gs_extra(g, j, i)) * g.tick_seconds;
-  uint32_t idx = d.adj_idx[i];
-  gs_coord_client_update(c, other, rtt, d.adj + i, cap, &idx, g.seed_lo, g.seed_hi, i, t);
-  d.adj_idx[i] = idx;
-  double* out = d.coord + ((size_t)spare * GS_COORD_WORDS) * cap + i;
+  uint32_t idx = adj_idx[i];
+  gs_coord_client_update(c, other, rtt, adj + i, cap, &idx, g.seed_lo, g.seed_hi, i, t);
+  adj_idx[i] = idx;
+  double* out = coord + ((size_t)spare * GS_COORD_WORDS) * cap + i;
   for (uint32_t x = 0; x < GS_COORD_DIM; ++x) out[(size_t)x * cap] = c.vec[x];
   out[(size_t)8 * cap] = c.error;
   out[(size_t)9 * cap] = c.adjustment;
   out[(size_t)10 * cap] = c.height;
-  d.ctag[(size_t)spare * cap + i] = t + 1u;
+  ctag[(size_t)spare * cap + i] = t + 1u;
 }
 
 // kRandomNodes ([U] memberlist/util.go): up to min(3n, 32) uniform draws `rand % n`,
@@ -670,7 +679,9 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           m = gs_meta_set_aw(m, aw ? aw - 1u : 0u);
           due = t + g.P;
           sink.stat(GS_ST_ACKS, 1);
-          if (d.coord != nullptr) gs_coord_on_ack(d, g, i, target, t);  // the ack carries the peer's coordinate
+          if constexpr (Sink::kCoords) {  // the ack carries the peer's coordinate
+            if (d.coord != nullptr) gs_coord_on_ack(d.coord, d.ctag, d.adj, d.adj_idx, g, i, target, t);
+          }
         } else {
           m = gs_meta_set_stage(m, GS_STAGE_WAIT_T);
           d.probe_tgt[i] = target;

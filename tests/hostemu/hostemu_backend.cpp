@@ -23,6 +23,7 @@
 namespace {
 
 struct HostSink {
+  static constexpr bool kCoords = true;  // the host build always carries the coordinate update
   uint64_t* stats;
   uint32_t* heard_cnt;
   uint32_t local_heard[32];
