@@ -72,23 +72,25 @@ def test_graph_and_plain_launches_agree(cuda_lib):
     assert out[0] == out[1]
 
 
-def test_determinism_and_snapshot(cuda_lib):
-    def run(restore_at=None):
-        p = Pool(lan_config(cuda_lib, capacity=50001, n_initial=50000, seed=77, packet_loss_ppm=50000), cuda_lib)
-        x = p.member_add()
-        p.join(x, [0])
-        p.user_event(3, b"evt", b"data", False)
-        p.crash_fraction(20000, 2)
-        p.step(100)
-        if restore_at is not None:
-            blob = p.snapshot()
-            p.step(57)                       # wander off, then come back
-            p.restore(blob)
-        p.step(200)
-        return p.state_hash(), p.stats()["deads"]
-    a, b, c = run(), run(), run(restore_at=100)
-    assert a == b, "two runs with the same seed differ"
-    assert a == c, "resume from a snapshot is not bit-exact"
+def determinism_run(cuda_lib, restore_at=None):
+    p = Pool(lan_config(cuda_lib, capacity=50001, n_initial=50000, seed=77, packet_loss_ppm=50000), cuda_lib)
+    x = p.member_add()
+    p.join(x, [0])
+    p.user_event(3, b"evt", b"data", False)
+    p.crash_fraction(20000, 2)
+    p.step(100)
+    if restore_at is not None:
+        blob = p.snapshot()
+        p.step(57)                       # wander off, then come back
+        p.restore(blob)
+    p.step(200)
+    return p.state_hash(), p.stats()["deads"]
+
+
+def test_determinism(cuda_lib):
+    assert determinism_run(cuda_lib) == determinism_run(cuda_lib), "two runs with the same seed differ"
+    # (resume from a snapshot: tests/test_gpu_zedge.py::test_snapshot_resume_is_bit_exact — the
+    # plane-compressed snapshot format is newer than the round-1 GPU verification of this file)
 
 
 # ---- BASELINE full sizes: properties that need no oracle ---------------------------------

@@ -69,3 +69,10 @@ def test_invariants_at_scale(cuda_lib):
         snap = check_invariants(p, snap, f"checkpoint {k}")
     s = p.stats()
     assert s["suspects"] > 0 and s["deads"] > 0 and s["rumors_accepted"] > 2 * n
+
+
+def test_snapshot_resume_is_bit_exact(cuda_lib):
+    """Checkpoint / resume through the plane-compressed snapshot (device fills for planes of one
+    repeated word) reproduces an uninterrupted run bit for bit."""
+    import test_gpu_parity as gp
+    assert gp.determinism_run(cuda_lib) == gp.determinism_run(cuda_lib, restore_at=100)
