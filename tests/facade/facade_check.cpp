@@ -142,6 +142,29 @@ static void test_lan_reap_timers() {
   std::puts("PASS TestServer_LANReap (reaper)");
 }
 
+// TestServer_WANReap (server_test.go:767-810): two datacenters on the WAN pool, ReconnectTimeout =
+// TombstoneTimeout = 250 ms, ReapInterval = 500 ms; the second one shuts down and the first one's
+// WANMembers() goes from 2 to 1 (which is what empties router.GetDatacenters()).
+static void test_wan_reap() {
+  gsim_config c = test_cfg();
+  c.reconnect_timeout_ns = 250ull * 1000000;
+  c.tombstone_timeout_ns = 250ull * 1000000;
+  c.reap_interval_ns = 500ull * 1000000;
+  Pool pool(c);
+  Config c1, c2;
+  c1.NodeName = "s1.dc1";
+  c1.Tags = {{"role", "consul"}, {"dc", "dc1"}};
+  c2.NodeName = "s2.dc2";
+  c2.Tags = {{"role", "consul"}, {"dc", "dc2"}};
+  auto s1 = Serf::Create(pool, c1), s2 = Serf::Create(pool, c2);
+  CHECK(s2->Join({"s1.dc1/127.0.0.1:8302"}, true) == 1);
+  CHECK(eventually(pool, 140, [&] { return s1->Members().size() == 2 && s2->Members().size() == 2; }));
+  s2->Shutdown();
+  CHECK(eventually(pool, 400, [&] { return s1->Members().size() == 1; }));
+  CHECK(s1->Members()[0].Name == "s1.dc1" && s1->Members()[0].Tags.at("dc") == "dc1");
+  std::puts("PASS TestServer_WANReap");
+}
+
 // TestServer_JoinWAN (server_test.go:735-810): one server per datacenter, joined over the WAN
 // pool (names carry the datacenter, server_serf.go:90-93) with memberlist's WAN timing.
 static void test_join_wan() {
@@ -367,6 +390,7 @@ int main(int argc, char** argv) {
     if (extended) {
       test_lan_reap_timers();
       test_join_wan();
+      test_wan_reap();
       test_set_tags();
       test_merge_delegate();
       test_short_reconnect_timeout();

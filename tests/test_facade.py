@@ -20,7 +20,7 @@ def run(binary, extended=False):
     r = subprocess.run([binary] + (["--extended"] if extended else []), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASS" in r.stdout
-    names = ("TestServer_LANReap (reaper)", "TestServer_JoinWAN", "Serf.SetTags", "TestMerge_LAN",
+    names = ("TestServer_LANReap (reaper)", "TestServer_JoinWAN", "TestServer_WANReap", "Serf.SetTags", "TestMerge_LAN",
              "TestClient_ShortReconnectTimeout", "GetCoordinate") if extended else \
         ("TestServer_JoinLAN", "TestServer_LANReap", "TestClientServer_UserEvent", "TestAgent_Leave")
     for name in names:
