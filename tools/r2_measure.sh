@@ -44,4 +44,6 @@ for cfg in "default consul_b200/libgsim.so" "both consul_b200/libgsim_both.so"; 
         -o $OUT/prof_$1_$n -f python tools/prof_target.py --members $n --ticks 40 --nograph > $OUT/ncu_$1_$n.log 2>&1
   done
 done
+# 4. BASELINE's second metric: ticks-to-full-convergence of configs 2-5 on one GPU
+python tools/configs_report.py > $OUT/configs.jsonl 2>&1
 tail -n 40 $OUT/variants.log
