@@ -36,6 +36,7 @@ TICKS_PER_STEP = 2048
 SEED = 0x5EED0001
 N_HBM = 67_108_864          # secondary roofline point: 268 MB mailbox column + cold columns exceed the 126 MB L2
 HBM_TICKS = 256
+MEMBERS_PER_GPU_SHARDED = 1024 * 1024   # ~ the single-GPU workload per GPU: an honest weak-scaling curve
 
 # Algorithmic bytes.  Every member every tick reads its 4-byte mailbox word;
 # tiles whose ticker phase can be due at this tick (2 of every P ticks) also read `due`.
@@ -49,11 +50,6 @@ B_PACKET = 12.0     # peer key gather + mailbox atomic RMW
 B_RUMOR_TX = 2.0    # tx counter r/w per broadcast carried
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gs_tick_kernel launch in LAN steady state,
-# from the `ncu --set full` captures committed as profiles/r1h_1m_raw.csv and r1h_64m_raw.csv
-# (tools/prof_target.py --members N --nograph).  They belong to the workload, not to this run.
-TRAFFIC_1M_BYTES = 10.73e6       # 1 M members: the hot columns sit in L2, DRAM sees ~11 B/member
-TRAFFIC_64M_BYTES = 1.208e9      # 64 Mi members: 18.0 B/member against 8.9 B algorithmic
 
 
 def algorithmic_bytes(d: dict, probe_interval_ticks: int) -> float:
@@ -112,84 +108,240 @@ def measured_peak_gbs():
 
 
 # --------------------------------------------------------------------------------------------
-def run_reference(args, rank: int, world: int):
-    """Reference arm: the CPU implementation of the path (the oracle port — the Go modules are
-    not in /root/reference and there is no Go toolchain) on all host threads, bounded sample."""
-    if rank != 0:
-        return
+# CPU side: the oracle (oracle/oracle.cpp, kind "port" — the Go modules that hold the reference
+# arithmetic are not in /root/reference and there is no Go toolchain).  Nothing below
+# imports the product package's loader or maps consul_b200/libgsim.so.
+CASCADE_TICKS = 128          # the join cascade and its retransmissions end well before this
+
+
+def _oracle():
+    """oracle_binding without building or loading anything of the product."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import __graft_entry__ as ge
-    ge.build()
-    from consul_b200.pool import lan_config
-    from oracle_binding import OraclePool
-    ticks = 256         # bounded sample of the 2048-tick step: join cascade + first steady ticks
-    cfg = lan_config(capacity=N_MEMBERS + args.steps + args.warmup + 2, n_initial=N_MEMBERS, seed=SEED)
-    o = OraclePool(cfg, threads=0)
-    conv = []
+    ge.build_oracle()
+    import oracle_binding
+    return oracle_binding
+
+
+def host_cores() -> dict:
+    """Logical CPUs this process may run on, and how many distinct physical cores they are."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in allowed:
+        try:
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            with open(base + "physical_package_id") as f1, open(base + "core_id") as f2:
+                cores.add((f1.read().strip(), f2.read().strip()))
+        except OSError:
+            cores.add(("?", str(c)))
+    return {"logical": len(allowed), "physical": len(cores)}
+
+
+def pick_threads(o, probe_ticks: int = 4) -> tuple:
+    """Give the CPU arm its best thread count: time a few ticks at each candidate (all logical
+    CPUs, the physical cores, half of them) and keep the fastest.  OpenMP with static chunks and a
+    barrier per tick collapses when threads outnumber the cores it really gets (round 1: 128 threads
+    on the bench box ran 32x slower than 64), so the count is measured, not assumed."""
+    hc = host_cores()
+    cands = sorted({hc["logical"], hc["physical"], max(1, hc["physical"] // 2)}, reverse=True)
+    best, tried = None, {}
+    for th in cands:
+        o.set_threads(th)
+        o.step(1)
+        t0 = time.perf_counter()
+        o.step(probe_ticks)
+        dt = time.perf_counter() - t0
+        tried[th] = dt / probe_ticks
+        if best is None or dt < best[1]:
+            best = (th, dt)
+    o.set_threads(best[0])
+    return best[0], {"host": hc, "s_per_tick_by_threads": {str(k): round(v, 5) for k, v in tried.items()}}
+
+
+def oracle_step_sampled(o, ticks: int, budget_s: float) -> tuple:
+    """One step (after the join) on the oracle: the cascade part is always timed in full; the steady
+    remainder is timed until `ticks` are done or the budget is spent, and then scaled to `ticks`.
+    Returns (seconds for the whole step — measured or scaled —, ticks actually executed)."""
+    t0 = time.perf_counter()
+    head = min(ticks, CASCADE_TICKS)
+    o.step(head)
+    t_head = time.perf_counter() - t0
+    done, t_tail = head, 0.0
+    while done < ticks and (done == head or (t_head + t_tail) < budget_s):   # at least one steady chunk
+        c = min(64, ticks - done)
+        t1 = time.perf_counter()
+        o.step(c)
+        t_tail += time.perf_counter() - t1
+        done += c
+    if done == ticks:
+        return t_head + t_tail, done
+    per_tick = t_tail / (done - head) if done > head else t_head / head
+    return t_head + t_tail + per_tick * (ticks - done), done
+
+
+def workload_config(n: int, ticks: int, world: int, sharded: bool) -> dict:
+    """The `config` object of the bench line — built by ONE function for both arms so that the
+    reference line carries exactly the repo arm's config."""
+    return {"workload": f"C2: {n:,} converged members + 1 joiner per step, LAN defaults "
+                        f"(probe 1s/500ms, gossip 200ms x3), tau=100 ms, {ticks} ticks/step",
+            "members": n, "members_per_gpu": n // world if sharded else n, "ticks_per_step": ticks, "seed": hex(SEED),
+            "parallelism": (f"one pool range-sharded over {world} GPUs, P2P mailboxes over NVLink inside the tick "
+                            "kernel, device barrier per tick") if sharded else "single GPU",
+            "l2": "not flushed: a step is 2048 dependent ticks over the same state, whose hot "
+                  "columns are L2-resident by construction; see roofline_hbm for the >L2 size"}
+
+
+def workload_shape(args, world: int) -> tuple:
+    """(members, capacity, sharded) of the pool both arms simulate at this --gpus."""
+    total_steps = args.steps + args.warmup
+    if world > 1:
+        per_gpu = args.members_per_gpu
+        return per_gpu * world - 256, per_gpu * world, True
+    return args.members, args.members + 2 * total_steps + 8, False
+
+
+def mapped_native_libs() -> list:
+    out = set()
+    try:
+        with open("/proc/self/maps") as f:
+            for ln in f:
+                path = ln.split()[-1]
+                if path.startswith(ROOT) and path.endswith(".so"):
+                    out.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(out)
+
+
+def run_reference(args, rank: int, world: int):
+    """Reference arm: the CPU implementation of the path on the host cores, the SAME cluster
+    (members, seed, config) and the same step (join + `--ticks` ticks) as the repo arm at this
+    --gpus.  Under torchrun only rank 0 works."""
+    if rank != 0:
+        return
+    # torchrun pins OMP_NUM_THREADS=1 in its workers: this arm is a CPU program and takes the cores
+    os.environ.pop("OMP_NUM_THREADS", None)
+    ob = _oracle()
+    n, cap, sharded = workload_shape(args, max(world, args.gpus))
+    w = max(world, args.gpus)
+    ticks = args.ticks
+    cfg = ob.oracle_config("lan", capacity=cap, n_initial=n, seed=SEED)
+    o = ob.OraclePool(cfg, threads=0)
+    threads, tune = pick_threads(o)
+    total = args.steps + args.warmup
+    budget = float(os.environ.get("GSIM_REF_BUDGET_S", "300")) / max(1, total)
 
     def one_step():
+        t0 = time.perf_counter()
         x = o.member_add()
-        o.join(x, [0])
-        t0 = o.now
-        o.step(ticks)
-        info_tick = None
-        return t0, info_tick
+        assert o.join(x, [0]) == 1
+        t_host = time.perf_counter() - t0
+        secs, done = oracle_step_sampled(o, ticks, budget)
+        return t_host + secs, done
 
     for _ in range(args.warmup):
         one_step()
-    n0 = o.stats()["node_ticks"]
-    t0 = time.perf_counter()
+    secs, executed = 0.0, 0
     for _ in range(args.steps):
-        one_step()
-    dt = time.perf_counter() - t0
-    nt = o.stats()["node_ticks"] - n0
-    val = nt / dt / 1e6
+        s_, d_ = one_step()
+        secs += s_
+        executed += d_
+    n_now = o.stats()["n_members"]
+    val = float(n_now) * ticks * args.steps / secs / 1e6
+    exact = executed == ticks * args.steps
+    sample = (f"{args.steps} steps x (join + {ticks} ticks) x {n_now:,} members, every tick executed" if exact else
+              f"{args.steps} steps x {n_now:,} members: join + ticks 0..{CASCADE_TICKS} timed in full, then "
+              f"{executed // args.steps - CASCADE_TICKS} steady ticks per step timed and scaled to {ticks} "
+              f"(budget {budget:.0f} s per step)")
     line = {
         "impl": "reference", "metric": "million node-ticks/sec", "value": val, "unit": "M node-ticks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "C2: 1,000,000 converged members + 1 joiner per step, LAN defaults, tau=100 ms",
-                   "ticks_per_step": ticks, "sample": f"first {ticks} ticks of each {TICKS_PER_STEP}-tick step"},
-        "cpu_baseline": {"value": val, "unit": "M node-ticks/s", "cores": o.threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {ticks} ticks x {N_MEMBERS} members (join cascade + first steady ticks)"},
+        "config": workload_config(n, ticks, w, sharded),
+        "cpu_baseline": {"value": val, "unit": "M node-ticks/s", "cores": threads, "kind": "port",
+                         "sample": sample, "thread_tuning": tune},
         "e2e": {"value": val, "unit": "M node-ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "digest": "%016x" % o.state_hash()[0],
+        "native_so_loaded": mapped_native_libs(),
     }
+    assert not any("libgsim" in x for x in line["native_so_loaded"]), line["native_so_loaded"]
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(budget_s: float = 12.0) -> dict:
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from consul_b200.pool import lan_config
-    from oracle_binding import OraclePool
-    cfg = lan_config(capacity=N_MEMBERS + 1, n_initial=N_MEMBERS, seed=SEED)
-    o = OraclePool(cfg, threads=0)
+def cpu_baseline_sample(n: int, cap: int, ticks: int, budget_s: float = 15.0) -> dict:
+    """cpu_baseline of the repo arm's line: one step of the same workload on the oracle."""
+    os.environ.pop("OMP_NUM_THREADS", None)
+    ob = _oracle()
+    o = ob.OraclePool(ob.oracle_config("lan", capacity=cap, n_initial=n, seed=SEED), threads=0)
+    threads, tune = pick_threads(o)
     x = o.member_add()
     o.join(x, [0])
-    o.step(8)                                     # warm
-    n0 = o.stats()["node_ticks"]
-    t0 = time.perf_counter()
-    ticks = 0
-    while time.perf_counter() - t0 < budget_s and ticks < TICKS_PER_STEP:
-        o.step(32)
-        ticks += 32
-    dt = time.perf_counter() - t0
-    nt = o.stats()["node_ticks"] - n0
-    return {"value": nt / dt / 1e6, "unit": "M node-ticks/s", "cores": o.threads, "kind": "port",
-            "sample": f"ticks 8..{8 + ticks} of the same 1,000,001-member join cascade ({dt:.1f} s of CPU)"}
+    secs, done = oracle_step_sampled(o, ticks, budget_s)
+    return {"value": float(n + 1) * ticks / secs / 1e6, "unit": "M node-ticks/s", "cores": threads, "kind": "port",
+            "sample": (f"one step of the same workload ({n + 1:,} members, join + {ticks} ticks): "
+                       + ("every tick executed" if done == ticks else
+                          f"ticks 0..{CASCADE_TICKS} in full + {done - CASCADE_TICKS} steady ticks scaled to {ticks}")
+                       + f", {secs:.1f} s"), "thread_tuning": tune}
+
+
+PARITY_TICKS = 96
+
+
+def parity_script(p) -> dict:
+    """The parity replay both sides run on a fresh pool: one joiner through seed 0, PARITY_TICKS
+    ticks (cascade converged and retransmissions finished), digest + the counters that must match."""
+    x = p.member_add()
+    joined = p.join(x, [0])
+    p.step(PARITY_TICKS)
+    st = p.stats()
+    return {"digest": "%016x" % p.state_hash()[0], "joined": joined, "now": p.now,
+            "counters": {k: st[k] for k in ("probes", "acks", "gossip_packets", "rumors_sent", "rumors_accepted")}}
 
 
 # --------------------------------------------------------------------------------------------
+def kernel_source_sha() -> str:
+    """Identity of the tick-kernel sources: profiles/traffic.json is trusted only for this build."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "consul_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".h", ".cu", ".cpp")):
+            with open(os.path.join(csrc, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the
+    `ncu --set full` capture of THIS build (tools/ncu_traffic.py writes profiles/traffic.json with
+    the source hash it profiled); null when the kernel sources have changed since."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if t.get("kernel_source_sha") != kernel_source_sha():
+            return None
+        return t.get(key)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsim", choices=["gsim", "reference"])
-    ap.add_argument("--members", type=int, default=N_MEMBERS)
+    ap.add_argument("--members", type=int, default=N_MEMBERS, help="members of the single-GPU pool")
+    ap.add_argument("--members-per-gpu", type=int, default=MEMBERS_PER_GPU_SHARDED,
+                    help="members per GPU of the sharded pool (--gpus > 1)")
     ap.add_argument("--ticks", type=int, default=TICKS_PER_STEP)
     ap.add_argument("--skip-hbm-point", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,21 +366,46 @@ def main():
 
     from consul_b200.pool import Pool, lan_config, PRED_RUMOR_CONVERGED
 
-    n, ticks = args.members, args.ticks
-    total_steps = args.steps + args.warmup
-    sharded = world > 1
+    ticks = args.ticks
+    n, cap, sharded = workload_shape(args, world)
     if sharded:
-        # one pool sharded over all ranks: 2 Mi members per GPU (the VMM mapping
-        # granularity makes 2 Mi rows the shard quantum), the last 256 ids are left for joiners
+        # one pool sharded over all ranks; the last 256 ids are left for joiners
         from consul_b200.sharded import ShardedPool
-        per_gpu = 2 * 1024 * 1024
-        n = per_gpu * world - 256
-        cfg = lan_config(capacity=per_gpu * world, n_initial=n, seed=SEED, device=local_rank)
+        cfg = lan_config(capacity=cap, n_initial=n, seed=SEED, device=local_rank)
         pool = ShardedPool(cfg)
     else:
-        cfg = lan_config(capacity=n + 2 * total_steps + 4, n_initial=n, seed=SEED + rank, device=local_rank)
+        cfg = lan_config(capacity=cap, n_initial=n, seed=SEED, device=local_rank)
         pool = Pool(cfg)
     gi = pool.stats()["probe_interval_ticks"]  # P: the due column is read on 2/P of the ticks
+
+    # ---- parity of THIS run's pool: the first step is replayed on the CPU oracle (and, for a
+    # sharded pool, on one GPU) and the 256-bit state digests must be equal ---------------------
+    parity = None
+    if not args.skip_parity:
+        got = parity_script(pool)
+        parity = {"what": f"fresh pool of {n:,} members: member_add + join(seed 0) + {PARITY_TICKS} ticks; "
+                          "first 64 bits of the 256-bit order-independent state digest + counters",
+                  "digest": got["digest"]}
+        if rank == 0:
+            omp_saved = os.environ.pop("OMP_NUM_THREADS", None)
+            ob = _oracle()
+            o = ob.OraclePool(ob.oracle_config("lan", capacity=cap, n_initial=n, seed=SEED), threads=0)
+            pick_threads(o, 2) if n > 4_000_000 else None
+            want = parity_script(o)
+            o.close()
+            if omp_saved is not None:
+                os.environ["OMP_NUM_THREADS"] = omp_saved
+            parity["digest_oracle"] = want["digest"]
+            ok = got == want
+            if sharded:
+                ref = Pool(lan_config(capacity=cap, n_initial=n, seed=SEED, device=local_rank))
+                one = parity_script(ref)
+                ref.close()
+                parity["digest_single_gpu"] = one["digest"]
+                ok = ok and got == one
+            parity["parity_ok"] = bool(ok)
+            if not ok:
+                sys.stderr.write(f"bench.py: PARITY MISMATCH got={got} oracle={want}\n")
 
     def step_resident():
         x = pool.member_add()
@@ -237,7 +414,6 @@ def main():
         pool.step(ticks)
         return x, t_start
 
-    conv_ticks = []
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local_rank)
@@ -276,6 +452,7 @@ def main():
 
     # ---- e2e: HOST buffers through the C ABI, H2D + D2H inside the timed region -----------
     import ctypes as C
+    restore_ok = False
     if sharded:
         # sharded pool: the cluster stays resident on the GPUs; the per-step host traffic is the
         # join operation (pokes) and the result read-back (stats, NumNodes of the joiner)
@@ -294,7 +471,7 @@ def main():
         sampler.join(timeout=2)
         n_now = pool.stats()["n_members"]
         e2e_nodeticks = float(n_now) * ticks * args.steps
-        h2d, d2h = 4096, 4096 + 4 * n_now
+        h2d, d2h = 4096, 4096
         blob = None
     else:
         blob = pool.snapshot()
@@ -302,7 +479,7 @@ def main():
         pinned.numpy()[:] = memoryview(blob)
         blob_ptr = C.c_void_p(pinned.data_ptr())
         from consul_b200._lib import GsimMember
-        mem_cap = n + 2 * total_steps + 4
+        mem_cap = cap
         mem_buf = (GsimMember * mem_cap)()
         mem_n = C.c_size_t()
         lib = pool.lib
@@ -354,19 +531,22 @@ def main():
     dt_max, dte_max, kms_max = [float(v) for v in tt.tolist()]
     node_ticks_all, e2e_all = [float(v) for v in nt.tolist()]
 
-    # ---- roofline of the dominant kernel (gs_tick_kernel) ---------------------------------------
+    # ---- roofline of the dominant kernel (gs_tick_kernel), PER GPU --------------------------------
+    # a sharded pool's counters are whole-job totals: each GPU moves 1/world of the bytes, and the
+    # peak is one GPU's
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(d, gi)
-    launch_us = kernel_ms * 1e3 / max(1, tick_launches)
-    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    alg = algorithmic_bytes(d, gi) / world
+    launch_us = kms_max * 1e3 / max(1, tick_launches)
+    achieved = alg / (kms_max * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "gs_tick_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TRAFFIC_1M_BYTES if (not sharded and n == N_MEMBERS) else None,
+                "unit": "GB/s", "frac": achieved / peak, "per_gpu": True,
+                "traffic": measured_traffic("traffic_1m_bytes") if (not sharded and n == N_MEMBERS) else None,
                 "peak_source": peak_src, "bytes_per_launch": alg / max(1, tick_launches),
                 "launch_us": launch_us, "launches": tick_launches,
-                "bytes_per_node_tick": alg / max(1.0, d["node_ticks"]),
-                "note": "1M members: the hot columns (8 MB of mailboxes + due) are L2-resident by construction (2048 dependent "
-                        "ticks over the same state); roofline_hbm below is the HBM-bound size"}
+                "ticks_per_launch": ticks * args.steps / max(1, tick_launches),
+                "bytes_per_node_tick": alg * world / max(1.0, d["node_ticks"]),
+                "note": "1M members: the hot columns are L2-resident by construction (2048 dependent ticks over the "
+                        "same state); roofline_hbm below is the HBM-bound size"}
 
     roofline_hbm = None
     if sharded:
@@ -383,8 +563,9 @@ def main():
         algb = algorithmic_bytes(db, gi)
         roofline_hbm = {"members": N_HBM, "ticks": HBM_TICKS, "achieved": algb / (ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": algb / (ms * 1e-3) / 1e9 / peak,
-                        "launch_us": ms * 1e3 / nl, "node_ticks_per_s": db["node_ticks"] / (ms * 1e-3),
-                        "traffic": TRAFFIC_64M_BYTES, "bytes_per_launch": algb / nl,
+                        "launch_us": ms * 1e3 / nl, "launches": nl, "node_ticks_per_s": db["node_ticks"] / (ms * 1e-3),
+                        "traffic": measured_traffic("traffic_64m_bytes"), "bytes_per_launch": algb / nl,
+                        "bytes_per_node_tick": algb / max(1.0, db["node_ticks"]),
                         "workload": f"{N_HBM:,} members, LAN steady state (4x BASELINE config 4 on one GPU; hot columns exceed L2)"}
         big.close()
 
@@ -395,9 +576,7 @@ def main():
 
     cpu = None
     if not args.skip_cpu_baseline:
-        import __graft_entry__ as ge
-        ge.build()
-        cpu = cpu_baseline_sample()
+        cpu = cpu_baseline_sample(n, cap, ticks)
 
     value = node_ticks_all / dt_max / 1e6
     line = {
@@ -405,14 +584,11 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"C2: {n:,} converged members + 1 joiner per step, LAN defaults "
-                               f"(probe 1s/500ms, gossip 200ms x3), tau=100 ms, {ticks} ticks/step",
-                   "members_per_gpu": n, "ticks_per_step": ticks, "seed": hex(SEED),
-                   "parallelism": (f"one pool range-sharded over {world} GPUs, {n // world:,} members per GPU, P2P mailboxes "
-                                   "over NVLink inside the tick kernel, device barrier per tick") if sharded else "single GPU",
-                   "l2": "not flushed: a step is 2048 dependent ticks over the same state, whose hot "
-                         "columns are L2-resident by construction; see roofline_hbm for the >L2 size"},
+        "config": workload_config(n, ticks, world, sharded),
         "ticks_to_convergence": ticks_to_conv,
+        "parity": parity, "digest": parity["digest"] if parity else None,
+        "digest_oracle": parity.get("digest_oracle") if parity else None,
+        "parity_ok": parity.get("parity_ok") if parity else None,
         "kernel_ms_per_step": kms_max / args.steps,
         "e2e": {"value": e2e_all / dte_max / 1e6, "unit": "M node-ticks/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

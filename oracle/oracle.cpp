@@ -1171,6 +1171,66 @@ void* oracle_create(const gsim_config* cfg, int threads) {
 
 void oracle_destroy(void* h) { delete (Oracle*)h; }
 int oracle_threads(void* h) { return ((Oracle*)h)->threads; }
+int oracle_set_threads(void* h, int threads) {
+  Oracle& o = *(Oracle*)h;
+#ifdef _OPENMP
+  o.threads = threads > 0 ? threads : omp_get_max_threads();
+#else
+  (void)threads;
+#endif
+  return o.threads;
+}
+
+// Config presets, restated from the files that pin them (NOT read from libgsim: bench.py's reference
+// arm must not map the product library).  LAN: [U] memberlist DefaultLANConfig as documented at
+// agent/config/runtime.go:1271-1336; serf with Consul's overrides, internal/gossip/libserf/serf.go:19-36
+// and agent/consul/config.go:622-623.  WAN: runtime.go:1348-1413.  Test harness: server_test.go:221-237.
+void oracle_config_default_lan(gsim_config* c) {
+  const uint64_t ms = 1000000ull, sec = 1000ull * ms, hour = 3600ull * sec;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (uint32_t)sizeof(*c);
+  c->seed = 0x5EED0001ull;
+  c->capacity = 1024;
+  c->probe_interval_ns = sec;          // gossip_lan.probe_interval 1s
+  c->probe_timeout_ns = 500 * ms;      // probe_timeout 500ms
+  c->gossip_interval_ns = 200 * ms;    // gossip_interval 200ms
+  c->gossip_nodes = 3;                 // gossip_nodes 3
+  c->retransmit_mult = 4;              // retransmit_mult 4
+  c->suspicion_mult = 4;               // suspicion_mult 4
+  c->indirect_checks = 3;
+  c->suspicion_max_timeout_mult = 6;
+  c->awareness_max_multiplier = 8;
+  c->gossip_to_the_dead_ns = 30 * sec;
+  c->push_pull_interval_ns = 30 * sec;
+  c->udp_buffer_size = 1400;
+  c->event_buffer = 512;
+  c->user_event_size_limit = 512;
+  c->leave_propagate_delay_ns = 3 * sec;
+  c->broadcast_timeout_ns = 5 * sec;
+  c->reap_interval_ns = 15 * sec;
+  c->reconnect_timeout_ns = 72 * hour;
+  c->tombstone_timeout_ns = 24 * hour;
+  c->world_size = 1;
+  c->device = -1;
+}
+void oracle_config_default_wan(gsim_config* c) {
+  const uint64_t ms = 1000000ull, sec = 1000ull * ms;
+  oracle_config_default_lan(c);
+  c->probe_interval_ns = 5 * sec;
+  c->probe_timeout_ns = 3 * sec;
+  c->gossip_interval_ns = 500 * ms;
+  c->gossip_to_the_dead_ns = 60 * sec;
+  c->push_pull_interval_ns = 60 * sec;
+  c->suspicion_mult = 6;
+}
+void oracle_config_consul_test(gsim_config* c) {
+  const uint64_t ms = 1000000ull;
+  oracle_config_default_lan(c);
+  c->probe_interval_ns = 100 * ms;
+  c->probe_timeout_ns = 50 * ms;
+  c->gossip_interval_ns = 100 * ms;
+  c->suspicion_mult = 2;
+}
 
 int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   Oracle& o = *(Oracle*)h;

@@ -30,6 +30,10 @@ _SIGS = [
     ("oracle_create", _P, [C.POINTER(GsimConfig), _i32]),
     ("oracle_destroy", None, [_P]),
     ("oracle_threads", _i32, [_P]),
+    ("oracle_set_threads", _i32, [_P, _i32]),
+    ("oracle_config_default_lan", None, [C.POINTER(GsimConfig)]),
+    ("oracle_config_default_wan", None, [C.POINTER(GsimConfig)]),
+    ("oracle_config_consul_test", None, [C.POINTER(GsimConfig)]),
     ("oracle_member_add", _i32, [_P, C.POINTER(GsimMemberDesc), C.POINTER(_u32)]),
     ("oracle_join", _i32, [_P, _u32, C.POINTER(_u32), _sz, _i32, C.POINTER(_i32)]),
     ("oracle_leave", _i32, [_P, _u32]),
@@ -73,6 +77,16 @@ def oracle_lib():
     return _LIB
 
 
+def oracle_config(preset: str = "lan", **kw) -> GsimConfig:
+    """A preset config from the ORACLE's own restatement of the defaults (libgsim is not touched)."""
+    c = GsimConfig()
+    getattr(oracle_lib(), {"lan": "oracle_config_default_lan", "wan": "oracle_config_default_wan",
+                           "consul_test": "oracle_config_consul_test"}[preset])(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
 class OraclePool:
     def __init__(self, cfg: GsimConfig, threads: int = 1):
         self.lib = oracle_lib()
@@ -100,6 +114,9 @@ class OraclePool:
     @property
     def threads(self):
         return self.lib.oracle_threads(self.h)
+
+    def set_threads(self, n: int) -> int:
+        return self.lib.oracle_set_threads(self.h, n)
 
     def member_add(self, alive_msg_size=0, watched=False):
         d = GsimMemberDesc(alive_msg_size, 1 if watched else 0)
