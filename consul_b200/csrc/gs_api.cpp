@@ -1187,17 +1187,37 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
   for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
     if (!((g.active_mask >> r) & 1u) || g.rumors[r].kind != GSIM_RUMOR_USER_EVENT) continue;
     if (g.rumors[r].ltime == le && p->rh[r].name == nm && p->rh[r].payload == pl) {
-      if (!poke(p, p->d.ltime_event, id, le + 1u)) return fail(p, GSIM_ERR_CUDA, "poke");
+      // [U] serf.UserEvent -> handleUserEvent on the caller's own buffer, then QueueBroadcast: a
+      // member that had not seen this (LTime, Name, Payload) delivers it now; either way its copy
+      // is (re)queued with transmits = 0.
+      uint32_t h, q;
+      if (!peek(p, p->d.heard, id, &h) || !peek(p, p->d.queued, id, &q)) return fail(p, GSIM_ERR_CUDA, "peek");
+      if (!((h >> r) & 1u)) {
+        uint32_t c, ct;
+        if (!poke(p, p->d.heard, id, h | (1u << r)) || !peek(p, p->d.heard_cnt, r, &c) ||
+            !poke(p, p->d.heard_cnt, r, c + 1u) || !peek(p, p->d.conv_tick, r, &ct))
+          return fail(p, GSIM_ERR_CUDA, "poke");
+        if (c + 1u == g.up_count && ct == GS_EMPTY32 && !poke(p, p->d.conv_tick, r, p->now))
+          return fail(p, GSIM_ERR_CUDA, "poke");
+        if (m & GS_META_WATCHED) log_host_event(p, GSIM_EVENT_USER, r, id, le);
+      }
+      if (!poke(p, p->d.queued, id, q | (1u << r)) || !poke(p, p->d.tx, GS_TX(r, g.cap, id), (uint8_t)0) ||
+          !post_wake(p, id) || !poke(p, p->d.ltime_event, id, le + 1u))
+        return fail(p, GSIM_ERR_CUDA, "poke");
+      p->counts_stale = true;
       if (slot_out) *slot_out = r;
       return GSIM_OK;
     }
   }
-  uint32_t slot;
-  int rc = alloc_slot(p, &slot);
-  if (rc) return fail(p, rc, "no free rumor slot");
   // msgpack size of messageUserEvent{LTime,Name,Payload,CC} + 1 type byte
   uint32_t size = 1 + 1 + (6 + msgpack_uint_size(le)) + (5 + msgpack_str_size(name_len)) +
                   (8 + msgpack_str_size(payload_len)) + (3 + 1);
+  // [U] serf.UserEvent checks the limit a second time on the ENCODED message
+  if (size > p->cfg.user_event_size_limit)
+    return fail(p, GSIM_ERR_TOO_LARGE, "encoded user event exceeds UserEventSizeLimit");
+  uint32_t slot;
+  int rc = alloc_slot(p, &slot);
+  if (rc) return fail(p, rc, "no free rumor slot");
   rc = start_rumor(p, slot, GSIM_RUMOR_USER_EVENT, id, 0u, le, id, size, 2u);
   if (rc) return fail(p, rc, "start_rumor");
   p->rh[slot].name = nm;
@@ -1867,10 +1887,38 @@ struct SnapHeader {
   uint32_t version, cap;
   uint32_t now, n_sched;
   uint64_t node_ticks;
-  uint32_t n_established, pad;
+  uint32_t n_established;
+  uint32_t layout;       // which optional column sets the blob carries (snap_layout)
+  uint64_t graph_hash;   // FNV-1a of the CSR peer graph the state was produced on (0: complete graph)
   GsGlobals g;
 };
 static const uint64_t SNAP_MAGIC = 0x4753494D534E4150ull;  // "GSIMSNAP"
+static const uint32_t SNAP_VERSION = 3;
+
+// The optional column sets of a pool, as a bit mask: a blob is only ever parsed by a pool with the
+// same set (the planes follow each other without per-plane names).
+static uint32_t snap_layout(const gsim_pool* p) {
+  uint32_t m = 0;
+  if (p->d.coord) m |= 1u;
+  if (p->d.ppreq) m |= 2u;
+  if (p->d.kst) m |= 4u;
+  if (p->d.mailmap[0]) m |= 8u;
+  if (p->sharded) m |= 16u;
+  return m;
+}
+static uint64_t snap_graph_hash(const gsim_pool* p) {
+  if (p->g.graph_n == 0u) return 0ull;
+  uint64_t h = 0xCBF29CE484222325ull;
+  auto mix = [&](const std::vector<uint32_t>& v) {
+    for (uint32_t x : v) {
+      h ^= x;
+      h *= 0x100000001B3ull;
+    }
+  };
+  mix(p->graph_rp);
+  mix(p->graph_col);
+  return h ? h : 1ull;
+}
 
 static size_t snap_size(gsim_pool* p) {
   size_t s = sizeof(SnapHeader) + p->sched.size() * sizeof(Sched);
@@ -1899,7 +1947,9 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
   SnapHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = SNAP_MAGIC;
-  h.version = 2;
+  h.version = SNAP_VERSION;
+  h.layout = snap_layout(p);
+  h.graph_hash = snap_graph_hash(p);
   h.cap = p->g.cap;
   h.now = p->now;
   h.n_sched = (uint32_t)p->sched.size();
@@ -1945,9 +1995,15 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   SnapHeader h;
   memcpy(&h, r, sizeof(h));
   r += sizeof(h);
-  if (h.magic != SNAP_MAGIC || h.version != 2 || h.cap != p->g.cap || h.g.ring_mask != p->g.ring_mask ||
-      (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u) || h.g.graph_n != p->g.graph_n)
-    return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool");
+  if (h.magic != SNAP_MAGIC || h.version != SNAP_VERSION) return fail(p, GSIM_ERR_INVALID, "not a gsim snapshot of this version");
+  // The blob is trusted for nothing that selects memory: stride, member count, column set, sharding
+  // geometry and peer graph must be this pool's before a single plane is copied.
+  if (h.cap != p->g.cap || h.g.cap != p->g.cap || h.g.n > p->cfg.capacity || h.g.n > p->g.cap ||
+      h.g.ring_mask != p->g.ring_mask || (h.g.pp_interval != 0u) != (p->g.pp_interval != 0u) ||
+      h.layout != snap_layout(p) || h.g.world != p->g.world || h.g.key_stride != p->g.key_stride ||
+      h.g.rows_per_rank != p->g.rows_per_rank || h.g.phase_group != p->g.phase_group ||
+      h.g.graph_n != p->g.graph_n || h.graph_hash != snap_graph_hash(p) || h.n_established > h.g.n)
+    return fail(p, GSIM_ERR_INVALID, "snapshot does not match this pool (capacity, column set, sharding or peer graph)");
   if ((size_t)(end - r) < (size_t)h.n_sched * sizeof(Sched)) return fail(p, GSIM_ERR_INVALID, "truncated");
   p->sched.resize(h.n_sched);
   if (h.n_sched) memcpy(p->sched.data(), r, (size_t)h.n_sched * sizeof(Sched));
@@ -2003,7 +2059,16 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
     }
     r += c.bytes;
   }
-  p->g = h.g;
+  {
+    // topology fields stay the live pool's (they were checked equal above, except the rank, which is
+    // this process's own on a sharded pool)
+    const uint32_t world = p->g.world, rank = p->g.rank, stride = p->g.key_stride, rpr = p->g.rows_per_rank;
+    p->g = h.g;
+    p->g.world = world;
+    p->g.rank = rank;
+    p->g.key_stride = stride;
+    p->g.rows_per_rank = rpr;
+  }
   p->now = h.now;
   p->node_ticks = h.node_ticks;
   p->n_established = h.n_established;

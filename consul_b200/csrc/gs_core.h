@@ -113,7 +113,7 @@ GS_HD uint32_t gs_meta_set_stage(uint32_t m, uint32_t s) {
   return (m & ~(3u << GS_META_STAGE_SHIFT)) | (s << GS_META_STAGE_SHIFT);
 }
 GS_HD uint32_t gs_meta_set_nmiss(uint32_t m, uint32_t n) {
-  return (m & ~(7u << GS_META_NMISS_SHIFT)) | (n << GS_META_NMISS_SHIFT);
+  return (m & ~(7u << GS_META_NMISS_SHIFT)) | ((n & 7u) << GS_META_NMISS_SHIFT);
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter based: no RNG state in HBM ----

@@ -8,10 +8,11 @@
 //   gs_advance_kernel   bumps the device tick counter at the end of a CUDA-graph chunk
 //   gs_init_kernel, gs_crash_kernel, gs_recount_kernel, gs_hash_kernel   control plane
 //
-// Launch shape: 256 threads/CTA, one member per thread, consecutive members in a warp so
-// the four hot columns (key, inbox, due, meta) are read as four fully coalesced 128 B
-// requests per warp.  Ticks are chained inside a CUDA graph of GS_GRAPH_TICKS launches so
-// the ~2 us per-launch host cost is off the critical path.
+// Launch shape of the tick: a persistent grid (SMs x resident CTAs) of 256-thread CTAs; every warp
+// owns a contiguous chunk of 128-member tiles, scans their 4-byte mailbox words through a
+// shared-memory ring and works only on tiles with mail or a due probe ticker.
+// Ticks are chained inside a CUDA graph of GS_GRAPH_TICKS launches with programmatic dependent
+// launch, so the per-launch host cost is off the critical path.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,14 +40,18 @@ struct DevSinkT {
   uint32_t* s_heard;
   __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx], v); }
   __device__ __forceinline__ void heard(uint32_t r) { atomicAdd(&s_heard[r], 1u); }
+  // Pool-wide words (crashed_alive, the event-log cursor, heard_cnt) live in rank 0's page on a
+  // sharded pool and are updated by every GPU: system-scope atomics (device scope is not atomic
+  // across GPUs).  They are rare — one per event, not per member — so single-GPU pools pay nothing
+  // measurable for the wider scope.
   __device__ __forceinline__ void crashed_dead(const GsDev& d, uint32_t t) {
-    uint32_t old = atomicSub(d.crashed_alive, 1u);
+    uint32_t old = atomicSub_system(d.crashed_alive, 1u);
     if (old == 1u) *d.crashed_dead_tick = t;
   }
   __device__ __forceinline__ void log_event(const GsDev& d, const GsGlobals& g, uint32_t t,
                                             uint32_t type, uint32_t subject, uint32_t observer,
                                             uint32_t ltime) {
-    uint32_t pos = atomicAdd(&d.evlog_cursor[0], 1u);
+    uint32_t pos = atomicAdd_system(&d.evlog_cursor[0], 1u);
     if (pos < g.evlog_cap) {
       GsEventRec e;
       e.tick = t;
@@ -57,7 +62,7 @@ struct DevSinkT {
       e.reserved = 0u;
       d.evlog[pos] = e;
     } else {
-      atomicAdd(&d.evlog_cursor[1], 1u);
+      atomicAdd_system(&d.evlog_cursor[1], 1u);
     }
   }
 };
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   } else if (tid >= 32u && tid < 32u + GS_MAX_RUMORS) {
     uint32_t r = tid - 32u, c = s_heard[r];
     if (c) {
-      uint32_t old = atomicAdd(&d.heard_cnt[r], c);
+      uint32_t old = atomicAdd_system(&d.heard_cnt[r], c);  // rank 0's page on a sharded pool
       if (old + c == g.up_count) d.conv_tick[r] = t;  // every UP member has heard rumor r
     }
   }

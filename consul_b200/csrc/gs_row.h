@@ -614,6 +614,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         sink.stat(GS_ST_ACKS, 1);
       } else {
         uint32_t miss = nr > 0u ? nr - nacks : 1u;
+        if (miss > 7u) miss = 7u;  // 3-bit field; awareness saturates at <= 7, so 8 misses change nothing
         m = gs_meta_set_nmiss(gs_meta_set_stage(m, GS_STAGE_WAIT_P), miss);
         due = t0 + g.P * (gs_meta_aw(m) + 1u);
       }

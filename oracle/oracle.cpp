@@ -1365,13 +1365,24 @@ int oracle_user_event(void* h, uint32_t id, const void* name, size_t nl, const v
   for (uint32_t r = 0; r < GSIM_MAX_RUMORS; ++r)
     if (((o.active >> r) & 1) && o.rumor[r].kind == GSIM_RUMOR_USER_EVENT && o.rumor[r].ltime == lt &&
         o.rumor[r].name == nm && o.rumor[r].payload == pd) {
-      o.m[id].ltime_event = lt + 1;
+      // the caller's own event buffer decides whether this is new to IT; the broadcast is queued anyway
+      Member& me = o.m[id];
+      if (!((me.heard >> r) & 1)) {
+        me.heard |= 1u << r;
+        o.rumor[r].heard_count++;
+        if (o.rumor[r].heard_count == o.up_count && o.rumor[r].converged_tick == NONE32) o.rumor[r].converged_tick = o.now;
+        if (me.watched) host_event(o, GSIM_EVENT_USER, r, id, lt);
+      }
+      me.queued |= 1u << r;
+      me.tx[r] = 0;
+      me.ltime_event = lt + 1;
       if (slot_out) *slot_out = r;
       return GSIM_OK;
     }
+  uint32_t size = 1 + 1 + (6 + mp_uint(lt)) + (5 + mp_str(nl)) + (8 + mp_str(pl)) + (3 + 1);
+  if (size > o.cfg.user_event_size_limit) return GSIM_ERR_TOO_LARGE;  // second check, on the encoded message
   int slot = free_slot(o);
   if (slot < 0) return GSIM_ERR_CAPACITY;
-  uint32_t size = 1 + 1 + (6 + mp_uint(lt)) + (5 + mp_str(nl)) + (8 + mp_str(pl)) + (3 + 1);
   start_rumor(o, slot, GSIM_RUMOR_USER_EVENT, id, 0, lt, id, size, 2);
   o.rumor[slot].name = nm;
   o.rumor[slot].payload = pd;

@@ -113,3 +113,33 @@ def test_zero_length_horizons(make, hostemu_lib):
     raises_both(pools, lambda p: p.run_until(99, 0, 10, 1))                    # unknown predicate
     raises_both(pools, lambda p: p.rumor_info(5))                              # free slot
     compare_pools(*pools, "untouched")
+
+
+def test_identical_event_fired_by_a_second_member(make, hostemu_lib):
+    """[U] serf.UserEvent: the (LTime, Name, Payload) de-dup is per member buffer — a second member that
+    fires the identical event while it has not seen the first one delivers it itself (exactly once)
+    and queues its own broadcast; a member that already holds it re-queues with transmits = 0."""
+    n = 400
+    pools = make(lan_config(hostemu_lib, capacity=n, n_initial=n, seed=11))
+    for p in pools:
+        p.member_watch(7, True)
+    s0 = sc.both(pools, lambda p: p.user_event(3, b"deploy", b"v1", False))
+    s1 = sc.both(pools, lambda p: p.user_event(7, b"deploy", b"v1", False))     # same LTime 1, same bytes
+    assert s1 == s0
+    for p in pools:
+        assert p.rumor_info(s0)["heard_count"] == 2
+        assert [(e.type, e.observer) for e in p.poll_events()] == [(5, 7)]       # EventUser at member 7, once
+    s2 = sc.both(pools, lambda p: p.user_event(3, b"deploy", b"v1", False))     # origin again: LTime now 2 -> new event
+    assert s2 != s0
+    sc.step_compare(pools, 80, 10, "two origins")
+    for p in pools:
+        assert p.rumor_info(s0)["heard_count"] == n and p.rumor_info(s2)["heard_count"] == n
+    compare_pools(*pools, "dedup")
+
+
+def test_encoded_user_event_size_limit(make, hostemu_lib):
+    """name+payload may pass the first check and still be refused once encoded (second check of
+    [U] serf.UserEvent): 500 raw bytes encode to more than UserEventSizeLimit = 512."""
+    pools = make(lan_config(hostemu_lib, capacity=8, n_initial=8, seed=2))
+    raises_both(pools, lambda p: p.user_event(0, b"n" * 250, b"p" * 250, False), code=-7)
+    assert sc.both(pools, lambda p: p.user_event(0, b"n" * 200, b"p" * 200, False)) is not None
