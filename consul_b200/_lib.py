@@ -139,6 +139,7 @@ SIGNATURES = [
     ("gsim_shard_ready", _i32, [_P]),
     ("gsim_last_step_timing", _i32, [_P, C.POINTER(C.c_double), C.POINTER(_u64)]),
     ("gsim_launch_count", _u64, [_P]),
+    ("gsim_sched_counts", _i32, [_P, C.POINTER(_u64)]),
 ]
 
 

@@ -192,7 +192,19 @@ struct gsim_pool {
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
   std::vector<uint32_t> graph_rp, graph_col;  // host copy of the CSR peer graph (gsim_graph_set)
   GsXbar xb;
+  // quiet-window scheduling
+  bool quiet = false;        // the pool is known to be quiet at p->now: windows may run
+  uint32_t dirty_seq = 0;    // bumped by every host-side write to device state (quiet no longer known)
+  uint32_t dirty_tick = 0;   // p->now at that write
+  uint32_t retry_at = 0;     // do not look for quietness again before this tick
+  uint64_t sched_counts[4] = {0, 0, 0, 0};  // window launches, ticks run in windows, single-tick launches, horizon scans
 };
+
+static void mark_dirty(gsim_pool* p) {
+  p->quiet = false;
+  p->dirty_seq++;
+  p->dirty_tick = p->now;
+}
 
 static uint64_t gcd64(uint64_t a, uint64_t b) {
   while (b) {
@@ -217,6 +229,7 @@ static bool peek(gsim_pool* p, const T* col, size_t i, T* out) {
 }
 template <class T>
 static bool poke(gsim_pool* p, T* col, size_t i, T v) {
+  mark_dirty(p);  // a host write to device state: whatever was known about quietness is void
   return p->be->h2d(col + i, &v, sizeof(T));
 }
 
@@ -294,14 +307,16 @@ static bool upload_globals(gsim_pool* p) {
 // barrier; the other ranks enter the barrier, read the blob and adopt the state.
 struct BlobHdr {
   int32_t rc;
-  uint32_t now, n_established, n_sched, out_bytes, pad;
+  uint32_t now, n_established, n_sched, out_bytes, dirty_seq;
   uint64_t node_ticks;
+  uint32_t call_seq, want_bytes;  // which call this blob answers: a rank out of step must fail, not adopt
 };
 
 template <class F>
 static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
   if (!p->sharded) return f();
-  const uint32_t slot = p->call_seq++ & 1u;
+  const uint32_t seq = p->call_seq++;
+  const uint32_t slot = seq & 1u;
   uint8_t* blob_dev = p->pages + GS_PG_BLOB + (size_t)slot * GS_BLOB_BYTES;  // in rank 0's page
   std::vector<uint8_t> blob(GS_BLOB_BYTES, 0);
   BlobHdr h;
@@ -314,6 +329,9 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     h.n_sched = (uint32_t)p->sched.size();
     h.out_bytes = (uint32_t)(out ? out_bytes : 0);
     h.node_ticks = p->node_ticks;
+    h.dirty_seq = p->dirty_seq;
+    h.call_seq = seq;
+    h.want_bytes = (uint32_t)out_bytes;
     uint8_t* w = blob.data();
     if (sizeof(h) + sizeof(GsGlobals) + (size_t)h.n_sched * sizeof(Sched) + h.out_bytes > GS_BLOB_BYTES) {
       // every rank must still leave the barrier: publish the error instead of the state
@@ -336,6 +354,13 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
   if (!p->be->d2h(blob.data(), blob_dev, GS_BLOB_BYTES)) return fail(p, GSIM_ERR_CUDA, "blob d2h");
   const uint8_t* r = blob.data();
   memcpy(&h, r, sizeof(h)); r += sizeof(h);
+  if (h.call_seq != seq || h.want_bytes != (uint32_t)out_bytes) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "controller protocol out of step: call %u (%zu bytes out) met the blob of call %u (%u bytes out)",
+             seq, out_bytes, h.call_seq, h.want_bytes);
+    if (getenv("GSIM_DEBUG_PROTOCOL")) fprintf(stderr, "libgsim rank %u: %s\n", p->rank, msg);
+    return fail(p, GSIM_ERR_STATE, msg);
+  }
   memcpy(&p->g, r, sizeof(GsGlobals)); r += sizeof(GsGlobals);
   p->g.rank = p->rank;
   p->sched.resize(h.n_sched);
@@ -345,6 +370,11 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
   p->now = h.now;
   p->n_established = h.n_established;
   p->node_ticks = h.node_ticks;
+  if (h.dirty_seq != p->dirty_seq) {  // the controller wrote device state: same consequence on every rank
+    p->dirty_seq = h.dirty_seq;
+    p->dirty_tick = p->now;
+    p->quiet = false;
+  }
   p->g_dirty = false;
   p->counts_stale = true;
   if (h.rc) p->err = "controller reported an error";
@@ -387,6 +417,15 @@ static bool reset_tick_flags(gsim_pool* p) {
   return true;
 }
 
+// Quiet-window words of every rank: nothing known (controller only).
+static bool reset_qstate(gsim_pool* p) {
+  const uint32_t words[GS_Q_WORDS] = {p->now, GS_NEVER, p->now, 0u};  // last-active+1 = now: tick now-1 counts as active
+  for (uint32_t r = 0; r < (p->sharded ? p->world : 1u); ++r)
+    if (!p->be->h2d(p->d.qstate[r], words, sizeof(words))) return false;
+  mark_dirty(p);
+  return true;
+}
+
 // Device-side initial state: empty columns, zeroed counters, the converged initial members.
 // On a sharded pool this runs on rank 0 only and reaches every GPU through the unified columns.
 static int init_device_state(gsim_pool* p) {
@@ -420,6 +459,7 @@ static int init_device_state(gsim_pool* p) {
   okk = okk && be->fill32(d.crashed_dead_tick, GS_EMPTY32, 1);
   okk = okk && be->fill32(d.evlog_cursor, 0, 2) && be->fill32(d.tick_base, 0, 1);
   if (!p->sharded) okk = okk && be->fill32(d.done_ctr, 0, 1);
+  okk = okk && reset_qstate(p);
 
   p->g_dirty = true;
   okk = okk && upload_globals(p);
@@ -580,6 +620,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
     okk = okk && alloc_col(p, &d.evlog, (size_t)evcap) && alloc_col(p, &d.evlog_cursor, (size_t)2);
     okk = okk && alloc_col(p, &d.tick_base, (size_t)1);
     okk = okk && alloc_col(p, &d.done_ctr, (size_t)1);  // grid barrier of multi-tick launches
+    okk = okk && alloc_col(p, &d.qstate[0], (size_t)GS_Q_WORDS);
     okk = okk && alloc_col(p, &p->g_dev, (size_t)1);
   } else if (okk) {
     // pool-wide words: one 2 MB page per rank; counters and the event log live in rank 0's
@@ -605,6 +646,8 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       for (uint32_t r = 0; r < GS_MAX_WORLD; ++r)
         d.tick_flags[r] = reinterpret_cast<uint32_t*>(p->pages + (size_t)(r < p->world ? r : 0) * GS_PAGE_BYTES + GS_PG_TICK_FLAGS);
       d.done_ctr = reinterpret_cast<uint32_t*>(mine + GS_PG_DONE_CTR);
+      for (uint32_t r = 0; r < p->world; ++r)
+        d.qstate[r] = reinterpret_cast<uint32_t*>(p->pages + (size_t)r * GS_PAGE_BYTES + GS_PG_QSTATE);
       p->xb.epoch = reinterpret_cast<uint32_t*>(mine + GS_PG_XBAR_EPOCH);
       p->xb.rank = p->rank;
       p->xb.world = p->world;
@@ -745,6 +788,7 @@ static int retire_slot(gsim_pool* p, uint32_t slot) {
 
 // heard/queued/inbox bits of a freed slot must be zero before the slot is reused.
 static bool and_bit_columns(gsim_pool* p, uint32_t keep) {
+  mark_dirty(p);
   return p->be->and_columns(p->d, p->g, keep);
 }
 
@@ -1045,6 +1089,7 @@ extern "C" int gsim_crash_fraction(gsim_pool* p, uint32_t ppm, uint32_t salt, ui
   uint32_t thr = ppm >= 1000000u ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)ppm << 32) / 1000000ull);
   uint32_t cnt = 0;
   if (!upload_globals(p)) return fail(p, GSIM_ERR_CUDA, "upload");
+  mark_dirty(p);
   if (!p->be->crash_fraction(p->d, p->g_dev, p->g, thr, salt, p->now, &cnt))
     return fail(p, GSIM_ERR_CUDA, "crash_fraction");
   if (n_crashed) *n_crashed = cnt;
@@ -1456,12 +1501,110 @@ static int reap_pass(gsim_pool* p) {
   if (p->now <= youngest) return GSIM_OK;
   uint32_t counts[2] = {0, 0};
   if (!upload_globals(p)) return GSIM_ERR_CUDA;
+  mark_dirty(p);
   if (!p->be->reap_rows(p->d, p->g_dev, p->g, p->now, r.reconnect, r.tombstone,
                         (p->cfg.flags & GSIM_FLAG_LOG_GLOBAL_EVENTS) != 0, counts))
     return GSIM_ERR_CUDA;
   if (!counts[0]) return GSIM_OK;
   p->n_established -= counts[1];
   return refresh_after_truth_change(p);
+}
+
+// ---- quiet-window scheduling --------------------------------------------------
+static bool windows_possible(const gsim_pool* p) {
+  static const bool env_off = getenv("GSIM_NO_WINDOWS") != nullptr;
+  const GsGlobals& g = p->g;
+  // per-tile ticker phases (the window kernel derives a tile's due ticks from its phase), no
+  // per-member periodic tickers besides the probe (push-pull), no coordinate exchange on acks
+  return !env_off && !(p->cfg.flags & GSIM_FLAG_NO_WINDOWS) && g.phase_gate != 0u && g.pp_interval == 0u &&
+         p->d.coord == nullptr && g.P >= 2u && g.T < g.P && g.n != 0u;
+}
+
+// After single ticks: has the pool been quiet long enough, and how far is the horizon?
+static int try_quiet(gsim_pool* p) {
+  GsBackend* be = p->be;
+  const GsGlobals& g = p->g;
+  const uint32_t depth = g.ring_mask + 1u;
+  uint32_t* qs = p->d.qstate[p->sharded ? p->rank : 0u];
+  if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;  // every rank's last tick has published
+  uint32_t la = 0;
+  if (!be->d2h(&la, qs + GS_Q_LAST_ACTIVE, 4)) return GSIM_ERR_CUDA;
+  // ... and nobody runs on (and writes this rank's copy from its next tick) before everybody has read
+  if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;
+  if (p->dirty_tick + 1u > la) la = p->dirty_tick + 1u;  // a host write at tick T counts like mail at T
+  // every arrival slot has been scanned empty once and nobody posted meanwhile: `depth` quiet ticks
+  if (p->now < la + depth) {
+    p->retry_at = la + depth;
+    return GSIM_OK;
+  }
+  const uint32_t never = GS_NEVER;
+  if (!be->h2d(qs + GS_Q_HORIZON, &never, 4)) return GSIM_ERR_CUDA;
+  if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;
+  uint32_t first = 0, count = g.n;
+  if (p->sharded) {
+    first = p->rank * (uint32_t)p->rows_per_rank < g.n ? p->rank * (uint32_t)p->rows_per_rank : g.n;
+    count = first + (uint32_t)p->rows_per_rank < g.n ? (uint32_t)p->rows_per_rank : g.n - first;
+  }
+  if (!be->quiet_scan(p->d, p->g_dev, g, p->now, first, count)) return GSIM_ERR_CUDA;
+  if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;
+  p->sched_counts[3]++;
+  uint32_t hz = 0;
+  if (!be->d2h(&hz, qs + GS_Q_HORIZON, 4)) return GSIM_ERR_CUDA;
+  if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;  // (same: read before anybody moves on)
+  if (hz >= p->now + g.P / 2u + 1u) {
+    p->quiet = true;
+  } else {  // a probe deadline is upon us: single ticks until it has passed, then look again
+    p->retry_at = (hz > p->now ? hz : p->now) + depth + 1u;
+  }
+  return GSIM_OK;
+}
+
+// `chunk` ticks, as quiet windows where the pool allows it and as single ticks where it does not.
+static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
+  GsBackend* be = p->be;
+  const GsXbar* xb = p->sharded ? &p->xb : nullptr;
+  uint32_t left = chunk;
+  const bool can_window = windows_possible(p);
+  while (left) {
+    if (can_window && p->quiet) {
+      uint32_t done = 0;
+      uint64_t nl = 0;
+      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, use_graph, &p->last_ms, &nl, &done, xb))
+        return GSIM_ERR_CUDA;
+      p->last_launches += nl;
+      p->sched_counts[0] += nl;
+      p->sched_counts[1] += done;
+      p->now += done;
+      p->node_ticks += (uint64_t)done * p->g.n;
+      left -= done;
+      if (left) {  // the chain stopped at the horizon: single ticks from here
+        p->quiet = false;
+        p->retry_at = p->now + 1u;
+      }
+      continue;
+    }
+    uint32_t c = left;
+    if (can_window && c > 16u) c = 16u;  // look for quietness every few ticks
+    if (can_window && p->retry_at > p->now && p->retry_at - p->now < c) c = p->retry_at - p->now;
+    if (!be->run_ticks(p->d, p->g_dev, p->g, p->now, c, use_graph, &p->last_ms, &p->last_launches, xb))
+      return GSIM_ERR_CUDA;
+    p->sched_counts[2] += c;
+    p->now += c;
+    p->node_ticks += (uint64_t)c * p->g.n;
+    left -= c;
+    if (can_window && left && p->now >= p->retry_at) {
+      int rc = try_quiet(p);
+      if (rc) return rc;
+    }
+  }
+  return GSIM_OK;
+}
+
+extern "C" int gsim_sched_counts(gsim_pool* p, uint64_t out[4]) {
+  if (!p || !out) return GSIM_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(p->mu);
+  memcpy(out, p->sched_counts, sizeof(p->sched_counts));
+  return GSIM_OK;
 }
 
 static int step_locked(gsim_pool* p, uint32_t ticks) {
@@ -1484,11 +1627,8 @@ static int step_locked(gsim_pool* p, uint32_t ticks) {
       if (s.tick > p->now && s.tick - p->now < chunk) chunk = s.tick - p->now;
     const uint32_t reap_at = next_reap_tick(p, p->now);
     if (reap_at != GS_NEVER && reap_at - p->now < chunk) chunk = reap_at - p->now;
-    if (!p->be->run_ticks(p->d, p->g_dev, p->g, p->now, chunk, use_graph, &p->last_ms,
-                          &p->last_launches, p->sharded ? &p->xb : nullptr))
-      return GSIM_ERR_CUDA;
-    p->now += chunk;
-    p->node_ticks += (uint64_t)chunk * p->g.n;
+    rc = advance_ticks(p, chunk, use_graph);
+    if (rc) return rc;
     left -= chunk;
     p->counts_stale = true;
   }
@@ -2074,7 +2214,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   p->n_established = h.n_established;
   p->g_dirty = true;
   p->counts_stale = true;
-  if (!poke(p, p->d.tick_base, 0, p->now) || !reset_tick_flags(p)) return fail(p, GSIM_ERR_CUDA, "poke");
+  if (!poke(p, p->d.tick_base, 0, p->now) || !reset_tick_flags(p) || !reset_qstate(p)) return fail(p, GSIM_ERR_CUDA, "poke");
   uint32_t zero2[2] = {0, 0};
   if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
   return GSIM_OK;

@@ -36,6 +36,16 @@ class GsBackend {
   virtual bool run_ticks(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0,
                          uint32_t nticks, bool use_graph, double* kernel_ms, uint64_t* launches,
                          const GsXbar* xbar = nullptr) = 0;
+  // Quiet windows: advance up to `nticks` ticks starting at t0 as a chain of launches
+  // of <= ProbeInterval ticks each, on a pool whose mailboxes are known to be empty.  The chain stops at
+  // the horizon (GS_Q_HORIZON); *ticks_done = how far it got (tick_base == t0 + *ticks_done on exit).
+  virtual bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
+                           bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done,
+                           const GsXbar* xbar) = 0;
+  // lowers GS_Q_HORIZON (every rank's copy) to the earliest accusation the probes in flight of rows
+  // [first, first+count) can produce
+  virtual bool quiet_scan(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first,
+                          uint32_t count) = 0;
   // ---- sharded (multi-GPU) pools, see gs_vmm.h; unsupported by default ------------------------
   virtual bool shard_begin(uint32_t, uint32_t) { return false; }
   virtual size_t shard_granularity() { return 0; }

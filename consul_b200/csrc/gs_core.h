@@ -347,6 +347,23 @@ struct GsDev {
   // sharded pools: inter-tick barrier state (gs_tick_kernel); null on single-GPU pools
   uint32_t* tick_flags[GS_MAX_WORLD_];  // tick_flags[r] = rank r's array of per-rank progress words
   uint32_t* done_ctr;
+  // quiet-window scheduling: qstate[r] = rank r's copy of the GS_Q_* words; this
+  // rank reads qstate[rank], writers update every rank's copy (like key_rep)
+  uint32_t* qstate[GS_MAX_WORLD_];
+};
+
+// Pool-wide scheduling words (one copy per rank).  A pool is QUIET when every mailbox slot is empty
+// and nothing time-driven is pending except probe tickers: then a tick changes nothing but the rows
+// whose ticker fires, those rows write only themselves, and the first tick at which any member can
+// touch another one again is known in advance (the deadline of an unanswered probe, >= ProbeInterval
+// after it started).  Up to that HORIZON the ticks of a tile are independent of every other tile, so
+// one launch may run a whole window of them without looking at a single mailbox word.
+enum {
+  GS_Q_LAST_ACTIVE = 0,  // last tick at which a mailbox word was non-zero or a member posted one (+1; 0 = never)
+  GS_Q_HORIZON = 1,      // lower bound of the next tick at which a member may post (deadline of a failed probe)
+  GS_Q_WIN_END = 2,      // tick the chain of window launches has reached (windows stop at the horizon)
+  GS_Q_VIOLATION = 3,    // set if a window launch ever met mail or posted: internal error, checked by the host
+  GS_Q_WORDS = 4
 };
 
 // Per-row outputs that the launch wrapper reduces (warp/block aggregated atomics).
@@ -375,6 +392,7 @@ struct GsRowOut {
 #define GS_PG_XBAR_FLAGS 832u
 #define GS_PG_TICK_FLAGS 896u   // [GS_MAX_WORLD] "rank r has completed every tick < value"
 #define GS_PG_DONE_CTR 960u     // CTAs of this rank that have finished the current tick
+#define GS_PG_QSTATE 976u       // [GS_Q_WORDS] quiet-window scheduling words of this rank
 #define GS_PG_GLOBALS 1024u
 #define GS_PG_SCRATCH 8192u
 #define GS_PG_BLOB 16384u      // 2 slots of GS_BLOB_BYTES

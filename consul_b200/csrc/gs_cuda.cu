@@ -26,6 +26,7 @@
 
 #define GS_BLOCK 256
 #define GS_GRAPH_TICKS 64
+#define GS_WIN_GRAPH 8   // quiet windows per CUDA graph
 
 namespace {
 
@@ -38,6 +39,9 @@ struct DevSinkT {
   static constexpr bool kCoords = COORDS;
   uint32_t* s_stat;
   uint32_t* s_heard;
+  uint32_t* s_q;  // [0] this CTA saw mail or posted some, [1] min horizon raised by its members
+  __device__ __forceinline__ void activity() { s_q[0] = 1u; }
+  __device__ __forceinline__ void horizon(uint32_t h) { atomicMin(&s_q[1], h); }
   __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx], v); }
   __device__ __forceinline__ void heard(uint32_t r) { atomicAdd(&s_heard[r], 1u); }
   // Pool-wide words (crashed_alive, the event-log cursor, heard_cnt) live in rank 0's page on a
@@ -86,6 +90,51 @@ __device__ __forceinline__ void gs_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- sharded pools: the inter-tick barrier lives inside the kernels ---------------------------
+// Acquire side: tick t may start once every rank has published "all ticks < t done" in this rank's
+// progress array (written by the peers over NVLink with st.release.sys at the end of their
+// previous launch).
+__device__ __forceinline__ void gs_ranks_wait(const GsDev& d, const GsGlobals& g, uint32_t t) {
+  if (threadIdx.x < g.world) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(d.tick_flags[g.rank] + threadIdx.x) : "memory");
+    } while ((int32_t)(v - t) < 0);
+  }
+  __syncthreads();
+}
+// Release side.  Every thread that delivered something fenced at system scope, so its mailbox
+// clears, key updates and remote deliveries are performed; CTAs count in with a device-scope atomic
+// and the last one publishes `t_done` to every rank.  The chain (write -> fence.sys -> bar -> atomic
+// ... atomic -> fence.sys -> st.release.sys) does not rely on kernel boundaries, which is what
+// makes it safe inside a CUDA graph.
+__device__ __forceinline__ void gs_ranks_release(const GsDev& d, const GsGlobals& g, uint32_t t_done) {
+  __syncthreads();
+  if (threadIdx.x == 0u) {
+    __threadfence_system();
+    const uint32_t arrived = atomicAdd(d.done_ctr, 1u);
+    if (arrived == gridDim.x - 1u) {
+      __threadfence_system();
+      *d.done_ctr = 0u;
+      __threadfence_system();
+      for (uint32_t r = 0; r < g.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(d.tick_flags[r] + g.rank), "r"(t_done) : "memory");
+    }
+  }
+}
+
+// Quiet-window scheduling words (GS_Q_*): every rank keeps a copy, writers update all of them.
+__device__ __forceinline__ void gs_q_publish(const GsDev& d, const GsGlobals& g, const uint32_t* s_q, uint32_t t) {
+  if (s_q[0] != 0u) {
+    if (g.world <= 1u) atomicMax(d.qstate[0] + GS_Q_LAST_ACTIVE, t + 1u);
+    else for (uint32_t r = 0; r < g.world; ++r) atomicMax_system(d.qstate[r] + GS_Q_LAST_ACTIVE, t + 1u);
+  }
+  if (s_q[1] != GS_NEVER) {
+    if (g.world <= 1u) atomicMin(d.qstate[0] + GS_Q_HORIZON, s_q[1]);
+    else for (uint32_t r = 0; r < g.world; ++r) atomicMin_system(d.qstate[r] + GS_Q_HORIZON, s_q[1]);
+  }
+}
+
 // Persistent, warp-centric tick.  Every warp owns a CONTIGUOUS chunk of tiles (128 members
 // each); because ticker phases are dealt round-robin over tiles, every chunk holds the same
 // number of probing tiles (+-1) at every tick, so the static split is balanced.
@@ -108,9 +157,12 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 #ifdef GS_MAILMAP
   __shared__ __align__(16) uint32_t s_flag[GS_STAGES][GS_WARPS][4];  // the tile's 128 mailbox bits
 #endif
+  __shared__ uint32_t s_q[2];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  if (tid == 64u) s_q[0] = 0u;
+  if (tid == 65u) s_q[1] = GS_NEVER;
   // Programmatic dependent launch: let the next tick's grid start launching now; it blocks in
   // its own griddepcontrol.wait until this grid has completed and flushed.  Everything above
   // this line touches no global memory.
@@ -124,18 +176,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // grid, cooperative launch).
   for (uint32_t kk = 0; kk < n_ticks; ++kk) {
   const uint32_t t = t_first + kk;
-  if (g.world > 1u) {
-    // Sharded pool, acquire side of the inter-tick barrier: tick t may start once every rank has
-    // published "all ticks < t done" in this rank's progress array (written by the peers over
-    // NVLink with st.release.sys at the end of their previous tick, see the end of this kernel).
-    if (tid < g.world) {
-      uint32_t v;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(d.tick_flags[g.rank] + tid) : "memory");
-      } while ((int32_t)(v - t) < 0);
-    }
-    __syncthreads();
-  }
+  if (g.world > 1u) gs_ranks_wait(d, g, t);
   const uint32_t cur = t & 1u, P = g.P, pslot = t % P, gslot = t % g.GI;
   const uint32_t pslot_t = (t + P - g.T % P) % P;
   const uint32_t lane = tid & 31u, wib = tid >> 5;
@@ -161,7 +202,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 #endif
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
-  DevSinkT<COORDS> sink{s_stat, s_heard};
+  DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
 
 #ifdef GS_EARLY_A
   // Performance variant: which tiles of this chunk start a probe at this tick is known
@@ -282,7 +323,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           bool acked = false;
-          const bool done = cand[u] && gs_fast_finish(d, g, base + 32u * u, t, f[u], &acked);  // C
+          const bool done = cand[u] && gs_fast_finish(d, g, sink, base + 32u * u, t, f[u], &acked);  // C
           if (done) act[u] = false;
           n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
           n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
@@ -324,25 +365,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       if (old + c == g.up_count) d.conv_tick[r] = t;  // every UP member has heard rumor r
     }
   }
-  if (g.world > 1u) {
-    // Release side of the inter-tick barrier.  Every thread fenced at system scope above, so
-    // its mailbox clears, key updates and remote deliveries are performed; CTAs count in with
-    // a device-scope atomic and the last one publishes t+1 to every rank.  The chain
-    // (write -> fence.sys -> bar -> atomic ... atomic -> fence.sys -> st.release.sys) does not
-    // rely on kernel boundaries, which is what makes it safe inside a CUDA graph.
-    __syncthreads();
-    if (tid == 0u) {
-      __threadfence_system();
-      const uint32_t arrived = atomicAdd(d.done_ctr, 1u);
-      if (arrived == gridDim.x - 1u) {
-        __threadfence_system();
-        *d.done_ctr = 0u;
-        __threadfence_system();
-        for (uint32_t r = 0; r < g.world; ++r)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(d.tick_flags[r] + g.rank), "r"(t + 1u) : "memory");
-      }
-    }
-  }
+  if (tid == 0u) gs_q_publish(d, g, s_q, t);  // (after the CTA barrier above: every warp's flags are in)
+  if (g.world > 1u) gs_ranks_release(d, g, t + 1u);
   if (kk + 1u < n_ticks) {
     // Grid barrier between ticks of one launch: every thread's writes are fenced (which also
     // drops this SM's L1), CTAs count in on a monotonic counter and wait for the whole grid.
@@ -360,10 +384,180 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     __syncthreads();
     if (tid < GS_NSTAT) s_stat[tid] = 0u;
     if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+    if (tid == 64u) s_q[0] = 0u;
+    if (tid == 65u) s_q[1] = GS_NEVER;
     __syncthreads();
   }
   }  // for kk
 }
+
+// ---------------------------------------------------------------------------------------------
+// Quiet window: up to ProbeInterval ticks in ONE launch.
+//
+// On a quiet pool (every mailbox slot empty, nothing time-driven pending but probe tickers) a tick
+// changes only the members whose ticker fires, and those write only their own row: the probe is
+// pull-evaluated from the target's published key, which nobody changes.  The first tick at which a
+// member can touch another one again is the deadline of an unanswered probe, at least
+// ProbeInterval after it started; the minimum over all members is the HORIZON word.  Up to the
+// horizon the ticks of a tile are independent of every other tile, so a warp runs all the ticks of
+// the window for its tiles back to back: no mailbox scan (the words are known to be zero), no
+// grid-wide synchronisation, and on a sharded pool one inter-rank barrier per window instead of one
+// per tick.  Results are bit-identical to running the ticks one by one — the per-row code is the
+// same gs_fast_* / gs_row_step — which tests/test_windows_cpu.py and the GPU parity tests check.
+//
+// A tile's members are due only at ticks congruent to its ticker phase (probe start, probe
+// deadline) or to phase + ProbeTimeout (indirect stage): at most two ticks of a window.
+template <bool COORDS>
+__global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
+    gs_window_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
+  __shared__ uint32_t s_stat[GS_NSTAT];
+  __shared__ uint32_t s_heard[32];
+  __shared__ uint32_t s_q[2];
+  const uint32_t tid = threadIdx.x;
+  if (tid < GS_NSTAT) s_stat[tid] = 0u;
+  if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  if (tid == 64u) s_q[0] = 0u;
+  if (tid == 65u) s_q[1] = GS_NEVER;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+  const GsGlobals& g = *gp;
+  uint32_t* const qs = d.qstate[g.rank];
+  const uint32_t t0 = *d.tick_base + k_off;
+  // Where the chain of windows stands and how far it may go.  Both words are stable for the whole
+  // launch: siblings only raise WIN_END to this window's own end, and lower HORIZON to ticks
+  // >= t0 + ProbeInterval >= t0 + n_ticks.
+  const uint32_t reached = __ldcg(qs + GS_Q_WIN_END), horizon = __ldcg(qs + GS_Q_HORIZON);
+  if (reached < t0) return;  // an earlier window of this chain stopped at the horizon
+  uint32_t w1 = t0 + n_ticks;
+  if (horizon < w1) w1 = horizon;  // (GS_NEVER = no probe in flight anywhere)
+  if (w1 <= t0) return;            // the horizon is here: the host goes back to single ticks
+  if (g.world > 1u) gs_ranks_wait(d, g, t0);
+  const uint32_t P = g.P, lane = tid & 31u, wib = tid >> 5;
+  uint32_t tile_lo = 0, tile_hi = (g.n + GS_TILE - 1u) / GS_TILE;
+  if (g.world > 1u) {
+    const uint32_t per = g.rows_per_rank / GS_TILE;
+    tile_lo = g.rank * per < tile_hi ? g.rank * per : tile_hi;
+    tile_hi = tile_lo + per < tile_hi ? tile_lo + per : tile_hi;
+  }
+  const uint32_t n_warps = gridDim.x * GS_WARPS;
+  const uint32_t chunk = (tile_hi - tile_lo + n_warps - 1u) / n_warps;
+  const uint32_t wid = blockIdx.x * GS_WARPS + wib;
+  const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
+  const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
+  const uint32_t shift = g.phase_shift, t0_mod = t0 % P;
+  DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
+  bool did_work = false;
+  // the `due` words of the next tile travel while this one is worked on
+  uint32_t nd[4] = {GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER};
+  if (t_begin < t_end) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nd[u] = __ldcg(d.due + (size_t)t_begin * GS_TILE + lane + 32u * u);
+  }
+  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+    uint32_t due[4] = {nd[0], nd[1], nd[2], nd[3]};
+    if (tile + 1u < t_end) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nd[u] = __ldcg(d.due + (size_t)(tile + 1u) * GS_TILE + lane + 32u * u);
+    }
+    const uint32_t base = tile * GS_TILE + lane;
+    const uint32_t pp = gs_probe_phase(g.rot_p, tile >> shift, P);
+    // first ticks >= t0 congruent to the phase / to phase + ProbeTimeout
+    const uint32_t ta = t0 + (pp + P - t0_mod) % P, tb = t0 + ((pp + g.T) % P + P - t0_mod) % P;
+    const uint32_t tlo = ta < tb ? ta : tb, thi = ta < tb ? tb : ta;
+#pragma unroll 1
+    for (uint32_t which = 0; which < 2u; ++which) {
+      const uint32_t t = which == 0u ? tlo : thi;
+      if (t >= w1) break;
+      if (which == 1u) {  // rows handled at the first tick may have moved their `due` to this one
+#pragma unroll
+        for (int u = 0; u < 4; ++u) due[u] = __ldcg(d.due + base + 32u * u);
+      }
+      bool act[4], cand[4];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        act[u] = cand[u] = due[u] == t;
+        any |= act[u];
+      }
+      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+      did_work = true;
+      const uint32_t cur = t & 1u;
+      GsFastProbe f[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cand[u]) gs_fast_load(d, cur, base + 32u * u, f[u]);               // A: own columns
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (cand[u]) cand[u] = gs_fast_target(d, g, cur, base + 32u * u, f[u]);  // B: gathers
+      uint32_t n_probe = 0, n_ack = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bool acked = false;
+        const bool done = cand[u] && gs_fast_finish(d, g, sink, base + 32u * u, t, f[u], &acked);  // C
+        if (done) act[u] = false;
+        n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
+        n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
+      }
+      if (lane == 0u && n_probe) {
+        atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
+        atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
+        if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
+      }
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const bool a = u == 0 ? act[0] : u == 1 ? act[1] : u == 2 ? act[2] : act[3];
+        if (__any_sync(0xFFFFFFFFu, a)) {
+          if (a) gs_row_step(d, g, base + 32u * u, t, t % g.GI, 0u, sink);
+        }
+      }
+    }
+  }
+  if (g.world > 1u && did_work) __threadfence_system();  // horizon words on the peers, before the release
+  __syncthreads();
+  if (tid < GS_NSTAT) {
+    uint32_t v = s_stat[tid];
+    if (v) atomicAdd(&d.stats[tid], (unsigned long long)v);
+  }
+  if (tid == 0u) {
+    // a quiet window never meets mail and never posts: if it did, the scheduling invariant is broken
+    if (s_q[0] != 0u) atomicExch(qs + GS_Q_VIOLATION, t0 + 1u);
+    s_q[0] = 0u;
+    gs_q_publish(d, g, s_q, t0);
+    atomicMax(qs + GS_Q_WIN_END, w1);
+  }
+  if (g.world > 1u) gs_ranks_release(d, g, w1);
+}
+
+// Horizon of the pool as it stands (run before the first window after single ticks): the minimum,
+// over running members with a probe in flight, of the tick at which it can end in an accusation.
+__global__ void __launch_bounds__(GS_BLOCK)
+    gs_quiet_scan_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, uint32_t first, uint32_t count) {
+  __shared__ uint32_t s_min;
+  if (threadIdx.x == 0u) s_min = GS_NEVER;
+  __syncthreads();
+  const GsGlobals& g = *gp;
+  uint32_t h = GS_NEVER;
+  for (uint32_t x = blockIdx.x * GS_BLOCK + threadIdx.x; x < count; x += gridDim.x * GS_BLOCK) {
+    const uint32_t i = first + x;
+    if (gs_key_truth(d.key[now & 1u][i]) != GS_TRUTH_UP) continue;
+    const uint32_t stage = gs_meta_stage(d.meta[i]);
+    if (stage == GS_STAGE_IDLE) continue;
+    const uint32_t due = d.due[i];
+    const uint32_t e = stage == GS_STAGE_WAIT_T ? due - g.T + g.P : due;  // probe start + P, or the deadline itself
+    if (e < h) h = e;
+  }
+  h = __reduce_min_sync(0xFFFFFFFFu, h);
+  if ((threadIdx.x & 31u) == 0u && h != GS_NEVER) atomicMin(&s_min, h);
+  __syncthreads();
+  if (threadIdx.x == 0u && s_min != GS_NEVER) {
+    if (g.world <= 1u) atomicMin(d.qstate[0] + GS_Q_HORIZON, s_min);
+    else for (uint32_t r = 0; r < g.world; ++r) atomicMin_system(d.qstate[r] + GS_Q_HORIZON, s_min);
+  }
+}
+
+// End of a chain of windows: the device clock moves to wherever the chain got.
+__global__ void gs_window_advance_kernel(uint32_t* tick_base, const uint32_t* qs) { *tick_base = qs[GS_Q_WIN_END]; }
 
 __global__ void gs_advance_kernel(uint32_t* tick_base, uint32_t k, uint32_t* done_ctr) {
   *tick_base += k;
@@ -415,7 +609,7 @@ __global__ void __launch_bounds__(GS_BLOCK)
   uint32_t r = 0;
   if (i < gp->n) r = gs_reap_row(d, *gp, i, now, reconnect_ticks, tombstone_ticks);
   if (r && log_events) {
-    DevSink sink{nullptr, nullptr};
+    DevSink sink{nullptr, nullptr, nullptr};
     sink.log_event(d, *gp, now, GS_EV_MEMBER_REAP, i, GS_EMPTY32, 0u);
   }
   const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (r & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (r & 2u) != 0u);
@@ -497,6 +691,22 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
                  : cudaLaunchKernelEx(&cfg, gs_tick_kernel<false>, d, g_dev, k, 1u);
 }
 
+static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const GsDev& d, const GsGlobals* g_dev,
+                                    uint32_t k_off, uint32_t n_ticks, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(GS_BLOCK);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks)
+                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks);
+}
+
 // Several ticks in one cooperative launch (single-GPU pools).
 static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const GsDev& d,
                                    const GsGlobals* g_dev, uint32_t n_ticks) {
@@ -550,6 +760,7 @@ class CudaBackend : public GsBackend {
   ~CudaBackend() override {
     cudaSetDevice(dev_);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : wgraphs_) cudaGraphExecDestroy(kv.second);
     if (sharded_) vmm_.destroy();
     if (scratch_) cudaFree(scratch_);
     cudaEventDestroy(ev0_);
@@ -676,6 +887,79 @@ class CudaBackend : public GsBackend {
     if (launches) *launches += nticks;
     return true;
   }
+  // Quiet windows (gs_window_kernel): `nticks` ticks as a chain of launches of up to ProbeInterval
+  // ticks each.  The chain stops by itself at the horizon; *ticks_done says how far it got.
+  bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
+                   bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done, const GsXbar* xbar) override {
+    cudaSetDevice(dev_);
+    *ticks_done = 0;
+    if (!nticks || !g.n) return true;
+    uint32_t* qs = d.qstate[g.rank];
+    uint32_t init[2] = {t0, 0u};  // WIN_END = t0, VIOLATION = 0
+    if (!ok(cudaMemcpyAsync(qs + GS_Q_WIN_END, init, 8, cudaMemcpyHostToDevice, stream_), "window init")) return false;
+    uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
+    if (g.world > 1 && tiles > g.rows_per_rank / GS_TILE) tiles = g.rows_per_rank / GS_TILE;
+    uint32_t blocks = (tiles + GS_WARPS - 1) / GS_WARPS;
+    if (blocks > full_grid_) blocks = full_grid_;
+    const uint32_t K = g.P;
+    const bool sharded = xbar != nullptr;
+    const bool pdl = pdl_ && !sharded;
+    if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
+    uint32_t left = nticks, n_launch = 0;
+    if (use_graph && (!sharded || !no_shard_graph_)) {
+      while (left >= GS_WIN_GRAPH * K) {
+        cudaGraphExec_t ge = window_graph_for(d, g_dev, blocks, K, pdl, g.rank);
+        if (!ge) return false;
+        if (!ok(cudaGraphLaunch(ge, stream_), "window graph launch")) return false;
+        left -= GS_WIN_GRAPH * K;
+        n_launch += GS_WIN_GRAPH;
+        launches_ += GS_WIN_GRAPH + 1;
+      }
+    }
+    if (left) {
+      uint32_t k = 0;
+      while (left) {
+        const uint32_t c = left < K ? left : K;
+        if (!ok(gs_launch_window(blocks, stream_, d, g_dev, k, c, pdl), "window launch")) return false;
+        k += c;
+        left -= c;
+        ++n_launch;
+        ++launches_;
+      }
+      gs_window_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, qs);
+      ++launches_;
+      if (!ok(cudaGetLastError(), "window launch")) return false;
+    }
+    if (!ok(cudaEventRecord(ev1_, stream_), "event")) return false;
+    uint32_t back[2] = {0, 0};
+    if (!ok(cudaMemcpyAsync(back, qs + GS_Q_WIN_END, 8, cudaMemcpyDeviceToHost, stream_), "window d2h")) return false;
+    if (!ok(cudaStreamSynchronize(stream_), "window sync")) return false;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0_, ev1_);
+    if (kernel_ms) *kernel_ms += ms;
+    if (launches) *launches += n_launch;
+    if (back[1] != 0u) {
+      snprintf(err_, sizeof(err_), "quiet window starting at tick %u met mail or posted some (scheduling invariant broken)", back[1] - 1u);
+      return false;
+    }
+    if (back[0] < t0 || back[0] > t0 + nticks) {
+      snprintf(err_, sizeof(err_), "window chain ended at tick %u outside [%u, %u]", back[0], t0, t0 + nticks);
+      return false;
+    }
+    *ticks_done = back[0] - t0;
+    return true;
+  }
+  bool quiet_scan(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first,
+                  uint32_t count) override {
+    cudaSetDevice(dev_);
+    if (!count) return true;
+    uint32_t blocks = (count + GS_BLOCK - 1) / GS_BLOCK;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    gs_quiet_scan_kernel<<<blocks, GS_BLOCK, 0, stream_>>>(d, g_dev, now, first, count);
+    ++launches_;
+    (void)g;
+    return ok(cudaGetLastError(), "quiet scan launch") && ok(cudaStreamSynchronize(stream_), "quiet scan");
+  }
   bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t thr,
                       uint32_t salt, uint32_t, uint32_t* n_crashed) override {
     cudaSetDevice(dev_);
@@ -790,6 +1074,8 @@ class CudaBackend : public GsBackend {
     if (have_graph_dev_ && memcmp(&graph_dev_, &d, sizeof(GsDev)) != 0) {
       for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
       graphs_.clear();
+      for (auto& kv : wgraphs_) cudaGraphExecDestroy(kv.second);
+      wgraphs_.clear();
     }
     graph_dev_ = d;
     have_graph_dev_ = true;
@@ -817,6 +1103,37 @@ class CudaBackend : public GsBackend {
     graphs_[blocks] = ge;
     return ge;
   }
+  cudaGraphExec_t window_graph_for(const GsDev& d, const GsGlobals* g_dev, uint32_t blocks, uint32_t K, bool pdl, uint32_t rank) {
+    if (have_graph_dev_ && memcmp(&graph_dev_, &d, sizeof(GsDev)) != 0) {
+      for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+      graphs_.clear();
+      for (auto& kv : wgraphs_) cudaGraphExecDestroy(kv.second);
+      wgraphs_.clear();
+    }
+    graph_dev_ = d;
+    have_graph_dev_ = true;
+    const uint64_t key = ((uint64_t)blocks << 32) | K;
+    auto it = wgraphs_.find(key);
+    if (it != wgraphs_.end()) return it->second;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture")) return nullptr;
+    bool good = true;
+    for (uint32_t j = 0; j < GS_WIN_GRAPH && good; ++j)
+      good = ok(gs_launch_window(blocks, stream_, d, g_dev, j * K, K, pdl), "window capture");
+    if (good) gs_window_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, d.qstate[rank]);
+    if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture") || !good) {
+      if (graph) cudaGraphDestroy(graph);
+      return nullptr;
+    }
+    if (!ok(cudaGraphInstantiate(&ge, graph, 0), "instantiate")) {
+      cudaGraphDestroy(graph);
+      return nullptr;
+    }
+    cudaGraphDestroy(graph);
+    wgraphs_[key] = ge;
+    return ge;
+  }
   bool ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     snprintf(err_, sizeof(err_), "%s: %s", what, cudaGetErrorString(e));
@@ -835,6 +1152,7 @@ class CudaBackend : public GsBackend {
   // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
   bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
+  std::map<uint64_t, cudaGraphExec_t> wgraphs_;
   GsDev graph_dev_;
   bool have_graph_dev_ = false;
   bool l2_window_set_ = false;

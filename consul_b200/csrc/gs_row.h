@@ -160,7 +160,9 @@ GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_
 // builds also raise the member's bit in the slot's bitmap when the word was empty: the word only
 // ever becomes non-zero through this function (or the host's post_wake), and nobody posts into
 // the slot that is being consumed, so "word != 0 implies bit set" holds at every scan.
-GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, uint32_t slot, uint32_t j, uint32_t bits) {
+template <class Sink>
+GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t slot, uint32_t j, uint32_t bits) {
+  sink.activity();  // a posted word is mail at its arrival tick: the pool is not quiet
   const uint32_t old = GS_ATOMIC_OR32(&d.inbox[slot][j], bits);
 #ifdef GS_MAILMAP
   if (old == 0u && d.mailmap[slot] != nullptr) GS_ATOMIC_OR32(&d.mailmap[slot][j >> 5], 1u << (j & 31u));
@@ -395,7 +397,13 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const uint32_t icur = t & g.ring_mask, inxt = (t + 1u) & g.ring_mask;  // mailbox ring slots
   const uint32_t k0 = d.key[cur][i];
   const uint32_t truth = gs_key_truth(k0);
-  if (truth == GS_TRUTH_NONE) return;
+  if (inb != 0u) sink.activity();
+  if (truth == GS_TRUTH_NONE) {
+    // no such member (never created, or reaped with packets still in flight): the mail is dropped,
+    // otherwise the word would keep its tile in the active set for ever
+    if (inb != 0u) d.inbox[icur][i] = 0u;
+    return;
+  }
   const uint32_t m0 = d.meta[i];
   const uint32_t due0 = d.due[i];
   const bool up = truth == GS_TRUTH_UP;
@@ -413,7 +421,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       gs_key_store(d, g, nxt, i, k0);
       d.meta[i] = m0 & ~GS_META_DIRTY;
     }
-    if (queued != 0u) gs_post(d, g, inxt, i, GS_WAKE_BIT);
+    if (queued != 0u) gs_post(d, g, sink, inxt, i, GS_WAKE_BIT);
     return;
   }
 
@@ -531,7 +539,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
         GS_ATOMIC_MAX32(&clk[from], d.ltime_member[i]);
         GS_ATOMIC_MAX32(&clk[cap + from], d.ltime_event[i]);
-        gs_post(d, g, inxt, from, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
+        gs_post(d, g, sink, inxt, from, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
       }
     }
   }
@@ -634,7 +642,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         if (old == v || old == GS_EMPTY64) break;
         if (old > v) v = old;  // displaced a larger entry: carry it to the next slot
       }
-      gs_post(d, g, inxt, j, GS_ACC_BIT);
+      gs_post(d, g, sink, inxt, j, GS_ACC_BIT);
       sink.stat(GS_ST_PROBE_FAILURES, 1);
       stage = GS_STAGE_IDLE;  // due == t: the buffered ticker fires immediately
     }
@@ -688,6 +696,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
           d.probe_tgt[i] = target;
           d.probe_inc[i] = GS_PEER_INC(d, cur, target, ktarget);  // the incarnation it will accuse
           due = t + g.T;
+          sink.horizon(t + g.P);  // the earliest tick this probe can end in an accusation
         }
       } else {
         due = t + g.P;
@@ -718,7 +727,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         }
         sink.stat(GS_ST_GOSSIP_PACKETS, 1);
         if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q))
-          gs_post(d, g, (t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask, peers[q], pkt);
+          gs_post(d, g, sink, (t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask, peers[q], pkt);
       }
       if (queued != q0) d.queued[i] = queued;
     }
@@ -741,7 +750,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
         uint32_t* clk = d.pp_clk + (size_t)nxt * 2u * cap;
         GS_ATOMIC_MAX32(&clk[j], d.ltime_member[i]);
         GS_ATOMIC_MAX32(&clk[cap + j], d.ltime_event[i]);
-        gs_post(d, g, inxt, j, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
+        gs_post(d, g, sink, inxt, j, (d.heard[i] & g.active_mask) | GS_ACC_BIT);
         sink.stat(GS_ST_PUSH_PULLS, 1);
       }
     }
@@ -760,7 +769,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   // stay in the active set while something time-driven is pending: a running suspicion
   // timer, a stale key buffer, or a non-empty broadcast queue
   if (gs_key_rank(k) == GS_RANK_SUSPECT || (m & GS_META_DIRTY) || queued != 0u)
-    gs_post(d, g, inxt, i, GS_WAKE_BIT);
+    gs_post(d, g, sink, inxt, i, GS_WAKE_BIT);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -798,7 +807,8 @@ GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uin
 
 // Returns true when the member was fully handled; *acked tells whether the direct probe
 // succeeded (stats: PROBES +1, ACKS +acked, ACTIVE_ROWS +1 are added by the caller).
-GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t t,
+template <class Sink>
+GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t i, uint32_t t,
                            const GsFastProbe& f, bool* acked) {
   const uint32_t rank = gs_key_rank(f.kc);
   if (gs_key_truth(f.kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD || rank == GS_RANK_LEFT ||
@@ -817,6 +827,7 @@ GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
     d.probe_tgt[i] = f.c;
     d.probe_inc[i] = GS_PEER_INC(d, t & 1u, f.c, f.kc);
     d.due[i] = t + g.T;
+    sink.horizon(t + g.P);  // the earliest tick this probe can end in an accusation
     *acked = false;
   }
   d.cursor[i] = f.cursor + 1u;

@@ -20,6 +20,7 @@ NEVER = 0xFFFFFFFF
 
 FLAG_LOG_GLOBAL_EVENTS = 1
 FLAG_NO_GRAPH = 2
+FLAG_NO_WINDOWS = 16
 FLAG_PUSH_PULL = 32
 FLAG_COORDINATES = 64
 MEMBER_WATCHED = 1
@@ -278,6 +279,12 @@ class Pool:
         n = C.c_uint64()
         self._ck(self.lib.gsim_last_step_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def sched_counts(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        self._ck(self.lib.gsim_sched_counts(self.h, out))
+        return {"window_launches": int(out[0]), "window_ticks": int(out[1]), "tick_launches": int(out[2]),
+                "horizon_scans": int(out[3])}
 
     def launch_count(self) -> int:
         return int(self.lib.gsim_launch_count(self.h))

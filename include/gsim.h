@@ -147,6 +147,9 @@ typedef struct gsim_config {
  * member exchanges its tracked-broadcast mask and Lamport clocks with one random alive peer
  * (push at tick t, the partner's answer arrives at t+2).  Off by default: the headline configs
  * of BASELINE.json run shorter than one push-pull interval at their sizes. */
+/* Run every tick as its own launch even while the pool is quiet (no quiet windows):
+ * for measurements and for tests that compare the two schedules.  Same results either way. */
+#define GSIM_FLAG_NO_WINDOWS 16u
 #define GSIM_FLAG_PUSH_PULL 32u
 /* Network coordinates ([U] serf/coordinate: Vivaldi with height, adjustment window and gravity;
  * SURVEY 8f N3).  Every direct probe ack updates the prober's coordinate with the measured round
@@ -396,6 +399,9 @@ int gsim_shard_ready(gsim_pool* p);
 int gsim_last_step_timing(gsim_pool* p, double* kernel_ms, uint64_t* launches);
 /* Total kernels launched by this pool since creation (bench "gpu_launches"). */
 uint64_t gsim_launch_count(gsim_pool* p);
+/* Scheduling counters since creation: out[0] = quiet-window launches, out[1] = ticks advanced inside
+ * quiet windows, out[2] = single-tick launches, out[3] = horizon scans. */
+int gsim_sched_counts(gsim_pool* p, uint64_t out[4]);
 
 #ifdef __cplusplus
 }

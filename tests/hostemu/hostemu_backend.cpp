@@ -27,6 +27,29 @@ struct HostSink {
   uint64_t* stats;
   uint32_t* heard_cnt;
   uint32_t local_heard[32];
+  bool active = false;           // this launch saw mail or posted some
+  uint32_t min_horizon = GS_NEVER;
+  void activity() { active = true; }
+  void horizon(uint32_t h) {
+    if (h < min_horizon) min_horizon = h;
+  }
+  // what gs_q_publish does at the end of a launch: every rank's copy of the scheduling words
+  void publish(const GsDev& d, const GsGlobals& g, uint32_t t, bool window) {
+    for (uint32_t r = 0; r < (g.world ? g.world : 1u); ++r) {
+      uint32_t* qs = d.qstate[r];
+      if (active && !window) {
+        uint32_t old = __atomic_load_n(qs + GS_Q_LAST_ACTIVE, __ATOMIC_RELAXED);
+        while (old < t + 1u && !__atomic_compare_exchange_n(qs + GS_Q_LAST_ACTIVE, &old, t + 1u, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        }
+      }
+      if (min_horizon != GS_NEVER) {
+        uint32_t old = __atomic_load_n(qs + GS_Q_HORIZON, __ATOMIC_RELAXED);
+        while (old > min_horizon && !__atomic_compare_exchange_n(qs + GS_Q_HORIZON, &old, min_horizon, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        }
+      }
+    }
+    if (active && window) d.qstate[g.rank][GS_Q_VIOLATION] = t + 1u;
+  }
   void stat(int idx, uint32_t v) { __atomic_fetch_add(&stats[idx], (uint64_t)v, __ATOMIC_RELAXED); }
   void heard(uint32_t r) { local_heard[r] += 1; }
   void crashed_dead(const GsDev& d, uint32_t t) {
@@ -101,6 +124,8 @@ class HostEmuBackend : public GsBackend {
       sink.stats = reinterpret_cast<uint64_t*>(d.stats);
       sink.heard_cnt = d.heard_cnt;
       memset(sink.local_heard, 0, sizeof(sink.local_heard));
+      sink.active = false;
+      sink.min_horizon = GS_NEVER;
       // same activity test as gs_tick_kernel: mailbox word, plus `due` only for tiles whose
       // ticker phase can be due at this tick
       const uint32_t pslot = t % g.P;
@@ -122,7 +147,7 @@ class HostEmuBackend : public GsBackend {
           GsFastProbe f;
           bool acked = false;
           gs_fast_load(d, t & 1u, i, f);
-          if (gs_fast_target(d, g, t & 1u, i, f) && gs_fast_finish(d, g, i, t, f, &acked)) {
+          if (gs_fast_target(d, g, t & 1u, i, f) && gs_fast_finish(d, g, sink, i, t, f, &acked)) {
             sink.stat(GS_ST_PROBES, 1);
             sink.stat(GS_ST_ACTIVE_ROWS, 1);
             if (acked) sink.stat(GS_ST_ACKS, 1);
@@ -140,12 +165,101 @@ class HostEmuBackend : public GsBackend {
           if (old + c == g.up_count) d.conv_tick[r] = t;
         }
       }
+      sink.publish(d, g, t, false);
       ++launches_;
       if (xbar) xbar_host(*xbar);
     }
     *d.tick_base += nticks;
     ++launches_;
     if (launches) *launches += nticks;
+    return true;
+  }
+  // gs_window_kernel on the host.  Rows are taken one after the other and each runs ALL its ticks of
+  // the window before the next row is looked at — as far from lock-step as an order can be, which is
+  // the point: inside a quiet window rows are independent.
+  bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0, uint32_t nticks, bool,
+                   double*, uint64_t* launches, uint32_t* ticks_done, const GsXbar* xbar) override {
+    const GsGlobals& g = *g_dev;
+    *ticks_done = 0;
+    if (!nticks || !g.n) return true;
+    uint32_t* qs = d.qstate[g.rank];
+    qs[GS_Q_WIN_END] = t0;
+    qs[GS_Q_VIOLATION] = 0u;
+    if (*d.tick_base != t0) {
+      snprintf(err_, sizeof(err_), "tick_base out of sync");
+      return false;
+    }
+    const uint32_t K = g.P;
+    uint32_t lo = 0, hi = g.n;
+    if (g.world > 1u) {
+      lo = g.rank * g.rows_per_rank < g.n ? g.rank * g.rows_per_rank : g.n;
+      hi = lo + g.rows_per_rank < g.n ? lo + g.rows_per_rank : g.n;
+    }
+    uint32_t n_launch = 0;
+    for (uint32_t w0 = t0; w0 < t0 + nticks; w0 += K) {
+      const uint32_t n_ticks = t0 + nticks - w0 < K ? t0 + nticks - w0 : K;
+      ++n_launch;
+      ++launches_;
+      const uint32_t reached = __atomic_load_n(qs + GS_Q_WIN_END, __ATOMIC_RELAXED);
+      const uint32_t horizon = __atomic_load_n(qs + GS_Q_HORIZON, __ATOMIC_RELAXED);
+      if (reached < w0) continue;
+      uint32_t w1 = w0 + n_ticks;
+      if (horizon < w1) w1 = horizon;
+      if (w1 <= w0) continue;
+      HostSink sink;
+      sink.stats = reinterpret_cast<uint64_t*>(d.stats);
+      sink.heard_cnt = d.heard_cnt;
+      memset(sink.local_heard, 0, sizeof(sink.local_heard));
+      for (uint32_t x = 0; x < hi - lo; ++x) {
+        const uint32_t i = lo + row_at(x, hi - lo);
+        const uint32_t pp = gs_probe_phase(g.rot_p, (i / GS_TILE) >> g.phase_shift, g.P);
+        const uint32_t ta = w0 + (pp + g.P - w0 % g.P) % g.P, tb = w0 + ((pp + g.T) % g.P + g.P - w0 % g.P) % g.P;
+        const uint32_t two[2] = {ta < tb ? ta : tb, ta < tb ? tb : ta};
+        for (uint32_t which = 0; which < 2u; ++which) {
+          const uint32_t t = two[which];
+          if (t >= w1) break;
+          if (d.due[i] != t) continue;
+          if (!no_fast_) {
+            GsFastProbe f;
+            bool acked = false;
+            gs_fast_load(d, t & 1u, i, f);
+            if (gs_fast_target(d, g, t & 1u, i, f) && gs_fast_finish(d, g, sink, i, t, f, &acked)) {
+              sink.stat(GS_ST_PROBES, 1);
+              sink.stat(GS_ST_ACTIVE_ROWS, 1);
+              if (acked) sink.stat(GS_ST_ACKS, 1);
+              continue;
+            }
+          }
+          gs_row_step(d, g, i, t, t % g.GI, 0u, sink);
+        }
+      }
+      sink.publish(d, g, w0, true);
+      qs[GS_Q_WIN_END] = w1;
+      if (xbar) xbar_host(*xbar);  // sharded: one inter-rank barrier per window
+    }
+    *d.tick_base = qs[GS_Q_WIN_END];
+    ++launches_;
+    if (launches) *launches += n_launch;
+    if (qs[GS_Q_VIOLATION] != 0u) {
+      snprintf(err_, sizeof(err_), "quiet window starting at tick %u met mail or posted some", qs[GS_Q_VIOLATION] - 1u);
+      return false;
+    }
+    *ticks_done = qs[GS_Q_WIN_END] - t0;
+    return true;
+  }
+  bool quiet_scan(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t now, uint32_t first,
+                  uint32_t count) override {
+    const GsGlobals& g = *g_dev;
+    HostSink sink;
+    for (uint32_t x = 0; x < count; ++x) {
+      const uint32_t i = first + x;
+      if (gs_key_truth(d.key[now & 1u][i]) != GS_TRUTH_UP) continue;
+      const uint32_t stage = gs_meta_stage(d.meta[i]);
+      if (stage == GS_STAGE_IDLE) continue;
+      sink.horizon(stage == GS_STAGE_WAIT_T ? d.due[i] - g.T + g.P : d.due[i]);
+    }
+    sink.publish(d, g, now, false);
+    ++launches_;
     return true;
   }
   bool crash_fraction(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t thr,

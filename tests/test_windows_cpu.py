@@ -1,0 +1,138 @@
+"""Quiet windows: up to ProbeInterval ticks of a quiet pool in one launch.  The
+schedule must be invisible in the results — same digest, counters and columns as one launch per tick
+and as the oracle — whatever happens around and inside the windows: joins, events, crashes (probe
+failures are what bounds a window: the horizon), packet loss, leaves, steps of any length, restores.
+The host emulation runs each row through ALL its ticks of a window before it looks at the next row,
+in forward / reverse / odd-even row order: inside a window rows really are independent."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from consul_b200.pool import (FLAG_NO_WINDOWS, PRED_ALL_RUMORS_CONVERGED, PRED_CRASHED_ALL_DEAD, Pool,
+                              consul_test_config, lan_config, wan_config)
+from oracle_binding import OraclePool
+from parity import compare_pools
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def trio(lib, cfg_fn, **kw):
+    """the same pool with windows, without, and on the oracle"""
+    flags = kw.pop("flags", 0)
+    return [Pool(cfg_fn(lib, flags=flags, **kw), lib), Pool(cfg_fn(lib, flags=flags | FLAG_NO_WINDOWS, **kw), lib),
+            OraclePool(cfg_fn(lib, flags=flags, **kw))]
+
+
+def all3(pools, fn):
+    out = [fn(p) for p in pools]
+    assert out[0] == out[1] == out[2], out
+    return out[0]
+
+
+def check(pools, where):
+    compare_pools(pools[0], pools[2], where + " (windows vs oracle)")
+    compare_pools(pools[0], pools[1], where + " (windows vs single ticks)")
+
+
+def test_steady_state_runs_in_windows(hostemu_lib):
+    pools = trio(hostemu_lib, lan_config, capacity=5000, n_initial=5000, seed=21)
+    for p in pools:
+        p.step(500)
+    check(pools, "steady 500")
+    sc = pools[0].sched_counts()
+    assert sc["window_ticks"] > 450 and sc["window_launches"] <= 60, sc     # 10 ticks per launch
+    assert pools[1].sched_counts()["window_ticks"] == 0
+    for k in (1, 3, 9, 10, 11, 27):                                         # windows of every length, partial tails
+        for p in pools:
+            p.step(k)
+        check(pools, f"steady +{k}")
+
+
+def test_join_cascade_then_windows(hostemu_lib):
+    pools = trio(hostemu_lib, lan_config, capacity=3001, n_initial=3000, seed=22)
+    x = all3(pools, lambda p: p.member_add())
+    assert all3(pools, lambda p: p.join(x, [0])) == 1
+    for p in pools:
+        p.step(400)
+    check(pools, "cascade + steady")
+    sc = pools[0].sched_counts()
+    assert sc["tick_launches"] >= 20 and sc["window_ticks"] >= 200, sc      # single ticks while the rumor runs, windows after
+    y = all3(pools, lambda p: p.user_event(7, b"deploy", b"now", False))    # a host call ends the quiet period
+    for p in pools:
+        p.step(300)
+    check(pools, "event + steady")
+    assert all3(pools, lambda p: p.rumor_info(y)["heard_count"]) == 3001
+
+
+@pytest.mark.parametrize("cfg_fn,ppm,ticks", [(lan_config, 20000, 700), (consul_test_config, 100000, 200), (wan_config, 30000, 900)])
+def test_crashes_bound_the_windows(hostemu_lib, cfg_fn, ppm, ticks):
+    """Crashed members make probes fail inside windows: the window that sees the failure lowers the
+    horizon, the chain stops there, accusations and suspicion run as single ticks, and once every
+    crashed member is Dead and the rumors have drained the pool is quiet again."""
+    pools = trio(hostemu_lib, cfg_fn, capacity=4000, n_initial=4000, seed=23)
+    for p in pools:
+        p.step(40)
+    crashed = all3(pools, lambda p: p.crash_fraction(ppm, 1))
+    assert crashed > 0
+    for chunk in (7, 64, 200, ticks):
+        for p in pools:
+            p.step(chunk)
+        check(pools, f"crash wave +{chunk}")
+    t = all3(pools, lambda p: p.run_until(PRED_CRASHED_ALL_DEAD, 0, 4000, 16))
+    for p in pools:
+        p.step(300)
+    check(pools, "after the wave")
+    sc = pools[0].sched_counts()
+    assert sc["window_ticks"] > 100 and sc["tick_launches"] > 30 and sc["horizon_scans"] >= 2, sc
+    assert pools[0].stats()["probe_failures"] > 0
+
+
+def test_lossy_pool_and_leave(hostemu_lib):
+    """Random probe failures (5 % loss) keep lowering the horizon; results still equal."""
+    pools = trio(hostemu_lib, lan_config, capacity=1200, n_initial=1200, seed=24, packet_loss_ppm=50000)
+    for p in pools:
+        p.step(333)
+    check(pools, "lossy steady")
+    all3(pools, lambda p: p.leave(17))
+    for p in pools:
+        p.step(444)
+    check(pools, "lossy + leave")
+    assert pools[0].stats()["nacks"] > 0
+
+
+def test_snapshot_restore_inside_a_quiet_period(hostemu_lib):
+    pools = trio(hostemu_lib, lan_config, capacity=2000, n_initial=2000, seed=25)
+    for p in pools:
+        p.step(123)
+    blobs = [p.snapshot() for p in pools[:2]]
+    for p in pools[:2]:
+        p.step(57)
+    for p, b in zip(pools[:2], blobs):
+        p.restore(b)
+    for p in pools[:2]:
+        p.step(200)
+    pools[2].step(200)
+    check(pools, "restore + 200")
+
+
+def test_window_schedule_is_independent_of_row_order():
+    """reverse and odd/even row orders inside windows (each row runs all its ticks of a window first)"""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from consul_b200 import _lib\n"
+        "from consul_b200.pool import Pool, lan_config\n"
+        "L = _lib.load(%r)\n"
+        "p = Pool(lan_config(L, capacity=3001, n_initial=3000, seed=26), L)\n"
+        "p.step(50); p.crash_fraction(30000, 2); p.step(40); x = p.member_add(); p.join(x, [1]); p.step(1500)\n"
+        "s = p.stats(); s.pop('active_rows')\n"
+        "print(p.state_hash(), sorted(s.items()), p.sched_counts()['window_ticks'] > 100)\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "hostemu", "libgsim_hostemu.so"))
+    outs = []
+    for order in ("0", "1", "2"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GSIM_HOSTEMU_ORDER=order),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] == outs[2] and outs[0].endswith("True"), outs
