@@ -235,7 +235,7 @@ static bool poke(gsim_pool* p, T* col, size_t i, T v) {
 
 // Host-side write of a member's key word: every replica on a sharded pool.
 static bool poke_key(gsim_pool* p, uint32_t buf, uint32_t i, uint32_t k) {
-  if (p->d.kst) {  // GS_KSTAT builds: keep the member's status byte in step (see gs_kst_code)
+  if (p->d.kst) {  // keep the member's status byte in step (see gs_kst_code)
     uint8_t b;
     if (!peek(p, p->d.kst, i, &b)) return false;
     const uint32_t code = gs_kst_code(k);
@@ -439,8 +439,6 @@ static int init_device_state(gsim_pool* p) {
   okk = okk && be->fill32(d.key_rep[0], 0, key_words) && be->fill32(d.key_rep[1], 0, key_words);
   for (uint32_t s = 0; s <= g.ring_mask; ++s) okk = okk && be->fill32(d.inbox[s], 0, cap);
   if (d.kst) okk = okk && be->fill8(d.kst, 0, cap);
-  for (uint32_t s = 0; s <= g.ring_mask; ++s)
-    if (d.mailmap[s]) okk = okk && be->fill32(d.mailmap[s], 0, cap / 32);
   okk = okk && be->fill32(d.due, GS_NEVER, cap);  // rows that do not exist are never due
   okk = okk && be->fill32(d.reap_after, 0, cap);
   // rows that were never created hold the same defaults gs_init_row writes, so that a column
@@ -576,13 +574,7 @@ extern "C" int gsim_pool_create(const gsim_config* cfg, gsim_pool** out) {
       d.key[b] = okk ? d.key_rep[b] + (size_t)cfg->rank * g.key_stride : nullptr;
     }
   }
-#ifdef GS_KSTAT
   if (!sharded) okk = okk && alloc_col(p, &d.kst, cap);  // performance variant: status replica
-#endif
-#ifdef GS_MAILMAP
-  if (!sharded)  // performance variant: 1 bit per member and arrival slot
-    for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && alloc_col(p, &d.mailmap[s], cap / 32);
-#endif
   g.ring_mask = ring_depth - 1u;
   for (uint32_t s = 0; s < ring_depth; ++s) okk = okk && acol(&d.inbox[s], 1);
   okk = okk && acol(&d.due, 1) && acol(&d.meta, 1);
@@ -834,10 +826,6 @@ static int alloc_slot(gsim_pool* p, uint32_t* slot_out) {
 // next tick: set the wake bit in the mailbox that tick will read.
 static bool post_wake(gsim_pool* p, uint32_t row) {
   uint32_t* col = p->d.inbox[p->now & p->g.ring_mask];
-  if (uint32_t* map = p->d.mailmap[p->now & p->g.ring_mask]) {  // GS_MAILMAP builds: raise the member's bit
-    uint32_t mw;
-    if (!peek(p, map, row >> 5, &mw) || !poke(p, map, row >> 5, mw | (1u << (row & 31u)))) return false;
-  }
   uint32_t w;
   if (!peek(p, col, row, &w)) return false;
   return poke(p, col, row, w | GS_WAKE_BIT);
@@ -2006,8 +1994,6 @@ static std::vector<SnapCol> snap_cols(gsim_pool* p) {
   add(d.ltime_member, cap * 4); add(d.ltime_event, cap * 4); add(d.event_min, cap * 4);
   add(d.heard, cap * 4); add(d.queued, cap * 4); add(d.tx, cap * GS_MAX_RUMORS, GS_MAX_RUMORS / 2);
   if (d.kst) add(d.kst, cap);
-  for (uint32_t s = 0; s <= p->g.ring_mask; ++s)
-    if (d.mailmap[s]) add(d.mailmap[s], cap / 32 * 4);
   if (d.coord) {
     add(d.coord, cap * 8 * 2 * GS_COORD_WORDS, 2 * GS_COORD_WORDS);
     add(d.ctag, cap * 4 * 2, 2);
@@ -2042,7 +2028,6 @@ static uint32_t snap_layout(const gsim_pool* p) {
   if (p->d.coord) m |= 1u;
   if (p->d.ppreq) m |= 2u;
   if (p->d.kst) m |= 4u;
-  if (p->d.mailmap[0]) m |= 8u;
   if (p->sharded) m |= 16u;
   return m;
 }

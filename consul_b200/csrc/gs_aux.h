@@ -16,7 +16,7 @@ GS_DEV void gs_init_row(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
   const uint32_t k = gs_key_make(1u, 0u, GS_RANK_ALIVE, GS_TRUTH_UP);
   gs_key_store(d, g, 0u, i, k);
   gs_key_store(d, g, 1u, i, k);
-  for (uint32_t s = 0; s <= g.ring_mask; ++s) d.inbox[s][i] = 0u;  // (mailmap bits: a set bit over an empty word is harmless)
+  for (uint32_t s = 0; s <= g.ring_mask; ++s) d.inbox[s][i] = 0u;
   d.meta[i] = gp << GS_META_GPHASE_SHIFT;
   d.due[i] = now + (pp + g.P - now % g.P) % g.P;  // first tick >= now congruent to the phase
   d.cursor[i] = 0u;

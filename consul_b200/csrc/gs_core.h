@@ -82,7 +82,7 @@ GS_HD uint32_t gs_key_pending(uint32_t k) { return (k >> 4) & 1u; }
 GS_HD uint32_t gs_key_inc(uint32_t k) { return k >> 5; }
 GS_HD uint32_t gs_key_with_rank(uint32_t k, uint32_t rank) { return (k & ~(3u << 2)) | (rank << 2); }
 GS_HD uint32_t gs_key_with_inc(uint32_t k, uint32_t inc) { return (k & 31u) | (inc << 5); }
-// Status replica (GS_KSTAT builds): what a prober or gossiper needs to know about a peer is its
+// Status replica: what a prober or gossiper needs to know about a peer is its
 // truth and rank — 4 bits — not its 27-bit incarnation.  At 64 Mi members the key column is 256 MB
 // per buffer and every random 4-byte gather costs a DRAM sector; one status byte per member holds
 // both buffers' views in 64 MB, small enough to stay in the 126 MB L2.  Code = rank<<2 | truth,
@@ -301,9 +301,6 @@ struct GsDev {
   uint32_t* key[2];      // the key column this rank READS (its own replica when sharded)
   uint32_t* key_rep[2];  // replica 0; replica r at + r*key_stride.  Writers update every replica.
   uint32_t* inbox[GS_RING_MAX];  // arrival-tick ring; slots >= ring depth are null
-  // GS_MAILMAP builds (performance variant): one bit per member and arrival slot, set whenever the
-  // mailbox word becomes non-zero — the scan reads 1 bit instead of 4 bytes per member; null otherwise
-  uint32_t* mailmap[GS_RING_MAX];
   uint32_t* due;
   uint32_t* meta;
   uint32_t* cursor;
@@ -327,8 +324,9 @@ struct GsDev {
   double* adj;          // [GS_ADJ_WINDOW][cap] adjustment samples
   uint32_t* adj_idx;    // [cap]
   // push-pull mailboxes (null unless the pool runs periodic push-pull), by arrival-tick parity
-  // GS_KSTAT builds (performance variant, see gs_kst_code): one byte per member with the 4-bit view
-  // of key[0] (low nibble) and key[1] (high nibble) that peer selection needs; null otherwise
+  // status replica (see gs_kst_code): one byte per member with the 4-bit view of key[0] (low nibble)
+  // and key[1] (high nibble) that peer selection needs; null on sharded pools (they gather from their
+  // own full key replica)
   uint8_t* kst;
   const uint32_t* row_ptr;  // [graph_n + 1] CSR peer graph, null on complete-graph pools
   const uint32_t* col_idx;  // [row_ptr[graph_n]]

@@ -149,14 +149,11 @@ __device__ __forceinline__ void gs_q_publish(const GsDev& d, const GsGlobals& g,
 // Whatever the fast path declines goes to the generic gs_row_step.
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
-    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
+    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
-#ifdef GS_MAILMAP
-  __shared__ __align__(16) uint32_t s_flag[GS_STAGES][GS_WARPS][4];  // the tile's 128 mailbox bits
-#endif
   __shared__ uint32_t s_q[2];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
@@ -170,12 +167,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const GsGlobals& g = *gp;
-  const uint32_t t_first = *d.tick_base + k_off;
-  // n_ticks > 1 (single-GPU pools): several ticks in one launch, separated by a grid barrier —
-  // the per-launch gap is most of a tick at 1 M members.  All CTAs are co-resident (persistent
-  // grid, cooperative launch).
-  for (uint32_t kk = 0; kk < n_ticks; ++kk) {
-  const uint32_t t = t_first + kk;
+  const uint32_t t = *d.tick_base + k_off;
   if (g.world > 1u) gs_ranks_wait(d, g, t);
   const uint32_t cur = t & 1u, P = g.P, pslot = t % P, gslot = t % g.GI;
   const uint32_t pslot_t = (t + P - g.T % P) % P;
@@ -193,33 +185,10 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
   const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
   const uint32_t* __restrict__ inbox_cur = d.inbox[t & g.ring_mask];  // this tick's arrival slot
-#ifdef GS_MAILMAP
-  // Performance variant: the scan reads one BIT per member (16 bytes per tile) and touches the
-  // 4-byte mailbox word only of members whose bit is raised; the warp lowers a tile's bits once
-  // the tile has been processed (nobody posts into the slot being consumed).
-  uint32_t* const mailmap_cur = d.mailmap[t & g.ring_mask];
-  const bool use_map = mailmap_cur != nullptr;
-#endif
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
   DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
 
-#ifdef GS_EARLY_A
-  // Performance variant: which tiles of this chunk start a probe at this tick is known
-  // arithmetically, so their own columns (key, meta, cursor, pass: 16 lines of 128 B per tile) are
-  // pulled towards this SM now, while the mailbox scan of the chunk is still in flight — one
-  // dependent L2 round trip less on the critical path of a latency-bound tick (1 M members).
-  if (gated) {
-    for (uint32_t tile = t_begin; tile < t_end; ++tile) {
-      if (gs_probe_phase(g.rot_p, tile >> shift, P) != pslot) continue;
-      if (lane < 16u) {
-        const uint32_t c4 = lane >> 2;
-        const uint32_t* col = c4 == 0u ? d.key[cur] : c4 == 1u ? d.meta : c4 == 2u ? d.cursor : d.pass;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (size_t)tile * GS_TILE + (lane & 3u) * 32u));
-      }
-    }
-  }
-#endif
   uint32_t tq = t_begin;  // next tile to issue
   bool did_work = false;  // this thread touched global state (needs the closing fence when sharded)
   auto issue = [&](uint32_t st) {
@@ -232,11 +201,6 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
                      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(inbox_cur + off) : "memory");
         *reinterpret_cast<uint4*>(&s_inb[st][wib][lane * 4u]) = v;
       } else {
-#ifdef GS_MAILMAP
-        if (use_map) {
-          if (lane == 0u) gs_cp_async16(&s_flag[st][wib][0], mailmap_cur + (size_t)tq * 4u);
-        } else
-#endif
         gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
       }
       bool gate = true;
@@ -259,17 +223,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   for (uint32_t tile = t_begin; tile < t_end; ++tile) {
     issue((st + GS_STAGES - 1u) % GS_STAGES);
     gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
-#ifdef GS_MAILMAP
-    uint4 i4;
-    if (use_map) {
-      __syncwarp();  // lane 0's copy of the tile's bits is visible to the whole warp
-      i4 = *reinterpret_cast<const uint4*>(&s_flag[st][wib][0]);
-    } else {
-      i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
-    }
-#else
     const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
-#endif
     const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
     bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
     // periodic push-pull (opt-in): the ticker of this tile's phase group (or, with per-member
@@ -293,18 +247,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       bool any_cand = false;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-#ifdef GS_MAILMAP
-        uint32_t w;
-        if (use_map) {  // member base + 32u is bit `lane` of the tile's word u
-          const uint32_t fw = u == 0 ? i4.x : u == 1 ? i4.y : u == 2 ? i4.z : i4.w;
-          w = ((fw >> lane) & 1u) ? __ldcg(inbox_cur + base + 32u * u) : 0u;  // L2: written by other SMs
-          s_inb[st][wib][u * 32 + lane] = w;  // gs_row_step below takes it from here
-        } else {
-          w = s_inb[st][wib][u * 32 + lane];
-        }
-#else
         const uint32_t w = s_inb[st][wib][u * 32 + lane];
-#endif
         const bool due_now = s_due[st][wib][u * 32 + lane] == t;
         act[u] = w != 0u || due_now ||
                  (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, (base + 32u * u) / g.phase_group, t));
@@ -341,10 +284,6 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
           if (a) gs_row_step(d, g, base + 32u * u, t, gslot, s_inb[st][wib][u * 32 + lane], sink);
         }
       }
-#ifdef GS_MAILMAP
-      if (use_map && lane == 0u && (i4.x | i4.y | i4.z | i4.w) != 0u)  // this tile's mail is consumed
-        *reinterpret_cast<uint4*>(mailmap_cur + (size_t)tile * 4u) = make_uint4(0u, 0u, 0u, 0u);
-#endif
       __syncwarp();  // everyone is done with this stage before it is refilled
     }
     st = (st + 1u) % GS_STAGES;
@@ -367,28 +306,6 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   }
   if (tid == 0u) gs_q_publish(d, g, s_q, t);  // (after the CTA barrier above: every warp's flags are in)
   if (g.world > 1u) gs_ranks_release(d, g, t + 1u);
-  if (kk + 1u < n_ticks) {
-    // Grid barrier between ticks of one launch: every thread's writes are fenced (which also
-    // drops this SM's L1), CTAs count in on a monotonic counter and wait for the whole grid.
-    __threadfence();
-    __syncthreads();
-    if (tid == 0u) {
-      const uint32_t target = (kk + 1u) * gridDim.x;
-      __threadfence();
-      atomicAdd(d.done_ctr, 1u);
-      uint32_t v, spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(d.done_ctr) : "memory");
-      } while (v < target && ++spins < (1u << 26));  // bounded: a bug must not hang the device
-    }
-    __syncthreads();
-    if (tid < GS_NSTAT) s_stat[tid] = 0u;
-    if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
-    if (tid == 64u) s_q[0] = 0u;
-    if (tid == 65u) s_q[1] = GS_NEVER;
-    __syncthreads();
-  }
-  }  // for kk
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -687,8 +604,8 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return d.coord ? cudaLaunchKernelEx(&cfg, gs_tick_kernel<true>, d, g_dev, k, 1u)
-                 : cudaLaunchKernelEx(&cfg, gs_tick_kernel<false>, d, g_dev, k, 1u);
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_tick_kernel<true>, d, g_dev, k)
+                 : cudaLaunchKernelEx(&cfg, gs_tick_kernel<false>, d, g_dev, k);
 }
 
 static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const GsDev& d, const GsGlobals* g_dev,
@@ -705,16 +622,6 @@ static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const 
   cfg.numAttrs = pdl ? 1 : 0;
   return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks)
                  : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks);
-}
-
-// Several ticks in one cooperative launch (single-GPU pools).
-static cudaError_t gs_launch_multi(uint32_t blocks, cudaStream_t stream, const GsDev& d,
-                                   const GsGlobals* g_dev, uint32_t n_ticks) {
-  GsDev dd = d;
-  uint32_t k0 = 0;
-  void* args[] = {(void*)&dd, (void*)&g_dev, (void*)&k0, (void*)&n_ticks};
-  const void* fn = d.coord ? (const void*)gs_tick_kernel<true> : (const void*)gs_tick_kernel<false>;
-  return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(GS_BLOCK), args, 0, stream);
 }
 
 __global__ void __launch_bounds__(GS_BLOCK) gs_fill32_kernel(uint32_t* dst, uint32_t value, size_t count) {
@@ -747,12 +654,6 @@ class CudaBackend : public GsBackend {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel<false>, GS_BLOCK, 0) != cudaSuccess || occ < 1)
       occ = 4;
-    // measurement knob: fewer resident CTAs per SM leave room for the NEXT tick's CTAs to become
-    // resident early under programmatic dependent launch (a full machine cannot overlap)
-    if (const char* e = getenv("GSIM_CTAS_PER_SM")) {
-      const int want = atoi(e);
-      if (want >= 1 && want < occ) occ = want;
-    }
     full_grid_ = (uint32_t)(sms * occ);
     scratch_ = nullptr;
     cudaMalloc(&scratch_, 4096);
@@ -820,7 +721,6 @@ class CudaBackend : public GsBackend {
       return true;
     }
     cudaSetDevice(dev_);
-#ifdef GS_KSTAT
     // performance variant: keep the status replica (1 byte per member, gathered at random by every
     // prober) resident in L2 — persisting hits for the window, streaming for everything else.
     // Set on the stream before any capture, so graph kernel nodes inherit it.
@@ -843,7 +743,6 @@ class CudaBackend : public GsBackend {
         cudaGetLastError();  // best effort: an unsupported attribute must not fail the step
       }
     }
-#endif
     // persistent launch: one warp per 128-member tile up to a full machine (SMs x resident CTAs)
     uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
     if (g.world > 1 && tiles > g.rows_per_rank / GS_TILE) tiles = g.rows_per_rank / GS_TILE;
@@ -852,16 +751,6 @@ class CudaBackend : public GsBackend {
     if (blocks > full_grid_) blocks = full_grid_;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks;
-    if (use_graph && !xbar && g.world <= 1u && multi_tick_ && d.done_ctr && left > 1u) {
-      // one cooperative launch for the whole chunk (bounded to keep any single launch short)
-      while (left) {
-        const uint32_t c = left > 4096u ? 4096u : left;
-        if (!ok(gs_launch_multi(blocks, stream_, d, g_dev, c), "multi-tick launch")) return false;
-        gs_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, c, d.done_ctr);
-        launches_ += 2;
-        left -= c;
-      }
-    }
     if (use_graph && (!xbar || !no_shard_graph_) && left >= GS_GRAPH_TICKS) {
       cudaGraphExec_t ge = graph_for(d, g_dev, blocks, xbar);
       if (!ge) return false;
@@ -1147,7 +1036,6 @@ class CudaBackend : public GsBackend {
   GsVmm vmm_;
   bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;
-  bool multi_tick_ = getenv("GSIM_MULTI_TICK") != nullptr;
   // sharded pools: stream launches measured faster than graph replay (21 vs 28 us/tick at 2 Mi
   // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
   bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;

@@ -123,12 +123,10 @@ enum {
 // in local HBM; a key changes rarely (suspect, dead, refute, join), and whoever changes it
 // writes all replicas (remote stores over NVLink, ordered by the closing fence.sys).
 GS_DEV void gs_key_store(const GsDev& d, const GsGlobals& g, uint32_t buf, uint32_t i, uint32_t k) {
-#ifdef GS_KSTAT
   if (d.kst != nullptr) {  // the member's status byte: only its owner (or the host) ever writes it
     const uint32_t b = d.kst[i], code = gs_kst_code(k);
     d.kst[i] = (uint8_t)(buf ? ((b & 0x0Fu) | (code << 4)) : ((b & 0xF0u) | code));
   }
-#endif
   if (g.world <= 1u) {
     d.key[buf][i] = k;
     return;
@@ -136,11 +134,12 @@ GS_DEV void gs_key_store(const GsDev& d, const GsGlobals& g, uint32_t buf, uint3
   for (uint32_t r = 0; r < g.world; ++r) d.key_rep[buf][(size_t)r * g.key_stride + i] = k;
 }
 
-// What member c looks like to its peers in buffer `cur`: the key word.  GS_KSTAT builds answer
-// from the status byte (inc reads as 0, pending as 0) unless the member is a pending joiner; a
-// caller that needs the incarnation asks for the full key.
+// What member c looks like to its peers in buffer `cur`.  Peer selection needs truth and rank only,
+// so it is answered from the status byte (1 B per member: 64 MB at 64 Mi members, L2-resident, where
+// a random 4-byte gather from the 256 MB key column costs a DRAM sector each) — inc reads as 0,
+// pending as 0 — unless the member is a pending joiner; a caller that needs the incarnation asks
+// for the full key.  Measured (profiles/README.md r2a): 234 -> 188 us/tick at 64 Mi members.
 GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_inc) {
-#ifdef GS_KSTAT
   if (d.kst != nullptr && !need_inc) {
 #if defined(__CUDA_ARCH__)
     const uint32_t b = __ldcg(reinterpret_cast<const unsigned char*>(d.kst) + c);
@@ -150,33 +149,18 @@ GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_
     const uint32_t code = (b >> (cur * 4u)) & 15u;
     if (code != GS_KST_PENDING) return code;
   }
-#else
-  (void)need_inc;
-#endif
   return GS_LD_OTHER(&d.key[cur][c]);
 }
 
-// Deliver `bits` into member j's mailbox word of arrival slot `slot` (commutative).  GS_MAILMAP
-// builds also raise the member's bit in the slot's bitmap when the word was empty: the word only
-// ever becomes non-zero through this function (or the host's post_wake), and nobody posts into
-// the slot that is being consumed, so "word != 0 implies bit set" holds at every scan.
+// Deliver `bits` into member j's mailbox word of arrival slot `slot` (commutative).
 template <class Sink>
 GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t slot, uint32_t j, uint32_t bits) {
   sink.activity();  // a posted word is mail at its arrival tick: the pool is not quiet
-  const uint32_t old = GS_ATOMIC_OR32(&d.inbox[slot][j], bits);
-#ifdef GS_MAILMAP
-  if (old == 0u && d.mailmap[slot] != nullptr) GS_ATOMIC_OR32(&d.mailmap[slot][j >> 5], 1u << (j & 31u));
-#else
-  (void)old;
-#endif
+  (void)GS_ATOMIC_OR32(&d.inbox[slot][j], bits);
 }
 
 // incarnation of peer c whose key-like word k came from gs_peer_key(..., false)
-#ifdef GS_KSTAT
 #define GS_PEER_INC(d, cur, c, k) gs_key_inc(gs_peer_key((d), (cur), (c), true))
-#else
-#define GS_PEER_INC(d, cur, c, k) gs_key_inc(k)
-#endif
 
 // WAN latency pools (BASELINE config 5): EXTRA one-way latency in ticks from src to dst on top
 // of the one tick every packet takes; 0 everywhere on a pool without datacenters.  An all-zero

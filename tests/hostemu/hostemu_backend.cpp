@@ -137,9 +137,7 @@ class HostEmuBackend : public GsBackend {
       }
       for (uint32_t x = 0; x < hi - lo; ++x) {
         const uint32_t i = lo + row_at(x, hi - lo);
-        // GS_MAILMAP builds look at the mailbox word only if the member's bit is raised
-        const uint32_t* map = d.mailmap[t & g.ring_mask];
-        const uint32_t inb = (map == nullptr || ((map[i >> 5] >> (i & 31u)) & 1u)) ? d.inbox[t & g.ring_mask][i] : 0u;
+        const uint32_t inb = d.inbox[t & g.ring_mask][i];
         uint32_t due = GS_NEVER;
         if (gs_tile_probe_gate(g, i / GS_TILE, pslot, (t + g.P - g.T % g.P) % g.P)) due = d.due[i];
         if (!(inb != 0u || due == t || gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t))) continue;
@@ -156,8 +154,6 @@ class HostEmuBackend : public GsBackend {
         }
         gs_row_step(d, g, i, t, gslot, inb, sink);
       }
-      if (uint32_t* map = d.mailmap[t & g.ring_mask])  // this arrival slot is consumed: lower its bits
-        for (uint32_t w = lo / 32u; w < (hi + 31u) / 32u; ++w) map[w] = 0u;
       for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r) {
         uint32_t c = sink.local_heard[r];
         if (c) {
