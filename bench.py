@@ -38,9 +38,10 @@ N_HBM = 67_108_864          # secondary roofline point: 268 MB mailbox column + 
 HBM_TICKS = 256
 MEMBERS_PER_GPU_SHARDED = 1024 * 1024   # ~ the single-GPU workload per GPU: an honest weak-scaling curve
 
-# Algorithmic bytes.  Every member every tick reads its 4-byte mailbox word;
-# tiles whose ticker phase can be due at this tick (2 of every P ticks) also read `due`.
-# Members that act pay for the cold columns they touch (useful bytes, not sectors).
+# Algorithmic bytes: useful bytes the algorithm has to move, not sectors.
+# gs_tick_kernel (one tick per launch): every member reads its 4-byte mailbox word; tiles whose
+# ticker phase can be due at this tick (2 of every P ticks) also read `due`; members that act pay
+# for the cold columns they touch.
 B_SCAN = 4.0        # inbox[t&1][i]
 B_DUE = 4.0         # due[i], on 2/P of the ticks
 B_ACTIVE = 24.0     # key, meta, due, queued reads; inbox clear; wake / write-back word
@@ -48,14 +49,37 @@ B_PROBE = 12.0      # extra for a probe start: cursor r/w, pass, target key gath
 B_ACCEPT = 21.0     # heard r/w, queued write, tx init, Lamport clock witness
 B_PACKET = 12.0     # peer key gather + mailbox atomic RMW
 B_RUMOR_TX = 2.0    # tx counter r/w per broadcast carried
+# gs_window_kernel (up to P ticks per launch, quiet pool): no mailbox word is read at all; every
+# member's `due` once per launch, and per probe the prober's key, meta, cursor (r/w), pass, the
+# target's status byte and the new `due`.
+B_WIN_DUE = 4.0
+B_WIN_PROBE = 4.0 + 4.0 + 8.0 + 4.0 + 1.0 + 4.0
 
 
-
-
-def algorithmic_bytes(d: dict, probe_interval_ticks: int) -> float:
-    return (d["node_ticks"] * (B_SCAN + B_DUE * 2.0 / probe_interval_ticks) +
-            d["active_rows"] * B_ACTIVE + d["probes"] * B_PROBE + d["rumors_accepted"] * B_ACCEPT +
+def split_bytes(d: dict, sc: dict, n_members: float, P: int) -> dict:
+    """Algorithmic bytes of the timed region by kernel.  `d` = counter deltas, `sc` = scheduling
+    deltas (window launches / ticks, single ticks).  Inside quiet windows every member starts exactly
+    one probe per P ticks and nothing else happens, so the window kernel's share of the shared
+    counters is window_ticks * n / P probes."""
+    win_probes = min(float(d["probes"]), sc["window_ticks"] * n_members / P)
+    win = sc["window_launches"] * n_members * B_WIN_DUE + win_probes * B_WIN_PROBE
+    tick_nt = sc["tick_launches"] * n_members
+    tick = (tick_nt * (B_SCAN + B_DUE * 2.0 / P) + max(0.0, d["active_rows"] - win_probes) * B_ACTIVE +
+            max(0.0, d["probes"] - win_probes) * B_PROBE + d["rumors_accepted"] * B_ACCEPT +
             d["gossip_packets"] * B_PACKET + d["rumors_sent"] * B_RUMOR_TX)
+    return {"window": win, "tick": tick}
+
+
+def roofline_of(kernel: str, bytes_: float, ms: float, launches: int, ticks: int, n_members: float, peak: float,
+                peak_src: str, traffic) -> dict:
+    if launches == 0 or ms <= 0:
+        return None
+    achieved = bytes_ / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "per_gpu": True, "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": bytes_ / launches, "launch_us": ms * 1e3 / launches, "launches": launches,
+            "ticks_per_launch": ticks / launches, "bytes_per_node_tick": bytes_ / max(1.0, ticks * n_members),
+            "share_of_kernel_time": None}
 
 
 def stat_delta(a: dict, b: dict) -> dict:
@@ -420,6 +444,7 @@ def main():
     sampler.start()
     s0 = pool.stats()
     l0 = pool.launch_count()
+    c0 = pool.sched_counts()
     kernel_ms, tick_launches = 0.0, 0
     barrier()
     t0 = time.perf_counter()
@@ -432,7 +457,9 @@ def main():
     dt = time.perf_counter() - t0
     s1 = pool.stats()
     l1 = pool.launch_count()
+    c1 = pool.sched_counts()
     d = stat_delta(s0, s1)
+    sc = {k: c1[k] - c0[k] for k in c1}
 
     # ticks-to-full-convergence of one cascade (untimed, exact tick recorded on the device)
     x = pool.member_add()
@@ -531,22 +558,26 @@ def main():
     dt_max, dte_max, kms_max = [float(v) for v in tt.tolist()]
     node_ticks_all, e2e_all = [float(v) for v in nt.tolist()]
 
-    # ---- roofline of the dominant kernel (gs_tick_kernel), PER GPU --------------------------------
-    # a sharded pool's counters are whole-job totals: each GPU moves 1/world of the bytes, and the
-    # peak is one GPU's
+    # ---- roofline per kernel, PER GPU (a sharded pool's counters are whole-job totals: each GPU moves
+    # 1/world of the bytes against one GPU's peak).  `roofline` = the kernel that took more of the time.
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(d, gi) / world
-    launch_us = kms_max * 1e3 / max(1, tick_launches)
-    achieved = alg / (kms_max * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gs_tick_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "per_gpu": True,
-                "traffic": measured_traffic("traffic_1m_bytes") if (not sharded and n == N_MEMBERS) else None,
-                "peak_source": peak_src, "bytes_per_launch": alg / max(1, tick_launches),
-                "launch_us": launch_us, "launches": tick_launches,
-                "ticks_per_launch": ticks * args.steps / max(1, tick_launches),
-                "bytes_per_node_tick": alg * world / max(1.0, d["node_ticks"]),
-                "note": "1M members: the hot columns are L2-resident by construction (2048 dependent ticks over the "
-                        "same state); roofline_hbm below is the HBM-bound size"}
+    by = split_bytes(d, sc, float(n), gi)
+    one_m = (not sharded and n == N_MEMBERS)
+    r_tick = roofline_of("gs_tick_kernel", by["tick"] / world, sc["tick_ms"], sc["tick_launches"], sc["tick_launches"],
+                         float(n) / world, peak, peak_src, measured_traffic("traffic_tick_cascade_1m_bytes") if one_m else None)
+    r_win = roofline_of("gs_window_kernel", by["window"] / world, sc["window_ms"], sc["window_launches"], sc["window_ticks"],
+                        float(n) / world, peak, peak_src, measured_traffic("traffic_window_1m_bytes") if one_m else None)
+    total_ms = sc["tick_ms"] + sc["window_ms"]
+    for r, ms_ in ((r_tick, sc["tick_ms"]), (r_win, sc["window_ms"])):
+        if r:
+            r["share_of_kernel_time"] = ms_ / total_ms if total_ms > 0 else None
+    roofline = r_tick if (r_tick and (not r_win or sc["tick_ms"] >= sc["window_ms"])) else r_win
+    roofline = dict(roofline)
+    roofline["note"] = ("the kernel with the larger share of the step's kernel time; both kernels are in roofline_kernels. "
+                        "1M members: the hot columns are L2-resident by construction (2048 dependent ticks over the same "
+                        "state); roofline_hbm below is the HBM-bound size")
+    roofline["whole_step"] = {"achieved": (by["tick"] + by["window"]) / world / (total_ms * 1e-3) / 1e9 if total_ms > 0 else None,
+                              "unit": "GB/s", "bytes_per_node_tick": (by["tick"] + by["window"]) / max(1.0, d["node_ticks"])}
 
     roofline_hbm = None
     if sharded:
@@ -555,18 +586,22 @@ def main():
         pool.close()
         big = Pool(lan_config(capacity=N_HBM, n_initial=N_HBM, seed=SEED, device=local_rank))
         big.step(64)
-        b0 = big.stats()
+        b0, q0 = big.stats(), big.sched_counts()
         big.step(HBM_TICKS)
-        ms, nl = big.last_step_timing()
-        b1 = big.stats()
+        b1, q1 = big.stats(), big.sched_counts()
         db = stat_delta(b0, b1)
-        algb = algorithmic_bytes(db, gi)
-        roofline_hbm = {"members": N_HBM, "ticks": HBM_TICKS, "achieved": algb / (ms * 1e-3) / 1e9,
-                        "peak": peak, "unit": "GB/s", "frac": algb / (ms * 1e-3) / 1e9 / peak,
-                        "launch_us": ms * 1e3 / nl, "launches": nl, "node_ticks_per_s": db["node_ticks"] / (ms * 1e-3),
-                        "traffic": measured_traffic("traffic_64m_bytes"), "bytes_per_launch": algb / nl,
-                        "bytes_per_node_tick": algb / max(1.0, db["node_ticks"]),
-                        "workload": f"{N_HBM:,} members, LAN steady state (4x BASELINE config 4 on one GPU; hot columns exceed L2)"}
+        qd = {k: q1[k] - q0[k] for k in q1}
+        byb = split_bytes(db, qd, float(N_HBM), gi)
+        dominant_win = qd["window_ms"] >= qd["tick_ms"]
+        roofline_hbm = roofline_of("gs_window_kernel" if dominant_win else "gs_tick_kernel",
+                                   byb["window"] if dominant_win else byb["tick"],
+                                   qd["window_ms"] if dominant_win else qd["tick_ms"],
+                                   qd["window_launches"] if dominant_win else qd["tick_launches"],
+                                   qd["window_ticks"] if dominant_win else qd["tick_launches"], float(N_HBM), peak, peak_src,
+                                   measured_traffic("traffic_window_64m_bytes") if dominant_win else None)
+        roofline_hbm.update({"members": N_HBM, "ticks": HBM_TICKS, "sched": qd,
+                             "node_ticks_per_s": db["node_ticks"] / ((qd["window_ms"] + qd["tick_ms"]) * 1e-3),
+                             "workload": f"{N_HBM:,} members, LAN steady state (4x BASELINE config 4 on one GPU; hot columns exceed L2)"})
         big.close()
 
     if rank != 0:
@@ -597,7 +632,9 @@ def main():
                          "gsim_restore(pinned host snapshot) -> member_add -> join -> step -> members + stats" if restore_ok else
                          "member_add -> join -> step -> members + stats (cluster resident: restore self-check failed)")},
         "gpu_launches": int(l1 - l0),
-        "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "sched": sc,
+        "roofline": roofline, "roofline_kernels": {"gs_tick_kernel": r_tick, "gs_window_kernel": r_win},
+        "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }

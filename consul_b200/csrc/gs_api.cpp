@@ -197,7 +197,8 @@ struct gsim_pool {
   uint32_t dirty_seq = 0;    // bumped by every host-side write to device state (quiet no longer known)
   uint32_t dirty_tick = 0;   // p->now at that write
   uint32_t retry_at = 0;     // do not look for quietness again before this tick
-  uint64_t sched_counts[4] = {0, 0, 0, 0};  // window launches, ticks run in windows, single-tick launches, horizon scans
+  // window launches, ticks run in windows, single-tick launches, horizon scans, ns of window kernels, ns of tick kernels
+  uint64_t sched_counts[6] = {0, 0, 0, 0, 0, 0};
 };
 
 static void mark_dirty(gsim_pool* p) {
@@ -1557,8 +1558,11 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
     if (can_window && p->quiet) {
       uint32_t done = 0;
       uint64_t nl = 0;
-      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, use_graph, &p->last_ms, &nl, &done, xb))
+      double wms = 0;
+      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, use_graph, &wms, &nl, &done, xb))
         return GSIM_ERR_CUDA;
+      p->last_ms += wms;
+      p->sched_counts[4] += (uint64_t)(wms * 1e6);
       p->last_launches += nl;
       p->sched_counts[0] += nl;
       p->sched_counts[1] += done;
@@ -1574,8 +1578,11 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
     uint32_t c = left;
     if (can_window && c > 16u) c = 16u;  // look for quietness every few ticks
     if (can_window && p->retry_at > p->now && p->retry_at - p->now < c) c = p->retry_at - p->now;
-    if (!be->run_ticks(p->d, p->g_dev, p->g, p->now, c, use_graph, &p->last_ms, &p->last_launches, xb))
+    double tms = 0;
+    if (!be->run_ticks(p->d, p->g_dev, p->g, p->now, c, use_graph, &tms, &p->last_launches, xb))
       return GSIM_ERR_CUDA;
+    p->last_ms += tms;
+    p->sched_counts[5] += (uint64_t)(tms * 1e6);
     p->sched_counts[2] += c;
     p->now += c;
     p->node_ticks += (uint64_t)c * p->g.n;
@@ -1588,7 +1595,7 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
   return GSIM_OK;
 }
 
-extern "C" int gsim_sched_counts(gsim_pool* p, uint64_t out[4]) {
+extern "C" int gsim_sched_counts(gsim_pool* p, uint64_t out[6]) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
   memcpy(out, p->sched_counts, sizeof(p->sched_counts));

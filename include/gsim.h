@@ -400,8 +400,9 @@ int gsim_last_step_timing(gsim_pool* p, double* kernel_ms, uint64_t* launches);
 /* Total kernels launched by this pool since creation (bench "gpu_launches"). */
 uint64_t gsim_launch_count(gsim_pool* p);
 /* Scheduling counters since creation: out[0] = quiet-window launches, out[1] = ticks advanced inside
- * quiet windows, out[2] = single-tick launches, out[3] = horizon scans. */
-int gsim_sched_counts(gsim_pool* p, uint64_t out[4]);
+ * quiet windows, out[2] = single-tick launches, out[3] = horizon scans, out[4] / out[5] = nanoseconds of
+ * CUDA-event time spent in window / single-tick launches. */
+int gsim_sched_counts(gsim_pool* p, uint64_t out[6]);
 
 #ifdef __cplusplus
 }

@@ -28,4 +28,4 @@ if a.crash_ppm:
     p.crash_fraction(a.crash_ppm, 0)
 p.step(a.ticks)
 ms, n = p.last_step_timing()
-print(f"members={a.members} ticks={a.ticks} kernel_ms={ms:.3f} us_per_tick={ms * 1e3 / n:.2f}")
+print(f"members={a.members} ticks={a.ticks} kernel_ms={ms:.3f} launches={n} sched={p.sched_counts()}")
