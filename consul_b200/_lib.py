@@ -52,7 +52,8 @@ class GsimConfig(C.Structure):
 
 
 class GsimMemberDesc(C.Structure):
-    _fields_ = [("alive_msg_size", C.c_uint32), ("flags", C.c_uint32)]
+    _fields_ = [("alive_msg_size", C.c_uint32), ("flags", C.c_uint32), ("name_len", C.c_uint32),
+                ("meta_len", C.c_uint32)]
 
 
 class GsimMember(C.Structure):
@@ -140,6 +141,16 @@ SIGNATURES = [
     ("gsim_last_step_timing", _i32, [_P, C.POINTER(C.c_double), C.POINTER(_u64)]),
     ("gsim_launch_count", _u64, [_P]),
     ("gsim_sched_counts", _i32, [_P, C.POINTER(_u64)]),
+    ("gsim_wire_alive", _sz, [_P, _sz, _u32, C.c_char_p, _P, _sz, C.c_uint16, _P, _sz, C.POINTER(C.c_uint8)]),
+    ("gsim_wire_suspect", _sz, [_P, _sz, _u32, C.c_char_p, C.c_char_p]),
+    ("gsim_wire_dead", _sz, [_P, _sz, _u32, C.c_char_p, C.c_char_p]),
+    ("gsim_wire_join_intent", _sz, [_P, _sz, _u64, C.c_char_p]),
+    ("gsim_wire_leave_intent", _sz, [_P, _sz, _u64, C.c_char_p, _i32]),
+    ("gsim_wire_user_event", _sz, [_P, _sz, _u64, _P, _sz, _P, _sz, _i32]),
+    ("gsim_wire_compound", _sz, [_P, _sz, C.POINTER(_P), C.POINTER(_sz), _sz]),
+    ("gsim_wire_wanfed_frame", _sz, [_P, _sz, _P, _sz]),
+    ("gsim_wire_consul_user_event", _sz, [_P, _sz, C.c_char_p, C.c_char_p, _P, _sz, C.c_char_p, C.c_char_p,
+                                          C.c_char_p, _i32]),
 ]
 
 

@@ -18,6 +18,7 @@
 
 #include "../../include/gsim.h"
 #include "gs_backend.h"
+#include "gs_wire.h"
 #include "gs_coord.h"
 
 #ifndef GS_MAKE_BACKEND
@@ -192,6 +193,7 @@ struct gsim_pool {
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
   std::vector<uint32_t> graph_rp, graph_col;  // host copy of the CSR peer graph (gsim_graph_set)
   GsXbar xb;
+  std::vector<std::pair<uint32_t, uint32_t>> name_lens;  // (member, bytes of its node name) where not canonical
   // quiet-window scheduling
   bool quiet = false;        // the pool is known to be quiet at p->now: windows may run
   uint32_t dirty_seq = 0;    // bumped by every host-side write to device state (quiet no longer known)
@@ -832,6 +834,24 @@ static bool post_wake(gsim_pool* p, uint32_t row) {
   return poke(p, col, row, w | GS_WAKE_BIT);
 }
 
+// ---- message sizes: what the encoder (gs_wire.h) produces for this member ------------------------
+// A virtual member is called "node-<id>" unless gsim_member_desc.name_len said otherwise.
+static uint32_t member_name_len(const gsim_pool* p, uint32_t id) {
+  for (const auto& kv : p->name_lens)
+    if (kv.first == id) return kv.second;
+  uint32_t digits = 1;
+  for (uint32_t v = id; v >= 10u; v /= 10u) ++digits;
+  return 5u + digits;
+}
+static uint32_t alive_size(const gsim_pool* p, uint32_t id, uint32_t inc, uint32_t meta_len) {
+  static const uint8_t vsn[6] = {1, 5, 2, 2, 5, 4}, addr[4] = {10, 0, 0, 1};
+  static const char none = 0;
+  return (uint32_t)gsw::alive(nullptr, 0, inc, nullptr, member_name_len(p, id), addr, 4, 8301, &none, meta_len, vsn);
+}
+static uint32_t intent_size(const gsim_pool* p, uint32_t id, bool leave, uint32_t ltime) {
+  return (uint32_t)gsw::serf_intent(nullptr, 0, leave, ltime, nullptr, member_name_len(p, id), false, false);
+}
+
 static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subject, uint32_t inc,
                        uint32_t ltime, uint32_t origin, uint32_t size, uint32_t qclass) {
   GsGlobals& g = p->g;
@@ -901,7 +921,8 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
   g.n += 1;
   g.up_count += 1;
   recompute_tables(p);
-  uint32_t size = desc && desc->alive_msg_size ? desc->alive_msg_size : 64u;
+  if (desc && desc->name_len) p->name_lens.push_back(std::make_pair(id, desc->name_len));
+  uint32_t size = desc && desc->alive_msg_size ? desc->alive_msg_size : alive_size(p, id, 1u, desc ? desc->meta_len : 0u);
   rc = start_rumor(p, slot, GSIM_RUMOR_ALIVE, id, 1u, 0u, id, size, 0u);
   if (rc) return fail(p, rc, "start_rumor");
   *id_out = id;
@@ -1005,7 +1026,7 @@ extern "C" int gsim_join(gsim_pool* p, uint32_t id, const uint32_t* seeds, size_
     uint32_t slot;
     int rc = alloc_slot(p, &slot);
     if (rc == GSIM_OK) {
-      rc = start_rumor(p, slot, GSIM_RUMOR_JOIN_INTENT, id, 0u, lm, id, 40u, 1u);
+      rc = start_rumor(p, slot, GSIM_RUMOR_JOIN_INTENT, id, 0u, lm, id, intent_size(p, id, false, lm), 1u);
       if (rc) return fail(p, rc, "start_rumor");
     } else if (rc != GSIM_ERR_CAPACITY) {
       return fail(p, rc, "alloc_slot");
@@ -1112,7 +1133,7 @@ extern "C" int gsim_member_update(gsim_pool* p, uint32_t id, uint32_t alive_msg_
     if (!peek(p, p->d.key[b], id, &kk)) return fail(p, GSIM_ERR_CUDA, "peek");
     if (!poke_key(p, b, id, gs_key_with_inc(kk, inc))) return fail(p, GSIM_ERR_CUDA, "poke");
   }
-  rc = start_rumor(p, slot, GSIM_RUMOR_UPDATE, id, inc, 0u, id, alive_msg_size ? alive_msg_size : 64u, 0u);
+  rc = start_rumor(p, slot, GSIM_RUMOR_UPDATE, id, inc, 0u, id, alive_msg_size ? alive_msg_size : alive_size(p, id, inc, 0u), 0u);
   if (rc) return fail(p, rc, "start_rumor");
   *slot_out = slot;
   return GSIM_OK;
@@ -1137,7 +1158,7 @@ extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
   uint32_t slot;
   int rc = alloc_slot(p, &slot);
   if (rc == GSIM_OK) {
-    rc = start_rumor(p, slot, GSIM_RUMOR_LEAVE_INTENT, id, 0u, lm, id, 40u, 1u);
+    rc = start_rumor(p, slot, GSIM_RUMOR_LEAVE_INTENT, id, 0u, lm, id, intent_size(p, id, true, lm), 1u);
     if (rc) return fail(p, rc, "start_rumor");
   } else if (rc != GSIM_ERR_CAPACITY) {
     return fail(p, rc, "alloc_slot");
@@ -1192,11 +1213,6 @@ extern "C" int gsim_force_leave(gsim_pool* p, uint32_t via, uint32_t target, int
   });
 }
 
-static uint32_t msgpack_str_size(size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 256 ? 2 + n : 3 + n); }
-static uint32_t msgpack_uint_size(uint64_t v) {
-  return v < 128 ? 1 : v < 256 ? 2 : v < 65536 ? 3 : v < 4294967296ull ? 5 : 9;
-}
-
 extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size_t name_len,
                                const void* payload, size_t payload_len, int coalesce,
                                uint32_t* slot_out) {
@@ -1243,9 +1259,9 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
       return GSIM_OK;
     }
   }
-  // msgpack size of messageUserEvent{LTime,Name,Payload,CC} + 1 type byte
-  uint32_t size = 1 + 1 + (6 + msgpack_uint_size(le)) + (5 + msgpack_str_size(name_len)) +
-                  (8 + msgpack_str_size(payload_len)) + (3 + 1);
+  // the encoded messageUserEvent{LTime,Name,Payload,CC} behind its serf type byte
+  static const char some = 0;  // (a non-nil payload slice; sizing reads no bytes)
+  uint32_t size = (uint32_t)gsw::serf_user_event(nullptr, 0, le, nullptr, name_len, &some, payload_len, coalesce != 0, false);
   // [U] serf.UserEvent checks the limit a second time on the ENCODED message
   if (size > p->cfg.user_event_size_limit)
     return fail(p, GSIM_ERR_TOO_LARGE, "encoded user event exceeds UserEventSizeLimit");
@@ -2222,3 +2238,40 @@ extern "C" int gsim_last_step_timing(gsim_pool* p, double* kernel_ms, uint64_t* 
 }
 
 extern "C" uint64_t gsim_launch_count(gsim_pool* p) { return p && p->be ? p->be->total_launches() : 0; }
+
+// ---- wire formats (include/gsim.h; encoders in gs_wire.h) ---------------------------------------
+static size_t zlen(const char* s) { return s ? strlen(s) : 0; }
+extern "C" size_t gsim_wire_alive(void* out, size_t cap, uint32_t incarnation, const char* node, const void* addr,
+                                  size_t addr_len, uint16_t port, const void* meta, size_t meta_len, const uint8_t vsn[6]) {
+  static const uint8_t vsn0[6] = {0, 0, 0, 0, 0, 0};
+  return gsw::alive(out, cap, incarnation, node, zlen(node), addr, addr_len, port, meta, meta_len, vsn ? vsn : vsn0);
+}
+extern "C" size_t gsim_wire_suspect(void* out, size_t cap, uint32_t incarnation, const char* node, const char* from) {
+  return gsw::suspect_or_dead(out, cap, false, incarnation, node, zlen(node), from, zlen(from));
+}
+extern "C" size_t gsim_wire_dead(void* out, size_t cap, uint32_t incarnation, const char* node, const char* from) {
+  return gsw::suspect_or_dead(out, cap, true, incarnation, node, zlen(node), from, zlen(from));
+}
+extern "C" size_t gsim_wire_join_intent(void* out, size_t cap, uint64_t ltime, const char* node) {
+  return gsw::serf_intent(out, cap, false, ltime, node, zlen(node), false, false);
+}
+extern "C" size_t gsim_wire_leave_intent(void* out, size_t cap, uint64_t ltime, const char* node, int prune) {
+  return gsw::serf_intent(out, cap, true, ltime, node, zlen(node), prune != 0, false);
+}
+extern "C" size_t gsim_wire_user_event(void* out, size_t cap, uint64_t ltime, const void* name, size_t name_len,
+                                       const void* payload, size_t payload_len, int coalesce) {
+  return gsw::serf_user_event(out, cap, ltime, name, name_len, payload, payload_len, coalesce != 0, false);
+}
+extern "C" size_t gsim_wire_compound(void* out, size_t cap, const void* const* msgs, const size_t* lens, size_t count) {
+  if (count > 255 || (count && (!msgs || !lens))) return 0;
+  return gsw::compound(out, cap, msgs, lens, count);
+}
+extern "C" size_t gsim_wire_wanfed_frame(void* out, size_t cap, const void* packet, size_t len) {
+  return gsw::wanfed_frame(out, cap, packet, len);
+}
+extern "C" size_t gsim_wire_consul_user_event(void* out, size_t cap, const char* id, const char* name,
+                                              const void* payload, size_t payload_len, const char* node_filter,
+                                              const char* service_filter, const char* tag_filter, int version) {
+  return gsw::consul_user_event(out, cap, id ? id : "", name ? name : "", payload, payload_len, node_filter,
+                                service_filter, tag_filter, version);
+}

@@ -37,7 +37,7 @@ struct Buf {
     ++n;
   }
   void put(const void* s, size_t len) {  // (sizing calls pass no buffer and possibly no source)
-    if (len && n + len <= cap) memcpy(p + n, s, len);
+    if (s != nullptr && len && n + len <= cap) memcpy(p + n, s, len);
     n += len;
   }
   void be16(uint32_t v) { put((uint8_t)(v >> 8)); put((uint8_t)v); }

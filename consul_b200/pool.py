@@ -103,8 +103,8 @@ class Pool:
             raise GsimError(rc, msg)
 
     # -- membership operations --------------------------------------------------
-    def member_add(self, alive_msg_size: int = 0, watched: bool = False) -> int:
-        d = GsimMemberDesc(alive_msg_size, MEMBER_WATCHED if watched else 0)
+    def member_add(self, alive_msg_size: int = 0, watched: bool = False, name_len: int = 0, meta_len: int = 0) -> int:
+        d = GsimMemberDesc(alive_msg_size, MEMBER_WATCHED if watched else 0, name_len, meta_len)
         out = C.c_uint32()
         self._ck(self.lib.gsim_member_add(self.h, C.byref(d), C.byref(out)))
         return out.value

@@ -186,8 +186,11 @@ const char* gsim_last_error(gsim_pool* p);
 int gsim_abi_version(void);
 
 typedef struct gsim_member_desc {
-  uint32_t alive_msg_size; /* encoded size of this member's alive{} message incl. Meta (tags) */
+  uint32_t alive_msg_size; /* encoded size of this member's alive{} message incl. Meta (tags); 0 = computed
+                            * by the encoder (gsim_wire_alive) from name_len and meta_len */
   uint32_t flags;          /* GSIM_MEMBER_* */
+  uint32_t name_len;       /* bytes of the node name ("node" / "node.dc"); 0 = the canonical "node-<id>" */
+  uint32_t meta_len;       /* bytes of memberlist Meta (serf's encoded tags); used when alive_msg_size == 0 */
 } gsim_member_desc;
 #define GSIM_MEMBER_WATCHED 1u /* record this observer's serf events (EventCh) */
 
@@ -399,6 +402,28 @@ int gsim_shard_ready(gsim_pool* p);
 int gsim_last_step_timing(gsim_pool* p, double* kernel_ms, uint64_t* launches);
 /* Total kernels launched by this pool since creation (bench "gpu_launches"). */
 uint64_t gsim_launch_count(gsim_pool* p);
+/* ---- wire formats (consul_b200/csrc/gs_wire.h) -------------------------------------
+ * The encoders behind every message size the byte budget of a gossip packet is checked against:
+ * msgpack as hashicorp/go-msgpack v2 writes it for memberlist and serf (codec.MsgpackHandle{}: raw
+ * strings, no str8/bin), memberlist's alive / suspect / dead and compound packet, serf's join /
+ * leave intents and user event, the WAN-federation frame (agent/consul/wanfed/wanfed.go:112-121) and
+ * Consul's UserEvent payload (agent/user_event.go:27-52, msgpackHandleUserEvent: str8 and bin).
+ * Each call writes at most `cap` bytes to `out` (which may be NULL) and returns the encoded size. */
+size_t gsim_wire_alive(void* out, size_t cap, uint32_t incarnation, const char* node, const void* addr,
+                       size_t addr_len, uint16_t port, const void* meta, size_t meta_len, const uint8_t vsn[6]);
+size_t gsim_wire_suspect(void* out, size_t cap, uint32_t incarnation, const char* node, const char* from);
+size_t gsim_wire_dead(void* out, size_t cap, uint32_t incarnation, const char* node, const char* from);
+size_t gsim_wire_join_intent(void* out, size_t cap, uint64_t ltime, const char* node);
+size_t gsim_wire_leave_intent(void* out, size_t cap, uint64_t ltime, const char* node, int prune);
+size_t gsim_wire_user_event(void* out, size_t cap, uint64_t ltime, const void* name, size_t name_len,
+                            const void* payload, size_t payload_len, int coalesce);
+/* memberlist compound packet of `count` messages (count <= 255) */
+size_t gsim_wire_compound(void* out, size_t cap, const void* const* msgs, const size_t* lens, size_t count);
+size_t gsim_wire_wanfed_frame(void* out, size_t cap, const void* packet, size_t len);
+size_t gsim_wire_consul_user_event(void* out, size_t cap, const char* id, const char* name, const void* payload,
+                                   size_t payload_len, const char* node_filter, const char* service_filter,
+                                   const char* tag_filter, int version);
+
 /* Scheduling counters since creation: out[0] = quiet-window launches, out[1] = ticks advanced inside
  * quiet windows, out[2] = single-tick launches, out[3] = horizon scans, out[4] / out[5] = nanoseconds of
  * CUDA-event time spent in window / single-tick launches. */

@@ -154,9 +154,14 @@ class Serf {
   // serf.Create(conf): one more virtual agent on `pool`.
   static std::unique_ptr<Serf> Create(Pool& pool, const Config& conf) {
     if (pool.by_name_.count(conf.NodeName)) throw Error(GSIM_ERR_STATE, "node name conflict: " + conf.NodeName);
+    // The alive{} broadcast is sized by libgsim's encoder (gsim_wire_alive) from the real name and the
+    // real Meta: [U] serf.encodeTags = the magic byte 255 + msgpack(map[string]string) of the tags.
+    auto raw = [](size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 65536 ? 3 + n : 5 + n); };
     gsim_member_desc d;
-    d.alive_msg_size = 48 + (uint32_t)conf.NodeName.size();
-    for (auto& kv : conf.Tags) d.alive_msg_size += (uint32_t)(kv.first.size() + kv.second.size() + 2);
+    d.alive_msg_size = 0;
+    d.name_len = (uint32_t)conf.NodeName.size();
+    d.meta_len = 1u + (conf.Tags.size() < 16 ? 1u : 3u);
+    for (auto& kv : conf.Tags) d.meta_len += raw(kv.first.size()) + raw(kv.second.size());
     d.flags = GSIM_MEMBER_WATCHED;
     uint32_t id = 0;
     pool.check(gsim_member_add(pool.h_, &d, &id));

@@ -297,6 +297,7 @@ struct Oracle {
   uint32_t up_count = 0;
   uint32_t established = 0;  // members folded into the base set
   std::vector<Member> m;
+  std::vector<std::pair<uint32_t, uint32_t>> name_lens;  // (member, node-name bytes) where not the canonical "node-<id>"
   std::vector<View> pub;                 // published views (state at the start of the tick)
   std::vector<uint32_t> pub_change_tick; // published change ticks
   std::vector<Coordinate> pub_coord;     // published coordinates (GSIM_FLAG_COORDINATES), as of the tick start
@@ -1105,6 +1106,29 @@ uint32_t pack_meta(const Member& me) {
 
 }  // namespace
 
+// msgpack sizes as memberlist and serf encode (zero codec.MsgpackHandle: raw strings — fixraw up to 31
+// bytes, raw16 after that; there is no str8 without WriteExt).  Arithmetic only: the product has a
+// real encoder (csrc/gs_wire.h) and tests/test_wire.py holds the two against each other.
+static uint32_t mp_str(size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 65536 ? 3 + n : 5 + n); }
+static uint32_t mp_uint(uint64_t v) { return v < 128 ? 1 : v < 256 ? 2 : v < 65536 ? 3 : v < 4294967296ull ? 5 : 9; }
+// A virtual member is called "node-<id>" unless the descriptor gave the length of its real name.
+static uint32_t name_len_of(const Oracle& o, uint32_t id) {
+  for (const auto& kv : o.name_lens)
+    if (kv.first == id) return kv.second;
+  uint32_t digits = 1;
+  for (uint32_t v = id; v >= 10; v /= 10) ++digits;
+  return 5 + digits;
+}
+// [U] memberlist alive{Incarnation, Node, Addr(4), Port(8301), Meta, Vsn(6)} behind the message-type byte
+static uint32_t alive_bytes(const Oracle& o, uint32_t id, uint32_t inc, uint32_t meta_len) {
+  return 1 + 1 + (12 + mp_uint(inc)) + (5 + mp_str(name_len_of(o, id))) + (5 + mp_str(4)) + (5 + mp_uint(8301)) +
+         (5 + mp_str(meta_len)) + (4 + mp_str(6));
+}
+// [U] serf messageJoin{LTime, Node} / messageLeave{LTime, Node, Prune} behind the serf-type byte
+static uint32_t intent_bytes(const Oracle& o, uint32_t id, bool leave, uint32_t ltime) {
+  return 1 + 1 + (6 + mp_uint(ltime)) + (5 + mp_str(name_len_of(o, id))) + (leave ? 6 + 1 : 0);
+}
+
 // =============================================================================================
 // C interface used by the tests (mirrors include/gsim.h so scenarios read the same)
 // =============================================================================================
@@ -1257,7 +1281,9 @@ int oracle_member_add(void* h, const gsim_member_desc* desc, uint32_t* id_out) {
   publish(o, id);
   o.up_count++;
   retune(o);
-  start_rumor(o, slot, GSIM_RUMOR_ALIVE, id, 1, 0, id, desc && desc->alive_msg_size ? desc->alive_msg_size : 64, 0);
+  if (desc && desc->name_len) o.name_lens.push_back(std::make_pair(id, desc->name_len));
+  start_rumor(o, slot, GSIM_RUMOR_ALIVE, id, 1, 0, id,
+              desc && desc->alive_msg_size ? desc->alive_msg_size : alive_bytes(o, id, 1, desc ? desc->meta_len : 0), 0);
   *id_out = id;
   return GSIM_OK;
 }
@@ -1279,7 +1305,7 @@ int oracle_join(void* h, uint32_t id, const uint32_t* seeds, size_t n_seeds, int
   if (ok > 0) {
     uint32_t lt = o.m[id].ltime_member;  // [U] serf.broadcastJoin(clock.Time())
     int slot = free_slot(o);
-    if (slot >= 0) start_rumor(o, slot, GSIM_RUMOR_JOIN_INTENT, id, 0, lt, id, 40, 1);
+    if (slot >= 0) start_rumor(o, slot, GSIM_RUMOR_JOIN_INTENT, id, 0, lt, id, intent_bytes(o, id, false, lt), 1);
     o.m[id].ltime_member = lt + 1;
   }
   if (n_ok) *n_ok = ok;
@@ -1321,7 +1347,7 @@ int oracle_leave(void* h, uint32_t id) {
   if (me.v.truth != GSIM_TRUTH_UP || me.leaving) return GSIM_ERR_STATE;
   uint32_t lt = me.ltime_member;  // [U] serf.Leave: leave intent at clock.Time()
   int slot = free_slot(o);
-  if (slot >= 0) start_rumor(o, slot, GSIM_RUMOR_LEAVE_INTENT, id, 0, lt, id, 40, 1);
+  if (slot >= 0) start_rumor(o, slot, GSIM_RUMOR_LEAVE_INTENT, id, 0, lt, id, intent_bytes(o, id, true, lt), 1);
   Member& me2 = o.m[id];
   me2.ltime_member = lt + 1;
   me2.v.rank = GSIM_RANK_LEFT;  // [U] memberlist.Leave: dead{Node == From}
@@ -1350,8 +1376,6 @@ int oracle_force_leave(void* h, uint32_t via, uint32_t target, int prune) {
   return GSIM_OK;
 }
 
-static uint32_t mp_str(size_t n) { return (uint32_t)(n < 32 ? 1 + n : n < 256 ? 2 + n : 3 + n); }
-static uint32_t mp_uint(uint64_t v) { return v < 128 ? 1 : v < 256 ? 2 : v < 65536 ? 3 : v < 4294967296ull ? 5 : 9; }
 
 int oracle_user_event(void* h, uint32_t id, const void* name, size_t nl, const void* payload, size_t pl, int coalesce,
                       uint32_t* slot_out) {
@@ -1433,7 +1457,7 @@ int oracle_member_update(void* h, uint32_t id, uint32_t alive_msg_size, uint32_t
   Member& me = o.m[id];
   me.v.inc += 1;
   publish(o, id);
-  start_rumor(o, slot, GSIM_RUMOR_UPDATE, id, me.v.inc, 0, id, alive_msg_size ? alive_msg_size : 64, 0);
+  start_rumor(o, slot, GSIM_RUMOR_UPDATE, id, me.v.inc, 0, id, alive_msg_size ? alive_msg_size : alive_bytes(o, id, me.v.inc, 0), 0);
   if (slot_out) *slot_out = (uint32_t)slot;
   return GSIM_OK;
 }

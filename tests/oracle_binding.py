@@ -118,8 +118,8 @@ class OraclePool:
     def set_threads(self, n: int) -> int:
         return self.lib.oracle_set_threads(self.h, n)
 
-    def member_add(self, alive_msg_size=0, watched=False):
-        d = GsimMemberDesc(alive_msg_size, 1 if watched else 0)
+    def member_add(self, alive_msg_size=0, watched=False, name_len=0, meta_len=0):
+        d = GsimMemberDesc(alive_msg_size, 1 if watched else 0, name_len, meta_len)
         out = _u32()
         self._ck(self.lib.oracle_member_add(self.h, C.byref(d), C.byref(out)))
         return out.value

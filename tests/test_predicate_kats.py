@@ -85,7 +85,7 @@ def test_memberlist_broadcasts_before_serf_events(mk, hostemu_lib):
     """[U] serf/delegate.go GetBroadcasts: memberlist's own broadcasts, then intents, then user
     events.  One message per packet, one peer: the joiner's alive message leaves before its join
     intent, and both before an older user event."""
-    cfg = lan_config(hostemu_lib, capacity=70, n_initial=64, seed=5, gossip_nodes=1, udp_buffer_size=2 + 3 + 64)
+    cfg = lan_config(hostemu_lib, capacity=70, n_initial=64, seed=5, gossip_nodes=1, udp_buffer_size=2 + 3 + 40)
     p = mk(cfg)
     ev = p.user_event(0, b"e", b"p" * 8, False)
     x = p.member_add(alive_msg_size=40)
