@@ -196,6 +196,7 @@ struct gsim_pool {
   std::vector<std::pair<uint32_t, uint32_t>> name_lens;  // (member, bytes of its node name) where not canonical
   // quiet-window scheduling
   bool quiet = false;        // the pool is known to be quiet at p->now: windows may run
+  bool healthy = false;      // ... and no probe can go unanswered: a launch may cover many ProbeIntervals
   uint32_t dirty_seq = 0;    // bumped by every host-side write to device state (quiet no longer known)
   uint32_t dirty_tick = 0;   // p->now at that write
   uint32_t retry_at = 0;     // do not look for quietness again before this tick
@@ -205,6 +206,7 @@ struct gsim_pool {
 
 static void mark_dirty(gsim_pool* p) {
   p->quiet = false;
+  p->healthy = false;
   p->dirty_seq++;
   p->dirty_tick = p->now;
 }
@@ -377,6 +379,7 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     p->dirty_seq = h.dirty_seq;
     p->dirty_tick = p->now;
     p->quiet = false;
+    p->healthy = false;
   }
   p->g_dirty = false;
   p->counts_stale = true;
@@ -391,8 +394,12 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
 static void rebuild_class_masks(gsim_pool* p) {
   GsGlobals& g = p->g;
   g.class_mask[0] = g.class_mask[1] = g.class_mask[2] = 0;
+  g.active_bytes = 0;
   for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
-    if ((g.active_mask >> r) & 1u) g.class_mask[g.rumors[r].qclass] |= 1u << r;
+    if ((g.active_mask >> r) & 1u) {
+      g.class_mask[g.rumors[r].qclass] |= 1u << r;
+      g.active_bytes += g.rumors[r].size + (g.rumors[r].qclass ? 3u : 2u);
+    }
   p->g_dirty = true;
 }
 
@@ -1439,6 +1446,7 @@ extern "C" int gsim_latency_set(gsim_pool* p, uint32_t n_dcs, const uint8_t* lat
     for (uint32_t b = 0; b < n_dcs; ++b) g.lat[a * GS_MAX_DCS + b] = (uint8_t)(lat_ticks[a * n_dcs + b] - 1u);
   g.n_dcs = n_dcs;
   p->g_dirty = true;
+  mark_dirty(p);  // what a probe round trip costs has changed
   return GSIM_OK;
   });
 }
@@ -1525,6 +1533,12 @@ static bool windows_possible(const gsim_pool* p) {
          p->d.coord == nullptr && g.P >= 2u && g.T < g.P && g.n != 0u;
 }
 
+#define GS_LONG_WINDOW 32u  // ProbeIntervals one launch covers on a healthy quiet pool
+static bool long_windows_on() {
+  static const bool off = getenv("GSIM_NO_LONG_WINDOWS") != nullptr;
+  return !off;
+}
+
 // After single ticks: has the pool been quiet long enough, and how far is the horizon?
 static int try_quiet(gsim_pool* p) {
   GsBackend* be = p->be;
@@ -1558,6 +1572,24 @@ static int try_quiet(gsim_pool* p) {
   if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;  // (same: read before anybody moves on)
   if (hz >= p->now + g.P / 2u + 1u) {
     p->quiet = true;
+    // No probe in flight, and can one fail at all?  Not if every member the cluster lists as alive or
+    // suspect is actually running, no packet is lost and no link is slower than ProbeTimeout: then the
+    // horizon cannot move and one launch may run many ProbeIntervals (the controller counts, every
+    // rank adopts the answer).
+    uint32_t ok_long = 0;
+    bool links_ok = true;  // every round trip of the latency matrix fits ProbeTimeout
+    for (uint32_t a = 0; a < g.n_dcs && links_ok; ++a)
+      for (uint32_t b = 0; b < g.n_dcs; ++b)
+        if ((uint32_t)g.lat[a * GS_MAX_DCS + b] + g.lat[b * GS_MAX_DCS + a] > g.T) links_ok = false;
+    if (hz == GS_NEVER && g.loss_thr == 0u && links_ok) {
+      int rc = controller_call(p, &ok_long, sizeof(ok_long), [&]() -> int {
+        if (!do_recount(p)) return GSIM_ERR_CUDA;
+        ok_long = p->rc.unreachable_live == 0u ? 1u : 0u;
+        return GSIM_OK;
+      });
+      if (rc) return rc;
+    }
+    p->healthy = ok_long != 0u;
   } else {  // a probe deadline is upon us: single ticks until it has passed, then look again
     p->retry_at = (hz > p->now ? hz : p->now) + depth + 1u;
   }
@@ -1575,7 +1607,9 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
       uint32_t done = 0;
       uint64_t nl = 0;
       double wms = 0;
-      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, use_graph, &wms, &nl, &done, xb))
+      // ticks per launch: one ProbeInterval; up to GS_LONG_WINDOW of them on a healthy pool
+      const uint32_t per_launch = p->healthy && long_windows_on() ? p->g.P * GS_LONG_WINDOW : p->g.P;
+      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, per_launch, use_graph, &wms, &nl, &done, xb))
         return GSIM_ERR_CUDA;
       p->last_ms += wms;
       p->sched_counts[4] += (uint64_t)(wms * 1e6);
@@ -1587,6 +1621,7 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
       left -= done;
       if (left) {  // the chain stopped at the horizon: single ticks from here
         p->quiet = false;
+        p->healthy = false;
         p->retry_at = p->now + 1u;
       }
       continue;

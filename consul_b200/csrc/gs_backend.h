@@ -16,6 +16,8 @@ struct GsRecount {
   uint32_t rank_cnt[4];
   uint32_t crashed_alive;
   uint32_t isolated_up;  // running members that have not joined the established set
+  uint32_t unreachable_live;  // members whose process is gone (crashed / shut down) but whom the cluster
+                              // still lists as alive or suspect: the targets an unanswered probe can hit
 };
 
 class GsBackend {
@@ -39,9 +41,11 @@ class GsBackend {
   // Quiet windows: advance up to `nticks` ticks starting at t0 as a chain of launches
   // of <= ProbeInterval ticks each, on a pool whose mailboxes are known to be empty.  The chain stops at
   // the horizon (GS_Q_HORIZON); *ticks_done = how far it got (tick_base == t0 + *ticks_done on exit).
+  // `per_launch` = ticks one launch may cover: ProbeInterval in general; more when the caller knows that
+  // no probe can go unanswered (every listed member runs, no loss, no slow link), so the horizon cannot move.
   virtual bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
-                           bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done,
-                           const GsXbar* xbar) = 0;
+                           uint32_t per_launch, bool use_graph, double* kernel_ms, uint64_t* launches,
+                           uint32_t* ticks_done, const GsXbar* xbar) = 0;
   // lowers GS_Q_HORIZON (every rank's copy) to the earliest accusation the probes in flight of rows
   // [first, first+count) can produce
   virtual bool quiet_scan(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first,

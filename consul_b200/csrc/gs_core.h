@@ -285,7 +285,8 @@ struct GsGlobals {
   // graph_n == n rows are described (static topology: restricted segments, partial views).
   uint32_t graph_n;
   uint32_t reap_min_override;  // smallest per-member ReconnectTimeout override so far (ticks), 0 = none
-  uint32_t coord_pad;
+  uint32_t active_bytes;       // every tracked broadcast with its per-message overhead: <= udp_avail means the
+                               // byte budget of a packet can never bind (the common case), whatever is queued
   // network coordinates (gs_coord.h, GSIM_FLAG_COORDINATES): round trip fed to Vivaldi on a direct
   // ack = coord_base_rtt_s + (extra latency there and back) * tick_seconds
   double coord_base_rtt_s, tick_seconds;

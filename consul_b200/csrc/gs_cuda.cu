@@ -73,10 +73,11 @@ struct DevSinkT {
 typedef DevSinkT<false> DevSink;
 
 #ifndef GS_MIN_BLOCKS
-#define GS_MIN_BLOCKS 3
+#define GS_MIN_BLOCKS 4
 #endif
 #define GS_STAGES 4                  // cp.async pipeline depth of the scan (tiles in flight per warp)
 #define GS_WARPS (GS_BLOCK / 32)
+#define GS_ROUND 8                   // tiles a warp scans between two drains of the CTA's work queue
 
 // Asynchronous 16-byte global -> shared copy (LDGSTS.128, L2 only): the scan words of the
 // tiles ahead are in flight without holding registers or stalling the warp.
@@ -135,6 +136,17 @@ __device__ __forceinline__ void gs_q_publish(const GsDev& d, const GsGlobals& g,
   }
 }
 
+// The generic row step, out of line.  Inlined into the persistent loops it costs every launch its
+// registers (80 -> 3 resident CTAs per SM); as a call it costs the members that take it ~30
+// instructions on top of several hundred, and the loops around it fit 64 registers (4 CTAs per SM:
+// a quarter more warps to hide the L2 round trips, and at 1 M members two tiles per warp, not three).
+template <bool COORDS>
+__device__ __noinline__ void gs_row_step_call(const GsDev* dp, const GsGlobals* gp, uint32_t i, uint32_t t,
+                                              uint32_t inb, uint32_t* s_stat, uint32_t* s_heard, uint32_t* s_q) {
+  DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
+  gs_row_step(*dp, *gp, i, t, t % gp->GI, inb, sink);
+}
+
 // Persistent, warp-centric tick.  Every warp owns a CONTIGUOUS chunk of tiles (128 members
 // each); because ticker phases are dealt round-robin over tiles, every chunk holds the same
 // number of probing tiles (+-1) at every tick, so the static split is balanced.
@@ -149,17 +161,23 @@ __device__ __forceinline__ void gs_q_publish(const GsDev& d, const GsGlobals& g,
 // Whatever the fast path declines goes to the generic gs_row_step.
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
-    gs_tick_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
+    gs_tick_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ uint32_t s_q[2];
+  // groups of 32 members that need the generic step, queued by the scanning warps and taken by
+  // whichever warp of the CTA is free (two counters each: rounds alternate, see below)
+  __shared__ uint32_t s_work[GS_WARPS * GS_ROUND * 4];
+  __shared__ uint32_t s_wn[2], s_wtake[2];
   const uint32_t tid = threadIdx.x;
   if (tid < GS_NSTAT) s_stat[tid] = 0u;
   if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
   if (tid == 64u) s_q[0] = 0u;
   if (tid == 65u) s_q[1] = GS_NEVER;
+  if (tid >= 66u && tid < 68u) s_wn[tid - 66u] = 0u;
+  if (tid >= 68u && tid < 70u) s_wtake[tid - 68u] = 0u;
   // Programmatic dependent launch: let the next tick's grid start launching now; it blocks in
   // its own griddepcontrol.wait until this grid has completed and flushed.  Everything above
   // this line touches no global memory.
@@ -179,20 +197,32 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     tile_lo = g.rank * per < tile_hi ? g.rank * per : tile_hi;
     tile_hi = tile_lo + per < tile_hi ? tile_lo + per : tile_hi;
   }
-  const uint32_t n_warps = gridDim.x * GS_WARPS;
-  const uint32_t chunk = (tile_hi - tile_lo + n_warps - 1u) / n_warps;
+  // contiguous runs of tiles, floor or ceil of tiles / warps each: every warp (and so every SM) gets
+  // its share — with ceil-sized chunks the last quarter of the grid had nothing to do at 1 M members
+  const uint32_t n_warps = gridDim.x * GS_WARPS, n_tiles = tile_hi - tile_lo;
   const uint32_t wid = blockIdx.x * GS_WARPS + wib;
-  const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
-  const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
+  const uint32_t t_begin = tile_lo + (uint32_t)(((uint64_t)wid * n_tiles) / n_warps);
+  const uint32_t t_end = tile_lo + (uint32_t)(((uint64_t)(wid + 1u) * n_tiles) / n_warps);
   const uint32_t* __restrict__ inbox_cur = d.inbox[t & g.ring_mask];  // this tick's arrival slot
   const bool gated = g.phase_gate != 0u;
   const uint32_t shift = g.phase_shift;
   DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
 
-  uint32_t tq = t_begin;  // next tile to issue
+  // Rounds.  A warp scans up to GS_ROUND of its tiles and runs the staged probe fast path inline;
+  // every group that needs the generic step goes into the CTA's queue instead.  Then the whole CTA
+  // drains the queue, one group per warp at a time: a warp whose tiles were idle helps the warp whose
+  // tiles all gossip (ticker phases come in runs of ProbeInterval tiles, so consecutive tiles are
+  // busy together and a static split leaves half the warps waiting at the closing barrier).  Results
+  // do not depend on who steps a group: everything a member sends is a commutative atomic.
+  const uint32_t max_run = (n_tiles + n_warps - 1u) / n_warps, n_rounds = (max_run + GS_ROUND - 1u) / GS_ROUND;
   bool did_work = false;  // this thread touched global state (needs the closing fence when sharded)
+  for (uint32_t round = 0; round < n_rounds; ++round) {
+  const uint32_t par = round & 1u;
+  const uint32_t r_begin = t_begin + round * GS_ROUND < t_end ? t_begin + round * GS_ROUND : t_end;
+  const uint32_t r_end = r_begin + GS_ROUND < t_end ? r_begin + GS_ROUND : t_end;
+  uint32_t tq = r_begin;  // next tile to issue
   auto issue = [&](uint32_t st) {
-    if (tq < t_end) {
+    if (tq < r_end) {
       const size_t off = (size_t)tq * GS_TILE + lane * 4u;  // columns are padded to whole tiles
       if (g.world > 1u && (g.flags & 4u)) {  // GSIM_FLAG_SHARD_SYNC_SCAN (debug)
         // sharded pool: this mailbox word is written by other GPUs; read it at system scope
@@ -220,7 +250,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 #pragma unroll
   for (uint32_t q = 0; q < GS_STAGES - 1; ++q) issue(q);
   uint32_t st = 0;
-  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+  for (uint32_t tile = r_begin; tile < r_end; ++tile) {
     issue((st + GS_STAGES - 1u) % GS_STAGES);
     gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
     const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
@@ -277,17 +307,34 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
           if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
         }
       }
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const bool a = u == 0 ? act[0] : u == 1 ? act[1] : u == 2 ? act[2] : act[3];
-        if (__any_sync(0xFFFFFFFFu, a)) {
-          if (a) gs_row_step(d, g, base + 32u * u, t, gslot, s_inb[st][wib][u * 32 + lane], sink);
-        }
+        if (__any_sync(0xFFFFFFFFu, act[u]) && lane == 0u) s_work[atomicAdd(&s_wn[par], 1u)] = tile * 4u + (uint32_t)u;
       }
       __syncwarp();  // everyone is done with this stage before it is refilled
     }
     st = (st + 1u) % GS_STAGES;
   }
+  gs_cp_async_wait<0>();
+  __syncthreads();  // the queue of this round is complete
+  if (tid == 0u) s_wn[par ^ 1u] = s_wtake[par ^ 1u] = 0u;  // the next round's counters (nobody uses them now)
+  const uint32_t n_work = s_wn[par];
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0u) idx = atomicAdd(&s_wtake[par], 1u);
+    idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+    if (idx >= n_work) break;
+    did_work = true;
+    const uint32_t i = s_work[idx] * 32u + lane;
+    // which members of the group: mail, a probe action due (members the fast path finished have moved
+    // their `due` on), or the push-pull ticker
+    const uint32_t w = __ldcg(inbox_cur + i);
+    const bool a = w != 0u || __ldcg(d.due + i) == t ||
+                   (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, i / g.phase_group, t));
+    if (a) gs_row_step_call<COORDS>(&d, gp, i, t, w, s_stat, s_heard, s_q);
+  }
+  __syncthreads();  // the queue is drained (and its counters may be reused two rounds from now)
+  }  // rounds
   // Sharded pools: mailbox deliveries to other GPUs are fire-and-forget reductions over NVLink;
   // a system-scope fence by the issuing thread is what guarantees they have been performed at
   // the owner before this rank can signal the inter-tick barrier.
@@ -324,9 +371,14 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 //
 // A tile's members are due only at ticks congruent to its ticker phase (probe start, probe
 // deadline) or to phase + ProbeTimeout (indirect stage): at most two ticks of a window.
+#ifndef GS_WIN_BLOCKS
+#define GS_WIN_BLOCKS 4
+#endif
+// (resident CTAs per SM the window kernel is compiled for: 4 = 64 registers per thread)
+
 template <bool COORDS>
-__global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
-    gs_window_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
+__global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
+    gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
   __shared__ uint32_t s_stat[GS_NSTAT];
   __shared__ uint32_t s_heard[32];
   __shared__ uint32_t s_q[2];
@@ -339,7 +391,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const GsGlobals& g = *gp;
-  uint32_t* const qs = d.qstate[g.rank];
+  const GsHot h = gs_hot(g);
+  const uint32_t world = g.world, rank = g.rank;
+  uint32_t* const qs = d.qstate[rank];
   const uint32_t t0 = *d.tick_base + k_off;
   // Where the chain of windows stands and how far it may go.  Both words are stable for the whole
   // launch: siblings only raise WIN_END to this window's own end, and lower HORIZON to ticks
@@ -349,88 +403,130 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   uint32_t w1 = t0 + n_ticks;
   if (horizon < w1) w1 = horizon;  // (GS_NEVER = no probe in flight anywhere)
   if (w1 <= t0) return;            // the horizon is here: the host goes back to single ticks
-  if (g.world > 1u) gs_ranks_wait(d, g, t0);
-  const uint32_t P = g.P, lane = tid & 31u, wib = tid >> 5;
-  uint32_t tile_lo = 0, tile_hi = (g.n + GS_TILE - 1u) / GS_TILE;
-  if (g.world > 1u) {
+  if (world > 1u) gs_ranks_wait(d, g, t0);
+  const uint32_t P = h.P, T = h.T, lane = tid & 31u, wib = tid >> 5;
+  // this rank's groups of 32 members (4 per tile), dealt to the warps in contiguous runs: inside a
+  // window rows are independent, so the unit of work need not be the 128-member phase tile
+  uint32_t tile_lo = 0, tile_hi = (h.n + GS_TILE - 1u) / GS_TILE;
+  if (world > 1u) {
     const uint32_t per = g.rows_per_rank / GS_TILE;
-    tile_lo = g.rank * per < tile_hi ? g.rank * per : tile_hi;
+    tile_lo = rank * per < tile_hi ? rank * per : tile_hi;
     tile_hi = tile_lo + per < tile_hi ? tile_lo + per : tile_hi;
   }
-  const uint32_t n_warps = gridDim.x * GS_WARPS;
-  const uint32_t chunk = (tile_hi - tile_lo + n_warps - 1u) / n_warps;
+  const uint32_t n_warps = gridDim.x * GS_WARPS, grp_lo = tile_lo * 4u, grp_hi = tile_hi * 4u;
+  const uint32_t run = (grp_hi - grp_lo + n_warps - 1u) / n_warps;
   const uint32_t wid = blockIdx.x * GS_WARPS + wib;
-  const uint32_t t_begin = tile_lo + wid * chunk < tile_hi ? tile_lo + wid * chunk : tile_hi;
-  const uint32_t t_end = t_begin + chunk < tile_hi ? t_begin + chunk : tile_hi;
-  const uint32_t shift = g.phase_shift, t0_mod = t0 % P;
+  const uint32_t g_begin = grp_lo + wid * run < grp_hi ? grp_lo + wid * run : grp_hi;
+  const uint32_t g_end = g_begin + run < grp_hi ? g_begin + run : grp_hi;
+  const uint32_t shift = g.phase_shift + 2u, t0_mod = t0 % P, rot_p = g.rot_p;
+  // the batch is taken through the probe fast path together if the pool allows the fast path at all
+  const bool fast_ok = h.loss_thr == 0u && h.graph_n == 0u && d.coord == nullptr && h.pp_interval == 0u;
   DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
   bool did_work = false;
-  // the `due` words of the next tile travel while this one is worked on
-  uint32_t nd[4] = {GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER};
-  if (t_begin < t_end) {
+  uint32_t n_probe = 0, n_ack = 0;
+  // phase of the first group, then incrementally (one division per warp, not per tile)
+  uint32_t pg = g_begin >> shift;              // phase group of the current group
+  uint32_t pp = (pg % P + rot_p) % P;          // its probe phase
+  for (uint32_t gb = g_begin; gb < g_end; gb += 4u) {
+    uint32_t tf0[4], tx0[4];
+    // ---- 0. the first ticks >= t0 at which each group of the batch can be due ----
 #pragma unroll
-    for (int u = 0; u < 4; ++u) nd[u] = __ldcg(d.due + (size_t)t_begin * GS_TILE + lane + 32u * u);
-  }
-  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
-    uint32_t due[4] = {nd[0], nd[1], nd[2], nd[3]};
-    if (tile + 1u < t_end) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) nd[u] = __ldcg(d.due + (size_t)(tile + 1u) * GS_TILE + lane + 32u * u);
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t grp = gb + u;
+      if (grp < g_end) {
+        const uint32_t q = grp >> shift;
+        if (q != pg) {                                   // groups are consecutive: the next phase group, phase + 1 (mod P)
+          pp = pp + 1u == P ? 0u : pp + 1u;
+          pg = q;
+        }
+        uint32_t a = pp + P - t0_mod;                    // first tick >= t0 congruent to the phase ...
+        a = a >= P ? a - P : a;
+        uint32_t b = a + T;                              // ... and to phase + ProbeTimeout
+        b = b >= P ? b - P : b;
+        tf0[u] = t0 + a;
+        tx0[u] = t0 + b;
+      } else {
+        tf0[u] = tx0[u] = GS_NEVER;
+      }
     }
-    const uint32_t base = tile * GS_TILE + lane;
-    const uint32_t pp = gs_probe_phase(g.rot_p, tile >> shift, P);
-    // first ticks >= t0 congruent to the phase / to phase + ProbeTimeout
-    const uint32_t ta = t0 + (pp + P - t0_mod) % P, tb = t0 + ((pp + g.T) % P + P - t0_mod) % P;
-    const uint32_t tlo = ta < tb ? ta : tb, thi = ta < tb ? tb : ta;
+    // A launch usually covers one ProbeInterval; when the host knows that no probe can go unanswered it
+    // covers many, and the batch runs them back to back (rows are independent inside a quiet window, so
+    // a warp may finish all the ticks of its groups before it looks at the next ones — their columns
+    // stay in L1/L2 meanwhile).
 #pragma unroll 1
-    for (uint32_t which = 0; which < 2u; ++which) {
-      const uint32_t t = which == 0u ? tlo : thi;
-      if (t >= w1) break;
-      if (which == 1u) {  // rows handled at the first tick may have moved their `due` to this one
+    for (uint32_t s0 = t0; s0 < w1; s0 += P) {
+    const uint32_t off = s0 - t0;
+    uint32_t tf[4], tx[4], due[4];
+    bool cand[4], slow[4];
+    bool any_slow = false;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) due[u] = __ldcg(d.due + base + 32u * u);
+    for (int u = 0; u < 4; ++u) {
+      if (gb + u < g_end) {
+        tf[u] = tf0[u] + off;
+        tx[u] = tx0[u] + off;
+        due[u] = __ldcg(d.due + (gb + u) * 32u + lane);
+      } else {
+        tf[u] = tx[u] = GS_NEVER;
+        due[u] = GS_NEVER - 1u;
       }
-      bool act[4], cand[4];
-      bool any = false;
+      cand[u] = fast_ok && due[u] == tf[u] && tf[u] < w1;
+      // anything else that is due inside the window takes the generic step below
+      slow[u] = (due[u] == tf[u] && tf[u] < w1 && !fast_ok) || (due[u] == tx[u] && tx[u] < w1);
+    }
+    // ---- A. own columns of every candidate (independent loads, issued together) ----
+    GsFastProbe f[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        act[u] = cand[u] = due[u] == t;
-        any |= act[u];
+    for (int u = 0; u < 4; ++u)
+      if (cand[u]) gs_fast_load(d, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
+    // ---- B. ring entry -> target, status gathers ----
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cand[u]) {
+        const bool okk = gs_fast_target(d, h, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
+        if (!okk) { cand[u] = false; slow[u] = true; }
       }
-      if (!__any_sync(0xFFFFFFFFu, any)) continue;
+    // ---- C. commit ----
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bool acked = false, done = false;
+      if (cand[u]) {
+        done = gs_fast_finish(d, h, sink, (gb + u) * 32u + lane, tf[u], f[u], &acked);
+        if (!done) slow[u] = true;
+        // an unanswered probe reaches its indirect stage at tf + T: inside this window it is stepped below
+        else if (!acked && tf[u] + T < w1) slow[u] = true;
+      }
+      n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
+      n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
+      any_slow |= slow[u];
+    }
+    // ---- D. whatever is left: the generic step, tick by tick in ascending order ----
+    if (__any_sync(0xFFFFFFFFu, any_slow)) {
       did_work = true;
-      const uint32_t cur = t & 1u;
-      GsFastProbe f[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (cand[u]) gs_fast_load(d, cur, base + 32u * u, f[u]);               // A: own columns
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (cand[u]) cand[u] = gs_fast_target(d, g, cur, base + 32u * u, f[u]);  // B: gathers
-      uint32_t n_probe = 0, n_ack = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        bool acked = false;
-        const bool done = cand[u] && gs_fast_finish(d, g, sink, base + 32u * u, t, f[u], &acked);  // C
-        if (done) act[u] = false;
-        n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
-        n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
-      }
-      if (lane == 0u && n_probe) {
-        atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
-        atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
-        if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
-      }
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
-        const bool a = u == 0 ? act[0] : u == 1 ? act[1] : u == 2 ? act[2] : act[3];
-        if (__any_sync(0xFFFFFFFFu, a)) {
-          if (a) gs_row_step(d, g, base + 32u * u, t, t % g.GI, 0u, sink);
+        const bool sl = u == 0 ? slow[0] : u == 1 ? slow[1] : u == 2 ? slow[2] : slow[3];
+        if (!__any_sync(0xFFFFFFFFu, sl)) continue;
+        const uint32_t a = u == 0 ? tf[0] : u == 1 ? tf[1] : u == 2 ? tf[2] : tf[3];
+        const uint32_t b = u == 0 ? tx[0] : u == 1 ? tx[1] : u == 2 ? tx[2] : tx[3];
+        const uint32_t i = (gb + u) * 32u + lane;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t t = which == 0 ? (a < b ? a : b) : (a < b ? b : a);
+          if (t >= w1) break;
+          // (a member the fast path finished at `a` has moved its `due` on: it is not stepped twice)
+          if (sl && __ldcg(d.due + i) == t) gs_row_step_call<COORDS>(&d, gp, i, t, 0u, s_stat, s_heard, s_q);
         }
       }
     }
+    }  // ProbeIntervals of this launch
   }
-  if (g.world > 1u && did_work) __threadfence_system();  // horizon words on the peers, before the release
+  did_work |= n_probe != 0u;
+  if (lane == 0u && n_probe) {
+    atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
+    atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
+    if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
+  }
+  if (world > 1u && did_work) __threadfence_system();  // horizon words on the peers, before the release
   __syncthreads();
   if (tid < GS_NSTAT) {
     uint32_t v = s_stat[tid];
@@ -438,12 +534,13 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   }
   if (tid == 0u) {
     // a quiet window never meets mail and never posts: if it did, the scheduling invariant is broken
-    if (s_q[0] != 0u) atomicExch(qs + GS_Q_VIOLATION, t0 + 1u);
+    // ... and a launch that covers several ProbeIntervals was promised that no probe goes unanswered
+    if (s_q[0] != 0u || (n_ticks > P && s_q[1] != GS_NEVER)) atomicExch(qs + GS_Q_VIOLATION, t0 + 1u);
     s_q[0] = 0u;
     gs_q_publish(d, g, s_q, t0);
     atomicMax(qs + GS_Q_WIN_END, w1);
   }
-  if (g.world > 1u) gs_ranks_release(d, g, w1);
+  if (world > 1u) gs_ranks_release(d, g, w1);
 }
 
 // Horizon of the pool as it stands (run before the first window after single ticks): the minimum,
@@ -550,6 +647,7 @@ __global__ void __launch_bounds__(GS_BLOCK)
     atomicAdd(&s.truth_cnt[truth], 1u);
     if (truth != GS_TRUTH_NONE) atomicAdd(&s.rank_cnt[rank], 1u);
     if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) atomicAdd(&s.crashed_alive, 1u);
+    if ((truth == GS_TRUTH_CRASHED || truth == GS_TRUTH_GONE) && rank < GS_RANK_DEAD) atomicAdd(&s.unreachable_live, 1u);
     if (truth == GS_TRUTH_UP && (d.meta[i] & GS_META_ISOLATED)) atomicAdd(&s.isolated_up, 1u);
     if (truth == GS_TRUTH_UP && g.active_mask) {
       uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
@@ -655,6 +753,10 @@ class CudaBackend : public GsBackend {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs_tick_kernel<false>, GS_BLOCK, 0) != cudaSuccess || occ < 1)
       occ = 4;
     full_grid_ = (uint32_t)(sms * occ);
+    int wocc = GS_WIN_BLOCKS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, gs_window_kernel<false>, GS_BLOCK, 0) != cudaSuccess || wocc < 1)
+      wocc = GS_WIN_BLOCKS;
+    win_grid_ = (uint32_t)(sms * wocc);
     scratch_ = nullptr;
     cudaMalloc(&scratch_, 4096);
   }
@@ -779,7 +881,8 @@ class CudaBackend : public GsBackend {
   // Quiet windows (gs_window_kernel): `nticks` ticks as a chain of launches of up to ProbeInterval
   // ticks each.  The chain stops by itself at the horizon; *ticks_done says how far it got.
   bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
-                   bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done, const GsXbar* xbar) override {
+                   uint32_t per_launch, bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done,
+                   const GsXbar* xbar) override {
     cudaSetDevice(dev_);
     *ticks_done = 0;
     if (!nticks || !g.n) return true;
@@ -788,14 +891,14 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaMemcpyAsync(qs + GS_Q_WIN_END, init, 8, cudaMemcpyHostToDevice, stream_), "window init")) return false;
     uint32_t tiles = (g.n + GS_TILE - 1) / GS_TILE;
     if (g.world > 1 && tiles > g.rows_per_rank / GS_TILE) tiles = g.rows_per_rank / GS_TILE;
-    uint32_t blocks = (tiles + GS_WARPS - 1) / GS_WARPS;
-    if (blocks > full_grid_) blocks = full_grid_;
-    const uint32_t K = g.P;
+    uint32_t blocks = (tiles * 4u + GS_WARPS - 1) / GS_WARPS;  // a warp per group of 32 members, up to a full machine
+    if (blocks > win_grid_) blocks = win_grid_;
+    const uint32_t K = per_launch < g.P ? g.P : per_launch;
     const bool sharded = xbar != nullptr;
     const bool pdl = pdl_ && !sharded;
     if (!ok(cudaEventRecord(ev0_, stream_), "event")) return false;
     uint32_t left = nticks, n_launch = 0;
-    if (use_graph && (!sharded || !no_shard_graph_)) {
+    if (use_graph && K == g.P && (!sharded || !no_shard_graph_)) {
       while (left >= GS_WIN_GRAPH * K) {
         cudaGraphExec_t ge = window_graph_for(d, g_dev, blocks, K, pdl, g.rank);
         if (!ge) return false;
@@ -1033,6 +1136,7 @@ class CudaBackend : public GsBackend {
   cudaEvent_t ev0_, ev1_;
   void* scratch_;
   uint32_t full_grid_ = 592;
+  uint32_t win_grid_ = 592;
   GsVmm vmm_;
   bool sharded_ = false;
   bool pdl_ = getenv("GSIM_NO_PDL") == nullptr;

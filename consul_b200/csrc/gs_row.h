@@ -165,7 +165,25 @@ GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t slo
 // WAN latency pools (BASELINE config 5): EXTRA one-way latency in ticks from src to dst on top
 // of the one tick every packet takes; 0 everywhere on a pool without datacenters.  An all-zero
 // matrix is indistinguishable from n_dcs == 0 (tests/test_latency_cpu.py).
-GS_DEV uint32_t gs_extra(const GsGlobals& g, uint32_t src, uint32_t dst) {
+// The pool constants the probe fast path reads, copied out of the device-resident GsGlobals once per
+// launch: they are warp-uniform, so they sit in (uniform) registers instead of costing a global load
+// each time the 32 members of a group ask for them.  Same field names as GsGlobals: the fast-path
+// functions are templates over "something with these fields".
+struct GsHot {
+  uint32_t n, P, T, seed_lo, seed_hi, perm_half_bits, loss_thr, graph_n, pp_interval, rot_pp, phase_group, n_dcs;
+  const uint8_t* lat;
+};
+GS_DEV GsHot gs_hot(const GsGlobals& g) {
+  GsHot h;
+  h.n = g.n; h.P = g.P; h.T = g.T; h.seed_lo = g.seed_lo; h.seed_hi = g.seed_hi;
+  h.perm_half_bits = g.perm_half_bits; h.loss_thr = g.loss_thr; h.graph_n = g.graph_n;
+  h.pp_interval = g.pp_interval; h.rot_pp = g.rot_pp; h.phase_group = g.phase_group; h.n_dcs = g.n_dcs;
+  h.lat = g.lat;
+  return h;
+}
+
+template <class G>
+GS_DEV uint32_t gs_extra(const G& g, uint32_t src, uint32_t dst) {
   if (g.n_dcs == 0u) return 0u;
   return g.lat[((src / GS_TILE) % g.n_dcs) * GS_MAX_DCS + (dst / GS_TILE) % g.n_dcs];
 }
@@ -281,26 +299,37 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
   uint32_t tries = 3u * n;
   if (tries > GS_KR_MAX_TRIES || n > 0x55555555u) tries = GS_KR_MAX_TRIES;
   uint32_t cnt = 0;
-  GsU4 blk;
-  blk.x = blk.y = blk.z = blk.w = 0;
-  for (uint32_t dr = 0; dr < tries && cnt < k; ++dr) {
-    if ((dr & 3u) == 0u) blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, dr >> 2);
-    uint32_t c = gs_peer_at(d, g, i, gs_u4_get(blk, dr & 3u) % n);
-    if (c == i || c == exclude2) continue;
-    uint32_t kc = gs_peer_key(d, t & 1u, c, false);
-    if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
-    uint32_t rank = gs_key_rank(kc);
-    if (mode == 1u) {
-      if (rank != GS_RANK_ALIVE) continue;
-    } else {
-      if (rank == GS_RANK_LEFT) continue;
-      if (rank == GS_RANK_DEAD && (t - GS_LD_OTHER(&d.change_tick[c])) > g.gtd_ticks) continue;
+  // One Philox block = four draws.  Their candidates and the candidates' status words are fetched
+  // together (four independent gathers in flight instead of a chain of dependent ones); the draws
+  // are then judged strictly in order, exactly like the sequential loop — a fetched status that
+  // turns out not to be needed (enough peers already) was only read.
+  for (uint32_t b4 = 0; b4 * 4u < tries && cnt < k; ++b4) {
+    const GsU4 blk = gs_philox(g.seed_lo, g.seed_hi, i, t, purpose, b4);
+    uint32_t cc[4], kk[4];
+#pragma unroll
+    for (uint32_t x = 0; x < 4u; ++x) {
+      cc[x] = gs_peer_at(d, g, i, gs_u4_get(blk, x) % n);
+      kk[x] = (b4 * 4u + x < tries && cc[x] != i && cc[x] != exclude2) ? gs_peer_key(d, t & 1u, cc[x], false) : 0u;
     }
-    if (!gs_knows(d, g, i, c, kc, meta_i)) continue;
-    bool dup = false;
-    for (uint32_t q = 0; q < cnt; ++q) dup = dup || (out[q] == c);
-    if (dup) continue;
-    out[cnt++] = c;
+#pragma unroll
+    for (uint32_t x = 0; x < 4u; ++x) {
+      if (!(b4 * 4u + x < tries && cnt < k)) continue;
+      const uint32_t c = cc[x], kc = kk[x];
+      if (c == i || c == exclude2) continue;
+      if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
+      const uint32_t rank = gs_key_rank(kc);
+      if (mode == 1u) {
+        if (rank != GS_RANK_ALIVE) continue;
+      } else {
+        if (rank == GS_RANK_LEFT) continue;
+        if (rank == GS_RANK_DEAD && (t - GS_LD_OTHER(&d.change_tick[c])) > g.gtd_ticks) continue;
+      }
+      if (!gs_knows(d, g, i, c, kc, meta_i)) continue;
+      bool dup = false;
+      for (uint32_t q = 0; q < cnt; ++q) dup = dup || (out[q] == c);
+      if (dup) continue;
+      out[cnt++] = c;
+    }
   }
   return cnt;
 }
@@ -310,6 +339,7 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
 // every message that still fits the UDP budget.  Class order = memberlist broadcasts,
 // then serf intents, then serf user events ([U] serf/delegate.go GetBroadcasts).
 GS_DEV uint32_t gs_select_packet(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t queued) {
+  if (g.active_bytes <= g.udp_avail) return queued;  // every tracked broadcast together fits one packet
   uint32_t total = 0, qm = queued;
   while (qm) {
 #if defined(__CUDA_ARCH__)
@@ -693,6 +723,62 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       uint32_t kk = g.gossip_nodes > 8u ? 8u : g.gossip_nodes;
       uint32_t np = gs_krandom(d, g, i, t, GS_PUR_GOSSIP, kk, 0u, GS_EMPTY32, m, peers);
       const uint32_t q0 = queued;
+      if (g.active_bytes <= g.udp_avail && np != 0u) {
+        // Every packet carries the whole queue (the byte budget cannot bind).  Broadcast r then rides
+        // in packets 0 .. sends_r - 1 with sends_r = min(np, max(1, limit - transmits_r)): one read
+        // and one write of its counter instead of one per packet, same counters and same packets as
+        // the general loop below.
+        uint32_t sends[GS_MAX_RUMORS > 8 ? 8 : GS_MAX_RUMORS];
+        uint32_t n_pkts = 0, n_q = 0, pm = queued;
+        bool few = true;
+        while (pm) {
+#if defined(__CUDA_ARCH__)
+          const uint32_t r = __ffs(pm) - 1;
+#else
+          const uint32_t r = (uint32_t)__builtin_ctz(pm);
+#endif
+          pm &= pm - 1;
+          if (n_q == 8u) { few = false; break; }
+          const uint32_t tx = d.tx[GS_TX(r, cap, i)];
+          uint32_t room = g.retransmit_limit > tx ? g.retransmit_limit - tx : 1u;
+          if (room == 0u) room = 1u;
+          const uint32_t s = room < np ? room : np;
+          sends[n_q++] = s;
+          if (s > n_pkts) n_pkts = s;
+        }
+        if (few) {
+          pm = queued;
+          for (uint32_t x = 0; x < n_q; ++x) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t r = __ffs(pm) - 1;
+#else
+            const uint32_t r = (uint32_t)__builtin_ctz(pm);
+#endif
+            pm &= pm - 1;
+            const uint32_t tx = (uint32_t)d.tx[GS_TX(r, cap, i)] + sends[x];
+            d.tx[GS_TX(r, cap, i)] = (uint8_t)tx;
+            if (tx >= g.retransmit_limit) queued &= ~(1u << r);  // broadcast finished
+            sink.stat(GS_ST_RUMORS_SENT, sends[x]);
+          }
+          sink.stat(GS_ST_GOSSIP_PACKETS, n_pkts);
+          for (uint32_t q = 0; q < n_pkts; ++q) {
+            uint32_t pkt = 0;
+            pm = q0;
+            for (uint32_t x = 0; x < n_q; ++x) {
+#if defined(__CUDA_ARCH__)
+              const uint32_t r = __ffs(pm) - 1;
+#else
+              const uint32_t r = (uint32_t)__builtin_ctz(pm);
+#endif
+              pm &= pm - 1;
+              if (sends[x] > q) pkt |= 1u << r;
+            }
+            if (!gs_lost(g, sink, i, peers[q], t, GS_LK_GOSSIP, q))
+              gs_post(d, g, sink, (t + 1u + gs_extra(g, i, peers[q])) & g.ring_mask, peers[q], pkt);
+          }
+          np = 0u;  // done: the general loop below has nothing left to do
+        }
+      }
       for (uint32_t q = 0; q < np && queued != 0u; ++q) {
         uint32_t pkt = gs_select_packet(d, g, i, queued);
         if (pkt == 0u) break;
@@ -776,7 +862,8 @@ GS_DEV void gs_fast_load(const GsDev& d, uint32_t cur, uint32_t i, GsFastProbe& 
   f.pass = d.pass[i];
 }
 
-GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uint32_t i,
+template <class G>
+GS_DEV bool gs_fast_target(const GsDev& d, const G& g, uint32_t cur, uint32_t i,
                            GsFastProbe& f) {
   if (g.loss_thr != 0u || g.graph_n != 0u || d.coord != nullptr) return false;  // CSR rows, coordinates: generic path
   if (gs_key_truth(f.k) != GS_TRUTH_UP || gs_key_rank(f.k) != GS_RANK_ALIVE) return false;
@@ -791,8 +878,8 @@ GS_DEV bool gs_fast_target(const GsDev& d, const GsGlobals& g, uint32_t cur, uin
 
 // Returns true when the member was fully handled; *acked tells whether the direct probe
 // succeeded (stats: PROBES +1, ACKS +acked, ACTIVE_ROWS +1 are added by the caller).
-template <class Sink>
-GS_DEV bool gs_fast_finish(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t i, uint32_t t,
+template <class G, class Sink>
+GS_DEV bool gs_fast_finish(const GsDev& d, const G& g, Sink& sink, uint32_t i, uint32_t t,
                            const GsFastProbe& f, bool* acked) {
   const uint32_t rank = gs_key_rank(f.kc);
   if (gs_key_truth(f.kc) == GS_TRUTH_NONE || rank == GS_RANK_DEAD || rank == GS_RANK_LEFT ||

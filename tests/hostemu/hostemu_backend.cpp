@@ -173,8 +173,9 @@ class HostEmuBackend : public GsBackend {
   // gs_window_kernel on the host.  Rows are taken one after the other and each runs ALL its ticks of
   // the window before the next row is looked at — as far from lock-step as an order can be, which is
   // the point: inside a quiet window rows are independent.
-  bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0, uint32_t nticks, bool,
-                   double*, uint64_t* launches, uint32_t* ticks_done, const GsXbar* xbar) override {
+  bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals&, uint32_t t0, uint32_t nticks,
+                   uint32_t per_launch, bool, double*, uint64_t* launches, uint32_t* ticks_done,
+                   const GsXbar* xbar) override {
     const GsGlobals& g = *g_dev;
     *ticks_done = 0;
     if (!nticks || !g.n) return true;
@@ -185,7 +186,7 @@ class HostEmuBackend : public GsBackend {
       snprintf(err_, sizeof(err_), "tick_base out of sync");
       return false;
     }
-    const uint32_t K = g.P;
+    const uint32_t K = per_launch < g.P ? g.P : per_launch;
     uint32_t lo = 0, hi = g.n;
     if (g.world > 1u) {
       lo = g.rank * g.rows_per_rank < g.n ? g.rank * g.rows_per_rank : g.n;
@@ -209,11 +210,10 @@ class HostEmuBackend : public GsBackend {
       for (uint32_t x = 0; x < hi - lo; ++x) {
         const uint32_t i = lo + row_at(x, hi - lo);
         const uint32_t pp = gs_probe_phase(g.rot_p, (i / GS_TILE) >> g.phase_shift, g.P);
-        const uint32_t ta = w0 + (pp + g.P - w0 % g.P) % g.P, tb = w0 + ((pp + g.T) % g.P + g.P - w0 % g.P) % g.P;
-        const uint32_t two[2] = {ta < tb ? ta : tb, ta < tb ? tb : ta};
-        for (uint32_t which = 0; which < 2u; ++which) {
-          const uint32_t t = two[which];
-          if (t >= w1) break;
+        // every tick of the launch at which this member can be due: congruent to its ticker phase or to
+        // phase + ProbeTimeout (a launch covers one ProbeInterval in general, many when no probe can fail)
+        for (uint32_t t = w0; t < w1; ++t) {
+          if (t % g.P != pp && t % g.P != (pp + g.T) % g.P) continue;
           if (d.due[i] != t) continue;
           if (!no_fast_) {
             GsFastProbe f;
@@ -229,6 +229,7 @@ class HostEmuBackend : public GsBackend {
           gs_row_step(d, g, i, t, t % g.GI, 0u, sink);
         }
       }
+      if (K > g.P && sink.min_horizon != GS_NEVER) sink.active = true;  // a probe went unanswered in a long launch
       sink.publish(d, g, w0, true);
       qs[GS_Q_WIN_END] = w1;
       if (xbar) xbar_host(*xbar);  // sharded: one inter-rank barrier per window
@@ -288,6 +289,7 @@ class HostEmuBackend : public GsBackend {
       out->truth_cnt[truth]++;
       if (truth != GS_TRUTH_NONE) out->rank_cnt[rank]++;
       if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) out->crashed_alive++;
+      if ((truth == GS_TRUTH_CRASHED || truth == GS_TRUTH_GONE) && rank < GS_RANK_DEAD) out->unreachable_live++;
       if (truth == GS_TRUTH_UP && (d.meta[i] & GS_META_ISOLATED)) out->isolated_up++;
       if (truth == GS_TRUTH_UP) {
         uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;

@@ -136,3 +136,30 @@ def test_window_schedule_is_independent_of_row_order():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1] == outs[2] and outs[0].endswith("True"), outs
+
+
+def test_long_launches_only_while_no_probe_can_fail(hostemu_lib):
+    """On a quiet pool where every listed member runs (no loss, no slow link) no probe can go unanswered,
+    so one launch covers many ProbeIntervals; one crashed member that is still listed alive ends that
+    (launches of one ProbeInterval, bounded by the horizon, then single ticks), and once it is Dead —
+    skipped by every probe ring — the long launches are back.  Same results as single ticks throughout."""
+    pools = trio(hostemu_lib, lan_config, capacity=3000, n_initial=3000, seed=27)
+    for p in pools:
+        p.step(700)
+    check(pools, "healthy 700")
+    sc = pools[0].sched_counts()
+    assert sc["window_ticks"] >= 650 and sc["window_launches"] <= 8, sc              # 320 ticks per launch
+    all3(pools, lambda p: p.crash(1234))
+    before = pools[0].sched_counts()
+    for p in pools:
+        p.step(60)
+    check(pools, "one crashed, still listed")
+    mid = pools[0].sched_counts()
+    assert mid["tick_launches"] > before["tick_launches"]                           # the failed probe ended the windows
+    t = all3(pools, lambda p: p.run_until(PRED_CRASHED_ALL_DEAD, 0, 3000, 32))
+    for p in pools:
+        p.step(800)
+    check(pools, "dead, skipped by the rings")
+    after = pools[0].sched_counts()
+    assert after["window_ticks"] - mid["window_ticks"] >= 600
+    assert after["window_launches"] - mid["window_launches"] <= 40, (mid, after)    # long launches again
