@@ -42,8 +42,10 @@ struct DevSinkT {
   uint32_t* s_q;  // [0] this CTA saw mail or posted some, [1] min horizon raised by its members
   __device__ __forceinline__ void activity() { s_q[0] = 1u; }
   __device__ __forceinline__ void horizon(uint32_t h) { atomicMin(&s_q[1], h); }
-  __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx], v); }
-  __device__ __forceinline__ void heard(uint32_t r) { atomicAdd(&s_heard[r], 1u); }
+  // Counters are kept per lane (one shared-memory bank each): the 32 members of a group bump the same
+  // counter at the same instruction, and 32 atomics on ONE shared word replay 32 times.
+  __device__ __forceinline__ void stat(int idx, uint32_t v) { atomicAdd(&s_stat[idx * 32 + (threadIdx.x & 31u)], v); }
+  __device__ __forceinline__ void heard(uint32_t r) { atomicAdd(&s_heard[r * 32u + (threadIdx.x & 31u)], 1u); }
   // Pool-wide words (crashed_alive, the event-log cursor, heard_cnt) live in rank 0's page on a
   // sharded pool and are updated by every GPU: system-scope atomics (device scope is not atomic
   // across GPUs).  They are rare — one per event, not per member — so single-GPU pools pay nothing
@@ -162,8 +164,8 @@ __device__ __noinline__ void gs_row_step_call(const GsDev* dp, const GsGlobals* 
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     gs_tick_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
-  __shared__ uint32_t s_stat[GS_NSTAT];
-  __shared__ uint32_t s_heard[32];
+  __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
+  __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
   __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
   __shared__ uint32_t s_q[2];
@@ -172,8 +174,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   __shared__ uint32_t s_work[GS_WARPS * GS_ROUND * 4];
   __shared__ uint32_t s_wn[2], s_wtake[2];
   const uint32_t tid = threadIdx.x;
-  if (tid < GS_NSTAT) s_stat[tid] = 0u;
-  if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  for (uint32_t x = tid; x < GS_NSTAT * 32u; x += GS_BLOCK) s_stat[x] = 0u;
+  for (uint32_t x = tid; x < 32u * 32u; x += GS_BLOCK) s_heard[x] = 0u;
   if (tid == 64u) s_q[0] = 0u;
   if (tid == 65u) s_q[1] = GS_NEVER;
   if (tid >= 66u && tid < 68u) s_wn[tid - 66u] = 0u;
@@ -302,9 +304,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
           n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
         }
         if (lane == 0u && n_probe) {
-          atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
-          atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
-          if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
+          atomicAdd(&s_stat[GS_ST_PROBES * 32], n_probe);
+          atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS * 32], n_probe);
+          if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS * 32], n_ack);
         }
       }
 #pragma unroll
@@ -342,10 +344,12 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   __syncthreads();
   // one global atomic per counter per CTA, and only for CTAs that saw activity
   if (tid < GS_NSTAT) {
-    uint32_t v = s_stat[tid];
+    uint32_t v = 0;
+    for (uint32_t x = 0; x < 32u; ++x) v += s_stat[tid * 32u + ((x + tid) & 31u)];
     if (v) atomicAdd(&d.stats[tid], (unsigned long long)v);
   } else if (tid >= 32u && tid < 32u + GS_MAX_RUMORS) {
-    uint32_t r = tid - 32u, c = s_heard[r];
+    uint32_t r = tid - 32u, c = 0;
+    for (uint32_t x = 0; x < 32u; ++x) c += s_heard[r * 32u + ((x + r) & 31u)];
     if (c) {
       uint32_t old = atomicAdd_system(&d.heard_cnt[r], c);  // rank 0's page on a sharded pool
       if (old + c == g.up_count) d.conv_tick[r] = t;  // every UP member has heard rumor r
@@ -379,12 +383,12 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
     gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
-  __shared__ uint32_t s_stat[GS_NSTAT];
-  __shared__ uint32_t s_heard[32];
+  __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
+  __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
   __shared__ uint32_t s_q[2];
   const uint32_t tid = threadIdx.x;
-  if (tid < GS_NSTAT) s_stat[tid] = 0u;
-  if (tid >= 32u && tid < 64u) s_heard[tid - 32u] = 0u;
+  for (uint32_t x = tid; x < GS_NSTAT * 32u; x += GS_BLOCK) s_stat[x] = 0u;
+  for (uint32_t x = tid; x < 32u * 32u; x += GS_BLOCK) s_heard[x] = 0u;
   if (tid == 64u) s_q[0] = 0u;
   if (tid == 65u) s_q[1] = GS_NEVER;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -522,14 +526,15 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   }
   did_work |= n_probe != 0u;
   if (lane == 0u && n_probe) {
-    atomicAdd(&s_stat[GS_ST_PROBES], n_probe);
-    atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS], n_probe);
-    if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS], n_ack);
+    atomicAdd(&s_stat[GS_ST_PROBES * 32], n_probe);
+    atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS * 32], n_probe);
+    if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS * 32], n_ack);
   }
   if (world > 1u && did_work) __threadfence_system();  // horizon words on the peers, before the release
   __syncthreads();
   if (tid < GS_NSTAT) {
-    uint32_t v = s_stat[tid];
+    uint32_t v = 0;
+    for (uint32_t x = 0; x < 32u; ++x) v += s_stat[tid * 32u + ((x + tid) & 31u)];
     if (v) atomicAdd(&d.stats[tid], (unsigned long long)v);
   }
   if (tid == 0u) {

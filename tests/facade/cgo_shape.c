@@ -1,0 +1,149 @@
+/* cgo_shape.c — drives the C ABI exactly the way the cgo binding of third_party/gsim-go/serf does
+ * (VERDICT r1 next-step 7): plain C (cgo compiles the preamble as C, not C++), every out-buffer
+ * allocated by the caller with a (cap, *n) pair and a first sizing call with a NULL buffer, strings
+ * and payloads copied on entry — the caller scribbles over and frees its buffers right after each
+ * call, as Go's garbage collector may —, no pointer retained by the library, negative error codes
+ * instead of aborts, and several threads (goroutines: the clock / event pump, HTTP and RPC handlers,
+ * the Flood ticker) calling into ONE pool at the same time.
+ * Built with gcc against libgsim_hostemu.so (CPU suite) and libgsim.so (GPU suite). */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gsim.h"
+
+#define CHECK(cond)                                                              \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);            \
+      exit(1);                                                                   \
+    }                                                                            \
+  } while (0)
+
+static gsim_pool* pool;
+static volatile int stop_clock;
+static int n_errors;
+
+/* the pool's clock goroutine: gsim_step(1) then gsim_poll_events into a caller buffer */
+static void* clock_thread(void* arg) {
+  (void)arg;
+  gsim_event evs[64];
+  size_t n;
+  unsigned polled = 0;
+  while (!stop_clock) {
+    if (gsim_step(pool, 1) != GSIM_OK) __sync_fetch_and_add(&n_errors, 1);
+    if (gsim_poll_events(pool, evs, 64, &n) != GSIM_OK) __sync_fetch_and_add(&n_errors, 1);
+    polled += (unsigned)n;
+    memset(evs, 0xAB, sizeof(evs)); /* the buffer is the caller's: reused for anything */
+  }
+  return (void*)(size_t)polled;
+}
+
+/* a handler goroutine: Members() with the two-call sizing protocol, NumNodes, Stats */
+static void* reader_thread(void* arg) {
+  const uint32_t observer = (uint32_t)(size_t)arg;
+  for (int round = 0; round < 200; ++round) {
+    size_t n = 0, n2 = 0;
+    if (gsim_members(pool, observer, NULL, 0, &n) != GSIM_OK) { __sync_fetch_and_add(&n_errors, 1); continue; }
+    gsim_member* buf = (gsim_member*)malloc((n + 8) * sizeof(gsim_member));
+    int rc = gsim_members(pool, observer, buf, n + 8, &n2); /* the pool may have grown: room to spare */
+    if (rc != GSIM_OK || n2 < n || n2 > n + 8) __sync_fetch_and_add(&n_errors, 1);
+    free(buf);
+    uint32_t nodes = 0;
+    if (gsim_num_nodes(pool, observer, &nodes) != GSIM_OK || nodes == 0) __sync_fetch_and_add(&n_errors, 1);
+    gsim_stats st;
+    if (gsim_stats_get(pool, &st) != GSIM_OK) __sync_fetch_and_add(&n_errors, 1);
+  }
+  return NULL;
+}
+
+/* another handler: fires user events from heap strings that are destroyed right after the call */
+static void* event_thread(void* arg) {
+  (void)arg;
+  for (int k = 0; k < 6; ++k) {
+    char* name = (char*)malloc(32);
+    char* payload = (char*)malloc(64);
+    snprintf(name, 32, "consul:event:deploy-%d", k);
+    memset(payload, 'p', 64);
+    uint32_t slot = 0;
+    int rc = gsim_user_event(pool, 3 + (uint32_t)k, name, strlen(name), payload, 64, 0, &slot);
+    if (rc != GSIM_OK) __sync_fetch_and_add(&n_errors, 1);
+    memset(name, 0, 32); /* Go may move or free it: the library must have copied */
+    memset(payload, 0, 64);
+    free(name);
+    free(payload);
+    /* ... and it did: the stored copy is intact */
+    char nb[64], pb[128];
+    size_t nl = 0, pl = 0;
+    if (rc == GSIM_OK && (gsim_user_event_get(pool, slot, nb, sizeof(nb), &nl, pb, sizeof(pb), &pl) != GSIM_OK || pl != 64 ||
+                          nl < 20 || memcmp(nb, "consul:event:deploy-", 20) != 0 || pb[63] != 'p'))
+      __sync_fetch_and_add(&n_errors, 1);
+  }
+  return NULL;
+}
+
+int main(void) {
+  gsim_config cfg;
+  gsim_config_default_lan(&cfg);
+  CHECK(cfg.struct_size == sizeof(gsim_config));
+  cfg.capacity = 2100;
+  cfg.n_initial = 2000;
+  cfg.seed = 77;
+  int rc = gsim_pool_create(&cfg, &pool);
+  if (rc == GSIM_ERR_NO_DEVICE) { /* libgsim.so without a GPU: the error path is the contract */
+    printf("SKIP no device: %s\n", gsim_strerror(rc));
+    return 0;
+  }
+  CHECK(rc == GSIM_OK && pool != NULL);
+  /* errors are codes, never aborts; messages are library-owned strings */
+  uint32_t id = 0;
+  CHECK(gsim_join(pool, 99999, &id, 1, 1, NULL) < 0);
+  CHECK(strlen(gsim_last_error(pool)) > 0 && strlen(gsim_strerror(GSIM_ERR_NOT_FOUND)) > 0);
+  CHECK(gsim_members(pool, 99999, NULL, 0, NULL) < 0);
+  gsim_member small[5];
+  memset(small, 0xEE, sizeof(small));
+  size_t n = 0;
+  /* a buffer that is too small is filled up to its capacity, never beyond, and *n reports the size needed */
+  CHECK(gsim_members(pool, 0, small, 4, &n) == GSIM_OK && n == 2000 && small[3].id == 3 && small[4].id == 0xEEEEEEEEu);
+
+  pthread_t clock, readers[5], events;
+  pthread_create(&clock, NULL, clock_thread, NULL);
+  for (size_t k = 0; k < 5; ++k) pthread_create(&readers[k], NULL, reader_thread, (void*)(k * 7));
+  pthread_create(&events, NULL, event_thread, NULL);
+  /* the main goroutine: serf.Create + Join of a few agents while everything else is running */
+  for (int k = 0; k < 8; ++k) {
+    gsim_member_desc d;
+    memset(&d, 0, sizeof(d));
+    d.flags = GSIM_MEMBER_WATCHED;
+    d.name_len = 12;
+    d.meta_len = 90;
+    CHECK(gsim_member_add(pool, &d, &id) == GSIM_OK && id == 2000u + (uint32_t)k);
+    uint32_t* seeds = (uint32_t*)malloc(2 * sizeof(uint32_t));
+    seeds[0] = (uint32_t)k;
+    seeds[1] = 1999;
+    int n_ok = 0;
+    CHECK(gsim_join(pool, id, seeds, 2, 1, &n_ok) == GSIM_OK && n_ok == 2);
+    free(seeds);
+  }
+  pthread_join(events, NULL);
+  for (size_t k = 0; k < 5; ++k) pthread_join(readers[k], NULL);
+  stop_clock = 1;
+  void* polled = NULL;
+  pthread_join(clock, &polled);
+  CHECK(n_errors == 0);
+  CHECK(gsim_step(pool, 200) == GSIM_OK);
+  gsim_stats st;
+  CHECK(gsim_stats_get(pool, &st) == GSIM_OK && st.n_members == 2008 && st.n_view_alive == 2008);
+  for (uint32_t slot = 0; slot < GSIM_MAX_RUMORS; ++slot) {
+    gsim_rumor_info info;
+    if (gsim_rumor_info_get(pool, slot, &info) == GSIM_OK && info.kind == GSIM_RUMOR_USER_EVENT)
+      CHECK(info.heard_count == 2008); /* every event reached every agent, joiners included */
+  }
+  uint64_t h[4];
+  CHECK(gsim_state_hash(pool, h) == GSIM_OK);
+  gsim_pool_destroy(pool);
+  printf("ALL PASS cgo call shape: 8 threads on one pool, %zu events polled by the clock thread, digest %016llx\n",
+         (size_t)polled, (unsigned long long)h[0]);
+  return 0;
+}

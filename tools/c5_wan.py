@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--bridges", type=int, default=5)
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED0051)
     ap.add_argument("--max-ticks", type=int, default=600)
+    ap.add_argument("--check", action="store_true", help="rank 0 replays the run on ONE GPU and compares digests")
     a = ap.parse_args()
 
     import torch
@@ -59,9 +60,24 @@ def main():
         kernel_ms += sum(p.last_step_timing()[0] for p in fed.pools)
     wall_s = time.time() - t0
     stats = [p.stats() for p in fed.pools]               # collective on sharded pools: every rank calls
+    digests = [["%016x" % h for h in p.state_hash()] for p in fed.pools]
     now = fed.pools[0].now
+    check = {}
+    if a.check and world > 1:
+        for p in fed.pools:
+            p.close()
+        if rank == 0:                                    # the same federation on one GPU
+            one = lambda seed: Pool(wan_config(capacity=a.members, n_initial=a.members, seed=seed, mailbox_depth=8, device=local))
+            ref = WanFederation(one(a.seed), one(a.seed + 1), n_dcs=a.dcs, bridges_per_dc=a.bridges, n_members=a.members)
+            ref.fire(0, a.bridges + 2, name, payload)
+            t_ref = ref.run_until_converged(name, payload, a.max_ticks)
+            d_ref = [["%016x" % h for h in p.state_hash()] for p in ref.pools]
+            check = {"digest_single_gpu": d_ref, "ticks_single_gpu": t_ref,
+                     "parity_ok": d_ref == digests and t_ref == ticks and ref.forwarded == fed.forwarded}
+            for p in ref.pools:
+                p.close()
     if rank == 0:
-        print(json.dumps({
+        print(json.dumps({**check, "digest": digests,
             "config": "C5: two WAN pools, %d members each, %d DCs, %d bridges/DC, L[a][b]=1+((7a+13b) mod 5)"
                       % (a.members, a.dcs, a.bridges),
             "n_gpus": world, "ticks_to_convergence": ticks, "ticks_run": now,
@@ -70,10 +86,12 @@ def main():
             "kernel_ms": kernel_ms, "wall_s": wall_s, "setup_s": setup_s,
             "node_ticks_per_s_kernel": 2 * a.members * now / (kernel_ms / 1e3) if kernel_ms else None,
         }), flush=True)
-    for p in fed.pools:
-        p.close()
+    if not (a.check and world > 1):
+        for p in fed.pools:
+            p.close()
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 
