@@ -375,6 +375,95 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
 //
 // A tile's members are due only at ticks congruent to its ticker phase (probe start, probe
 // deadline) or to phase + ProbeTimeout (indirect stage): at most two ticks of a window.
+// The generic path of a window for one batch of four groups: one ProbeInterval after the other (rows are
+// independent inside a quiet window, so a warp finishes all the ticks of its groups before it looks at
+// the next ones), staged probe fast path first, then the generic row step for whatever it declines.
+template <bool COORDS>
+__device__ __noinline__ void gs_window_generic(const GsDev* dp, const GsGlobals* gp, uint32_t gb, uint32_t g_end,
+                                               uint32_t tf00, uint32_t tf01, uint32_t tf02, uint32_t tf03,
+                                               uint32_t tx00, uint32_t tx01, uint32_t tx02, uint32_t tx03,
+                                               uint32_t t0, uint32_t w1, uint32_t* s_stat, uint32_t* s_heard,
+                                               uint32_t* s_q, uint32_t* counts) {
+  const GsDev& d = *dp;
+  const GsGlobals& g = *gp;
+  const GsHot h = gs_hot(g);
+  const uint32_t P = h.P, T = h.T, lane = threadIdx.x & 31u;
+  const uint32_t tf0[4] = {tf00, tf01, tf02, tf03}, tx0[4] = {tx00, tx01, tx02, tx03};
+  const bool fast_ok = h.loss_thr == 0u && h.graph_n == 0u && d.coord == nullptr && h.pp_interval == 0u;
+  DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
+  uint32_t n_probe = 0, n_ack = 0;
+  bool did_work = false;
+  (void)did_work;
+#pragma unroll 1
+    for (uint32_t s0 = t0; s0 < w1; s0 += P) {
+    const uint32_t off = s0 - t0;
+    uint32_t tf[4], tx[4], due[4];
+    bool cand[4], slow[4];
+    bool any_slow = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (gb + u < g_end) {
+        tf[u] = tf0[u] + off;
+        tx[u] = tx0[u] + off;
+        due[u] = __ldcg(d.due + (gb + u) * 32u + lane);
+      } else {
+        tf[u] = tx[u] = GS_NEVER;
+        due[u] = GS_NEVER - 1u;
+      }
+      cand[u] = fast_ok && due[u] == tf[u] && tf[u] < w1;
+      // anything else that is due inside the window takes the generic step below
+      slow[u] = (due[u] == tf[u] && tf[u] < w1 && !fast_ok) || (due[u] == tx[u] && tx[u] < w1);
+    }
+    // ---- A. own columns of every candidate (independent loads, issued together) ----
+    GsFastProbe f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cand[u]) gs_fast_load(d, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
+    // ---- B. ring entry -> target, status gathers ----
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (cand[u]) {
+        const bool okk = gs_fast_target(d, h, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
+        if (!okk) { cand[u] = false; slow[u] = true; }
+      }
+    // ---- C. commit ----
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bool acked = false, done = false;
+      if (cand[u]) {
+        done = gs_fast_finish(d, h, sink, (gb + u) * 32u + lane, tf[u], f[u], &acked);
+        if (!done) slow[u] = true;
+        // an unanswered probe reaches its indirect stage at tf + T: inside this window it is stepped below
+        else if (!acked && tf[u] + T < w1) slow[u] = true;
+      }
+      n_probe += done ? 1u : 0u;  // (per lane; summed over the warp at the end)
+      n_ack += done && acked ? 1u : 0u;
+      any_slow |= slow[u];
+    }
+    // ---- D. whatever is left: the generic step, tick by tick in ascending order ----
+    if (__any_sync(0xFFFFFFFFu, any_slow)) {
+      did_work = true;
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const bool sl = u == 0 ? slow[0] : u == 1 ? slow[1] : u == 2 ? slow[2] : slow[3];
+        if (!__any_sync(0xFFFFFFFFu, sl)) continue;
+        const uint32_t a = u == 0 ? tf[0] : u == 1 ? tf[1] : u == 2 ? tf[2] : tf[3];
+        const uint32_t b = u == 0 ? tx[0] : u == 1 ? tx[1] : u == 2 ? tx[2] : tx[3];
+        const uint32_t i = (gb + u) * 32u + lane;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t t = which == 0 ? (a < b ? a : b) : (a < b ? b : a);
+          if (t >= w1) break;
+          // (a member the fast path finished at `a` has moved its `due` on: it is not stepped twice)
+          if (sl && __ldcg(d.due + i) == t) gs_row_step_call<COORDS>(&d, gp, i, t, 0u, s_stat, s_heard, s_q);
+        }
+      }
+    }
+    }  // ProbeIntervals of this launch
+  counts[0] = n_probe;
+  counts[1] = n_ack;
+}
+
 #ifndef GS_WIN_BLOCKS
 #define GS_WIN_BLOCKS 4
 #endif
@@ -453,82 +542,112 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
         tf0[u] = tx0[u] = GS_NEVER;
       }
     }
-    // A launch usually covers one ProbeInterval; when the host knows that no probe can go unanswered it
-    // covers many, and the batch runs them back to back (rows are independent inside a quiet window, so
-    // a warp may finish all the ticks of its groups before it looks at the next ones — their columns
-    // stay in L1/L2 meanwhile).
-#pragma unroll 1
-    for (uint32_t s0 = t0; s0 < w1; s0 += P) {
-    const uint32_t off = s0 - t0;
-    uint32_t tf[4], tx[4], due[4];
-    bool cand[4], slow[4];
-    bool any_slow = false;
+    // ---- 1. fast-forward.  A member that is up, listed alive, idle and due at its ticker phase keeps its
+    // probe state in registers and runs ALL its probes of the launch in a row: ring entry -> target ->
+    // the target's status byte -> ack -> awareness - 1, due + ProbeInterval, cursor + 1.  A launch covers
+    // one ProbeInterval in general and many when the host knows that no probe can go unanswered; either
+    // way the loop stops at the first thing that is not this common case (ring wrap, a target that is
+    // not up-alive-established, a slow link), writes the member's state back as it stood BEFORE that
+    // probe, and the generic code below carries on from there.  Four groups in lock step: four
+    // independent permutations and four gathers in flight per lane.
+    bool pending_any = false;
+    {
+      uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4];
+      GsU4 rk[4];
+      bool live[4], in_rng[4];
+      uint32_t cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (gb + u < g_end) {
-        tf[u] = tf0[u] + off;
-        tx[u] = tx0[u] + off;
-        due[u] = __ldcg(d.due + (gb + u) * 32u + lane);
-      } else {
-        tf[u] = tx[u] = GS_NEVER;
-        due[u] = GS_NEVER - 1u;
-      }
-      cand[u] = fast_ok && due[u] == tf[u] && tf[u] < w1;
-      // anything else that is due inside the window takes the generic step below
-      slow[u] = (due[u] == tf[u] && tf[u] < w1 && !fast_ok) || (due[u] == tx[u] && tx[u] < w1);
-    }
-    // ---- A. own columns of every candidate (independent loads, issued together) ----
-    GsFastProbe f[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (cand[u]) gs_fast_load(d, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
-    // ---- B. ring entry -> target, status gathers ----
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (cand[u]) {
-        const bool okk = gs_fast_target(d, h, tf[u] & 1u, (gb + u) * 32u + lane, f[u]);
-        if (!okk) { cand[u] = false; slow[u] = true; }
-      }
-    // ---- C. commit ----
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      bool acked = false, done = false;
-      if (cand[u]) {
-        done = gs_fast_finish(d, h, sink, (gb + u) * 32u + lane, tf[u], f[u], &acked);
-        if (!done) slow[u] = true;
-        // an unanswered probe reaches its indirect stage at tf + T: inside this window it is stepped below
-        else if (!acked && tf[u] + T < w1) slow[u] = true;
-      }
-      n_probe += __popc(__ballot_sync(0xFFFFFFFFu, done));
-      n_ack += __popc(__ballot_sync(0xFFFFFFFFu, done && acked));
-      any_slow |= slow[u];
-    }
-    // ---- D. whatever is left: the generic step, tick by tick in ascending order ----
-    if (__any_sync(0xFFFFFFFFu, any_slow)) {
-      did_work = true;
-#pragma unroll 1
       for (int u = 0; u < 4; ++u) {
-        const bool sl = u == 0 ? slow[0] : u == 1 ? slow[1] : u == 2 ? slow[2] : slow[3];
-        if (!__any_sync(0xFFFFFFFFu, sl)) continue;
-        const uint32_t a = u == 0 ? tf[0] : u == 1 ? tf[1] : u == 2 ? tf[2] : tf[3];
-        const uint32_t b = u == 0 ? tx[0] : u == 1 ? tx[1] : u == 2 ? tx[2] : tx[3];
         const uint32_t i = (gb + u) * 32u + lane;
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-          const uint32_t t = which == 0 ? (a < b ? a : b) : (a < b ? b : a);
-          if (t >= w1) break;
-          // (a member the fast path finished at `a` has moved its `due` on: it is not stepped twice)
-          if (sl && __ldcg(d.due + i) == t) gs_row_step_call<COORDS>(&d, gp, i, t, 0u, s_stat, s_heard, s_q);
+        in_rng[u] = gb + u < g_end;
+        live[u] = false;
+        mm[u] = cu[u] = 0u;
+        du[u] = GS_NEVER;
+        if (in_rng[u]) {
+          du[u] = __ldcg(d.due + i);
+          if (fast_ok && du[u] == tf0[u] && du[u] < w1) {
+            const uint32_t k = d.key[du[u] & 1u][i];
+            mm[u] = d.meta[i];
+            cu[u] = d.cursor[i];
+            const uint32_t pa = d.pass[i];
+            live[u] = gs_key_truth(k) == GS_TRUTH_UP && gs_key_rank(k) == GS_RANK_ALIVE &&
+                      gs_meta_stage(mm[u]) == GS_STAGE_IDLE && !(mm[u] & (GS_META_DIRTY | GS_META_ISOLATED));
+            rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa);
+          }
+        }
+        m_in[u] = mm[u];
+        cu_in[u] = cu[u];
+        du_in[u] = du[u];
+      }
+      for (;;) {
+        bool go[4];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          go[u] = live[u] && du[u] < w1;
+          any |= go[u];
+        }
+        if (!__any_sync(0xFFFFFFFFu, any)) break;
+        uint32_t c[4], kc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          c[u] = 0u;
+          if (go[u]) {
+            if (cu[u] >= h.n) {  // ring wrap: re-keyed by the generic step
+              live[u] = go[u] = false;
+            } else {
+              c[u] = gs_perm(cu[u], h.n, h.perm_half_bits, rk[u]);
+              if (c[u] == (gb + u) * 32u + lane) live[u] = go[u] = false;  // own entry: skipped by the generic step
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kc[u] = go[u] ? gs_peer_key(d, du[u] & 1u, c[u], false) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!go[u]) continue;
+          const uint32_t i = (gb + u) * 32u + lane;
+          if (gs_key_truth(kc[u]) != GS_TRUTH_UP || gs_key_rank(kc[u]) != GS_RANK_ALIVE || gs_key_pending(kc[u]) ||
+              gs_extra(h, i, c[u]) + gs_extra(h, c[u], i) > T) {
+            live[u] = false;  // anything but a prompt ack: the generic step decides
+            continue;
+          }
+          const uint32_t aw = gs_meta_aw(mm[u]);
+          mm[u] = gs_meta_set_aw(mm[u], aw ? aw - 1u : 0u);
+          du[u] += P;
+          cu[u] += 1u;
+          ++cnt;
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!in_rng[u]) continue;
+        const uint32_t i = (gb + u) * 32u + lane;
+        if (cu[u] != cu_in[u]) d.cursor[i] = cu[u];
+        if (du[u] != du_in[u]) d.due[i] = du[u];
+        if (mm[u] != m_in[u]) d.meta[i] = mm[u];
+        pending_any |= du[u] >= t0 && du[u] < w1;  // still something due inside the launch
+      }
+      n_probe += cnt;  // per lane; summed over the warp once, at the end
+      n_ack += cnt;
     }
-    }  // ProbeIntervals of this launch
+    if (!__any_sync(0xFFFFFFFFu, pending_any)) continue;
+    // ---- 2. whatever is left takes the generic path (out of line: it is rare, and its staging arrays
+    // would cost the loop above its registers)
+    {
+      uint32_t add[2] = {0u, 0u};
+      gs_window_generic<COORDS>(&d, gp, gb, g_end, tf0[0], tf0[1], tf0[2], tf0[3], tx0[0], tx0[1], tx0[2], tx0[3], t0, w1,
+                                s_stat, s_heard, s_q, add);
+      n_probe += add[0];
+      n_ack += add[1];
+      did_work = true;
+    }
   }
   did_work |= n_probe != 0u;
-  if (lane == 0u && n_probe) {
-    atomicAdd(&s_stat[GS_ST_PROBES * 32], n_probe);
-    atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS * 32], n_probe);
-    if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS * 32], n_ack);
+  if (n_probe) {  // one shared-memory counter per lane (DevSinkT::stat)
+    atomicAdd(&s_stat[GS_ST_PROBES * 32 + lane], n_probe);
+    atomicAdd(&s_stat[GS_ST_ACTIVE_ROWS * 32 + lane], n_probe);
+    if (n_ack) atomicAdd(&s_stat[GS_ST_ACKS * 32 + lane], n_ack);
   }
   if (world > 1u && did_work) __threadfence_system();  // horizon words on the peers, before the release
   __syncthreads();

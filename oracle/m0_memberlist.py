@@ -42,6 +42,13 @@ class Config:
     disable_tcp: bool = False
     event_buffer: int = 512
     tick_seconds: float = 0.1
+    # [U] memberlist/net.go sendMsg / encodeAndSendMsg: every ping, ack, indirect ping, forwarded ack and
+    # nack is sent as a compound packet with whatever broadcasts still fit (getBroadcasts), and carrying
+    # them counts as a transmission.  Off by default: M1 and the CUDA path do not model it (probes are
+    # pull-evaluated, there is no probe packet to ride on); tests/test_m0_crosscheck.py measures what
+    # that omission costs.
+    piggyback: bool = False
+    ping_size: int = 40            # a ping / ack / nack with its node names, before any piggybacked broadcast
 
 
 def retransmit_limit(mult, n):
@@ -268,13 +275,23 @@ class Agent:
             relays = self.k_random(cfg.indirect_checks, lambda c, st: c != j and st.state == ALIVE)
             ok, nacks = False, 0
             for r in relays:
-                if not net.agents[r].up or net.lost():
+                ra, ja = net.agents[r], net.agents[j]
+                l_req = net.lost()
+                self.piggyback(r, t, l_req)                       # indirect-ping request i -> relay
+                if not ra.up or l_req:
                     continue
-                acked = net.agents[j].up and not net.lost() and not net.lost()
+                l_ping = net.lost()
+                ra.piggyback(j, t, l_ping)                        # relay's ping -> target
+                l_ack = net.lost() if (ja.up and not l_ping) else True
+                if ja.up and not l_ping:
+                    ja.piggyback(r, t, l_ack)                     # target's ack -> relay
+                acked = ja.up and not l_ping and not l_ack
+                l_back = net.lost()
+                ra.piggyback(self.id, t, l_back)                  # forwarded ack, or the nack, relay -> i
                 if acked:
-                    if not net.lost():
+                    if not l_back:
                         ok = True
-                elif not net.lost():
+                elif not l_back:
                     nacks += 1
             if not cfg.disable_tcp and net.agents[j].up:
                 ok = True
@@ -300,7 +317,13 @@ class Agent:
                 return
             self.stats["probes"] += 1
             st = self.views[target]
-            if net.agents[target].up and not net.lost() and not net.lost():
+            ta = net.agents[target]
+            l_ping = net.lost()
+            self.piggyback(target, t, l_ping)                     # ping i -> target
+            l_ack = net.lost() if (ta.up and not l_ping) else True
+            if ta.up and not l_ping:
+                ta.piggyback(self.id, t, l_ack)                   # ack target -> i
+            if ta.up and not l_ping and not l_ack:
                 self.awareness = max(0, self.awareness - 1)
                 self.next_probe = t + cfg.probe_interval
             else:
@@ -326,29 +349,48 @@ class Agent:
             return c
         return None
 
+    def take_broadcasts(self, budget):
+        """[U] TransmitLimitedQueue.GetBroadcasts through serf's delegate: memberlist's queue first, then
+        intents, then user events; fewest transmits first, then longest, then newest; every message taken
+        counts one transmission and retires at the retransmit limit."""
+        limit = retransmit_limit(self.net.cfg.retransmit_mult, self.n())
+        packet, used = [], 0
+        for q, overhead in ((self.queue, 2), (self.intents, 3), (self.events_q, 3)):
+            for b in sorted(q, key=lambda b: (b.transmits, -b.size, -b.seq)):
+                if used + overhead + b.size > budget:
+                    continue
+                packet.append(b)
+                used += overhead + b.size
+                b.transmits += 1
+            q[:] = [b for b in q if b.transmits < limit]
+        return [Broadcast(b.kind, b.node, b.inc, b.frm, b.ltime, b.key, b.size) for b in packet]
+
+    def piggyback(self, dst, t, lost):
+        """A probe-traffic packet from this agent to `dst` leaves now: it carries queued broadcasts
+        (and they count as transmitted whether or not the packet arrives)."""
+        if not self.net.cfg.piggyback or not self.up:
+            return
+        msgs = self.take_broadcasts(self.net.cfg.udp_budget - self.net.cfg.ping_size)
+        if msgs:
+            self.net.stats["piggyback_packets"] += 1
+            self.net.stats["piggyback_msgs"] += len(msgs)
+            if not lost:
+                self.net.deliver(dst, msgs, t + 1)
+
     def gossip(self, t):
         cfg, net = self.net.cfg, self.net
         if not (self.queue or self.intents or self.events_q):
             return
         peers = self.k_random(cfg.gossip_nodes, lambda c, st: st.state in (ALIVE, SUSPECT) or
                               (st.state == DEAD and t - st.change <= cfg.gossip_to_the_dead))
-        limit = retransmit_limit(cfg.retransmit_mult, self.n())
         for peer in peers:
-            packet, used = [], 0
-            for q, overhead in ((self.queue, 2), (self.intents, 3), (self.events_q, 3)):
-                for b in sorted(q, key=lambda b: (b.transmits, -b.size, -b.seq)):
-                    if used + overhead + b.size > cfg.udp_budget:
-                        continue
-                    packet.append(b)
-                    used += overhead + b.size
-                    b.transmits += 1
-                q[:] = [b for b in q if b.transmits < limit]
+            packet = self.take_broadcasts(cfg.udp_budget)
             if not packet:
                 break
             net.stats["packets"] += 1
             net.stats["msgs"] += len(packet)
             if not net.lost():
-                net.deliver(peer, [Broadcast(b.kind, b.node, b.inc, b.frm, b.ltime, b.key, b.size) for b in packet], t + 1)
+                net.deliver(peer, packet, t + 1)
 
 
 class Network:
@@ -358,7 +400,7 @@ class Network:
         self.inflight = {}
         self.seq = 0
         self.alive_size = alive_size
-        self.stats = dict(packets=0, msgs=0)
+        self.stats = dict(packets=0, msgs=0, piggyback_packets=0, piggyback_msgs=0)
 
     def next_seq(self):
         self.seq += 1
