@@ -188,3 +188,37 @@ def test_stranded_broadcast_coverage_matches_full_fidelity_model(hostemu_lib):
         p.step(120)
         c1.append(p.rumor_info(slot)["heard_count"] / n)
     assert 0.3 < st.mean(c0) < 1.0 and abs(st.mean(c0) - st.mean(c1)) <= 0.08, (c0, c1)
+
+
+def test_piggyback_on_probe_traffic_shifts_dissemination_by_about_one_tick():
+    """[U] memberlist/net.go sendMsg: pings, acks, indirect pings and nacks carry queued broadcasts and
+    count as transmissions.  M1 and the CUDA path do not model it (probes are pull-evaluated: there is
+    no probe packet to ride on); M0 can (Config.piggyback).  What the omission costs, measured here over
+    8 seeds at 200 and 400 agents: the retransmit budget is conserved exactly (every agent still
+    transmits an event RetransmitMult*ceil(log10(n+1)) times), 8-16 % of those transmissions move from
+    gossip packets to probe packets, and the event reaches everybody 0.3-2 ticks (3-12 %) sooner — so
+    M1's ticks-to-convergence are conservative by about one tick."""
+    import statistics
+    for n, limit in ((200, 12), (400, 12)):
+        res = {}
+        for piggy in (False, True):
+            ticks, gossip, ridden = [], [], []
+            for seed in range(1, 9):
+                net = m0.Network(m0.Config(piggyback=piggy), seed=seed)
+                net.converged_cluster(n)
+                net.step(7)
+                key = net.user_event(3, b"deploy", b"x" * 8)
+                t0 = net.now
+                t = net.first_tick(lambda: all(any(k == key for _, k in a.delivered) for a in net.up_agents()), 400)
+                assert t is not None
+                net.step(80)                                      # drain the queues
+                ticks.append(t - t0)
+                gossip.append(net.stats["msgs"])
+                ridden.append(net.stats["piggyback_msgs"])
+                assert net.stats["msgs"] + net.stats["piggyback_msgs"] == n * limit   # budget conserved
+            res[piggy] = (statistics.mean(ticks), statistics.mean(gossip), statistics.mean(ridden))
+        assert res[False][2] == 0
+        share = res[True][2] / (n * limit)
+        assert 0.06 < share < 0.2, share
+        shift = res[False][0] - res[True][0]
+        assert 0.0 < shift < 2.5, (n, res)
