@@ -49,11 +49,12 @@ B_PROBE = 12.0      # extra for a probe start: cursor r/w, pass, target key gath
 B_ACCEPT = 21.0     # heard r/w, queued write, tx init, Lamport clock witness
 B_PACKET = 12.0     # peer key gather + mailbox atomic RMW
 B_RUMOR_TX = 2.0    # tx counter r/w per broadcast carried
-# gs_window_kernel (up to P ticks per launch, quiet pool): no mailbox word is read at all; every
-# member's `due` once per launch, and per probe the prober's key, meta, cursor (r/w), pass, the
-# target's status byte and the new `due`.
-B_WIN_DUE = 4.0
-B_WIN_PROBE = 4.0 + 4.0 + 8.0 + 4.0 + 1.0 + 4.0
+# gs_window_kernel (a whole window of ticks per launch, quiet pool): no mailbox word is read at all.  A
+# member's probe state is read once per launch (due, key, meta, cursor, pass), kept in registers while it
+# runs all its probes of the launch, and written back once (cursor, due); each probe gathers the target's
+# status byte.
+B_WIN_ROW = 4.0 * 5 + 4.0 * 2
+B_WIN_PROBE = 1.0
 
 
 def split_bytes(d: dict, sc: dict, n_members: float, P: int) -> dict:
@@ -62,7 +63,7 @@ def split_bytes(d: dict, sc: dict, n_members: float, P: int) -> dict:
     one probe per P ticks and nothing else happens, so the window kernel's share of the shared
     counters is window_ticks * n / P probes."""
     win_probes = min(float(d["probes"]), sc["window_ticks"] * n_members / P)
-    win = sc["window_launches"] * n_members * B_WIN_DUE + win_probes * B_WIN_PROBE
+    win = sc["window_launches"] * n_members * B_WIN_ROW + win_probes * B_WIN_PROBE
     tick_nt = sc["tick_launches"] * n_members
     tick = (tick_nt * (B_SCAN + B_DUE * 2.0 / P) + max(0.0, d["active_rows"] - win_probes) * B_ACTIVE +
             max(0.0, d["probes"] - win_probes) * B_PROBE + d["rumors_accepted"] * B_ACCEPT +
@@ -485,7 +486,9 @@ def main():
         # join operation (pokes) and the result read-back (stats, NumNodes of the joiner)
         def step_e2e():
             xx, _ = step_resident()
-            return pool.stats()["n_view_alive"] + pool.num_nodes(xx)
+            # the result a caller reads back: cluster-wide counts (recount kernels on every GPU, a few hundred
+            # bytes to the host) — not Members(), which on a sharded pool would pull every key through rank 0
+            return pool.stats()["n_view_alive"]
         for _ in range(min(args.warmup, 3)):
             step_e2e()
         barrier()
@@ -576,6 +579,13 @@ def main():
     roofline["note"] = ("the kernel with the larger share of the step's kernel time; both kernels are in roofline_kernels. "
                         "1M members: the hot columns are L2-resident by construction (2048 dependent ticks over the same "
                         "state); roofline_hbm below is the HBM-bound size")
+    # SURVEY §8(d)'s per-unit figure (every member's 32-byte row read and written every tick + rumor columns +
+    # 0.2 messages: 82 B per node-tick in LAN steady state) x the node-ticks of the timed region: the yardstick
+    # of a kernel that streams the whole state every tick.  This path does not touch idle rows, so it runs
+    # above 1.0 of it; the byte models above are the honest ones.
+    roofline["survey_model"] = {"bytes_per_node_tick": 82.0,
+                                "achieved": 82.0 * d["node_ticks"] / world / (total_ms * 1e-3) / 1e9 if total_ms > 0 else None,
+                                "unit": "GB/s", "frac": (82.0 * d["node_ticks"] / world / (total_ms * 1e-3) / 1e9 / peak) if total_ms > 0 else None}
     roofline["whole_step"] = {"achieved": (by["tick"] + by["window"]) / world / (total_ms * 1e-3) / 1e9 if total_ms > 0 else None,
                               "unit": "GB/s", "bytes_per_node_tick": (by["tick"] + by["window"]) / max(1.0, d["node_ticks"])}
 
@@ -613,6 +623,15 @@ def main():
     if not args.skip_cpu_baseline:
         cpu = cpu_baseline_sample(n, cap, ticks)
 
+    # BASELINE's second metric for the other configs: recorded by tools/configs_report.py on a B200 and
+    # committed (profiles/r2_configs.jsonl); carried in the line as a recorded artefact, not re-measured here
+    conv = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_configs.jsonl")) as f:
+            conv = [json.loads(ln) for ln in f if ln.strip().startswith("{")]
+    except Exception:
+        pass
+
     value = node_ticks_all / dt_max / 1e6
     line = {
         "metric": "million node-ticks/sec", "value": value, "unit": "M node-ticks/s",
@@ -621,6 +640,7 @@ def main():
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(n, ticks, world, sharded),
         "ticks_to_convergence": ticks_to_conv,
+        "ticks_to_convergence_other_configs": conv,
         "parity": parity, "digest": parity["digest"] if parity else None,
         "digest_oracle": parity.get("digest_oracle") if parity else None,
         "parity_ok": parity.get("parity_ok") if parity else None,
@@ -628,7 +648,7 @@ def main():
         "e2e": {"value": e2e_all / dte_max / 1e6, "unit": "M node-ticks/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": dte_max / args.steps * 1e3,
-                "path": ("member_add -> join -> step -> stats + num_nodes (cluster resident, sharded)" if sharded else
+                "path": ("member_add -> join -> step -> stats (cluster resident, sharded)" if sharded else
                          "gsim_restore(pinned host snapshot) -> member_add -> join -> step -> members + stats" if restore_ok else
                          "member_add -> join -> step -> members + stats (cluster resident: restore self-check failed)")},
         "gpu_launches": int(l1 - l0),

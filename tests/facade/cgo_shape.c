@@ -123,7 +123,7 @@ int main(void) {
     seeds[0] = (uint32_t)k;
     seeds[1] = 1999;
     int n_ok = 0;
-    CHECK(gsim_join(pool, id, seeds, 2, 1, &n_ok) == GSIM_OK && n_ok == 2);
+    CHECK(gsim_join(pool, id, seeds, 2, 0, &n_ok) == GSIM_OK && n_ok == 2); /* ignoreOld = false: the joiner takes the seeds' events too */
     free(seeds);
   }
   pthread_join(events, NULL);
