@@ -235,7 +235,7 @@ static bool peek(gsim_pool* p, const T* col, size_t i, T* out) {
 template <class T>
 static bool poke(gsim_pool* p, T* col, size_t i, T v) {
   mark_dirty(p);  // a host write to device state: whatever was known about quietness is void
-  return p->be->h2d(col + i, &v, sizeof(T));
+  return p->be->h2d_word(col + i, &v, sizeof(T));
 }
 
 // Host-side write of a member's key word: every replica on a sharded pool.
@@ -941,13 +941,9 @@ extern "C" int gsim_member_add(gsim_pool* p, const gsim_member_desc* desc, uint3
 // ([U] memberlist.mergeState -> aliveNode; [U] serf/delegate.go MergeRemoteState).
 static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_old_events) {
   GsGlobals& g = p->g;
-  uint32_t hs, hd, qd, lm_s, le_s, lm_d, le_d, emin, md;
-  if (!peek(p, p->d.heard, src, &hs) || !peek(p, p->d.heard, dst, &hd) ||
-      !peek(p, p->d.queued, dst, &qd) || !peek(p, p->d.ltime_member, src, &lm_s) ||
-      !peek(p, p->d.ltime_event, src, &le_s) || !peek(p, p->d.ltime_member, dst, &lm_d) ||
-      !peek(p, p->d.ltime_event, dst, &le_d) || !peek(p, p->d.event_min, dst, &emin) ||
-      !peek(p, p->d.meta, dst, &md))
-    return GSIM_ERR_CUDA;
+  uint32_t rs[8], rd[8];  // {key0, key1, meta, heard, queued, ltime_member, ltime_event, event_min} of both ends
+  if (!p->be->row_read(p->d, src, rs) || !p->be->row_read(p->d, dst, rd)) return GSIM_ERR_CUDA;
+  uint32_t hs = rs[3], hd = rd[3], qd = rd[4], lm_s = rs[5], le_s = rs[6], lm_d = rd[5], le_d = rd[6], emin = rd[7], md = rd[2];
   // clocks: Witness(remote - 1)  ==  max(local, remote)
   if (lm_s > lm_d) lm_d = lm_s;
   if (le_s > le_d) le_d = le_s;

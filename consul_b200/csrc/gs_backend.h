@@ -28,6 +28,14 @@ class GsBackend {
   virtual void release(void* p) = 0;
   virtual bool h2d(void* dst, const void* src, size_t bytes) = 0;
   virtual bool d2h(void* dst, const void* src, size_t bytes) = 0;
+  // A few bytes host -> device, ordered on the pool's stream but NOT waited for: the source may be reused
+  // as soon as the call returns (the driver stages small pageable copies before returning), everything
+  // the pool launches or reads later comes after it.  The host side of Join / UserEvent is dozens of
+  // single-word writes; waiting for each one was most of its cost.
+  virtual bool h2d_word(void* dst, const void* src, size_t bytes) { return h2d(dst, src, bytes); }
+  // The per-member words the host side of a state exchange needs, in one round trip:
+  // out = {key[0], key[1], meta, heard, queued, ltime_member, ltime_event, event_min}
+  virtual bool row_read(const GsDev& d, uint32_t i, uint32_t out[8]) = 0;
   virtual bool fill32(uint32_t* dst, uint32_t value, size_t count) = 0;
   virtual bool fill8(uint8_t* dst, uint8_t value, size_t count) = 0;
   // rows [first, first+count): converged members, inc=1, clocks=1, phases from Philox

@@ -846,6 +846,11 @@ static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const 
                  : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks);
 }
 
+__global__ void gs_row_read_kernel(GsDev d, uint32_t i, uint32_t* out) {
+  const uint32_t* col[8] = {d.key[0], d.key[1], d.meta, d.heard, d.queued, d.ltime_member, d.ltime_event, d.event_min};
+  if (threadIdx.x < 8u) out[threadIdx.x] = col[threadIdx.x][i];
+}
+
 __global__ void __launch_bounds__(GS_BLOCK) gs_fill32_kernel(uint32_t* dst, uint32_t value, size_t count) {
   for (size_t x = (size_t)blockIdx.x * GS_BLOCK + threadIdx.x; x < count; x += (size_t)gridDim.x * GS_BLOCK)
     dst[x] = value;
@@ -914,6 +919,18 @@ class CudaBackend : public GsBackend {
     cudaSetDevice(dev_);
     return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "d2h") &&
            ok(cudaStreamSynchronize(stream_), "d2h sync");
+  }
+  bool h2d_word(void* dst, const void* src, size_t bytes) override {
+    if (bytes > 64) return h2d(dst, src, bytes);
+    cudaSetDevice(dev_);
+    return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_), "h2d");
+  }
+  bool row_read(const GsDev& d, uint32_t i, uint32_t out[8]) override {
+    cudaSetDevice(dev_);
+    uint32_t* w = reinterpret_cast<uint32_t*>(scratch_) + 256;  // (the first KB of scratch belongs to the counters)
+    gs_row_read_kernel<<<1, 32, 0, stream_>>>(d, i, w);
+    ++launches_;
+    return ok(cudaGetLastError(), "row read launch") && d2h(out, w, 32);
   }
   bool fill32(uint32_t* dst, uint32_t value, size_t count) override {
     cudaSetDevice(dev_);

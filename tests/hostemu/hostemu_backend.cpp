@@ -89,6 +89,11 @@ class HostEmuBackend : public GsBackend {
     memcpy(dst, src, bytes);
     return true;
   }
+  bool row_read(const GsDev& d, uint32_t i, uint32_t out[8]) override {
+    const uint32_t* col[8] = {d.key[0], d.key[1], d.meta, d.heard, d.queued, d.ltime_member, d.ltime_event, d.event_min};
+    for (int x = 0; x < 8; ++x) out[x] = col[x][i];
+    return true;
+  }
   bool fill32(uint32_t* dst, uint32_t value, size_t count) override {
     for (size_t i = 0; i < count; ++i) dst[i] = value;
     return true;
