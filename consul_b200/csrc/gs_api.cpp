@@ -2168,7 +2168,7 @@ extern "C" int gsim_snapshot(gsim_pool* p, void* out, size_t cap_bytes, size_t* 
 extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   if (!p || !blob || n_bytes < sizeof(SnapHeader)) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
-  return controller_call(p, nullptr, 0, [&]() -> int {
+  const int rc_all = controller_call(p, nullptr, 0, [&]() -> int {
   const uint8_t* r = reinterpret_cast<const uint8_t*>(blob);
   const uint8_t* end = r + n_bytes;
   SnapHeader h;
@@ -2213,7 +2213,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
           r += 8;
         } else if (tag == 0u) {
           if ((size_t)(end - r) < 4 + pb) return fail(p, GSIM_ERR_INVALID, "truncated");
-          if (!p->be->h2d(dst, r + 4, pb)) return fail(p, GSIM_ERR_CUDA, "h2d");
+          if (!p->be->h2d_async(dst, r + 4, pb)) return fail(p, GSIM_ERR_CUDA, "h2d");
           r += 4 + pb;
         } else {
           return fail(p, GSIM_ERR_INVALID, "corrupt snapshot");
@@ -2223,12 +2223,12 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
     }
     if ((size_t)(end - r) < 4 + c.bytes) return fail(p, GSIM_ERR_INVALID, "truncated");
     r += 4;  // tag 0 (these columns are always stored raw)
-    if (!p->be->h2d(c.ptr, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+    if (!p->be->h2d_async(c.ptr, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
     if (p->sharded && (c.ptr == p->d.key[0] || c.ptr == p->d.key[1])) {
       // the key column is replicated per rank: restore every replica
       uint32_t* rep0 = c.ptr == p->d.key[0] ? p->d.key_rep[0] : p->d.key_rep[1];
       for (uint32_t q = 0; q < p->world; ++q)
-        if (!p->be->h2d(rep0 + (size_t)q * p->g.key_stride, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
+        if (!p->be->h2d_async(rep0 + (size_t)q * p->g.key_stride, r, c.bytes)) return fail(p, GSIM_ERR_CUDA, "h2d");
     }
     if (p->sharded && c.ptr == (void*)p->d.stats) {
       // counters restore into rank 0's page; the other ranks' partial sums restart at zero
@@ -2238,6 +2238,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
     }
     r += c.bytes;
   }
+  if (!p->be->sync()) return fail(p, GSIM_ERR_CUDA, "sync");  // every plane has left the caller's blob
   {
     // topology fields stay the live pool's (they were checked equal above, except the rank, which is
     // this process's own on a sharded pool)
@@ -2258,6 +2259,8 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");
   return GSIM_OK;
   });
+  p->be->sync();  // whatever happened, no copy out of the caller's blob is still in flight
+  return rc_all;
 }
 
 // ---- measurement hooks ------------------------------------------------------------

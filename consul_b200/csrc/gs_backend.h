@@ -33,6 +33,9 @@ class GsBackend {
   // the pool launches or reads later comes after it.  The host side of Join / UserEvent is dozens of
   // single-word writes; waiting for each one was most of its cost.
   virtual bool h2d_word(void* dst, const void* src, size_t bytes) { return h2d(dst, src, bytes); }
+  // Bulk host -> device, enqueued only: the caller keeps `src` alive and calls sync() before it returns
+  // (gsim_restore streams its planes back to back and waits once).
+  virtual bool h2d_async(void* dst, const void* src, size_t bytes) { return h2d(dst, src, bytes); }
   // The per-member words the host side of a state exchange needs, in one round trip:
   // out = {key[0], key[1], meta, heard, queued, ltime_member, ltime_event, event_min}
   virtual bool row_read(const GsDev& d, uint32_t i, uint32_t out[8]) = 0;

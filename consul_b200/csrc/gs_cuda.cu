@@ -925,6 +925,10 @@ class CudaBackend : public GsBackend {
     cudaSetDevice(dev_);
     return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_), "h2d");
   }
+  bool h2d_async(void* dst, const void* src, size_t bytes) override {
+    cudaSetDevice(dev_);
+    return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_), "h2d");
+  }
   bool row_read(const GsDev& d, uint32_t i, uint32_t out[8]) override {
     cudaSetDevice(dev_);
     uint32_t* w = reinterpret_cast<uint32_t*>(scratch_) + 256;  // (the first KB of scratch belongs to the counters)
