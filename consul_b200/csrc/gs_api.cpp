@@ -83,6 +83,12 @@ extern "C" uint32_t gsim_refute_incarnation(uint32_t cur, uint32_t accused) {
   return inc;
 }
 
+extern "C" uint32_t gsim_ring_entry(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t position) {
+  if (n == 0 || position >= n) return GS_EMPTY32;
+  const GsU4 rk = gs_perm_keys((uint32_t)seed, (uint32_t)(seed >> 32), member, pass);
+  return gs_perm(position, n, gs_perm_bits_of(n), rk);
+}
+
 extern "C" void gsim_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   GsU4 r = gs_philox(key[0], key[1], ctr[0], ctr[1], ctr[2], ctr[3]);
   out[0] = r.x;
@@ -272,11 +278,7 @@ static void recompute_tables(gsim_pool* p) {
     uint32_t cc = q > g.sus_k ? g.sus_k : q;
     g.sus_ticks[q] = ceil_ticks(suspicion_total_ns(cc, g.sus_k, min_ns, max_ns), p->tick_ns);
   }
-  uint32_t bits = 0;
-  while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
-  if (bits < 2) bits = 2;
-  if (bits & 1u) ++bits;
-  g.perm_half_bits = bits / 2;
+  g.perm_bits = gs_perm_bits_of(n);
   // [U] memberlist/state.go schedule: the push-pull ticker runs every pushPullScale(PushPullInterval, n)
   g.pp_interval = 0;
   g.rot_pp = 0;

@@ -203,23 +203,26 @@ GS_HD GsU4 gs_perm_keys(uint32_t seed_lo, uint32_t seed_hi, uint32_t member, uin
   k.w = (k.y * 0x85EBCA77u) ^ k.x;
   return k;
 }
-// half the bit width of the smallest even-width power of two >= n (>= 4): the Feistel domain
-GS_HD uint32_t gs_perm_half_bits_of(uint32_t n) {
+// bit width of the smallest power of two >= n (>= 4): the Feistel domain.  The two halves may differ by
+// one bit (an "unbalanced" Feistel network: each round XORs one half with a keyed function of the other,
+// halves alternating — a bijection for any pair of widths), so the domain is never more than twice n and
+// cycle walking takes < 2 rounds on average for every n, not only for those just below an even power of
+// two.  With equal halves this is exactly the classic swap-and-XOR network.
+GS_HD uint32_t gs_perm_bits_of(uint32_t n) {
   uint32_t bits = 2u;
   while (bits < 32u && (1ull << bits) < (unsigned long long)n) ++bits;
-  bits += bits & 1u;
-  return bits >> 1;
+  return bits;
 }
-GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t half_bits, const GsU4& rk) {
-  const uint32_t mask = (1u << half_bits) - 1u;
+GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t bits, const GsU4& rk) {
+  const uint32_t lo_bits = bits >> 1, hi_bits = bits - lo_bits;
+  const uint32_t lo_mask = (1u << lo_bits) - 1u, hi_mask = (1u << hi_bits) - 1u;
   do {
-    uint32_t l = x >> half_bits, r = x & mask;
-    uint32_t t;
-    t = l ^ (gs_feistel_round(r, rk.x) & mask); l = r; r = t;
-    t = l ^ (gs_feistel_round(r, rk.y) & mask); l = r; r = t;
-    t = l ^ (gs_feistel_round(r, rk.z) & mask); l = r; r = t;
-    t = l ^ (gs_feistel_round(r, rk.w) & mask); l = r; r = t;
-    x = (l << half_bits) | r;
+    uint32_t hi = x >> lo_bits, lo = x & lo_mask;
+    hi ^= gs_feistel_round(lo, rk.x) & hi_mask;
+    lo ^= gs_feistel_round(hi, rk.y) & lo_mask;
+    hi ^= gs_feistel_round(lo, rk.z) & hi_mask;
+    lo ^= gs_feistel_round(hi, rk.w) & lo_mask;
+    x = (hi << lo_bits) | lo;
   } while (x >= n);
   return x;
 }
@@ -260,7 +263,7 @@ struct GsGlobals {
   uint32_t seed_lo, seed_hi;
   uint32_t active_mask;    // non-free rumor slots
   uint32_t class_mask[3];  // rumor slots by queue class
-  uint32_t perm_half_bits;
+  uint32_t perm_bits;    // gs_perm_bits_of(n)
   uint32_t flags;
   uint32_t evlog_cap;
   uint32_t world, rank;

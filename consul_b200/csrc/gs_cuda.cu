@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
             if (cu[u] >= h.n) {  // ring wrap: re-keyed by the generic step
               live[u] = go[u] = false;
             } else {
-              c[u] = gs_perm(cu[u], h.n, h.perm_half_bits, rk[u]);
+              c[u] = gs_perm(cu[u], h.n, h.perm_bits, rk[u]);
               if (c[u] == (gb + u) * 32u + lane) live[u] = go[u] = false;  // own entry: skipped by the generic step
             }
           }

@@ -170,13 +170,13 @@ GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t slo
 // each time the 32 members of a group ask for them.  Same field names as GsGlobals: the fast-path
 // functions are templates over "something with these fields".
 struct GsHot {
-  uint32_t n, P, T, seed_lo, seed_hi, perm_half_bits, loss_thr, graph_n, pp_interval, rot_pp, phase_group, n_dcs;
+  uint32_t n, P, T, seed_lo, seed_hi, perm_bits, loss_thr, graph_n, pp_interval, rot_pp, phase_group, n_dcs;
   const uint8_t* lat;
 };
 GS_DEV GsHot gs_hot(const GsGlobals& g) {
   GsHot h;
   h.n = g.n; h.P = g.P; h.T = g.T; h.seed_lo = g.seed_lo; h.seed_hi = g.seed_hi;
-  h.perm_half_bits = g.perm_half_bits; h.loss_thr = g.loss_thr; h.graph_n = g.graph_n;
+  h.perm_bits = g.perm_bits; h.loss_thr = g.loss_thr; h.graph_n = g.graph_n;
   h.pp_interval = g.pp_interval; h.rot_pp = g.rot_pp; h.phase_group = g.phase_group; h.n_dcs = g.n_dcs;
   h.lat = g.lat;
   return h;
@@ -665,7 +665,7 @@ GS_DEV void gs_row_step(const GsDev& d, const GsGlobals& g, uint32_t i, uint32_t
       // dead/left members; a wrap re-keys the permutation (resetNodes + shuffle).
       uint32_t cursor = d.cursor[i], pass = d.pass[i];
       const uint32_t n = gs_peer_count(d, g, i);
-      const uint32_t hb = g.graph_n == 0u ? g.perm_half_bits : gs_perm_half_bits_of(n);
+      const uint32_t hb = g.graph_n == 0u ? g.perm_bits : gs_perm_bits_of(n);
       GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, pass);
       uint32_t checked = 0, target = GS_EMPTY32, ktarget = 0;
       const uint32_t limit = n < GS_PROBE_SKIP_CAP ? n : GS_PROBE_SKIP_CAP;
@@ -870,7 +870,7 @@ GS_DEV bool gs_fast_target(const GsDev& d, const G& g, uint32_t cur, uint32_t i,
   if (gs_meta_stage(f.m) != GS_STAGE_IDLE || (f.m & (GS_META_DIRTY | GS_META_ISOLATED))) return false;
   if (f.cursor >= g.n) return false;  // ring wrap: re-key in the generic path
   GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, f.pass);
-  f.c = gs_perm(f.cursor, g.n, g.perm_half_bits, rk);
+  f.c = gs_perm(f.cursor, g.n, g.perm_bits, rk);
   if (f.c == i) return false;
   f.kc = gs_peer_key(d, cur, f.c, false);
   return true;

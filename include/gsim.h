@@ -424,6 +424,11 @@ size_t gsim_wire_consul_user_event(void* out, size_t cap, const char* id, const 
                                    size_t payload_len, const char* node_filter, const char* service_filter,
                                    const char* tag_filter, int version);
 
+/* Entry `position` of the probe ring of `member` in its pass number `pass` over a member list of n entries:
+ * the keyed Feistel permutation of [0, n) that stands in for memberlist's shuffled node slice ([U] state.go
+ * resetNodes / shuffleNodes).  Pure function, exported for known-answer tests. */
+uint32_t gsim_ring_entry(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t position);
+
 /* Scheduling counters since creation: out[0] = quiet-window launches, out[1] = ticks advanced inside
  * quiet windows, out[2] = single-tick launches, out[3] = horizon scans, out[4] / out[5] = nanoseconds of
  * CUDA-event time spent in window / single-tick launches. */

@@ -57,6 +57,13 @@ const uint32_t KRANDOM_MAX_TRIES = 32;  // upstream: 3n (memberlist/util.go kRan
 const uint32_t PROBE_SKIP_CAP = 1024;   // upstream: len(nodes)
 const int MAX_SUS = GSIM_MAX_SUSPICION_SLOTS;
 
+// width in bits of the probe ring's permutation domain: the smallest power of two >= n (at least 4)
+uint32_t ring_bits(uint32_t n) {
+  uint32_t bits = 0;
+  while (bits < 32 && (1ull << bits) < n) ++bits;
+  return std::max(bits, 2u);
+}
+
 // ---- Philox4x32-10, written from the Random123 specification ----------------------
 struct Rand4 {
   uint32_t v[4];
@@ -293,7 +300,7 @@ struct Oracle {
   uint64_t tick_ns = 0;
   uint32_t now = 0;
   uint32_t P = 0, T = 0, GI = 0, gtd = 0, udp_avail = 0, loss_thr = 0;
-  uint32_t limit = 0, sus_k = 0, sus_ticks[MAX_SUS], perm_half_bits = 1;
+  uint32_t limit = 0, sus_k = 0, sus_ticks[MAX_SUS], perm_bits = 2;
   uint32_t up_count = 0;
   uint32_t established = 0;  // members folded into the base set
   std::vector<Member> m;
@@ -342,11 +349,7 @@ void retune(Oracle& o) {
   uint64_t mx = (uint64_t)o.cfg.suspicion_max_timeout_mult * mn;
   for (int c = 0; c < MAX_SUS; ++c)
     o.sus_ticks[c] = to_ticks_ceil(suspicion_total_ns(std::min<uint32_t>(c, o.sus_k), o.sus_k, mn, mx), o.tick_ns);
-  uint32_t bits = 0;
-  while (bits < 32 && (1ull << bits) < n) ++bits;
-  bits = std::max(bits, 2u);
-  bits += bits & 1;
-  o.perm_half_bits = bits / 2;
+  o.perm_bits = ring_bits(n);
   // [U] state.go schedule: push-pull every pushPullScale(PushPullInterval, n)
   o.pp_every = 0;
   if ((o.cfg.flags & GSIM_FLAG_PUSH_PULL) && o.cfg.push_pull_interval_ns) {
@@ -374,22 +377,25 @@ Rand4 ring_keys(uint64_t seed, uint32_t member, uint32_t pass) {
   return k;
 }
 
-// Feistel permutation of [0,n) with cycle walking — the probe ring of one (member, pass).
-uint32_t ring_entry(const Oracle& o, uint32_t position, uint32_t n, const Rand4& keys, uint32_t half_bits = 0) {
-  const uint32_t hb = half_bits ? half_bits : o.perm_half_bits, mask = (1u << hb) - 1;
+// Feistel permutation of [0,n) with cycle walking — the probe ring of one (member, pass).  The domain is
+// the smallest power of two >= n; its two halves differ by one bit when that width is odd (the wider one
+// on top), and every round XORs one half with the round function of the other: top, bottom, top, bottom.
+uint32_t ring_entry(const Oracle& o, uint32_t position, uint32_t n, const Rand4& keys, uint32_t width = 0) {
+  const uint32_t bits = width ? width : o.perm_bits;
+  const uint32_t bottom_bits = bits / 2, top_bits = bits - bottom_bits;
   uint32_t x = position;
   for (;;) {
-    uint32_t left = x >> hb, right = x & mask;
+    uint32_t half[2] = {x >> bottom_bits, x & ((1u << bottom_bits) - 1)};   // {top, bottom}
+    const uint32_t mask[2] = {(1u << top_bits) - 1, (1u << bottom_bits) - 1};
     for (int round = 0; round < 4; ++round) {
-      uint32_t f = (right + keys.v[round]) * 0x9E3779B1u;
+      const int into = round & 1, from = into ^ 1;
+      uint32_t f = (half[from] + keys.v[round]) * 0x9E3779B1u;
       f ^= f >> 15;
       f *= 0x85EBCA77u;
       f ^= f >> 13;
-      uint32_t nr = left ^ (f & mask);
-      left = right;
-      right = nr;
+      half[into] ^= f & mask[into];
     }
-    x = (left << hb) | right;
+    x = (half[0] << bottom_bits) | half[1];
     if (x < n) return x;
   }
 }
@@ -454,13 +460,6 @@ uint32_t list_length(const Oracle& o, uint32_t i) {
 }
 uint32_t list_entry(const Oracle& o, uint32_t i, uint32_t position) {
   return o.adjacency.empty() ? position : o.adjacency[i][position];
-}
-uint32_t ring_half_bits(uint32_t n) {
-  uint32_t bits = 0;
-  while (bits < 32 && (1ull << bits) < n) ++bits;
-  bits = std::max(bits, 2u);
-  bits += bits & 1;
-  return bits / 2;
 }
 
 // [U] memberlist/util.go kRandomNodes
@@ -716,7 +715,7 @@ void member_tick(Oracle& o, uint32_t i, uint32_t t, Tally& ta) {
     if (me.stage == ST_IDLE && me.due == t) {
       // [U] memberlist.probe: walk the ring to the next probe-able member
       const uint32_t n = list_length(o, i);
-      const uint32_t half_bits = o.adjacency.empty() ? 0 : ring_half_bits(n);
+      const uint32_t half_bits = o.adjacency.empty() ? 0 : ring_bits(n);
       Rand4 keys = ring_keys(o.cfg.seed, i, me.pass);
       uint32_t checked = 0, target = NONE32;
       const uint32_t cap = std::min(n, PROBE_SKIP_CAP);
@@ -1144,6 +1143,11 @@ int64_t oracle_remaining_suspicion_ns(uint32_t c, uint32_t k, uint64_t elapsed, 
 uint64_t oracle_push_pull_scale_ns(uint64_t interval, uint32_t n) { return push_pull_scale_ns(interval, n); }
 uint32_t oracle_lamport_witness(uint32_t clock, uint32_t v) { return lamport_witness(clock, v); }
 uint32_t oracle_refute_incarnation(uint32_t cur, uint32_t accused) { return refute_incarnation(cur, accused); }
+uint32_t oracle_ring_entry(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t position) {
+  if (n == 0 || position >= n) return NONE32;
+  Oracle tmp;
+  return ring_entry(tmp, position, n, ring_keys(seed, member, pass), ring_bits(n));
+}
 void oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   Rand4 r = philox4x32_10(((uint64_t)key[1] << 32) | key[0], ctr[0], ctr[1], ctr[2], ctr[3]);
   memcpy(out, r.v, 16);

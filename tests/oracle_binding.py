@@ -26,6 +26,7 @@ _SIGS = [
     ("oracle_push_pull_scale_ns", _u64, [_u64, _u32]),
     ("oracle_lamport_witness", _u32, [_u32, _u32]),
     ("oracle_refute_incarnation", _u32, [_u32, _u32]),
+    ("oracle_ring_entry", _u32, [_u64, _u32, _u32, _u32, _u32]),
     ("oracle_philox4x32", None, [C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     ("oracle_create", _P, [C.POINTER(GsimConfig), _i32]),
     ("oracle_destroy", None, [_P]),

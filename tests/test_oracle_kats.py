@@ -98,3 +98,46 @@ def test_config_presets_match_consul_pins():
             tst.suspicion_mult) == (100 * MS, 50 * MS, 100 * MS, 2)
     assert lan.leave_propagate_delay_ns == 3 * S                        # libserf/serf.go:33
     assert lan.reconnect_timeout_ns == 72 * 3600 * S                    # consul/config.go:622-623
+
+
+def _classic_feistel(seed, n, member, pas, position):
+    """The balanced 4-round swap-and-XOR network of round 1 (even domain widths), restated in Python."""
+    M = 0xFFFFFFFF
+    def fmix(x):
+        x ^= x >> 16; x = (x * 0x85EBCA6B) & M; x ^= x >> 13; x = (x * 0xC2B2AE35) & M; x ^= x >> 16
+        return x
+    lo, hi = seed & M, seed >> 32
+    k0 = fmix((member * 0x9E3779B1 + pas * 0x85EBCA77 + lo) & M)
+    k1 = fmix(k0 ^ hi ^ 0xC2B2AE3D)
+    keys = [k0, k1, (k0 * 0x9E3779B1 + k1) & M, ((k1 * 0x85EBCA77) & M) ^ k0]
+    bits = 2
+    while (1 << bits) < n:
+        bits += 1
+    assert bits % 2 == 0
+    hb, mask, x = bits // 2, (1 << (bits // 2)) - 1, position
+    while True:
+        left, right = x >> hb, x & mask
+        for k in keys:
+            f = ((right + k) * 0x9E3779B1) & M
+            f ^= f >> 15; f = (f * 0x85EBCA77) & M; f ^= f >> 13
+            left, right = right, left ^ (f & mask)
+        x = (left << hb) | right
+        if x < n:
+            return x
+
+
+def test_probe_ring_is_a_permutation_for_every_width(hostemu_lib):
+    """The probe ring (keyed Feistel with cycle walking) visits every entry exactly once per pass for member
+    lists of any length — domain widths even and odd (an odd width uses halves that differ by one bit) —,
+    product == oracle entry by entry, and for even widths it is still the classic balanced network."""
+    from oracle_binding import oracle_lib
+    O, L = oracle_lib(), hostemu_lib
+    for n in (1, 2, 3, 4, 5, 9, 16, 17, 100, 1000, 2048, 2049, 4097, 5000, 8192, 8193, 20000):
+        for member, pas in ((0, 0), (7, 3)):
+            got = [L.gsim_ring_entry(0x5EED0001, n, member, pas, p) for p in range(n)]
+            assert sorted(got) == list(range(n)), n
+            assert got == [O.oracle_ring_entry(0x5EED0001, n, member, pas, p) for p in range(n)], n
+            bits = max(2, (n - 1).bit_length())
+            if bits % 2 == 0 and n <= 5000:
+                assert got == [_classic_feistel(0x5EED0001, n, member, pas, p) for p in range(n)], n
+    assert L.gsim_ring_entry(1, 10, 0, 0, 10) == 0xFFFFFFFF
