@@ -77,20 +77,42 @@ typedef DevSinkT<false> DevSink;
 #ifndef GS_MIN_BLOCKS
 #define GS_MIN_BLOCKS 4
 #endif
-#define GS_STAGES 4                  // cp.async pipeline depth of the scan (tiles in flight per warp)
 #define GS_WARPS (GS_BLOCK / 32)
-#define GS_ROUND 8                   // tiles a warp scans between two drains of the CTA's work queue
+#define GS_ROUND 4                   // tiles a warp brings in with one bulk copy and scans between two drains of the CTA's queue
 
-// Asynchronous 16-byte global -> shared copy (LDGSTS.128, L2 only): the scan words of the
-// tiles ahead are in flight without holding registers or stalling the warp.
-__device__ __forceinline__ void gs_cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+// Bulk asynchronous copies (TMA, 1-D): ONE lane moves a whole run of tiles global -> shared with a single
+// instruction (cp.async.bulk: SASS UBLKCP) and the data's arrival is counted in bytes on an mbarrier in
+// shared memory (expect_tx / complete_tx: SASS SYNCS), which the warp then waits on.  The round-1 scan
+// issued a 16-byte cp.async per lane and tile (LDGSTS.128): ~40 warp instructions per idle tile, most of
+// them address arithmetic and commit/wait bookkeeping.
+__device__ __forceinline__ uint32_t gs_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gs_mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_addr(bar)), "r"(arrivals) : "memory");
 }
-__device__ __forceinline__ void gs_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void gs_cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void gs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   gs_smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(gs_smem_addr(bar))
+               : "memory");
+}
+// true once the phase with this parity has completed; bounded (a byte-count bug must not hang the device:
+// the caller raises the pool's VIOLATION word instead)
+__device__ __forceinline__ bool gs_mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(gs_smem_addr(bar)), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
 }
 
 // ---- sharded pools: the inter-tick barrier lives inside the kernels ---------------------------
@@ -166,8 +188,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
     gs_tick_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off) {
   __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
   __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
-  __shared__ __align__(16) uint32_t s_inb[GS_STAGES][GS_WARPS][GS_TILE];
-  __shared__ __align__(16) uint32_t s_due[GS_STAGES][GS_WARPS][GS_TILE];
+  __shared__ __align__(128) uint32_t s_inb[GS_WARPS][GS_ROUND][GS_TILE];  // a warp's round of mailbox words ...
+  __shared__ __align__(128) uint32_t s_due[GS_WARPS][GS_ROUND][GS_TILE];  // ... and `due` words (gated tiles only)
+  __shared__ __align__(8) uint64_t s_bar[GS_WARPS];                       // one transaction barrier per warp
   __shared__ uint32_t s_q[2];
   // groups of 32 members that need the generic step, queued by the scanning warps and taken by
   // whichever warp of the CTA is free (two counters each: rounds alternate, see below)
@@ -180,6 +203,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   if (tid == 65u) s_q[1] = GS_NEVER;
   if (tid >= 66u && tid < 68u) s_wn[tid - 66u] = 0u;
   if (tid >= 68u && tid < 70u) s_wtake[tid - 68u] = 0u;
+  if (tid >= 96u && tid < 96u + GS_WARPS) gs_mbar_init(&s_bar[tid - 96u], 1u);  // one arrival per phase: the issuing lane
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // Programmatic dependent launch: let the next tick's grid start launching now; it blocks in
   // its own griddepcontrol.wait until this grid has completed and flushed.  Everything above
   // this line touches no global memory.
@@ -218,45 +243,64 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
   // do not depend on who steps a group: everything a member sends is a commutative atomic.
   const uint32_t max_run = (n_tiles + n_warps - 1u) / n_warps, n_rounds = (max_run + GS_ROUND - 1u) / GS_ROUND;
   bool did_work = false;  // this thread touched global state (needs the closing fence when sharded)
+  const bool sys_scan = g.world > 1u && (g.flags & 4u);  // GSIM_FLAG_SHARD_SYNC_SCAN (debug): system-scope loads, no bulk copy
+  // Bring round r of this warp's tiles into its shared-memory buffers: ONE bulk copy for the mailbox words of
+  // the whole round, one per tile that can have a probe action due at this tick (2 of every P phases) for its
+  // `due` words; the other tiles' `due` reads as "never".  Issued for round r + 1 as soon as the warp has
+  // scanned round r, so the copy flies while the CTA drains its queue.
+  auto bring = [&](uint32_t r) {
+    const uint32_t b0 = t_begin + r * GS_ROUND < t_end ? t_begin + r * GS_ROUND : t_end;
+    const uint32_t b1 = b0 + GS_ROUND < t_end ? b0 + GS_ROUND : t_end;
+    const uint32_t tiles = b1 - b0;
+    if (!tiles) return;
+    uint32_t gate_mask = 0;
+    for (uint32_t x = 0; x < tiles; ++x) {
+      bool gate = true;
+      if (gated) {
+        const uint32_t pp = gs_probe_phase(g.rot_p, (b0 + x) >> shift, P);
+        gate = pp == pslot || pp == pslot_t;
+      }
+      gate_mask |= gate ? 1u << x : 0u;
+    }
+    const size_t off0 = (size_t)b0 * GS_TILE;  // columns are padded to whole tiles
+    if (sys_scan) {
+      for (uint32_t x = 0; x < tiles; ++x) {
+        uint4 v;
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(inbox_cur + off0 + x * GS_TILE + lane * 4u) : "memory");
+        *reinterpret_cast<uint4*>(&s_inb[wib][x][lane * 4u]) = v;
+        const uint4 dv = (gate_mask >> x) & 1u ? *reinterpret_cast<const uint4*>(d.due + off0 + x * GS_TILE + lane * 4u)
+                                               : make_uint4(GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER);
+        *reinterpret_cast<uint4*>(&s_due[wib][x][lane * 4u]) = dv;
+      }
+      __syncwarp();
+      return;
+    }
+    for (uint32_t x = 0; x < tiles; ++x)
+      if (!((gate_mask >> x) & 1u))
+        *reinterpret_cast<uint4*>(&s_due[wib][x][lane * 4u]) = make_uint4(GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER);
+    __syncwarp();
+    if (lane == 0u) {
+      // the buffers were last touched through the generic proxy: order that before the bulk writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      gs_mbar_expect_tx(&s_bar[wib], (tiles + __popc(gate_mask)) * GS_TILE * 4u);
+      gs_bulk_g2s(&s_inb[wib][0][0], inbox_cur + off0, tiles * GS_TILE * 4u, &s_bar[wib]);
+      for (uint32_t x = 0; x < tiles; ++x)
+        if ((gate_mask >> x) & 1u) gs_bulk_g2s(&s_due[wib][x][0], d.due + off0 + x * GS_TILE, GS_TILE * 4u, &s_bar[wib]);
+    }
+  };
+  bring(0u);
   for (uint32_t round = 0; round < n_rounds; ++round) {
   const uint32_t par = round & 1u;
   const uint32_t r_begin = t_begin + round * GS_ROUND < t_end ? t_begin + round * GS_ROUND : t_end;
   const uint32_t r_end = r_begin + GS_ROUND < t_end ? r_begin + GS_ROUND : t_end;
-  uint32_t tq = r_begin;  // next tile to issue
-  auto issue = [&](uint32_t st) {
-    if (tq < r_end) {
-      const size_t off = (size_t)tq * GS_TILE + lane * 4u;  // columns are padded to whole tiles
-      if (g.world > 1u && (g.flags & 4u)) {  // GSIM_FLAG_SHARD_SYNC_SCAN (debug)
-        // sharded pool: this mailbox word is written by other GPUs; read it at system scope
-        uint4 v;
-        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(inbox_cur + off) : "memory");
-        *reinterpret_cast<uint4*>(&s_inb[st][wib][lane * 4u]) = v;
-      } else {
-        gs_cp_async16(&s_inb[st][wib][lane * 4u], inbox_cur + off);
-      }
-      bool gate = true;
-      if (gated) {
-        const uint32_t pp = gs_probe_phase(g.rot_p, tq >> shift, P);
-        gate = pp == pslot || pp == pslot_t;
-      }
-      if (gate) {
-        gs_cp_async16(&s_due[st][wib][lane * 4u], d.due + off);
-      } else {
-        *reinterpret_cast<uint4*>(&s_due[st][wib][lane * 4u]) = make_uint4(GS_NEVER, GS_NEVER, GS_NEVER, GS_NEVER);
-      }
-    }
-    ++tq;
-    gs_cp_async_commit();
-  };
-#pragma unroll
-  for (uint32_t q = 0; q < GS_STAGES - 1; ++q) issue(q);
-  uint32_t st = 0;
+  if (r_end > r_begin && !sys_scan && !gs_mbar_wait(&s_bar[wib], round & 1u)) {  // (every lane waits: the data is then visible to it)
+    if (lane == 0u) atomicExch(d.qstate[g.rank] + GS_Q_VIOLATION, t + 1u);
+  }
   for (uint32_t tile = r_begin; tile < r_end; ++tile) {
-    issue((st + GS_STAGES - 1u) % GS_STAGES);
-    gs_cp_async_wait<GS_STAGES - 1>();  // the oldest tile in flight has landed
-    const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[st][wib][lane * 4u]);
-    const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[st][wib][lane * 4u]);
+    const uint32_t st = tile - r_begin;
+    const uint4 i4 = *reinterpret_cast<const uint4*>(&s_inb[wib][st][lane * 4u]);
+    const uint4 d4 = *reinterpret_cast<const uint4*>(&s_due[wib][st][lane * 4u]);
     bool mine = (i4.x | i4.y | i4.z | i4.w) != 0u || d4.x == t || d4.y == t || d4.z == t || d4.w == t;
     // periodic push-pull (opt-in): the ticker of this tile's phase group (or, with per-member
     // phases, of one of its members) fires at this tick
@@ -279,8 +323,8 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       bool any_cand = false;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t w = s_inb[st][wib][u * 32 + lane];
-        const bool due_now = s_due[st][wib][u * 32 + lane] == t;
+        const uint32_t w = s_inb[wib][st][u * 32 + lane];
+        const bool due_now = s_due[wib][st][u * 32 + lane] == t;
         act[u] = w != 0u || due_now ||
                  (g.pp_interval != 0u && gs_pp_due(g.pp_interval, g.rot_pp, (base + 32u * u) / g.phase_group, t));
         cand[u] = w == 0u && due_now;  // empty mailbox + ticker fired
@@ -313,11 +357,10 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_MIN_BLOCKS)
       for (int u = 0; u < 4; ++u) {
         if (__any_sync(0xFFFFFFFFu, act[u]) && lane == 0u) s_work[atomicAdd(&s_wn[par], 1u)] = tile * 4u + (uint32_t)u;
       }
-      __syncwarp();  // everyone is done with this stage before it is refilled
     }
-    st = (st + 1u) % GS_STAGES;
   }
-  gs_cp_async_wait<0>();
+  __syncwarp();                              // this warp is done with its round buffers:
+  if (round + 1u < n_rounds) bring(round + 1u);  // the next round's copy flies while the CTA drains its queue
   __syncthreads();  // the queue of this round is complete
   if (tid == 0u) s_wn[par ^ 1u] = s_wtake[par ^ 1u] = 0u;  // the next round's counters (nobody uses them now)
   const uint32_t n_work = s_wn[par];
