@@ -1059,11 +1059,20 @@ class CudaBackend : public GsBackend {
       if (!ok(cudaGetLastError(), "tick launch")) return false;
     }
     if (!ok(cudaEventRecord(ev1_, stream_), "event")) return false;
+    // the word a kernel raises when one of its internal invariants breaks (a bulk copy that never
+    // completed): read back with the synchronisation that happens anyway, so that it fails loudly
+    uint32_t violation = 0;
+    if (!ok(cudaMemcpyAsync(&violation, d.qstate[g.rank] + GS_Q_VIOLATION, 4, cudaMemcpyDeviceToHost, stream_), "tick d2h"))
+      return false;
     if (!ok(cudaStreamSynchronize(stream_), "tick sync")) return false;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0_, ev1_);
     if (kernel_ms) *kernel_ms += ms;
     if (launches) *launches += nticks;
+    if (violation != 0u) {
+      snprintf(err_, sizeof(err_), "tick %u: a bulk copy of the mailbox scan did not complete (kernel invariant broken)", violation - 1u);
+      return false;
+    }
     return true;
   }
   // Quiet windows (gs_window_kernel): `nticks` ticks as a chain of launches of up to ProbeInterval
