@@ -222,3 +222,34 @@ def test_piggyback_on_probe_traffic_shifts_dissemination_by_about_one_tick():
         assert 0.06 < share < 0.2, share
         shift = res[False][0] - res[True][0]
         assert 0.0 < shift < 2.5, (n, res)
+
+
+def test_dissemination_at_1600_agents_matches_the_projection(hostemu_lib):
+    """The cross-check at the largest size the Python model runs in seconds (1 600 agents, 2.6 M view
+    entries): both models transmit a user event exactly n * RetransmitMult * ceil(log10(n+1)) times and
+    reach every agent within a tick or two of each other (3 seeds each; M0 and M1 draw differently, so
+    the times are compared as means)."""
+    n, limit = 1600, 16
+    t_m0, t_m1 = [], []
+    for seed in (1, 2, 3):
+        net = m0.Network(m0.Config(), seed=seed)
+        net.converged_cluster(n)
+        net.step(5)
+        key = net.user_event(3, b"deploy", b"x" * 8)
+        s = net.now
+        t = net.first_tick(lambda: all(any(k == key for _, k in a.delivered) for a in net.up_agents()), 300)
+        assert t is not None
+        net.step(80)
+        assert net.stats["msgs"] == n * limit
+        t_m0.append(t - s)
+        p = Pool(lan_config(hostemu_lib, capacity=n, n_initial=n, seed=seed, phase_group=1), hostemu_lib)
+        p.step(5)
+        slot = p.user_event(3, b"deploy", b"x" * 8, False)
+        s = p.now
+        t = p.run_until(PRED_RUMOR_CONVERGED, slot, 300, 1)
+        assert t != NEVER
+        p.step(80)
+        assert p.stats()["rumors_sent"] == n * limit and p.rumor_info(slot)["heard_count"] == n
+        t_m1.append(t - s + 1)
+    assert abs(st.mean(t_m0) - st.mean(t_m1)) <= 3.0, (t_m0, t_m1)
+    assert 10 <= min(t_m0 + t_m1) and max(t_m0 + t_m1) <= 24
