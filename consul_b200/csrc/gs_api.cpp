@@ -279,6 +279,7 @@ static void recompute_tables(gsim_pool* p) {
     g.sus_ticks[q] = ceil_ticks(suspicion_total_ns(cc, g.sus_k, min_ns, max_ns), p->tick_ns);
   }
   g.perm_bits = gs_perm_bits_of(n);
+  g.n_magic = n ? 0xFFFFFFFFFFFFFFFFull / n + 1ull : 0ull;
   // [U] memberlist/state.go schedule: the push-pull ticker runs every pushPullScale(PushPullInterval, n)
   g.pp_interval = 0;
   g.rot_pp = 0;

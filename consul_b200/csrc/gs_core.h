@@ -179,6 +179,16 @@ GS_HD bool gs_pp_due(uint32_t pp_interval, uint32_t rot_pp, uint32_t group, uint
   return pp_interval != 0u && (t + rot_pp) % pp_interval == group % pp_interval;
 }
 
+// x mod n with the precomputed magic = ceil(2^64 / n)
+GS_HD uint32_t gs_fastmod(uint32_t x, uint32_t n, uint64_t magic) {
+  const uint64_t low = magic * (uint64_t)x;
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__umul64hi(low, (uint64_t)n);
+#else
+  return (uint32_t)(((unsigned __int128)low * n) >> 64);
+#endif
+}
+
 GS_HD uint32_t gs_u4_get(const GsU4& v, uint32_t idx) {
   return idx == 0 ? v.x : idx == 1 ? v.y : idx == 2 ? v.z : v.w;
 }
@@ -293,6 +303,9 @@ struct GsGlobals {
   // network coordinates (gs_coord.h, GSIM_FLAG_COORDINATES): round trip fed to Vivaldi on a direct
   // ack = coord_base_rtt_s + (extra latency there and back) * tick_seconds
   double coord_base_rtt_s, tick_seconds;
+  // ceil(2^64 / n): `x % n` for the complete graph's peer draws as two multiplications (Lemire, Kaser &
+  // Kurz 2019, exact for every 32-bit x and n) instead of an emulated 32-bit division per draw
+  uint64_t n_magic;
   GsRumor rumors[GS_MAX_RUMORS];
 };
 

@@ -308,7 +308,8 @@ GS_DEV uint32_t gs_krandom(const GsDev& d, const GsGlobals& g, uint32_t i, uint3
     uint32_t cc[4], kk[4];
 #pragma unroll
     for (uint32_t x = 0; x < 4u; ++x) {
-      cc[x] = gs_peer_at(d, g, i, gs_u4_get(blk, x) % n);
+      const uint32_t draw = gs_u4_get(blk, x);
+      cc[x] = gs_peer_at(d, g, i, g.graph_n == 0u ? gs_fastmod(draw, n, g.n_magic) : draw % n);
       kk[x] = (b4 * 4u + x < tries && cc[x] != i && cc[x] != exclude2) ? gs_peer_key(d, t & 1u, cc[x], false) : 0u;
     }
 #pragma unroll

@@ -141,3 +141,19 @@ def test_probe_ring_is_a_permutation_for_every_width(hostemu_lib):
             if bits % 2 == 0 and n <= 5000:
                 assert got == [_classic_feistel(0x5EED0001, n, member, pas, p) for p in range(n)], n
     assert L.gsim_ring_entry(1, 10, 0, 0, 10) == 0xFFFFFFFF
+
+
+def test_fastmod_is_exact():
+    """gs_fastmod (peer draws of the complete graph): ceil(2^64 / n) * x, high half times n == x % n for
+    every 32-bit x and n — checked on the edges and on random pairs with Python integers."""
+    import random
+    rnd = random.Random(5)
+    M = (1 << 64) - 1
+    pairs = [(x, n) for n in (1, 2, 3, 7, 1000, 1000001, 4000000, 2**24, 2**31 - 1, 2**31, 2**32 - 1)
+             for x in (0, 1, n - 1, n, n + 1, 2**32 - 1, 2**31)]
+    pairs += [(rnd.getrandbits(32), rnd.randrange(1, 2**32)) for _ in range(20000)]
+    for x, n in pairs:
+        x &= 0xFFFFFFFF
+        magic = (M // n + 1) & M
+        low = (magic * x) & M
+        assert (low * n) >> 64 == x % n, (x, n)
