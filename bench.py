@@ -414,8 +414,10 @@ def main():
         if rank == 0:
             omp_saved = os.environ.pop("OMP_NUM_THREADS", None)
             ob = _oracle()
-            o = ob.OraclePool(ob.oracle_config("lan", capacity=cap, n_initial=n, seed=SEED), threads=0)
-            pick_threads(o, 2) if n > 4_000_000 else None
+            # (no thread tuning on THIS pool: tuning steps the clock; half the physical cores is what the
+            # tuning picks on the bench boxes)
+            o = ob.OraclePool(ob.oracle_config("lan", capacity=cap, n_initial=n, seed=SEED),
+                              threads=max(1, host_cores()["physical"] // 2))
             want = parity_script(o)
             o.close()
             if omp_saved is not None:

@@ -4,7 +4,7 @@ LOG=$1; shift
 for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun "$@" > "$LOG" 2>&1
   rc=$?
-  [ $rc -ne 3 ] && exit $rc
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$LOG"; then exit $rc; fi
   sleep 120
 done
 exit 3
