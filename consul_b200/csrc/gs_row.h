@@ -37,8 +37,20 @@ __device__ __forceinline__ uint64_t gs_atomic_min_sys(uint64_t* p, uint64_t v) {
   asm volatile("atom.global.sys.min.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"((unsigned long long)v) : "memory");
   return old;
 }
+// Measurement variant (GSIM_FLAG_SHARD_RED): the mailbox OR as a system-scope REDUCTION — no value travels
+// back over NVLink, half the traffic of a fetching atomic; the issuing thread's fence.sys before the
+// inter-tick release is what orders it.
+__device__ __forceinline__ void gs_red_or_sys(uint32_t* p, uint32_t v) {
+  asm volatile("red.global.sys.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // (`g` is the GsGlobals in scope at every use: single-GPU pools keep the cheap device-scope forms)
 #define GS_ATOMIC_OR32(p, v) (g.world > 1u ? gs_atomic_or_sys((p), (v)) : atomicOr((p), (v)))
+#define GS_POST_OR32(p, v)                                                         \
+  do {                                                                             \
+    if (g.world <= 1u) (void)atomicOr((p), (v));                                   \
+    else if (g.flags & 128u) gs_red_or_sys((p), (v));                              \
+    else (void)gs_atomic_or_sys((p), (v));                                         \
+  } while (0)
 #define GS_ATOMIC_MIN64(p, v)                                                    \
   (g.world > 1u ? gs_atomic_min_sys((uint64_t*)(p), (uint64_t)(v))               \
                 : (uint64_t)atomicMin((unsigned long long*)(p), (unsigned long long)(v)))
@@ -72,6 +84,7 @@ __device__ __forceinline__ uint32_t gs_atomic_max32_sys(uint32_t* p, uint32_t v)
 #else
 #define GS_DEV inline
 #define GS_ATOMIC_OR32(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
+#define GS_POST_OR32(p, v) (void)__atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
 static inline uint64_t gs_host_atomic_min64(uint64_t* p, uint64_t v) {
   uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (old > v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED,
@@ -156,7 +169,7 @@ GS_DEV uint32_t gs_peer_key(const GsDev& d, uint32_t cur, uint32_t c, bool need_
 template <class Sink>
 GS_DEV void gs_post(const GsDev& d, const GsGlobals& g, Sink& sink, uint32_t slot, uint32_t j, uint32_t bits) {
   sink.activity();  // a posted word is mail at its arrival tick: the pool is not quiet
-  (void)GS_ATOMIC_OR32(&d.inbox[slot][j], bits);
+  GS_POST_OR32(&d.inbox[slot][j], bits);
 }
 
 // incarnation of peer c whose key-like word k came from gs_peer_key(..., false)
