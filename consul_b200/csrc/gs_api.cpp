@@ -197,6 +197,13 @@ struct gsim_pool {
   uint32_t attached = 1;     // ranks whose memory is mapped here (including this one)
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
+  // rank-local counting: every rank counts its own rows, rank 0 sums (collective_recount)
+  bool partials_fresh = false;  // (rank 0) the partial counts in its page describe (partials_seq, partials_now)
+  uint32_t partials_seq = 0, partials_now = 0;
+  // retirement at a step boundary clears the freed slots' bits rank by rank: the controller only collects
+  // the mask (defer_and), every rank applies it to its own rows after the call (pending_keep)
+  bool defer_and = false;
+  uint32_t pending_keep = 0xFFFFFFFFu;
   std::vector<uint32_t> graph_rp, graph_col;  // host copy of the CSR peer graph (gsim_graph_set)
   GsXbar xb;
   std::vector<std::pair<uint32_t, uint32_t>> name_lens;  // (member, bytes of its node name) where not canonical
@@ -209,6 +216,11 @@ struct gsim_pool {
   // window launches, ticks run in windows, single-tick launches, horizon scans, ns of window kernels, ns of tick kernels
   uint64_t sched_counts[6] = {0, 0, 0, 0, 0, 0};
 };
+
+static void counts_invalidate(gsim_pool* p) {
+  p->counts_stale = true;
+  p->partials_fresh = false;
+}
 
 static void mark_dirty(gsim_pool* p) {
   p->quiet = false;
@@ -318,6 +330,7 @@ struct BlobHdr {
   uint32_t now, n_established, n_sched, out_bytes, dirty_seq;
   uint64_t node_ticks;
   uint32_t call_seq, want_bytes;  // which call this blob answers: a rank out of step must fail, not adopt
+  uint32_t pending_keep;          // bit columns every rank still has to AND on its own rows (~0 = nothing)
 };
 
 template <class F>
@@ -340,6 +353,7 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     h.dirty_seq = p->dirty_seq;
     h.call_seq = seq;
     h.want_bytes = (uint32_t)out_bytes;
+    h.pending_keep = p->pending_keep;
     uint8_t* w = blob.data();
     if (sizeof(h) + sizeof(GsGlobals) + (size_t)h.n_sched * sizeof(Sched) + h.out_bytes > GS_BLOB_BYTES) {
       // every rank must still leave the barrier: publish the error instead of the state
@@ -378,6 +392,7 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
   p->now = h.now;
   p->n_established = h.n_established;
   p->node_ticks = h.node_ticks;
+  p->pending_keep = h.pending_keep;
   if (h.dirty_seq != p->dirty_seq) {  // the controller wrote device state: same consequence on every rank
     p->dirty_seq = h.dirty_seq;
     p->dirty_tick = p->now;
@@ -385,7 +400,7 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     p->healthy = false;
   }
   p->g_dirty = false;
-  p->counts_stale = true;
+  counts_invalidate(p);
   if (h.rc) p->err = "controller reported an error";
   return h.rc;
 }
@@ -756,10 +771,57 @@ extern "C" void gsim_pool_destroy(gsim_pool* p) {
 }
 
 // ---- rumor slots --------------------------------------------------------------
+static void shard_rows(const gsim_pool* p, uint32_t* first, uint32_t* count) {
+  const uint32_t n = p->g.n;
+  *first = 0;
+  *count = n;
+  if (p->sharded) {
+    const uint64_t f = (uint64_t)p->rank * p->rows_per_rank;
+    *first = f < n ? (uint32_t)f : n;
+    *count = *first + p->rows_per_rank < n ? (uint32_t)p->rows_per_rank : n - *first;
+  }
+}
+
+// Sharded pools count rank by rank: every rank runs the count over ITS rows (local HBM instead of a
+// walk of the whole pool over NVLink from GPU 0) and leaves the partial in rank 0's page; the
+// controller sums them in do_recount as long as nothing was written since.  Called by every rank,
+// outside controller_call, right before a call whose controller side wants counts.
+static int collective_recount(gsim_pool* p) {
+  if (!p->sharded || !p->ready) return GSIM_OK;
+  static_assert(sizeof(GsRecount) <= 512 && GS_PG_SCRATCH + 512u * GS_MAX_WORLD_ <= GS_PG_BLOB, "partial counts");
+  GsRecount part;
+  uint32_t first, count;
+  shard_rows(p, &first, &count);
+  // (the device copy of the globals is current: every controller call ends with the upload)
+  const bool usable = !(p->rank == 0 && p->g_dirty);
+  if (!p->be->recount(p->d, p->g_dev, p->g, p->now, first, count, &part)) return GSIM_ERR_CUDA;
+  if (!p->be->h2d(p->pages + GS_PG_SCRATCH + 512u * p->rank, &part, sizeof(part))) return GSIM_ERR_CUDA;
+  if (!p->be->xbar_host(p->xb)) return GSIM_ERR_CUDA;
+  if (p->rank == 0) {
+    p->partials_fresh = usable;
+    p->partials_seq = p->dirty_seq;
+    p->partials_now = p->now;
+  }
+  return GSIM_OK;
+}
+
 static bool do_recount(gsim_pool* p) {
   if (!p->counts_stale) return true;
   if (!upload_globals(p)) return false;
-  if (!p->be->recount(p->d, p->g_dev, p->g, p->now, &p->rc)) return false;
+  if (p->sharded && p->partials_fresh && p->partials_seq == p->dirty_seq && p->partials_now == p->now) {
+    std::vector<uint8_t> raw(512u * p->world);
+    if (!p->be->d2h(raw.data(), p->pages + GS_PG_SCRATCH, raw.size())) return false;
+    memset(&p->rc, 0, sizeof(p->rc));
+    uint32_t* sum = reinterpret_cast<uint32_t*>(&p->rc);
+    for (uint32_t r = 0; r < p->world; ++r) {
+      GsRecount part;
+      memcpy(&part, raw.data() + 512u * r, sizeof(part));
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&part);
+      for (size_t x = 0; x < sizeof(GsRecount) / 4; ++x) sum[x] += w[x];
+    }
+  } else if (!p->be->recount(p->d, p->g_dev, p->g, p->now, 0u, p->g.n, &p->rc)) {
+    return false;
+  }
   p->counts_stale = false;
   return true;
 }
@@ -787,14 +849,30 @@ static int retire_slot(gsim_pool* p, uint32_t slot) {
   if (!and_bit_columns(p, ~(1u << slot))) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.heard_cnt, slot, 0u) || !poke(p, p->d.conv_tick, slot, GS_EMPTY32))
     return GSIM_ERR_CUDA;
-  p->counts_stale = true;
+  counts_invalidate(p);
   return GSIM_OK;
 }
 
 // heard/queued/inbox bits of a freed slot must be zero before the slot is reused.
 static bool and_bit_columns(gsim_pool* p, uint32_t keep) {
   mark_dirty(p);
-  return p->be->and_columns(p->d, p->g, keep);
+  if (p->sharded && p->defer_and) {  // step boundary: every rank clears its own rows after the call
+    p->pending_keep &= keep;
+    return true;
+  }
+  return p->be->and_columns(p->d, p->g, keep, 0u, p->g.n);
+}
+
+// ... which is this, on every rank, right after the controller call that collected the mask.
+static int apply_pending_and(gsim_pool* p) {
+  if (!p->sharded || p->pending_keep == 0xFFFFFFFFu) return GSIM_OK;
+  uint32_t first, count;
+  shard_rows(p, &first, &count);
+  const bool ok = p->be->and_columns(p->d, p->g, p->pending_keep, first, count) && p->be->sync();
+  p->pending_keep = 0xFFFFFFFFu;
+  // nobody goes on (to reuse a freed slot, to tick) before every rank's rows are clean
+  if (!ok || !p->be->xbar_host(p->xb)) return GSIM_ERR_CUDA;
+  return GSIM_OK;
 }
 
 // Retire finished membership rumors (alive / intents): every UP member has heard them and
@@ -886,7 +964,7 @@ static int start_rumor(gsim_pool* p, uint32_t slot, uint32_t kind, uint32_t subj
   if (!post_wake(p, origin)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.heard_cnt, slot, 1u)) return GSIM_ERR_CUDA;
   if (!poke(p, p->d.conv_tick, slot, g.up_count == 1u ? p->now : GS_EMPTY32)) return GSIM_ERR_CUDA;
-  p->counts_stale = true;
+  counts_invalidate(p);
   return GSIM_OK;
 }
 
@@ -990,7 +1068,7 @@ static int merge_remote(gsim_pool* p, uint32_t dst, uint32_t src, bool ignore_ol
       !poke(p, p->d.ltime_member, dst, lm_d) || !poke(p, p->d.ltime_event, dst, le_d) ||
       !poke(p, p->d.event_min, dst, emin))
     return GSIM_ERR_CUDA;
-  p->counts_stale = true;
+  counts_invalidate(p);
   return GSIM_OK;
 }
 
@@ -1055,7 +1133,7 @@ static int set_truth(gsim_pool* p, uint32_t id, uint32_t truth) {
 }
 
 static int refresh_after_truth_change(gsim_pool* p) {
-  p->counts_stale = true;
+  counts_invalidate(p);
   if (!do_recount(p)) return GSIM_ERR_CUDA;
   GsGlobals& g = p->g;
   g.up_count = p->rc.truth_cnt[GS_TRUTH_UP];
@@ -1188,7 +1266,7 @@ extern "C" int gsim_leave(gsim_pool* p, uint32_t id) {
   uint32_t linger = 2 * drain + ceil_ticks(p->cfg.leave_propagate_delay_ns, p->tick_ns);
   Sched s = {p->now + linger, id, 1u};
   p->sched.push_back(s);
-  p->counts_stale = true;
+  counts_invalidate(p);
   return GSIM_OK;
   });
 }
@@ -1260,7 +1338,7 @@ extern "C" int gsim_user_event(gsim_pool* p, uint32_t id, const void* name, size
       if (!poke(p, p->d.queued, id, q | (1u << r)) || !poke(p, p->d.tx, GS_TX(r, g.cap, id), (uint8_t)0) ||
           !post_wake(p, id) || !poke(p, p->d.ltime_event, id, le + 1u))
         return fail(p, GSIM_ERR_CUDA, "poke");
-      p->counts_stale = true;
+      counts_invalidate(p);
       if (slot_out) *slot_out = r;
       return GSIM_OK;
     }
@@ -1332,7 +1410,7 @@ extern "C" int gsim_rumor_inject(gsim_pool* p, uint32_t slot, uint32_t id, int* 
     return fail(p, GSIM_ERR_CUDA, "poke");
   if (c + 1u == g.up_count && ct == GS_EMPTY32 && !poke(p, p->d.conv_tick, slot, p->now))
     return fail(p, GSIM_ERR_CUDA, "poke");
-  p->counts_stale = true;
+  counts_invalidate(p);
   *accepted_out = 1;
   return GSIM_OK;
   });
@@ -1581,7 +1659,10 @@ static int try_quiet(gsim_pool* p) {
       for (uint32_t b = 0; b < g.n_dcs; ++b)
         if ((uint32_t)g.lat[a * GS_MAX_DCS + b] + g.lat[b * GS_MAX_DCS + a] > g.T) links_ok = false;
     if (hz == GS_NEVER && g.loss_thr == 0u && links_ok) {
-      int rc = controller_call(p, &ok_long, sizeof(ok_long), [&]() -> int {
+      counts_invalidate(p);  // (ticks have run since the last count)
+      int rc = collective_recount(p);
+      if (rc) return rc;
+      rc = controller_call(p, &ok_long, sizeof(ok_long), [&]() -> int {
         if (!do_recount(p)) return GSIM_ERR_CUDA;
         ok_long = p->rc.unreachable_live == 0u ? 1u : 0u;
         return GSIM_OK;
@@ -1675,13 +1756,26 @@ static int step_locked(gsim_pool* p, uint32_t ticks) {
     rc = advance_ticks(p, chunk, use_graph);
     if (rc) return rc;
     left -= chunk;
-    p->counts_stale = true;
+    counts_invalidate(p);
   }
-  return controller_call(p, nullptr, 0, [&]() -> int {
+  // (the mask is the same on every rank: the loop's last controller call published it)
+  bool cand = false;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if (((p->g.active_mask >> r) & 1u) && p->g.rumors[r].kind != GSIM_RUMOR_USER_EVENT) cand = true;
+  if (cand) {
+    int rc = collective_recount(p);
+    if (rc) return rc;
+  }
+  int rc = controller_call(p, nullptr, 0, [&]() -> int {
     int r = apply_sched(p);
     if (r) return r;
-    return auto_retire(p);
+    p->defer_and = true;
+    r = auto_retire(p);
+    p->defer_and = false;
+    return r;
   });
+  if (rc) return rc;
+  return apply_pending_and(p);
 }
 
 extern "C" int gsim_step(gsim_pool* p, uint32_t ticks) {
@@ -1846,6 +1940,7 @@ extern "C" int gsim_poll_events(gsim_pool* p, gsim_event* out, size_t cap, size_
 extern "C" int gsim_rumor_info_get(gsim_pool* p, uint32_t slot, gsim_rumor_info* out) {
   if (!p || !out || slot >= GS_MAX_RUMORS) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  if (int rcc = collective_recount(p)) return fail(p, rcc, "recount");
   return controller_call(p, out, sizeof(gsim_rumor_info), [&]() -> int {
   const GsGlobals& g = p->g;
   if (!((g.active_mask >> slot) & 1u)) return fail(p, GSIM_ERR_NOT_FOUND, "slot is free");
@@ -1899,6 +1994,7 @@ extern "C" int gsim_user_event_get(gsim_pool* p, uint32_t slot, void* name, size
 extern "C" int gsim_stats_get(gsim_pool* p, gsim_stats* out) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
+  if (int rcc = collective_recount(p)) return fail(p, rcc, "recount");
   return controller_call(p, out, sizeof(gsim_stats), [&]() -> int {
   memset(out, 0, sizeof(*out));
   if (!do_recount(p)) return fail(p, GSIM_ERR_CUDA, "recount");
@@ -2256,7 +2352,7 @@ extern "C" int gsim_restore(gsim_pool* p, const void* blob, size_t n_bytes) {
   p->node_ticks = h.node_ticks;
   p->n_established = h.n_established;
   p->g_dirty = true;
-  p->counts_stale = true;
+  counts_invalidate(p);
   if (!poke(p, p->d.tick_base, 0, p->now) || !reset_tick_flags(p) || !reset_qstate(p)) return fail(p, GSIM_ERR_CUDA, "poke");
   uint32_t zero2[2] = {0, 0};
   if (!p->be->h2d(p->d.evlog_cursor, zero2, 8)) return fail(p, GSIM_ERR_CUDA, "h2d");

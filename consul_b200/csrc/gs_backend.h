@@ -70,8 +70,9 @@ class GsBackend {
   virtual bool xbar_host(const GsXbar&) { return false; }  // arrive, wait for every rank, sync
   virtual bool crash_fraction(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g,
                               uint32_t thr, uint32_t salt, uint32_t now, uint32_t* n_crashed) = 0;
-  virtual bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
-                       GsRecount* out) = 0;
+  // counts over members [first, first + count) (a rank of a sharded pool counts its own rows)
+  virtual bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first,
+                       uint32_t count, GsRecount* out) = 0;
   virtual bool state_hash(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
                           uint64_t out[4]) = 0;
   // serf's reaper (gs_aux.h gs_reap_row) over every row; counts[0] = members erased, counts[1] =
@@ -80,7 +81,7 @@ class GsBackend {
                          uint32_t reconnect_ticks, uint32_t tombstone_ticks, bool log_events,
                          uint32_t counts[2]) = 0;
   // clear rumor bits outside `keep` in the heard / queued / mailbox columns (slot retirement)
-  virtual bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) = 0;
+  virtual bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep, uint32_t first, uint32_t count) = 0;
   virtual bool sync() = 0;
   virtual const char* last_error() const = 0;
   virtual uint64_t total_launches() const = 0;

@@ -801,14 +801,14 @@ __global__ void __launch_bounds__(GS_BLOCK)
 }
 
 __global__ void __launch_bounds__(GS_BLOCK)
-    gs_recount_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, GsRecount* out) {
+    gs_recount_kernel(GsDev d, const GsGlobals* __restrict__ gp, uint32_t now, uint32_t first, uint32_t count, GsRecount* out) {
   __shared__ GsRecount s;
   uint32_t* sw = reinterpret_cast<uint32_t*>(&s);
   for (uint32_t x = threadIdx.x; x < sizeof(GsRecount) / 4; x += GS_BLOCK) sw[x] = 0u;
   __syncthreads();
   const GsGlobals& g = *gp;
-  uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
-  if (i < g.n) {
+  const uint32_t x = blockIdx.x * GS_BLOCK + threadIdx.x, i = first + x;
+  if (x < count && i < g.n) {
     uint32_t k = d.key[now & 1u][i];
     uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
     atomicAdd(&s.truth_cnt[truth], 1u);
@@ -899,9 +899,9 @@ __global__ void __launch_bounds__(GS_BLOCK) gs_fill32_kernel(uint32_t* dst, uint
     dst[x] = value;
 }
 
-__global__ void __launch_bounds__(GS_BLOCK) gs_and_kernel(GsDev d, uint32_t n, uint32_t keep) {
-  const uint32_t i = blockIdx.x * GS_BLOCK + threadIdx.x;
-  if (i >= n) return;
+__global__ void __launch_bounds__(GS_BLOCK) gs_and_kernel(GsDev d, uint32_t first, uint32_t count, uint32_t keep) {
+  const uint32_t x = blockIdx.x * GS_BLOCK + threadIdx.x, i = first + x;
+  if (x >= count) return;
   uint32_t v;
   v = d.heard[i];
   if (v & ~keep) d.heard[i] = v & keep;
@@ -1174,14 +1174,14 @@ class CudaBackend : public GsBackend {
     }
     return ok(cudaGetLastError(), "reap launch") && d2h(counts, cnt, 8);
   }
-  bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now,
+  bool recount(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first, uint32_t count,
                GsRecount* out) override {
     cudaSetDevice(dev_);
     GsRecount* dr = reinterpret_cast<GsRecount*>(scratch_);
     if (!ok(cudaMemsetAsync(dr, 0, sizeof(GsRecount), stream_), "memset")) return false;
-    if (g.n) {
-      gs_recount_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, now,
-                                                                                   dr);
+    if (first < g.n && count) {
+      if (count > g.n - first) count = g.n - first;
+      gs_recount_kernel<<<(count + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g_dev, now, first, count, dr);
       ++launches_;
     }
     return ok(cudaGetLastError(), "recount launch") && d2h(out, dr, sizeof(GsRecount));
@@ -1233,10 +1233,11 @@ class CudaBackend : public GsBackend {
     ++launches_;
     return ok(cudaGetLastError(), "xbar launch") && ok(cudaStreamSynchronize(stream_), "xbar");
   }
-  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) override {
+  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep, uint32_t first, uint32_t count) override {
     cudaSetDevice(dev_);
-    if (!g.n) return true;
-    gs_and_kernel<<<(g.n + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, g.n, keep);
+    if (first >= g.n || !count) return true;
+    if (count > g.n - first) count = g.n - first;
+    gs_and_kernel<<<(count + GS_BLOCK - 1) / GS_BLOCK, GS_BLOCK, 0, stream_>>>(d, first, count, keep);
     ++launches_;
     return ok(cudaGetLastError(), "and launch") && ok(cudaStreamSynchronize(stream_), "and");
   }

@@ -37,9 +37,10 @@ __device__ __forceinline__ uint64_t gs_atomic_min_sys(uint64_t* p, uint64_t v) {
   asm volatile("atom.global.sys.min.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"((unsigned long long)v) : "memory");
   return old;
 }
-// Measurement variant (GSIM_FLAG_SHARD_RED): the mailbox OR as a system-scope REDUCTION — no value travels
-// back over NVLink, half the traffic of a fetching atomic; the issuing thread's fence.sys before the
-// inter-tick release is what orders it.
+// Mailbox deliveries of a sharded pool are system-scope REDUCTIONS — nobody needs the old value, so none
+// travels back over NVLink (half the traffic of a fetching atomic; 2 GPUs: 98 -> 77 us per cascade tick); the
+// issuing thread's fence.sys before the inter-tick release is what orders them.  GSIM_FLAG_SHARD_ATOM (128)
+// keeps the fetching form for comparison.
 __device__ __forceinline__ void gs_red_or_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.global.sys.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -48,8 +49,8 @@ __device__ __forceinline__ void gs_red_or_sys(uint32_t* p, uint32_t v) {
 #define GS_POST_OR32(p, v)                                                         \
   do {                                                                             \
     if (g.world <= 1u) (void)atomicOr((p), (v));                                   \
-    else if (g.flags & 128u) gs_red_or_sys((p), (v));                              \
-    else (void)gs_atomic_or_sys((p), (v));                                         \
+    else if (g.flags & 128u) (void)gs_atomic_or_sys((p), (v));                     \
+    else gs_red_or_sys((p), (v));                                                  \
   } while (0)
 #define GS_ATOMIC_MIN64(p, v)                                                    \
   (g.world > 1u ? gs_atomic_min_sys((uint64_t*)(p), (uint64_t)(v))               \

@@ -151,9 +151,9 @@ typedef struct gsim_config {
  * for measurements and for tests that compare the two schedules.  Same results either way. */
 #define GSIM_FLAG_NO_WINDOWS 16u
 #define GSIM_FLAG_PUSH_PULL 32u
-/* Sharded pools, measurement variant: mailbox deliveries as system-scope reductions (red.sys) instead of
- * fetching atomics (atom.sys). */
-#define GSIM_FLAG_SHARD_RED 128u
+/* Sharded pools deliver mail with system-scope reductions (red.global.sys.or: nothing travels back over
+ * NVLink).  This flag selects the fetching form (atom.sys) instead — measurement variant; same results. */
+#define GSIM_FLAG_SHARD_ATOM 128u
 /* Network coordinates ([U] serf/coordinate: Vivaldi with height, adjustment window and gravity;
  * SURVEY 8f N3).  Every direct probe ack updates the prober's coordinate with the measured round
  * trip (0.5 ms + the latency matrix there and back) and the target's coordinate.  348 B per

@@ -285,10 +285,10 @@ class HostEmuBackend : public GsBackend {
     }
     return true;
   }
-  bool recount(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now,
+  bool recount(const GsDev& d, const GsGlobals*, const GsGlobals& g, uint32_t now, uint32_t first, uint32_t count,
                GsRecount* out) override {
     memset(out, 0, sizeof(*out));
-    for (uint32_t i = 0; i < g.n; ++i) {
+    for (uint32_t i = first; i < g.n && i - first < count; ++i) {
       uint32_t k = d.key[now & 1u][i];
       uint32_t truth = gs_key_truth(k), rank = gs_key_rank(k);
       out->truth_cnt[truth]++;
@@ -374,8 +374,8 @@ class HostEmuBackend : public GsBackend {
     *xb.epoch = e;
     return true;
   }
-  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep) override {
-    for (uint32_t i = 0; i < g.n; ++i) {
+  bool and_columns(const GsDev& d, const GsGlobals& g, uint32_t keep, uint32_t first, uint32_t count) override {
+    for (uint32_t i = first; i < g.n && i - first < count; ++i) {
       d.heard[i] &= keep;
       d.queued[i] &= keep;
       for (uint32_t s = 0; s <= g.ring_mask; ++s) d.inbox[s][i] &= keep;
