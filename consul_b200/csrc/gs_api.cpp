@@ -198,6 +198,7 @@ struct gsim_pool {
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
   // rank-local counting: every rank counts its own rows, rank 0 sums (collective_recount)
+  uint32_t quiet_fails = 0;  // consecutive looks at a pool that was still busy (try_quiet backs off)
   bool partials_fresh = false;  // (rank 0) the partial counts in its page describe (partials_seq, partials_now)
   uint32_t partials_seq = 0, partials_now = 0;
   // retirement at a step boundary clears the freed slots' bits rank by rank: the controller only collects
@@ -225,6 +226,8 @@ static void counts_invalidate(gsim_pool* p) {
 static void mark_dirty(gsim_pool* p) {
   p->quiet = false;
   p->healthy = false;
+  p->retry_at = 0;  // (the clock may have gone back: restore)
+  p->quiet_fails = 0;
   p->dirty_seq++;
   p->dirty_tick = p->now;
 }
@@ -398,6 +401,8 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     p->dirty_tick = p->now;
     p->quiet = false;
     p->healthy = false;
+    p->retry_at = 0;
+    p->quiet_fails = 0;
   }
   p->g_dirty = false;
   counts_invalidate(p);
@@ -1630,9 +1635,15 @@ static int try_quiet(gsim_pool* p) {
   if (p->dirty_tick + 1u > la) la = p->dirty_tick + 1u;  // a host write at tick T counts like mail at T
   // every arrival slot has been scanned empty once and nobody posted meanwhile: `depth` quiet ticks
   if (p->now < la + depth) {
-    p->retry_at = la + depth;
+    // Still busy.  Looking again after every tick would put a host round trip (on a sharded pool: two
+    // barriers) behind each tick of a cascade: back off 1, 2, 4, 8 ticks.  Finding the quiet a few ticks
+    // late only means those ticks ran as single launches.
+    const uint32_t wait = 1u << (p->quiet_fails < 3u ? p->quiet_fails : 3u);
+    if (p->quiet_fails < 3u) p->quiet_fails++;
+    p->retry_at = la + depth > p->now + wait ? la + depth : p->now + wait;
     return GSIM_OK;
   }
+  p->quiet_fails = 0;
   const uint32_t never = GS_NEVER;
   if (!be->h2d(qs + GS_Q_HORIZON, &never, 4)) return GSIM_ERR_CUDA;
   if (p->sharded && !be->xbar_host(p->xb)) return GSIM_ERR_CUDA;

@@ -30,6 +30,19 @@ for name, flags in (("windows", extra), ("single_ticks", extra | FLAG_NO_WINDOWS
             x = p.member_add(); p.join(x, [0]); p.step(2048)
         cascade()
         d = delta(p, cascade)
+        # where a bench step's wall time goes: each API call timed on the host (every rank issues every call)
+        import time
+        wall = {"member_add": 0.0, "join": 0.0, "step": 0.0, "stats": 0.0}
+        REP = 6
+        for _ in range(REP):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); x = p.member_add()
+            t1 = time.perf_counter(); p.join(x, [0])
+            t2 = time.perf_counter(); p.step(2048)
+            t3 = time.perf_counter(); p.stats()
+            t4 = time.perf_counter()
+            for k, v in zip(wall, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                wall[k] += v * 1e3 / REP
+        out["wall_ms_per_call"] = {k: round(v, 3) for k, v in wall.items()}
         out["cascade"] = {"tick_us": d["tick_ms"] * 1e3 / max(1, d["tick_launches"]), "ticks": d["tick_launches"],
                           "window_us_per_launch": d["window_ms"] * 1e3 / max(1, d["window_launches"]), "window_launches": d["window_launches"]}
     p.close()
