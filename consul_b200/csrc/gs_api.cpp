@@ -14,6 +14,8 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/gsim.h"
@@ -198,6 +200,8 @@ struct gsim_pool {
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
   // rank-local counting: every rank counts its own rows, rank 0 sums (collective_recount)
+  uint32_t* stage = nullptr;  // pinned host staging for bulk reads (host_stage)
+  size_t stage_words = 0;
   uint32_t quiet_fails = 0;  // consecutive looks at a pool that was still busy (try_quiet backs off)
   bool partials_fresh = false;  // (rank 0) the partial counts in its page describe (partials_seq, partials_now)
   uint32_t partials_seq = 0, partials_now = 0;
@@ -769,6 +773,7 @@ extern "C" void gsim_pool_destroy(gsim_pool* p) {
   if (!p) return;
   if (p->be) {
     p->be->sync();
+    if (p->stage) p->be->host_free(p->stage);
     for (void* q : p->allocs) p->be->release(q);
     delete p->be;
   }
@@ -1855,15 +1860,25 @@ static bool host_knows(const GsGlobals& g, uint32_t i, uint32_t c, uint32_t kc, 
   return false;
 }
 
+// Pinned staging for bulk reads (Members() pulls one key per member): grown on demand, freed with the pool.
+static uint32_t* host_stage(gsim_pool* p, size_t words) {
+  if (words > p->stage_words) {
+    if (p->stage) p->be->host_free(p->stage);
+    p->stage_words = 0;
+    p->stage = static_cast<uint32_t*>(p->be->host_alloc(words * 4u));
+    if (p->stage) p->stage_words = words;
+  }
+  return p->stage;
+}
+
 static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, size_t cap, size_t* n) {
   const GsGlobals& g = p->g;
   if (observer >= g.n) return GSIM_ERR_NOT_FOUND;
-  std::vector<uint32_t> keys(g.n);
+  uint32_t* keys = host_stage(p, g.n);
   uint32_t heard, meta;
-  if (!p->be->d2h(keys.data(), p->d.key[p->now & 1u], (size_t)g.n * 4) ||
+  if (!keys || !p->be->d2h(keys, p->d.key[p->now & 1u], (size_t)g.n * 4) ||
       !peek(p, p->d.heard, observer, &heard) || !peek(p, p->d.meta, observer, &meta))
     return GSIM_ERR_CUDA;
-  size_t cnt = 0;
   // on a CSR peer graph a member's list is itself plus its row
   std::vector<uint8_t> in_row;
   if (g.graph_n) {
@@ -1871,23 +1886,63 @@ static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, siz
     in_row[observer] = 1;
     for (uint32_t e = p->graph_rp[observer]; e < p->graph_rp[observer + 1]; ++e) in_row[p->graph_col[e]] = 1;
   }
-  for (uint32_t c = 0; c < g.n; ++c) {
-    uint32_t kc = keys[c];
-    if (gs_key_truth(kc) == GS_TRUTH_NONE) continue;
-    if (g.graph_n && !in_row[c]) continue;
-    if (!host_knows(g, observer, c, kc, heard, meta)) continue;
-    if (out && cnt < cap) {
-      gsim_member& mm = out[cnt];
-      mm.id = c;
-      mm.incarnation = gs_key_inc(kc);
-      mm.rank = gs_key_rank(kc);
-      // memberlist suspect is still serf alive; dead -> failed; left -> left
-      mm.status = mm.rank == GS_RANK_DEAD   ? GSIM_STATUS_FAILED
-                  : mm.rank == GS_RANK_LEFT ? GSIM_STATUS_LEFT
-                                            : GSIM_STATUS_ALIVE;
-    }
-    ++cnt;
+  auto visible = [&](uint32_t c) -> bool {
+    const uint32_t kc = keys[c];
+    if (gs_key_truth(kc) == GS_TRUTH_NONE) return false;
+    if (g.graph_n && !in_row[c]) return false;
+    return host_knows(g, observer, c, kc, heard, meta);
+  };
+  auto emit = [&](uint32_t c, gsim_member& mm) {
+    const uint32_t kc = keys[c];
+    mm.id = c;
+    mm.incarnation = gs_key_inc(kc);
+    mm.rank = gs_key_rank(kc);
+    // memberlist suspect is still serf alive; dead -> failed; left -> left
+    mm.status = mm.rank == GS_RANK_DEAD   ? GSIM_STATUS_FAILED
+                : mm.rank == GS_RANK_LEFT ? GSIM_STATUS_LEFT
+                                          : GSIM_STATUS_ALIVE;
+  };
+  // The list is 16 B per member: at a million members the host loop, not the 4 MB copy, is the cost of
+  // the call.  Large pools split the id range over a few threads (count, exclusive scan, fill).
+  unsigned nt = 1;
+  if (g.n >= (1u << 17)) {
+    nt = std::thread::hardware_concurrency();
+    nt = nt > 8u ? 8u : nt < 1u ? 1u : nt;
+    if (const char* e = getenv("GSIM_MEMBERS_THREADS")) nt = (unsigned)atoi(e) ? (unsigned)atoi(e) : 1u;
   }
+  if (!out) cap = 0;
+  if (nt <= 1) {
+    size_t cnt = 0;
+    for (uint32_t c = 0; c < g.n; ++c) {
+      if (!visible(c)) continue;
+      if (cnt < cap) emit(c, out[cnt]);
+      ++cnt;
+    }
+    if (n) *n = cnt;
+    return GSIM_OK;
+  }
+  std::vector<size_t> part(nt, 0);
+  std::atomic<unsigned> counted{0};
+  const uint32_t chunk = (g.n + nt - 1) / nt;
+  auto work = [&](unsigned w) {
+    const uint32_t lo = w * chunk < g.n ? w * chunk : g.n, hi = lo + chunk < g.n ? lo + chunk : g.n;
+    size_t mine = 0;
+    for (uint32_t c = lo; c < hi; ++c) mine += visible(c) ? 1u : 0u;
+    part[w] = mine;
+    counted.fetch_add(1, std::memory_order_release);
+    while (counted.load(std::memory_order_acquire) < nt) std::this_thread::yield();
+    size_t at = 0;
+    for (unsigned q = 0; q < w; ++q) at += part[q];
+    if (at >= cap) return;
+    for (uint32_t c = lo; c < hi && at < cap; ++c)
+      if (visible(c)) emit(c, out[at++]);
+  };
+  std::vector<std::thread> th;
+  for (unsigned w = 1; w < nt; ++w) th.emplace_back(work, w);
+  work(0);
+  for (auto& t : th) t.join();
+  size_t cnt = 0;
+  for (unsigned w = 0; w < nt; ++w) cnt += part[w];
   if (n) *n = cnt;
   return GSIM_OK;
 }

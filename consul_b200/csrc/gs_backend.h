@@ -6,6 +6,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gs_core.h"
 
@@ -35,6 +36,9 @@ class GsBackend {
   virtual bool h2d_word(void* dst, const void* src, size_t bytes) { return h2d(dst, src, bytes); }
   // Bulk host -> device, enqueued only: the caller keeps `src` alive and calls sync() before it returns
   // (gsim_restore streams its planes back to back and waits once).
+  // host staging memory for bulk copies (page-locked where that makes the copy a plain DMA)
+  virtual void* host_alloc(size_t bytes) { return malloc(bytes); }
+  virtual void host_free(void* q) { free(q); }
   virtual bool h2d_async(void* dst, const void* src, size_t bytes) { return h2d(dst, src, bytes); }
   // The per-member words the host side of a state exchange needs, in one round trip:
   // out = {key[0], key[1], meta, heard, queued, ltime_member, ltime_event, event_min}

@@ -963,6 +963,12 @@ class CudaBackend : public GsBackend {
     return ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "d2h") &&
            ok(cudaStreamSynchronize(stream_), "d2h sync");
   }
+  void* host_alloc(size_t bytes) override {
+    void* q = nullptr;
+    cudaSetDevice(dev_);
+    return cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess ? q : nullptr;
+  }
+  void host_free(void* q) override { cudaFreeHost(q); }
   bool h2d_word(void* dst, const void* src, size_t bytes) override {
     if (bytes > 64) return h2d(dst, src, bytes);
     cudaSetDevice(dev_);
