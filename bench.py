@@ -63,7 +63,9 @@ def split_bytes(d: dict, sc: dict, n_members: float, P: int) -> dict:
     one probe per P ticks and nothing else happens, so the window kernel's share of the shared
     counters is window_ticks * n / P probes."""
     win_probes = min(float(d["probes"]), sc["window_ticks"] * n_members / P)
-    win = sc["window_launches"] * n_members * B_WIN_ROW + win_probes * B_WIN_PROBE
+    # (launches in closed form — pristine pool — gather no status bytes: their probes cost no bytes at all)
+    gathered = min(win_probes, (sc["window_ticks"] - sc.get("closed_form_ticks", 0)) * n_members / P)
+    win = sc["window_launches"] * n_members * B_WIN_ROW + gathered * B_WIN_PROBE
     tick_nt = sc["tick_launches"] * n_members
     tick = (tick_nt * (B_SCAN + B_DUE * 2.0 / P) + max(0.0, d["active_rows"] - win_probes) * B_ACTIVE +
             max(0.0, d["probes"] - win_probes) * B_PROBE + d["rumors_accepted"] * B_ACCEPT +

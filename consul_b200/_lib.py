@@ -142,6 +142,7 @@ SIGNATURES = [
     ("gsim_launch_count", _u64, [_P]),
     ("gsim_sched_counts", _i32, [_P, C.POINTER(_u64)]),
     ("gsim_ring_entry", _u32, [_u64, _u32, _u32, _u32, _u32]),
+    ("gsim_ring_position", _u32, [_u64, _u32, _u32, _u32, _u32]),
     ("gsim_wire_alive", _sz, [_P, _sz, _u32, C.c_char_p, _P, _sz, C.c_uint16, _P, _sz, C.POINTER(C.c_uint8)]),
     ("gsim_wire_suspect", _sz, [_P, _sz, _u32, C.c_char_p, C.c_char_p]),
     ("gsim_wire_dead", _sz, [_P, _sz, _u32, C.c_char_p, C.c_char_p]),

@@ -91,6 +91,12 @@ extern "C" uint32_t gsim_ring_entry(uint64_t seed, uint32_t n, uint32_t member, 
   return gs_perm(position, n, gs_perm_bits_of(n), rk);
 }
 
+extern "C" uint32_t gsim_ring_position(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t entry) {
+  if (n == 0 || entry >= n) return GS_EMPTY32;
+  const GsU4 rk = gs_perm_keys((uint32_t)seed, (uint32_t)(seed >> 32), member, pass);
+  return gs_perm_inv(entry, n, gs_perm_bits_of(n), rk);
+}
+
 extern "C" void gsim_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   GsU4 r = gs_philox(key[0], key[1], ctr[0], ctr[1], ctr[2], ctr[3]);
   out[0] = r.x;
@@ -215,11 +221,12 @@ struct gsim_pool {
   // quiet-window scheduling
   bool quiet = false;        // the pool is known to be quiet at p->now: windows may run
   bool healthy = false;      // ... and no probe can go unanswered: a launch may cover many ProbeIntervals
+  bool pristine = false;     // ... and every member is up, listed alive and established: probes have a closed form
   uint32_t dirty_seq = 0;    // bumped by every host-side write to device state (quiet no longer known)
   uint32_t dirty_tick = 0;   // p->now at that write
   uint32_t retry_at = 0;     // do not look for quietness again before this tick
   // window launches, ticks run in windows, single-tick launches, horizon scans, ns of window kernels, ns of tick kernels
-  uint64_t sched_counts[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t sched_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static void counts_invalidate(gsim_pool* p) {
@@ -230,6 +237,7 @@ static void counts_invalidate(gsim_pool* p) {
 static void mark_dirty(gsim_pool* p) {
   p->quiet = false;
   p->healthy = false;
+  p->pristine = false;
   p->retry_at = 0;  // (the clock may have gone back: restore)
   p->quiet_fails = 0;
   p->dirty_seq++;
@@ -405,6 +413,7 @@ static int controller_call(gsim_pool* p, void* out, size_t out_bytes, F f) {
     p->dirty_tick = p->now;
     p->quiet = false;
     p->healthy = false;
+    p->pristine = false;
     p->retry_at = 0;
     p->quiet_fails = 0;
   }
@@ -1621,6 +1630,11 @@ static bool windows_possible(const gsim_pool* p) {
 }
 
 #define GS_LONG_WINDOW 32u  // ProbeIntervals one launch covers on a healthy quiet pool
+#define GS_PRISTINE_WINDOW 256u  // ... and on a pristine one (every probe a prompt ack: gs_pristine_probes)
+static bool pristine_windows_on() {
+  static const bool off = getenv("GSIM_NO_PRISTINE_WINDOWS") != nullptr;
+  return !off;
+}
 static bool long_windows_on() {
   static const bool off = getenv("GSIM_NO_LONG_WINDOWS") != nullptr;
   return !off;
@@ -1681,11 +1695,16 @@ static int try_quiet(gsim_pool* p) {
       rc = controller_call(p, &ok_long, sizeof(ok_long), [&]() -> int {
         if (!do_recount(p)) return GSIM_ERR_CUDA;
         ok_long = p->rc.unreachable_live == 0u ? 1u : 0u;
+        // everybody running, listed alive by everybody, folded into the established set
+        if (ok_long && p->rc.truth_cnt[GS_TRUTH_UP] == g.n && p->rc.rank_cnt[GS_RANK_ALIVE] == g.n &&
+            p->rc.pending == 0u && p->rc.isolated_up == 0u && pristine_windows_on())
+          ok_long |= 2u;
         return GSIM_OK;
       });
       if (rc) return rc;
     }
-    p->healthy = ok_long != 0u;
+    p->healthy = (ok_long & 1u) != 0u;
+    p->pristine = (ok_long & 2u) != 0u;
   } else {  // a probe deadline is upon us: single ticks until it has passed, then look again
     p->retry_at = (hz > p->now ? hz : p->now) + depth + 1u;
   }
@@ -1704,20 +1723,27 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
       uint64_t nl = 0;
       double wms = 0;
       // ticks per launch: one ProbeInterval; up to GS_LONG_WINDOW of them on a healthy pool
-      const uint32_t per_launch = p->healthy && long_windows_on() ? p->g.P * GS_LONG_WINDOW : p->g.P;
-      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, per_launch, use_graph, &wms, &nl, &done, xb))
+      const bool lng = p->healthy && long_windows_on();
+      const bool prist = lng && p->pristine;  // (the closed form costs the same for any number of probes)
+      const uint32_t per_launch = prist ? p->g.P * GS_PRISTINE_WINDOW : lng ? p->g.P * GS_LONG_WINDOW : p->g.P;
+      if (!be->run_windows(p->d, p->g_dev, p->g, p->now, left, per_launch, use_graph, &wms, &nl, &done, xb, prist))
         return GSIM_ERR_CUDA;
       p->last_ms += wms;
       p->sched_counts[4] += (uint64_t)(wms * 1e6);
       p->last_launches += nl;
       p->sched_counts[0] += nl;
       p->sched_counts[1] += done;
+      if (prist) {
+        p->sched_counts[6] += nl;
+        p->sched_counts[7] += done;
+      }
       p->now += done;
       p->node_ticks += (uint64_t)done * p->g.n;
       left -= done;
       if (left) {  // the chain stopped at the horizon: single ticks from here
         p->quiet = false;
         p->healthy = false;
+        p->pristine = false;
         p->retry_at = p->now + 1u;
       }
       continue;
@@ -1742,7 +1768,7 @@ static int advance_ticks(gsim_pool* p, uint32_t chunk, bool use_graph) {
   return GSIM_OK;
 }
 
-extern "C" int gsim_sched_counts(gsim_pool* p, uint64_t out[6]) {
+extern "C" int gsim_sched_counts(gsim_pool* p, uint64_t out[8]) {
   if (!p || !out) return GSIM_ERR_INVALID;
   std::lock_guard<std::mutex> lk(p->mu);
   memcpy(out, p->sched_counts, sizeof(p->sched_counts));

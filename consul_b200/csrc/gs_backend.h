@@ -17,6 +17,7 @@ struct GsRecount {
   uint32_t rank_cnt[4];
   uint32_t crashed_alive;
   uint32_t isolated_up;  // running members that have not joined the established set
+  uint32_t pending;           // members not yet folded into the established set (known through their alive rumor only)
   uint32_t unreachable_live;  // members whose process is gone (crashed / shut down) but whom the cluster
                               // still lists as alive or suspect: the targets an unanswered probe can hit
 };
@@ -60,7 +61,7 @@ class GsBackend {
   // no probe can go unanswered (every listed member runs, no loss, no slow link), so the horizon cannot move.
   virtual bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
                            uint32_t per_launch, bool use_graph, double* kernel_ms, uint64_t* launches,
-                           uint32_t* ticks_done, const GsXbar* xbar) = 0;
+                           uint32_t* ticks_done, const GsXbar* xbar, bool pristine) = 0;
   // lowers GS_Q_HORIZON (every rank's copy) to the earliest accusation the probes in flight of rows
   // [first, first+count) can produce
   virtual bool quiet_scan(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t now, uint32_t first,

@@ -237,6 +237,37 @@ GS_HD uint32_t gs_perm(uint32_t x, uint32_t n, uint32_t bits, const GsU4& rk) {
   return x;
 }
 
+// The position of ring entry y: the inverse network, walked the same way (F^-1 until it lands inside [0, n)).
+GS_HD uint32_t gs_perm_inv(uint32_t y, uint32_t n, uint32_t bits, const GsU4& rk) {
+  const uint32_t lo_bits = bits >> 1, hi_bits = bits - lo_bits;
+  const uint32_t lo_mask = (1u << lo_bits) - 1u, hi_mask = (1u << hi_bits) - 1u;
+  do {
+    uint32_t hi = y >> lo_bits, lo = y & lo_mask;
+    lo ^= gs_feistel_round(hi, rk.w) & lo_mask;
+    hi ^= gs_feistel_round(lo, rk.z) & hi_mask;
+    lo ^= gs_feistel_round(hi, rk.y) & lo_mask;
+    hi ^= gs_feistel_round(lo, rk.x) & hi_mask;
+    y = (hi << lo_bits) | lo;
+  } while (y >= n);
+  return y;
+}
+
+// Quiet windows of a PRISTINE pool (every member running, listed alive by everybody, established, every
+// link within ProbeTimeout, no loss): whoever a probe hits, it is acknowledged at once, so the outcome of
+// a member's next k probes does not depend on the k ring entries — cursor + k, due + k ProbeIntervals,
+// awareness - k (floored at 0) — and k is bounded by the launch, by the end of the ring pass, and by the
+// member's own entry in its ring (which the generic step skips): one inverse permutation instead of k
+// forward ones and k status gathers.  Returns k for a member whose ticker fires at `due` < w1.
+GS_HD uint32_t gs_pristine_probes(uint32_t n, uint32_t bits, const GsU4& rk, uint32_t self, uint32_t cursor,
+                                  uint32_t due, uint32_t w1, uint32_t P) {
+  if (cursor >= n) return 0u;  // ring wrap: re-keyed by the generic step
+  uint32_t k = (w1 - due + P - 1u) / P;
+  if (n - cursor < k) k = n - cursor;
+  const uint32_t pos = gs_perm_inv(self, n, bits, rk);
+  if (pos >= cursor && pos - cursor < k) k = pos - cursor;
+  return k;
+}
+
 // Retransmit counter of rumor r at member i.  Two rumors share one 16-bit element so that the
 // narrowest column has 2-byte elements: a sharded pool maps every (column, rank) slice with the
 // 2 MB granularity of the virtual-memory API, which then allows 1 Mi members per GPU (1-byte

@@ -514,7 +514,8 @@ __device__ __noinline__ void gs_window_generic(const GsDev* dp, const GsGlobals*
 
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
-    gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks) {
+    gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks,
+                     uint32_t pristine) {
   __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
   __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
   __shared__ uint32_t s_q[2];
@@ -621,6 +622,19 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
         m_in[u] = mm[u];
         cu_in[u] = cu[u];
         du_in[u] = du[u];
+      }
+      if (pristine) {  // closed form (gs_pristine_probes): no ring entries, no gathers
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!live[u]) continue;
+          const uint32_t k = gs_pristine_probes(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], du[u], w1, P);
+          const uint32_t aw = gs_meta_aw(mm[u]);
+          mm[u] = gs_meta_set_aw(mm[u], aw > k ? aw - k : 0u);
+          du[u] += k * P;
+          cu[u] += k;
+          cnt += k;
+          live[u] = false;
+        }
       }
       for (;;) {
         bool go[4];
@@ -816,6 +830,7 @@ __global__ void __launch_bounds__(GS_BLOCK)
     if (truth == GS_TRUTH_CRASHED && rank < GS_RANK_DEAD) atomicAdd(&s.crashed_alive, 1u);
     if ((truth == GS_TRUTH_CRASHED || truth == GS_TRUTH_GONE) && rank < GS_RANK_DEAD) atomicAdd(&s.unreachable_live, 1u);
     if (truth == GS_TRUTH_UP && (d.meta[i] & GS_META_ISOLATED)) atomicAdd(&s.isolated_up, 1u);
+    if (truth != GS_TRUTH_NONE && gs_key_pending(k)) atomicAdd(&s.pending, 1u);
     if (truth == GS_TRUTH_UP && g.active_mask) {
       uint32_t h = d.heard[i] & g.active_mask, q = d.queued[i] & g.active_mask;
       while (h) {
@@ -874,7 +889,7 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
 }
 
 static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const GsDev& d, const GsGlobals* g_dev,
-                                    uint32_t k_off, uint32_t n_ticks, bool pdl) {
+                                    uint32_t k_off, uint32_t n_ticks, bool pdl, bool pristine = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
   cfg.blockDim = dim3(GS_BLOCK);
@@ -885,8 +900,9 @@ static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks)
-                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks);
+  const uint32_t pr = pristine ? 1u : 0u;
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks, pr)
+                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks, pr);
 }
 
 __global__ void gs_row_read_kernel(GsDev d, uint32_t i, uint32_t* out) {
@@ -1085,7 +1101,7 @@ class CudaBackend : public GsBackend {
   // ticks each.  The chain stops by itself at the horizon; *ticks_done says how far it got.
   bool run_windows(const GsDev& d, const GsGlobals* g_dev, const GsGlobals& g, uint32_t t0, uint32_t nticks,
                    uint32_t per_launch, bool use_graph, double* kernel_ms, uint64_t* launches, uint32_t* ticks_done,
-                   const GsXbar* xbar) override {
+                   const GsXbar* xbar, bool pristine) override {
     cudaSetDevice(dev_);
     *ticks_done = 0;
     if (!nticks || !g.n) return true;
@@ -1115,7 +1131,7 @@ class CudaBackend : public GsBackend {
       uint32_t k = 0;
       while (left) {
         const uint32_t c = left < K ? left : K;
-        if (!ok(gs_launch_window(blocks, stream_, d, g_dev, k, c, pdl), "window launch")) return false;
+        if (!ok(gs_launch_window(blocks, stream_, d, g_dev, k, c, pdl, pristine), "window launch")) return false;
         k += c;
         left -= c;
         ++n_launch;

@@ -281,10 +281,11 @@ class Pool:
         return ms.value, n.value
 
     def sched_counts(self) -> dict:
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 8)()
         self._ck(self.lib.gsim_sched_counts(self.h, out))
         return {"window_launches": int(out[0]), "window_ticks": int(out[1]), "tick_launches": int(out[2]),
-                "horizon_scans": int(out[3]), "window_ms": out[4] / 1e6, "tick_ms": out[5] / 1e6}
+                "horizon_scans": int(out[3]), "window_ms": out[4] / 1e6, "tick_ms": out[5] / 1e6,
+                "closed_form_launches": int(out[6]), "closed_form_ticks": int(out[7])}
 
     def launch_count(self) -> int:
         return int(self.lib.gsim_launch_count(self.h))

@@ -431,11 +431,15 @@ size_t gsim_wire_consul_user_event(void* out, size_t cap, const char* id, const 
  * the keyed Feistel permutation of [0, n) that stands in for memberlist's shuffled node slice ([U] state.go
  * resetNodes / shuffleNodes).  Pure function, exported for known-answer tests. */
 uint32_t gsim_ring_entry(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t position);
+/* ... and the position at which `entry` appears in that ring (the inverse permutation; quiet windows of a
+ * pristine pool use it to find a member's own entry without walking the ring). */
+uint32_t gsim_ring_position(uint64_t seed, uint32_t n, uint32_t member, uint32_t pass, uint32_t entry);
 
 /* Scheduling counters since creation: out[0] = quiet-window launches, out[1] = ticks advanced inside
  * quiet windows, out[2] = single-tick launches, out[3] = horizon scans, out[4] / out[5] = nanoseconds of
- * CUDA-event time spent in window / single-tick launches. */
-int gsim_sched_counts(gsim_pool* p, uint64_t out[6]);
+ * CUDA-event time spent in window / single-tick launches, out[6] = those of the window launches that ran
+ * in closed form (pristine pool: every probe a prompt ack), out[7] = ticks they advanced. */
+int gsim_sched_counts(gsim_pool* p, uint64_t out[8]);
 
 #ifdef __cplusplus
 }

@@ -140,7 +140,10 @@ def test_probe_ring_is_a_permutation_for_every_width(hostemu_lib):
             bits = max(2, (n - 1).bit_length())
             if bits % 2 == 0 and n <= 5000:
                 assert got == [_classic_feistel(0x5EED0001, n, member, pas, p) for p in range(n)], n
+            # the inverse (where an entry sits in the ring): quiet windows of a pristine pool rely on it
+            assert [L.gsim_ring_position(0x5EED0001, n, member, pas, e) for e in got] == list(range(n)), n
     assert L.gsim_ring_entry(1, 10, 0, 0, 10) == 0xFFFFFFFF
+    assert L.gsim_ring_position(1, 10, 0, 0, 10) == 0xFFFFFFFF
 
 
 def test_fastmod_is_exact():

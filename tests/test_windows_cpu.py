@@ -50,6 +50,31 @@ def test_steady_state_runs_in_windows(hostemu_lib):
         check(pools, f"steady +{k}")
 
 
+@pytest.mark.parametrize("n,seed", [(257, 31), (1000, 32)])
+def test_pristine_pool_closed_form(hostemu_lib, n, seed, chunks=None):
+    """Everybody up, alive, established, no loss: a launch covers 256 ProbeIntervals and a member's probes
+    are advanced in closed form (gs_pristine_probes) — through the end of ring passes (n probes = 10 n ticks)
+    and past each member's own ring entry, which the generic step has to skip.  Same digest, counters and
+    columns as one launch per tick and as the oracle at every checkpoint."""
+    pools = trio(hostemu_lib, lan_config, capacity=n + 1, n_initial=n, seed=seed)
+    total = 0
+    for chunk in chunks or (100, 2560, 7, 5000, 1, 2559, 12 * n):
+        for p in pools:
+            p.step(chunk)
+        total += chunk
+        check(pools, f"pristine after {total}")
+    sc = pools[0].sched_counts()
+    assert sc["window_ticks"] > total - 200 and sc["window_launches"] <= 4 + total // 2560 + 7, sc
+    st = pools[0].stats()
+    assert st["probes"] == st["acks"] and st["probes"] >= (total // 10 - 2) * n      # every probe a prompt ack
+    # a member that is not established ends it: the joiner's alive rumor has to be heard first
+    x = all3(pools, lambda p: p.member_add())
+    assert all3(pools, lambda p: p.join(x, [0])) == 1
+    for p in pools:
+        p.step(3000)
+    check(pools, "joined + 3000")
+
+
 def test_join_cascade_then_windows(hostemu_lib):
     pools = trio(hostemu_lib, lan_config, capacity=3001, n_initial=3000, seed=22)
     x = all3(pools, lambda p: p.member_add())
