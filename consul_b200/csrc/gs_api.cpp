@@ -1696,8 +1696,12 @@ static int try_quiet(gsim_pool* p) {
         if (!do_recount(p)) return GSIM_ERR_CUDA;
         ok_long = p->rc.unreachable_live == 0u ? 1u : 0u;
         // everybody running, listed alive by everybody, folded into the established set
+        // (members still pending are the subjects of tracked alive rumors: the closed form stops in front
+        // of their ring entries as it does in front of a member's own)
+        uint32_t spec[GS_MAX_SPECIAL];
+        const uint32_t n_spec = gs_special_members(g, spec);
         if (ok_long && p->rc.truth_cnt[GS_TRUTH_UP] == g.n && p->rc.rank_cnt[GS_RANK_ALIVE] == g.n &&
-            p->rc.pending == 0u && p->rc.isolated_up == 0u && pristine_windows_on())
+            n_spec <= GS_MAX_SPECIAL && p->rc.pending <= n_spec && p->rc.isolated_up == 0u && pristine_windows_on())
           ok_long |= 2u;
         return GSIM_OK;
       });

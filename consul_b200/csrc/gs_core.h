@@ -259,12 +259,19 @@ GS_HD uint32_t gs_perm_inv(uint32_t y, uint32_t n, uint32_t bits, const GsU4& rk
 // member's own entry in its ring (which the generic step skips): one inverse permutation instead of k
 // forward ones and k status gathers.  Returns k for a member whose ticker fires at `due` < w1.
 GS_HD uint32_t gs_pristine_probes(uint32_t n, uint32_t bits, const GsU4& rk, uint32_t self, uint32_t cursor,
-                                  uint32_t due, uint32_t w1, uint32_t P) {
+                                  uint32_t due, uint32_t w1, uint32_t P, const uint32_t* special, uint32_t n_special) {
   if (cursor >= n) return 0u;  // ring wrap: re-keyed by the generic step
   uint32_t k = (w1 - due + P - 1u) / P;
   if (n - cursor < k) k = n - cursor;
-  const uint32_t pos = gs_perm_inv(self, n, bits, rk);
+  uint32_t pos = gs_perm_inv(self, n, bits, rk);
   if (pos >= cursor && pos - cursor < k) k = pos - cursor;
+  // members that are not established yet (subjects of alive rumors still tracked): whether a prober
+  // knows them is in its heard mask — the generic step's business, like the prober's own entry
+  for (uint32_t x = 0; x < n_special; ++x) {
+    if (special[x] >= n || special[x] == self) continue;
+    pos = gs_perm_inv(special[x], n, bits, rk);
+    if (pos >= cursor && pos - cursor < k) k = pos - cursor;
+  }
   return k;
 }
 
@@ -339,6 +346,20 @@ struct GsGlobals {
   uint64_t n_magic;
   GsRumor rumors[GS_MAX_RUMORS];
 };
+
+// Members that may still be "pending" (known only through their alive rumor): the subjects of the
+// tracked alive rumors.  Fills out[0 .. GS_MAX_SPECIAL) and returns how many there are in all
+// (more than GS_MAX_SPECIAL: the closed form of a pristine window is not used, see gs_api.cpp).
+#define GS_MAX_SPECIAL 8u
+GS_HD uint32_t gs_special_members(const GsGlobals& g, uint32_t* out) {
+  uint32_t cnt = 0;
+  for (uint32_t r = 0; r < GS_MAX_RUMORS; ++r)
+    if (((g.active_mask >> r) & 1u) && g.rumors[r].kind == GS_RUMOR_ALIVE) {
+      if (cnt < GS_MAX_SPECIAL) out[cnt] = g.rumors[r].subject;
+      ++cnt;
+    }
+  return cnt;
+}
 
 struct GsEventRec {
   uint32_t tick, type, subject, observer, ltime, reserved;

@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
   __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
   __shared__ uint32_t s_q[2];
+  __shared__ uint32_t s_spec[GS_MAX_SPECIAL + 1];  // [GS_MAX_SPECIAL] = how many
   const uint32_t tid = threadIdx.x;
   for (uint32_t x = tid; x < GS_NSTAT * 32u; x += GS_BLOCK) s_stat[x] = 0u;
   for (uint32_t x = tid; x < 32u * 32u; x += GS_BLOCK) s_heard[x] = 0u;
@@ -526,10 +527,11 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   if (tid == 65u) s_q[1] = GS_NEVER;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 66u) s_spec[GS_MAX_SPECIAL] = gs_special_members(*gp, s_spec);
   __syncthreads();
   const GsGlobals& g = *gp;
   const GsHot h = gs_hot(g);
-  const uint32_t world = g.world, rank = g.rank;
+  const uint32_t world = g.world, rank = g.rank, n_spec = s_spec[GS_MAX_SPECIAL];
   uint32_t* const qs = d.qstate[rank];
   const uint32_t t0 = *d.tick_base + k_off;
   // Where the chain of windows stands and how far it may go.  Both words are stable for the whole
@@ -594,110 +596,123 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
     // not up-alive-established, a slow link), writes the member's state back as it stood BEFORE that
     // probe, and the generic code below carries on from there.  Four groups in lock step: four
     // independent permutations and four gathers in flight per lane.
-    bool pending_any = false;
-    {
-      uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4];
-      GsU4 rk[4];
-      bool live[4], in_rng[4];
-      uint32_t cnt = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = (gb + u) * 32u + lane;
-        in_rng[u] = gb + u < g_end;
-        live[u] = false;
-        mm[u] = cu[u] = 0u;
-        du[u] = GS_NEVER;
-        if (in_rng[u]) {
-          du[u] = __ldcg(d.due + i);
-          if (fast_ok && du[u] == tf0[u] && du[u] < w1) {
-            const uint32_t k = d.key[du[u] & 1u][i];
-            mm[u] = d.meta[i];
-            cu[u] = d.cursor[i];
-            const uint32_t pa = d.pass[i];
-            live[u] = gs_key_truth(k) == GS_TRUTH_UP && gs_key_rank(k) == GS_RANK_ALIVE &&
-                      gs_meta_stage(mm[u]) == GS_STAGE_IDLE && !(mm[u] & (GS_META_DIRTY | GS_META_ISOLATED));
-            rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa);
-          }
-        }
-        m_in[u] = mm[u];
-        cu_in[u] = cu[u];
-        du_in[u] = du[u];
-      }
-      if (pristine) {  // closed form (gs_pristine_probes): no ring entries, no gathers
+    // After an obstacle the generic path (2.) takes the ONE ProbeInterval that contains it and the
+    // fast-forward resumes behind it: `lo` = the tick up to which this batch has been through 2.
+    uint32_t lo = t0;
+#pragma unroll 1
+    for (;;) {
+      uint32_t stuck = GS_NEVER;  // earliest ticker firing still inside the launch after the fast-forward
+      {
+        uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4];
+        GsU4 rk[4];
+        bool live[4], in_rng[4];
+        uint32_t cnt = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (!live[u]) continue;
-          const uint32_t k = gs_pristine_probes(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], du[u], w1, P);
-          const uint32_t aw = gs_meta_aw(mm[u]);
-          mm[u] = gs_meta_set_aw(mm[u], aw > k ? aw - k : 0u);
-          du[u] += k * P;
-          cu[u] += k;
-          cnt += k;
+          const uint32_t i = (gb + u) * 32u + lane;
+          in_rng[u] = gb + u < g_end;
           live[u] = false;
-        }
-      }
-      for (;;) {
-        bool go[4];
-        bool any = false;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          go[u] = live[u] && du[u] < w1;
-          any |= go[u];
-        }
-        if (!__any_sync(0xFFFFFFFFu, any)) break;
-        uint32_t c[4], kc[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          c[u] = 0u;
-          if (go[u]) {
-            if (cu[u] >= h.n) {  // ring wrap: re-keyed by the generic step
-              live[u] = go[u] = false;
-            } else {
-              c[u] = gs_perm(cu[u], h.n, h.perm_bits, rk[u]);
-              if (c[u] == (gb + u) * 32u + lane) live[u] = go[u] = false;  // own entry: skipped by the generic step
+          mm[u] = cu[u] = 0u;
+          du[u] = GS_NEVER;
+          if (in_rng[u]) {
+            du[u] = __ldcg(d.due + i);
+            // on the ticker schedule of its group (the first firing of the launch, or a later one)
+            const bool on_phase = du[u] == tf0[u] || (du[u] > tf0[u] && (du[u] - tf0[u]) % P == 0u);
+            if (fast_ok && du[u] >= lo && du[u] < w1 && on_phase) {
+              const uint32_t k = d.key[du[u] & 1u][i];
+              mm[u] = d.meta[i];
+              cu[u] = d.cursor[i];
+              const uint32_t pa = d.pass[i];
+              live[u] = gs_key_truth(k) == GS_TRUTH_UP && gs_key_rank(k) == GS_RANK_ALIVE &&
+                        gs_meta_stage(mm[u]) == GS_STAGE_IDLE && !(mm[u] & (GS_META_DIRTY | GS_META_ISOLATED));
+              rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa);
             }
           }
+          m_in[u] = mm[u];
+          cu_in[u] = cu[u];
+          du_in[u] = du[u];
         }
+        if (pristine) {  // closed form (gs_pristine_probes): no ring entries, no gathers
 #pragma unroll
-        for (int u = 0; u < 4; ++u) kc[u] = go[u] ? gs_peer_key(d, du[u] & 1u, c[u], false) : 0u;
+          for (int u = 0; u < 4; ++u) {
+            if (!live[u]) continue;
+            const uint32_t k = gs_pristine_probes(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], du[u], w1, P,
+                                                  s_spec, n_spec);
+            const uint32_t aw = gs_meta_aw(mm[u]);
+            mm[u] = gs_meta_set_aw(mm[u], aw > k ? aw - k : 0u);
+            du[u] += k * P;
+            cu[u] += k;
+            cnt += k;
+            live[u] = false;
+          }
+        }
+        for (;;) {
+          bool go[4];
+          bool any = false;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            go[u] = live[u] && du[u] < w1;
+            any |= go[u];
+          }
+          if (!__any_sync(0xFFFFFFFFu, any)) break;
+          uint32_t c[4], kc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            c[u] = 0u;
+            if (go[u]) {
+              if (cu[u] >= h.n) {  // ring wrap: re-keyed by the generic step
+                live[u] = go[u] = false;
+              } else {
+                c[u] = gs_perm(cu[u], h.n, h.perm_bits, rk[u]);
+                if (c[u] == (gb + u) * 32u + lane) live[u] = go[u] = false;  // own entry: skipped by the generic step
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) kc[u] = go[u] ? gs_peer_key(d, du[u] & 1u, c[u], false) : 0u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!go[u]) continue;
+            const uint32_t i = (gb + u) * 32u + lane;
+            if (gs_key_truth(kc[u]) != GS_TRUTH_UP || gs_key_rank(kc[u]) != GS_RANK_ALIVE || gs_key_pending(kc[u]) ||
+                gs_extra(h, i, c[u]) + gs_extra(h, c[u], i) > T) {
+              live[u] = false;  // anything but a prompt ack: the generic step decides
+              continue;
+            }
+            const uint32_t aw = gs_meta_aw(mm[u]);
+            mm[u] = gs_meta_set_aw(mm[u], aw ? aw - 1u : 0u);
+            du[u] += P;
+            cu[u] += 1u;
+            ++cnt;
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (!go[u]) continue;
+          if (!in_rng[u]) continue;
           const uint32_t i = (gb + u) * 32u + lane;
-          if (gs_key_truth(kc[u]) != GS_TRUTH_UP || gs_key_rank(kc[u]) != GS_RANK_ALIVE || gs_key_pending(kc[u]) ||
-              gs_extra(h, i, c[u]) + gs_extra(h, c[u], i) > T) {
-            live[u] = false;  // anything but a prompt ack: the generic step decides
-            continue;
-          }
-          const uint32_t aw = gs_meta_aw(mm[u]);
-          mm[u] = gs_meta_set_aw(mm[u], aw ? aw - 1u : 0u);
-          du[u] += P;
-          cu[u] += 1u;
-          ++cnt;
+          if (cu[u] != cu_in[u]) d.cursor[i] = cu[u];
+          if (du[u] != du_in[u]) d.due[i] = du[u];
+          if (mm[u] != m_in[u]) d.meta[i] = mm[u];
+          if (du[u] >= lo && du[u] < w1 && du[u] < stuck) stuck = du[u];  // still something due inside the launch
         }
+        n_probe += cnt;  // per lane; summed over the warp once, at the end
+        n_ack += cnt;
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!in_rng[u]) continue;
-        const uint32_t i = (gb + u) * 32u + lane;
-        if (cu[u] != cu_in[u]) d.cursor[i] = cu[u];
-        if (du[u] != du_in[u]) d.due[i] = du[u];
-        if (mm[u] != m_in[u]) d.meta[i] = mm[u];
-        pending_any |= du[u] >= t0 && du[u] < w1;  // still something due inside the launch
+      stuck = __reduce_min_sync(0xFFFFFFFFu, stuck);
+      if (stuck == GS_NEVER) break;
+      // ---- 2. the ProbeInterval of the earliest obstacle takes the generic path (out of line: it is rare,
+      // and its staging arrays would cost the loop above its registers)
+      {
+        const uint32_t off = (stuck - t0) / P * P, s_lo = t0 + off, s_hi = s_lo + P < w1 ? s_lo + P : w1;
+        uint32_t add[2] = {0u, 0u};
+        gs_window_generic<COORDS>(&d, gp, gb, g_end, tf0[0] + off, tf0[1] + off, tf0[2] + off, tf0[3] + off, tx0[0] + off,
+                                  tx0[1] + off, tx0[2] + off, tx0[3] + off, s_lo, s_hi, s_stat, s_heard, s_q, add);
+        n_probe += add[0];
+        n_ack += add[1];
+        did_work = true;
+        lo = s_lo + P;
+        if (lo >= w1) break;
       }
-      n_probe += cnt;  // per lane; summed over the warp once, at the end
-      n_ack += cnt;
-    }
-    if (!__any_sync(0xFFFFFFFFu, pending_any)) continue;
-    // ---- 2. whatever is left takes the generic path (out of line: it is rare, and its staging arrays
-    // would cost the loop above its registers)
-    {
-      uint32_t add[2] = {0u, 0u};
-      gs_window_generic<COORDS>(&d, gp, gb, g_end, tf0[0], tf0[1], tf0[2], tf0[3], tx0[0], tx0[1], tx0[2], tx0[3], t0, w1,
-                                s_stat, s_heard, s_q, add);
-      n_probe += add[0];
-      n_ack += add[1];
-      did_work = true;
     }
   }
   did_work |= n_probe != 0u;

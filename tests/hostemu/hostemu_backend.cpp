@@ -212,34 +212,38 @@ class HostEmuBackend : public GsBackend {
       sink.stats = reinterpret_cast<uint64_t*>(d.stats);
       sink.heard_cnt = d.heard_cnt;
       memset(sink.local_heard, 0, sizeof(sink.local_heard));
+      uint32_t spec[GS_MAX_SPECIAL];
+      const uint32_t n_spec = gs_special_members(g, spec);
+      const bool closed = pristine && !no_fast_ && g.loss_thr == 0u && g.graph_n == 0u && d.coord == nullptr &&
+                          g.pp_interval == 0u && n_spec <= GS_MAX_SPECIAL;
       for (uint32_t x = 0; x < hi - lo; ++x) {
         const uint32_t i = lo + row_at(x, hi - lo);
         const uint32_t pp = gs_probe_phase(g.rot_p, (i / GS_TILE) >> g.phase_shift, g.P);
-        if (pristine && !no_fast_ && g.loss_thr == 0u && g.graph_n == 0u && d.coord == nullptr && g.pp_interval == 0u) {
-          // the closed form of the window kernel (gs_pristine_probes), under the kernel's own conditions:
-          // the member is on its ticker schedule, up, listed alive, idle
-          const uint32_t first = w0 + (pp + g.P - w0 % g.P) % g.P, due = d.due[i];
-          const uint32_t k0 = d.key[due & 1u][i], m = d.meta[i];
-          if (due == first && due < w1 && gs_key_truth(k0) == GS_TRUTH_UP && gs_key_rank(k0) == GS_RANK_ALIVE &&
-              gs_meta_stage(m) == GS_STAGE_IDLE && !(m & (GS_META_DIRTY | GS_META_ISOLATED))) {
-            const GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, d.pass[i]);
-            const uint32_t k = gs_pristine_probes(g.n, g.perm_bits, rk, i, d.cursor[i], due, w1, g.P);
-            if (k) {
-              const uint32_t aw = gs_meta_aw(m);
-              d.meta[i] = gs_meta_set_aw(m, aw > k ? aw - k : 0u);
-              d.due[i] = due + k * g.P;
-              d.cursor[i] += k;
-              sink.stat(GS_ST_PROBES, k);
-              sink.stat(GS_ST_ACTIVE_ROWS, k);
-              sink.stat(GS_ST_ACKS, k);
-            }
-          }
-        }
         // every tick of the launch at which this member can be due: congruent to its ticker phase or to
         // phase + ProbeTimeout (a launch covers one ProbeInterval in general, many when no probe can fail)
         for (uint32_t t = w0; t < w1; ++t) {
           if (t % g.P != pp && t % g.P != (pp + g.T) % g.P) continue;
           if (d.due[i] != t) continue;
+          if (closed && t % g.P == pp) {
+            // the closed form of the window kernel (gs_pristine_probes), under the kernel's own conditions:
+            // the ticker fires, the member is up, listed alive, idle
+            const uint32_t k0 = d.key[t & 1u][i], m = d.meta[i];
+            if (gs_key_truth(k0) == GS_TRUTH_UP && gs_key_rank(k0) == GS_RANK_ALIVE && gs_meta_stage(m) == GS_STAGE_IDLE &&
+                !(m & (GS_META_DIRTY | GS_META_ISOLATED))) {
+              const GsU4 rk = gs_perm_keys(g.seed_lo, g.seed_hi, i, d.pass[i]);
+              const uint32_t k = gs_pristine_probes(g.n, g.perm_bits, rk, i, d.cursor[i], t, w1, g.P, spec, n_spec);
+              if (k) {
+                const uint32_t aw = gs_meta_aw(m);
+                d.meta[i] = gs_meta_set_aw(m, aw > k ? aw - k : 0u);
+                d.due[i] = t + k * g.P;
+                d.cursor[i] += k;
+                sink.stat(GS_ST_PROBES, k);
+                sink.stat(GS_ST_ACTIVE_ROWS, k);
+                sink.stat(GS_ST_ACKS, k);
+                continue;
+              }
+            }
+          }
           if (!no_fast_) {
             GsFastProbe f;
             bool acked = false;

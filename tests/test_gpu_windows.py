@@ -28,3 +28,7 @@ def test_pristine_pool_closed_form_ring_passes(cuda_lib):
 
 def test_pristine_pool_closed_form_200k(cuda_lib):
     wc.test_pristine_pool_closed_form(cuda_lib, 200_000, 33, chunks=(100, 2560, 7, 5000, 1, 2559))
+
+
+def test_closed_form_stops_at_a_member_somebody_has_not_heard_of(cuda_lib):
+    wc.test_closed_form_stops_at_a_member_somebody_has_not_heard_of(cuda_lib)

@@ -70,9 +70,42 @@ def test_pristine_pool_closed_form(hostemu_lib, n, seed, chunks=None):
     # a member that is not established ends it: the joiner's alive rumor has to be heard first
     x = all3(pools, lambda p: p.member_add())
     assert all3(pools, lambda p: p.join(x, [0])) == 1
+    cf0 = pools[0].sched_counts()["closed_form_ticks"]
+    assert cf0 > total - 200
     for p in pools:
-        p.step(3000)
+        p.step(3000)                      # ONE step: the alive rumor is retired (the joiner established) only at its end
     check(pools, "joined + 3000")
+    # ... but the closed form still runs once the rumor has been heard by everybody: it stops in front of the
+    # joiner's ring entry (whether a prober knows a pending member is the generic step's business)
+    assert pools[0].sched_counts()["closed_form_ticks"] - cf0 > 2000, pools[0].sched_counts()
+    for p in pools:
+        p.step(2000)
+    check(pools, "joined + 5000")
+
+
+def test_closed_form_stops_at_a_member_somebody_has_not_heard_of(hostemu_lib):
+    """A joiner whose alive rumor dies out before everybody has heard it (one peer per gossip tick, three
+    transmissions) stays pending: members that have heard of it probe it, the others skip its ring entry.
+    The closed form must leave that entry to the generic step."""
+    pools = trio(hostemu_lib, lan_config, capacity=301, n_initial=300, seed=35, gossip_nodes=1, retransmit_mult=1)
+    x = all3(pools, lambda p: p.member_add())
+    assert all3(pools, lambda p: p.join(x, [0])) == 1
+    for chunk in (200, 3100, 2900, 1):                       # every member passes the joiner's entry at least once
+        for p in pools:
+            p.step(chunk)
+        check(pools, f"half-heard joiner +{chunk}")
+    slot = []
+    for r in range(30):
+        try:
+            if pools[0].rumor_info(r)["kind"] == 1:          # GSIM_RUMOR_ALIVE
+                slot.append(r)
+        except Exception:
+            pass                                              # free slot
+    assert len(slot) == 1
+    heard = all3(pools, lambda p: p.rumor_info(slot[0])["heard_count"])
+    assert 100 < heard < 301, heard                          # some have heard it, some never will
+    sc = pools[0].sched_counts()
+    assert sc["closed_form_ticks"] > 5000, sc
 
 
 def test_join_cascade_then_windows(hostemu_lib):
