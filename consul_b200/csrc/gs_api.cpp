@@ -15,6 +15,8 @@
 #include <string>
 #include <type_traits>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -174,6 +176,66 @@ struct Sched {
   uint32_t tick, id, action;  // action 1 = shut down after Leave()
 };
 
+// A few host threads that stay around between calls (Members() of a large pool splits the id range over
+// them): creating threads per call costs more than the work in a process that has a GPU context mapped.
+class HostWorkers {
+ public:
+  explicit HostWorkers(unsigned n) : n_(n) {
+    for (unsigned w = 1; w < n_; ++w) th_.emplace_back([this, w] { loop(w); });
+  }
+  ~HostWorkers() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    start_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  unsigned size() const { return n_; }
+  // job(w) on every worker w in [0, n); the caller is worker 0; returns when all are done
+  void run(const std::function<void(unsigned)>& job) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &job;
+      pending_ = n_ - 1;
+      ++gen_;
+    }
+    start_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop(unsigned w) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(unsigned)>* job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        job = job_;
+      }
+      (*job)(w);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable start_, done_;
+  const std::function<void(unsigned)>* job_ = nullptr;
+  uint64_t gen_ = 0;
+  unsigned pending_ = 0;
+  bool stop_ = false;
+};
+
 struct gsim_pool {
   gsim_config cfg;
   GsBackend* be = nullptr;
@@ -206,6 +268,7 @@ struct gsim_pool {
   bool ready = true;         // false between gsim_pool_create and gsim_shard_ready
   uint32_t call_seq = 0;     // controller calls so far (selects the blob slot)
   // rank-local counting: every rank counts its own rows, rank 0 sums (collective_recount)
+  HostWorkers* workers = nullptr;  // created by the first bulk read that wants them
   uint32_t* stage = nullptr;  // pinned host staging for bulk reads (host_stage)
   size_t stage_words = 0;
   uint32_t quiet_fails = 0;  // consecutive looks at a pool that was still busy (try_quiet backs off)
@@ -783,6 +846,8 @@ extern "C" void gsim_pool_destroy(gsim_pool* p) {
   if (p->be) {
     p->be->sync();
     if (p->stage) p->be->host_free(p->stage);
+    delete p->workers;
+    p->workers = nullptr;
     for (void* q : p->allocs) p->be->release(q);
     delete p->be;
   }
@@ -1951,10 +2016,15 @@ static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, siz
     if (n) *n = cnt;
     return GSIM_OK;
   }
+  if (p->workers && p->workers->size() != nt) {
+    delete p->workers;
+    p->workers = nullptr;
+  }
+  if (!p->workers) p->workers = new HostWorkers(nt);
   std::vector<size_t> part(nt, 0);
   std::atomic<unsigned> counted{0};
   const uint32_t chunk = (g.n + nt - 1) / nt;
-  auto work = [&](unsigned w) {
+  const std::function<void(unsigned)> work = [&](unsigned w) {
     const uint32_t lo = w * chunk < g.n ? w * chunk : g.n, hi = lo + chunk < g.n ? lo + chunk : g.n;
     size_t mine = 0;
     for (uint32_t c = lo; c < hi; ++c) mine += visible(c) ? 1u : 0u;
@@ -1967,10 +2037,7 @@ static int members_locked(gsim_pool* p, uint32_t observer, gsim_member* out, siz
     for (uint32_t c = lo; c < hi && at < cap; ++c)
       if (visible(c)) emit(c, out[at++]);
   };
-  std::vector<std::thread> th;
-  for (unsigned w = 1; w < nt; ++w) th.emplace_back(work, w);
-  work(0);
-  for (auto& t : th) t.join();
+  p->workers->run(work);
   size_t cnt = 0;
   for (unsigned w = 0; w < nt; ++w) cnt += part[w];
   if (n) *n = cnt;

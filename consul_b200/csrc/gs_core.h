@@ -258,10 +258,10 @@ GS_HD uint32_t gs_perm_inv(uint32_t y, uint32_t n, uint32_t bits, const GsU4& rk
 // awareness - k (floored at 0) — and k is bounded by the launch, by the end of the ring pass, and by the
 // member's own entry in its ring (which the generic step skips): one inverse permutation instead of k
 // forward ones and k status gathers.  Returns k for a member whose ticker fires at `due` < w1.
-GS_HD uint32_t gs_pristine_probes(uint32_t n, uint32_t bits, const GsU4& rk, uint32_t self, uint32_t cursor,
-                                  uint32_t due, uint32_t w1, uint32_t P, const uint32_t* special, uint32_t n_special) {
+// (`k` on entry = ticker firings inside the launch, ceil((w1 - due) / P))
+GS_HD uint32_t gs_pristine_probes_k(uint32_t n, uint32_t bits, const GsU4& rk, uint32_t self, uint32_t cursor, uint32_t k,
+                                    const uint32_t* special, uint32_t n_special) {
   if (cursor >= n) return 0u;  // ring wrap: re-keyed by the generic step
-  uint32_t k = (w1 - due + P - 1u) / P;
   if (n - cursor < k) k = n - cursor;
   uint32_t pos = gs_perm_inv(self, n, bits, rk);
   if (pos >= cursor && pos - cursor < k) k = pos - cursor;
@@ -273,6 +273,10 @@ GS_HD uint32_t gs_pristine_probes(uint32_t n, uint32_t bits, const GsU4& rk, uin
     if (pos >= cursor && pos - cursor < k) k = pos - cursor;
   }
   return k;
+}
+GS_HD uint32_t gs_pristine_probes(uint32_t n, uint32_t bits, const GsU4& rk, uint32_t self, uint32_t cursor,
+                                  uint32_t due, uint32_t w1, uint32_t P, const uint32_t* special, uint32_t n_special) {
+  return gs_pristine_probes_k(n, bits, rk, self, cursor, (w1 - due + P - 1u) / P, special, n_special);
 }
 
 // Retransmit counter of rumor r at member i.  Two rumors share one 16-bit element so that the

@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   const uint32_t g_begin = grp_lo + wid * run < grp_hi ? grp_lo + wid * run : grp_hi;
   const uint32_t g_end = g_begin + run < grp_hi ? g_begin + run : grp_hi;
   const uint32_t shift = g.phase_shift + 2u, t0_mod = t0 % P, rot_p = g.rot_p;
+  const uint32_t win_q = (w1 - t0) / P, win_r = (w1 - t0) - win_q * P;
   // the batch is taken through the probe fast path together if the pool allows the fast path at all
   const bool fast_ok = h.loss_thr == 0u && h.graph_n == 0u && d.coord == nullptr && h.pp_interval == 0u;
   DevSinkT<COORDS> sink{s_stat, s_heard, s_q};
@@ -603,41 +604,60 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
     for (;;) {
       uint32_t stuck = GS_NEVER;  // earliest ticker firing still inside the launch after the fast-forward
       {
-        uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4];
+        uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4], kt[4];
         GsU4 rk[4];
         bool live[4], in_rng[4];
         uint32_t cnt = 0;
+        {
+          // every own column of the batch in ONE round of loads (a member that turns out not to be due costs
+          // 16 bytes it did not need; waiting for `due` first would cost every member a second round trip).
+          // The key is read at the parity of the group's first firing and again in the rare other case.
+          uint32_t kk[4], pa[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t i = (gb + u) * 32u + lane;
-          in_rng[u] = gb + u < g_end;
-          live[u] = false;
-          mm[u] = cu[u] = 0u;
-          du[u] = GS_NEVER;
-          if (in_rng[u]) {
-            du[u] = __ldcg(d.due + i);
-            // on the ticker schedule of its group (the first firing of the launch, or a later one)
-            const bool on_phase = du[u] == tf0[u] || (du[u] > tf0[u] && (du[u] - tf0[u]) % P == 0u);
-            if (fast_ok && du[u] >= lo && du[u] < w1 && on_phase) {
-              const uint32_t k = d.key[du[u] & 1u][i];
-              mm[u] = d.meta[i];
-              cu[u] = d.cursor[i];
-              const uint32_t pa = d.pass[i];
-              live[u] = gs_key_truth(k) == GS_TRUTH_UP && gs_key_rank(k) == GS_RANK_ALIVE &&
-                        gs_meta_stage(mm[u]) == GS_STAGE_IDLE && !(mm[u] & (GS_META_DIRTY | GS_META_ISOLATED));
-              rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa);
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = (gb + u) * 32u + lane;
+            in_rng[u] = gb + u < g_end;
+            du[u] = GS_NEVER;
+            kk[u] = mm[u] = cu[u] = pa[u] = 0u;
+            if (in_rng[u]) {
+              du[u] = __ldcg(d.due + i);
+              if (fast_ok) {
+                kk[u] = d.key[tf0[u] & 1u][i];
+                mm[u] = d.meta[i];
+                cu[u] = d.cursor[i];
+                pa[u] = d.pass[i];
+              }
             }
           }
-          m_in[u] = mm[u];
-          cu_in[u] = cu[u];
-          du_in[u] = du[u];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = (gb + u) * 32u + lane;
+            live[u] = false;
+            kt[u] = 0u;
+            m_in[u] = mm[u];
+            cu_in[u] = cu[u];
+            du_in[u] = du[u];
+            if (!in_rng[u] || !fast_ok || du[u] < lo || du[u] >= w1) continue;
+            // on the ticker schedule of its group: the first firing of the launch, or (after an obstacle) a later one
+            uint32_t later = 0u;
+            if (du[u] != tf0[u]) {
+              if (du[u] < tf0[u]) continue;
+              later = (du[u] - tf0[u]) / P;
+              if (later * P != du[u] - tf0[u]) continue;
+            }
+            const uint32_t k = ((du[u] ^ tf0[u]) & 1u) ? d.key[du[u] & 1u][i] : kk[u];
+            live[u] = gs_key_truth(k) == GS_TRUTH_UP && gs_key_rank(k) == GS_RANK_ALIVE &&
+                      gs_meta_stage(mm[u]) == GS_STAGE_IDLE && !(mm[u] & (GS_META_DIRTY | GS_META_ISOLATED));
+            rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa[u]);
+            // firings inside the launch: ceil((w1 - tf0) / P) without a division (w1 - t0 = win_q P + win_r)
+            kt[u] = win_q + (win_r > tf0[u] - t0 ? 1u : 0u) - later;
+          }
         }
         if (pristine) {  // closed form (gs_pristine_probes): no ring entries, no gathers
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (!live[u]) continue;
-            const uint32_t k = gs_pristine_probes(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], du[u], w1, P,
-                                                  s_spec, n_spec);
+            const uint32_t k = gs_pristine_probes_k(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], kt[u], s_spec, n_spec);
             const uint32_t aw = gs_meta_aw(mm[u]);
             mm[u] = gs_meta_set_aw(mm[u], aw > k ? aw - k : 0u);
             du[u] += k * P;
