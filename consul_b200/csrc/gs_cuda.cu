@@ -515,7 +515,7 @@ __device__ __noinline__ void gs_window_generic(const GsDev* dp, const GsGlobals*
 template <bool COORDS>
 __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
     gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks,
-                     uint32_t pristine) {
+                     uint32_t mode) {
   __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
   __shared__ uint32_t s_heard[32 * 32];       // [broadcast slot][lane]
   __shared__ uint32_t s_q[2];
@@ -531,6 +531,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   __syncthreads();
   const GsGlobals& g = *gp;
   const GsHot h = gs_hot(g);
+  // mode bit 0: the pool is pristine (closed form); bit 1: batches of four groups are dealt to the warps
+  // round-robin (neighbouring warps stream neighbouring lines) instead of one contiguous run per warp
+  const bool pristine = (mode & 1u) != 0u, cyclic = (mode & 2u) != 0u;
   const uint32_t world = g.world, rank = g.rank, n_spec = s_spec[GS_MAX_SPECIAL];
   uint32_t* const qs = d.qstate[rank];
   const uint32_t t0 = *d.tick_base + k_off;
@@ -567,13 +570,19 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   // phase of the first group, then incrementally (one division per warp, not per tile)
   uint32_t pg = g_begin >> shift;              // phase group of the current group
   uint32_t pp = (pg % P + rot_p) % P;          // its probe phase
-  for (uint32_t gb = g_begin; gb < g_end; gb += 4u) {
+  const uint32_t g_first = cyclic ? (grp_lo + wid * 4u < grp_hi ? grp_lo + wid * 4u : grp_hi) : g_begin;
+  const uint32_t g_step = cyclic ? n_warps * 4u : 4u, g_lim = cyclic ? grp_hi : g_end;
+  for (uint32_t gb = g_first; gb < g_lim; gb += g_step) {
+    if (cyclic) {  // (a division per batch instead of one per warp)
+      pg = gb >> shift;
+      pp = (pg % P + rot_p) % P;
+    }
     uint32_t tf0[4], tx0[4];
     // ---- 0. the first ticks >= t0 at which each group of the batch can be due ----
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint32_t grp = gb + u;
-      if (grp < g_end) {
+      if (grp < g_lim) {
         const uint32_t q = grp >> shift;
         if (q != pg) {                                   // groups are consecutive: the next phase group, phase + 1 (mod P)
           pp = pp + 1u == P ? 0u : pp + 1u;
@@ -616,7 +625,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const uint32_t i = (gb + u) * 32u + lane;
-            in_rng[u] = gb + u < g_end;
+            in_rng[u] = gb + u < g_lim;
             du[u] = GS_NEVER;
             kk[u] = mm[u] = cu[u] = pa[u] = 0u;
             if (in_rng[u]) {
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
       {
         const uint32_t off = (stuck - t0) / P * P, s_lo = t0 + off, s_hi = s_lo + P < w1 ? s_lo + P : w1;
         uint32_t add[2] = {0u, 0u};
-        gs_window_generic<COORDS>(&d, gp, gb, g_end, tf0[0] + off, tf0[1] + off, tf0[2] + off, tf0[3] + off, tx0[0] + off,
+        gs_window_generic<COORDS>(&d, gp, gb, g_lim, tf0[0] + off, tf0[1] + off, tf0[2] + off, tf0[3] + off, tx0[0] + off,
                                   tx0[1] + off, tx0[2] + off, tx0[3] + off, s_lo, s_hi, s_stat, s_heard, s_q, add);
         n_probe += add[0];
         n_ack += add[1];
@@ -924,7 +933,7 @@ static cudaError_t gs_launch_tick(uint32_t blocks, cudaStream_t stream, const Gs
 }
 
 static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const GsDev& d, const GsGlobals* g_dev,
-                                    uint32_t k_off, uint32_t n_ticks, bool pdl, bool pristine = false) {
+                                    uint32_t k_off, uint32_t n_ticks, bool pdl, uint32_t mode) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
   cfg.blockDim = dim3(GS_BLOCK);
@@ -935,9 +944,8 @@ static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  const uint32_t pr = pristine ? 1u : 0u;
-  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks, pr)
-                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks, pr);
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks, mode)
+                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks, mode);
 }
 
 __global__ void gs_row_read_kernel(GsDev d, uint32_t i, uint32_t* out) {
@@ -1166,7 +1174,8 @@ class CudaBackend : public GsBackend {
       uint32_t k = 0;
       while (left) {
         const uint32_t c = left < K ? left : K;
-        if (!ok(gs_launch_window(blocks, stream_, d, g_dev, k, c, pdl, pristine), "window launch")) return false;
+        if (!ok(gs_launch_window(blocks, stream_, d, g_dev, k, c, pdl, (pristine ? 1u : 0u) | win_mode_), "window launch"))
+          return false;
         k += c;
         left -= c;
         ++n_launch;
@@ -1367,7 +1376,7 @@ class CudaBackend : public GsBackend {
     if (!ok(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "capture")) return nullptr;
     bool good = true;
     for (uint32_t j = 0; j < GS_WIN_GRAPH && good; ++j)
-      good = ok(gs_launch_window(blocks, stream_, d, g_dev, j * K, K, pdl), "window capture");
+      good = ok(gs_launch_window(blocks, stream_, d, g_dev, j * K, K, pdl, win_mode_), "window capture");
     if (good) gs_window_advance_kernel<<<1, 1, 0, stream_>>>(d.tick_base, d.qstate[rank]);
     if (!ok(cudaStreamEndCapture(stream_, &graph), "end capture") || !good) {
       if (graph) cudaGraphDestroy(graph);
@@ -1398,6 +1407,8 @@ class CudaBackend : public GsBackend {
   // sharded pools: stream launches measured faster than graph replay (21 vs 28 us/tick at 2 Mi
   // members per GPU on 2 GPUs); GSIM_SHARD_GRAPH=1 turns the graph path on
   bool no_shard_graph_ = getenv("GSIM_SHARD_GRAPH") == nullptr;
+  // window kernel: how groups are dealt to the warps (bit 1 of the kernel's mode word); GSIM_WIN_CYCLIC=0/1
+  uint32_t win_mode_ = getenv("GSIM_WIN_CYCLIC") && atoi(getenv("GSIM_WIN_CYCLIC")) ? 2u : 0u;
   std::map<uint32_t, cudaGraphExec_t> graphs_;
   std::map<uint64_t, cudaGraphExec_t> wgraphs_;
   GsDev graph_dev_;
