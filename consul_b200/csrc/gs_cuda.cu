@@ -511,9 +511,14 @@ __device__ __noinline__ void gs_window_generic(const GsDev* dp, const GsGlobals*
 #define GS_WIN_BLOCKS 4
 #endif
 // (resident CTAs per SM the window kernel is compiled for: 4 = 64 registers per thread)
+#ifndef GS_WIN_BLOCKS_CLOSED
+#define GS_WIN_BLOCKS_CLOSED 4
+#endif
 
-template <bool COORDS>
-__global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
+// PRISTINE = the instantiation for pools whose probes have a closed form (its own register allocation: it
+// contains neither the per-probe loop nor that loop's arrays).
+template <bool COORDS, bool PRISTINE>
+__global__ void __launch_bounds__(GS_BLOCK, PRISTINE ? GS_WIN_BLOCKS_CLOSED : GS_WIN_BLOCKS)
     gs_window_kernel(const __grid_constant__ GsDev d, const GsGlobals* __restrict__ gp, uint32_t k_off, uint32_t n_ticks,
                      uint32_t mode) {
   __shared__ uint32_t s_stat[GS_NSTAT * 32];  // [counter][lane]
@@ -531,9 +536,9 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
   __syncthreads();
   const GsGlobals& g = *gp;
   const GsHot h = gs_hot(g);
-  // mode bit 0: the pool is pristine (closed form); bit 1: batches of four groups are dealt to the warps
-  // round-robin (neighbouring warps stream neighbouring lines) instead of one contiguous run per warp
-  const bool pristine = (mode & 1u) != 0u, cyclic = (mode & 2u) != 0u;
+  // mode bit 1: batches of four groups are dealt to the warps round-robin (neighbouring warps stream
+  // neighbouring lines) instead of one contiguous run per warp
+  const bool cyclic = (mode & 2u) != 0u;
   const uint32_t world = g.world, rank = g.rank, n_spec = s_spec[GS_MAX_SPECIAL];
   uint32_t* const qs = d.qstate[rank];
   const uint32_t t0 = *d.tick_base + k_off;
@@ -612,6 +617,64 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
 #pragma unroll 1
     for (;;) {
       uint32_t stuck = GS_NEVER;  // earliest ticker firing still inside the launch after the fast-forward
+      if constexpr (PRISTINE) {
+        // Closed form (gs_pristine_probes_k): every own column of the batch in ONE round of loads, then per
+        // member one inverse ring permutation, no ring entries, no gathers; written back at once.
+        uint32_t cnt = 0;
+        uint32_t du[4], kk[4], mm[4], cu[4], pa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = (gb + u) * 32u + lane;
+          du[u] = GS_NEVER;
+          kk[u] = mm[u] = cu[u] = pa[u] = 0u;
+          if (gb + u < g_lim) {
+            du[u] = __ldcg(d.due + i);
+            if (fast_ok) {
+              kk[u] = d.key[tf0[u] & 1u][i];  // (parity of the group's first firing; the rare other case reloads)
+              mm[u] = d.meta[i];
+              cu[u] = d.cursor[i];
+              pa[u] = d.pass[i];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (gb + u >= g_lim) continue;
+          const uint32_t i = (gb + u) * 32u + lane;
+          uint32_t due = du[u];
+          if (fast_ok && due >= lo && due < w1) {
+            // on the ticker schedule of its group: the first firing of the launch, or (after an obstacle) a later one
+            uint32_t later = 0u;
+            bool on_phase = due == tf0[u];
+            if (!on_phase && due > tf0[u]) {
+              later = (due - tf0[u]) / P;
+              on_phase = later * P == due - tf0[u];
+            }
+            if (on_phase) {
+              const uint32_t k0 = ((due ^ tf0[u]) & 1u) ? d.key[due & 1u][i] : kk[u];
+              const uint32_t m = mm[u];
+              if (gs_key_truth(k0) == GS_TRUTH_UP && gs_key_rank(k0) == GS_RANK_ALIVE && gs_meta_stage(m) == GS_STAGE_IDLE &&
+                  !(m & (GS_META_DIRTY | GS_META_ISOLATED))) {
+                const GsU4 rk = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa[u]);
+                // firings inside the launch: ceil((w1 - tf0) / P) without a division (w1 - t0 = win_q P + win_r)
+                const uint32_t kt = win_q + (win_r > tf0[u] - t0 ? 1u : 0u) - later;
+                const uint32_t k = gs_pristine_probes_k(h.n, h.perm_bits, rk, i, cu[u], kt, s_spec, n_spec);
+                if (k) {
+                  const uint32_t aw = gs_meta_aw(m);
+                  if (aw) d.meta[i] = gs_meta_set_aw(m, aw > k ? aw - k : 0u);
+                  d.cursor[i] = cu[u] + k;
+                  due += k * P;
+                  d.due[i] = due;
+                  cnt += k;
+                }
+              }
+            }
+          }
+          if (due >= lo && due < w1 && due < stuck) stuck = due;  // still something due inside the launch
+        }
+        n_probe += cnt;  // per lane; summed over the warp once, at the end
+        n_ack += cnt;
+      } else
       {
         uint32_t mm[4], cu[4], du[4], m_in[4], cu_in[4], du_in[4], kt[4];
         GsU4 rk[4];
@@ -660,19 +723,6 @@ __global__ void __launch_bounds__(GS_BLOCK, GS_WIN_BLOCKS)
             rk[u] = gs_perm_keys(h.seed_lo, h.seed_hi, i, pa[u]);
             // firings inside the launch: ceil((w1 - tf0) / P) without a division (w1 - t0 = win_q P + win_r)
             kt[u] = win_q + (win_r > tf0[u] - t0 ? 1u : 0u) - later;
-          }
-        }
-        if (pristine) {  // closed form (gs_pristine_probes): no ring entries, no gathers
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (!live[u]) continue;
-            const uint32_t k = gs_pristine_probes_k(h.n, h.perm_bits, rk[u], (gb + u) * 32u + lane, cu[u], kt[u], s_spec, n_spec);
-            const uint32_t aw = gs_meta_aw(mm[u]);
-            mm[u] = gs_meta_set_aw(mm[u], aw > k ? aw - k : 0u);
-            du[u] += k * P;
-            cu[u] += k;
-            cnt += k;
-            live[u] = false;
           }
         }
         for (;;) {
@@ -944,8 +994,11 @@ static cudaError_t gs_launch_window(uint32_t blocks, cudaStream_t stream, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true>, d, g_dev, k_off, n_ticks, mode)
-                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false>, d, g_dev, k_off, n_ticks, mode);
+  if (mode & 1u)  // pristine pool: the closed-form instantiation
+    return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true, true>, d, g_dev, k_off, n_ticks, mode)
+                   : cudaLaunchKernelEx(&cfg, gs_window_kernel<false, true>, d, g_dev, k_off, n_ticks, mode);
+  return d.coord ? cudaLaunchKernelEx(&cfg, gs_window_kernel<true, false>, d, g_dev, k_off, n_ticks, mode)
+                 : cudaLaunchKernelEx(&cfg, gs_window_kernel<false, false>, d, g_dev, k_off, n_ticks, mode);
 }
 
 __global__ void gs_row_read_kernel(GsDev d, uint32_t i, uint32_t* out) {
@@ -985,7 +1038,7 @@ class CudaBackend : public GsBackend {
       occ = 4;
     full_grid_ = (uint32_t)(sms * occ);
     int wocc = GS_WIN_BLOCKS;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, gs_window_kernel<false>, GS_BLOCK, 0) != cudaSuccess || wocc < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, gs_window_kernel<false, false>, GS_BLOCK, 0) != cudaSuccess || wocc < 1)
       wocc = GS_WIN_BLOCKS;
     win_grid_ = (uint32_t)(sms * wocc);
     scratch_ = nullptr;
