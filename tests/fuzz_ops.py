@@ -12,10 +12,26 @@ from parity import check_invariants, compare_pools
 MS = 1_000_000
 
 
-def random_config(rng: random.Random, lib):
+def random_config(rng: random.Random, lib, calm: bool = False):
+    """calm = a pool that can become quiet and pristine (no loss, no periodic tickers besides the probe):
+    the sequences then spend most of their ticks in quiet windows, closed form included."""
     preset = rng.choice(["lan", "lan", "wan", "test"])
     n0 = rng.choice([0, 1, 2, 3, 5, 40, 130, 300, 700])
     kw = dict(capacity=n0 + 24, n_initial=n0, seed=rng.getrandbits(48), flags=1)
+    if calm:
+        n0 = rng.choice([3, 17, 40, 130, 300, 700])
+        kw.update(capacity=n0 + 24, n_initial=n0)
+        if rng.random() < 0.3:
+            kw["retransmit_mult"] = rng.choice([1, 2])
+        if rng.random() < 0.3:
+            kw["gossip_nodes"] = 1
+        if rng.random() < 0.3:
+            kw.update(reap_interval_ns=rng.choice([100, 500]) * MS, reconnect_timeout_ns=rng.choice([200, 2000]) * MS,
+                      tombstone_timeout_ns=rng.choice([200, 2000]) * MS)
+        if n0 < 128 or rng.random() < 0.3:
+            kw["phase_group"] = 1
+        fn = {"lan": lan_config, "wan": wan_config, "test": consul_test_config}[preset]
+        return fn(lib, **kw), None
     if rng.random() < 0.5:
         kw["packet_loss_ppm"] = rng.choice([20000, 150000, 450000])
     if rng.random() < 0.25:
@@ -61,16 +77,17 @@ def random_graph(rng: random.Random, n: int):
     return rp, np.concatenate([np.array(r, dtype=np.uint32) for r in rows])
 
 
-def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True, single_gpu_features: bool = True):
+def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True, single_gpu_features: bool = True,
+                 calm: bool = False):
     rng = random.Random(seed)
-    cfg, latency = random_config(rng, lib)
+    cfg, latency = random_config(rng, lib, calm)
     if not single_gpu_features:                                # sharded pools: no network coordinates yet
         cfg.flags &= ~FLAG_COORDINATES
     pools = make(cfg)
     if latency is not None:
         for p in pools:
             p.latency_set(latency)
-    want_graph = cfg.n_initial >= 5 and rng.random() < 0.2    # static CSR topology (member_add then fails alike)
+    want_graph = cfg.n_initial >= 5 and rng.random() < 0.2 and not calm   # static CSR topology (member_add then fails alike)
     if want_graph and getattr(pools[0], "world", 1) == 1:      # (peer graphs are single-GPU for now)
         rp, ci = random_graph(rng, cfg.n_initial)
         for p in pools:
@@ -95,6 +112,10 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True, si
     for step in range(n_ops):
         n = pools[0].stats()["n_members"]
         r = rng.random()
+        if calm and rng.random() < 0.6:
+            r = 0.99                                           # mostly time passing
+        elif calm and 0.30 <= r < 0.45:
+            r = 0.05                                           # rather a joiner than a crash / leave: stays pristine
         pick = (lambda: rng.randrange(n)) if n else (lambda: 0)
         if r < 0.10:
             both(lambda p: p.member_add(watched=rng_bool(seed, step)), "add")
@@ -140,6 +161,8 @@ def run_sequence(make, lib, seed: int, n_ops: int = 60, columns: bool = True, si
             both(lambda p: p.crash_fraction(ppm, step), f"crash_fraction {ppm}")
         else:
             k = rng.choice([1, 1, 2, 3, 7, 20, 64, 65, 130])
+            if calm:                                       # long quiet stretches: ring passes end, own entries come up
+                k = rng.choice([1, 3, 20, 130, 400, 1300, 2560, 2561, 6000])
             for p in pools:
                 p.step(k)
             log.append((f"step {k}", None))

@@ -110,6 +110,13 @@ for fseed in (3, 17, 251, 404):
     except AssertionError as e:
         fuzz_ok = False
         print("FUZZ MISMATCH rank", rank, "seed", fseed, str(e)[:800], flush=True)
+for fseed in (3001, 3004, 3013):   # calm pools: quiet windows (closed form included) with one barrier per launch
+    try:
+        fuzz_ops.run_sequence(lambda cfg: [ShardedPool(cfg, L), _Oracle(cfg)], L, fseed, n_ops=30, columns=False,
+                              single_gpu_features=False, calm=True)
+    except AssertionError as e:
+        fuzz_ok = False
+        print("CALM FUZZ MISMATCH rank", rank, "seed", fseed, str(e)[:800], flush=True)
 
 mkf = lambda seed: wan_config(L, capacity=N, n_initial=N, seed=seed, mailbox_depth=8)  # noqa: E731
 gotf = federation_script(lambda seed: ShardedPool(mkf(seed), L))

@@ -23,3 +23,11 @@ def test_random_sequences(make, hostemu_lib, block):
 def test_regression_seeds(make, hostemu_lib):
     for seed in (251,):
         fuzz_ops.run_sequence(make, hostemu_lib, seed)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_calm_sequences_spend_their_ticks_in_quiet_windows(make, hostemu_lib, block):
+    """No loss, mostly time passing in steps of up to 6000 ticks on pools of 3 .. 700 members: quiet windows,
+    the closed form of pristine pools, ring passes ending, own ring entries, joiners that stay pending."""
+    for seed in range(3000 + block * 30, 3030 + block * 30):
+        fuzz_ops.run_sequence(make, hostemu_lib, seed, n_ops=40, calm=True)
