@@ -49,6 +49,12 @@ class Config:
     # that omission costs.
     piggyback: bool = False
     ping_size: int = 40            # a ping / ack / nack with its node names, before any piggybacked broadcast
+    # [U] serf/serf.go handleReconnect / reconnect: every ReconnectInterval (30 s) an agent with failed
+    # members in its list draws one with probability failed / alive and tries memberlist.Join on it (a TCP
+    # push-pull): a member that is really gone does not answer; one that was wrongly declared dead learns
+    # of it from the merged state and refutes.  0 = off (M1 and the CUDA path do not model it;
+    # tests/test_m0_crosscheck.py measures what it changes).
+    reconnect_interval: int = 0
 
 
 def retransmit_limit(mult, n):
@@ -118,7 +124,8 @@ class Agent:
         self.gossip_phase = net.rng.randrange(net.cfg.gossip_interval)
         self.next_probe = None
         self.probe = None               # in-flight probe: dict(target, start, stage, nacks_expected, nacks)
-        self.stats = dict(refutes=0, probes=0, failed_probes=0)
+        self.reconnect_phase = net.rng.randrange(net.cfg.reconnect_interval) if net.cfg.reconnect_interval else 0
+        self.stats = dict(refutes=0, probes=0, failed_probes=0, reconnect_attempts=0, reconnect_contacts=0)
 
     # ---- helpers -----------------------------------------------------------------------------
     def n(self):
@@ -266,6 +273,23 @@ class Agent:
         self.run_probe(t)
         if t % cfg.gossip_interval == self.gossip_phase:
             self.gossip(t)
+        if cfg.reconnect_interval and t % cfg.reconnect_interval == self.reconnect_phase:
+            self.reconnect(t)
+
+    def reconnect(self, t):
+        """[U] serf/serf.go reconnect(): one random failed member, throttled by failed / alive."""
+        failed = [n for n, st in self.views.items() if n != self.id and st.state == DEAD]
+        if not failed:
+            return
+        alive = sum(1 for st in self.views.values() if st.state in (ALIVE, SUSPECT)) or 1
+        if self.net.rng.random() > len(failed) / alive:
+            return                                        # "forgoing reconnect for random throttling"
+        target = self.net.agents[failed[self.net.rng.randrange(len(failed))]]
+        self.stats["reconnect_attempts"] += 1
+        if not target.up:
+            return                                        # nobody answers the TCP connect
+        self.stats["reconnect_contacts"] += 1
+        self.net.push_pull(self, target, t)
 
     def run_probe(self, t):
         cfg, net = self.net.cfg, self.net
@@ -435,6 +459,16 @@ class Network:
         if not s.up or not a.up or a is s:
             return 0
         t = self.now
+        self.push_pull(a, s, t)
+        if ignore_old:
+            a.event_min = max(a.event_min, s.clock_event)
+        lt = a.clock_member
+        a.clock_member += 1
+        a.handle_intent(Broadcast("join", a.id, ltime=lt), t)
+        return 1
+
+    def push_pull(self, a, s, t):
+        """[U] memberlist/state.go pushPullNode + mergeState, both directions, and serf's clocks"""
         for src, dst in ((s, a), (a, s)):
             for node, st in list(src.views.items()):
                 if st.state == ALIVE:
@@ -444,12 +478,6 @@ class Network:
                     dst.suspect_node(node, st.inc, src.id, t)        # remote Dead is only a suspicion
             dst.clock_member = max(dst.clock_member, src.clock_member)
             dst.clock_event = max(dst.clock_event, src.clock_event)
-        if ignore_old:
-            a.event_min = max(a.event_min, s.clock_event)
-        lt = a.clock_member
-        a.clock_member += 1
-        a.handle_intent(Broadcast("join", a.id, ltime=lt), t)
-        return 1
 
     def user_event(self, x, name, payload=b""):
         a = self.agents[x]

@@ -253,3 +253,32 @@ def test_dissemination_at_1600_agents_matches_the_projection(hostemu_lib):
         t_m1.append(t - s + 1)
     assert abs(st.mean(t_m0) - st.mean(t_m1)) <= 3.0, (t_m0, t_m1)
     assert 10 <= min(t_m0 + t_m1) and max(t_m0 + t_m1) <= 24
+
+
+def _false_dead_pairs(net):
+    up = net.up_agents()
+    return sum(1 for a in up for b in up if a is not b and a.views[b.id].state == m0.DEAD)
+
+
+def test_handle_reconnect_only_matters_where_running_members_stay_declared_dead():
+    """serf's handleReconnect (M0 only, `Config.reconnect_interval`): with memberlist's defaults (TCP fallback
+    ping) nobody running is ever declared dead at 30 % loss, so the ticker finds no failed member and does
+    nothing — the regime of every BASELINE config, which is why M1 and the CUDA path leave it out.  Where
+    running members do stay declared dead (no TCP fallback, 60 % loss: the accused never hears the rumor) the
+    reconnect's push-pull is what heals the lists."""
+    quiet = m0.Network(m0.Config(loss=0.30, reconnect_interval=300), seed=5)
+    quiet.converged_cluster(60)
+    quiet.step(1500)
+    assert sum(a.stats["reconnect_attempts"] for a in quiet.agents) == 0 and _false_dead_pairs(quiet) == 0
+    ends = {}
+    for rc in (0, 300):
+        tot = contacts = 0
+        for seed in (1, 2, 3):
+            net = m0.Network(m0.Config(loss=0.60, disable_tcp=True, reconnect_interval=rc), seed=seed)
+            net.converged_cluster(60)
+            net.step(2400)
+            tot += _false_dead_pairs(net)
+            contacts += sum(a.stats["reconnect_contacts"] for a in net.agents)
+        ends[rc] = (tot, contacts)
+    assert ends[0][1] == 0 and ends[300][1] > 0, ends
+    assert ends[0][0] > 0 and ends[300][0] < ends[0][0] * 0.7, ends      # healed lists: clearly fewer stale Dead entries
