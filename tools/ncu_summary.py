@@ -9,7 +9,8 @@ WANT = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
     "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_blocks", "launch__waves_per_multiprocessor",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
